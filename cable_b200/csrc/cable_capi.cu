@@ -1,0 +1,469 @@
+// cable_capi.cu -- C ABI (include/cable_b200.h) over the fused cbm() kernel.
+//
+// A handle owns: one device arena holding every registry field as a (mp,n1,n2)
+// column-major SoA block, a ring of forcing slots filled asynchronously on a side
+// stream, the compute stream, and the host bindings supplied by the caller (the
+// Fortran shim passes C_LOC of each derived-type member once).  There is no CPU
+// path in this library: every entry point that computes requires the CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "cbm_kernel.cuh"
+
+using namespace cbl;
+
+namespace {
+
+thread_local std::string g_err;
+const void *g_cfg_owner = nullptr;    // which handle's DevCfg currently sits in __constant__ c_cfg
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                          \
+  do { cudaError_t e_ = (expr);                                                                 \
+       if (e_ != cudaSuccess) return fail(CABLE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ---- registry table from the X-macro ----------------------------------------------------------
+constexpr unsigned FORCING = CABLE_ROLE_FORCING, PARAM = CABLE_ROLE_PARAM, STATE = CABLE_ROLE_STATE, DIAG = CABLE_ROLE_DIAG;
+template <typename T> struct dt_of;
+template <> struct dt_of<float>  { static constexpr int v = CABLE_DT_F32; };
+template <> struct dt_of<double> { static constexpr int v = CABLE_DT_F64; };
+template <> struct dt_of<int>    { static constexpr int v = CABLE_DT_I32; };
+
+const cable_field_info g_fields[] = {
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) {#T "_" #m, dt_of<ct>::v, n1, n2, role, (unsigned)(flags)},
+#include "../../include/cable_b200_fields.def"
+};
+static_assert(sizeof(g_fields) / sizeof(g_fields[0]) == NFIELDS, "registry size");
+
+size_t elem_size(int dt) { return dt == CABLE_DT_F64 ? 8 : 4; }
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+bool carbon_tables(int mvtype, float *rw, float *tfcl, float *tvclst) {   // cable_carbon.F90:94-150
+  static const float rw13[] = {16.f, 8.7f, 12.5f, 16.f, 18.f, 7.5f, 6.1f, .84f, 10.4f, 15.1f, 9.f, 5.8f, 0.001f};
+  static const float tf13[] = {0.248f, 0.345f, 0.31f, 0.42f, 0.38f, 0.35f, 0.997f, 0.95f, 2.4f, 0.73f, 2.4f, 0.55f, 0.9500f};
+  static const float tv13[] = {283.f, 278.f, 278.f, 235.f, 268.f, 278.0f, 278.0f, 278.0f, 278.0f, 235.f, 278.f, 278.f, 268.f};
+  static const float rw15[] = {16.f, 16.f, 18.f, 8.7f, 10.4f, 6.1f, 6.1f, 6.1f, 5.8f, 5.8f, 0.001f, 9.0f, 0.001f, 0.001f, 0.001f};
+  static const float tf15[] = {0.42f, 0.248f, 0.38f, 0.345f, 2.4f, 0.997f, 0.997f, 0.997f, 0.55f, 0.55f, 0.9500f, 2.4f, 0.9500f, 0.9500f, 0.9500f};
+  static const float tv15[] = {235.f, 283.f, 268.f, 278.f, 278.0f, 278.0f, 278.0f, 278.0f, 278.f, 278.f, 278.0f, 278.f, 278.f, 278.f, 268.f};
+  static const float rw17[] = {16.f, 16.f, 18.f, 8.7f, 12.5f, 15.1f, 10.4f, 7.5f, 6.1f, 6.1f, 0.001f, 5.8f, 0.001f, 5.8f, 0.001f, 9.0f, 0.001f};
+  static const float tf17[] = {0.42f, 0.248f, 0.38f, 0.345f, 0.31f, 0.73f, 2.4f, 0.35f, 0.997f, 0.997f, 0.9500f, 0.55f, 0.9500f, 0.55f, 0.9500f, 2.4f, 0.9500f};
+  static const float tv17[] = {235.f, 283.f, 268.f, 278.f, 278.f, 235.f, 278.0f, 278.0f, 278.0f, 278.0f, 278.0f, 278.f, 278.f, 278.f, 268.f, 278.f, 278.f};
+  const float *a, *b, *c; int n;
+  switch (mvtype) {
+    case 13: a = rw13; b = tf13; c = tv13; n = 13; break;
+    case 15: a = rw15; b = tf15; c = tv15; n = 15; break;
+    case 16: a = rw17; b = tf17; c = tv17; n = 16; break;   // IGBP without water bodies = first 16 of the 17 table
+    case 17: a = rw17; b = tf17; c = tv17; n = 17; break;
+    default: return false;
+  }
+  for (int i = 0; i < 17; i++) { rw[i] = i < n ? a[i] : 0.f; tfcl[i] = i < n ? b[i] : 0.f; tvclst[i] = i < n ? c[i] : 0.f; }
+  return true;
+}
+
+}  // namespace
+
+struct cable_handle {
+  int mp = 0, device = 0;
+  cable_cfg cfg{};
+  DevCfg dcfg{};
+  char *arena = nullptr; size_t arena_bytes = 0;
+  size_t off[NFIELDS]{};             // arena offset of each field (forcing: offset inside a slot)
+  size_t bytes[NFIELDS]{};
+  size_t forcing_slot_bytes = 0, forcing_base = 0;
+  int nslots = 2;
+  void *host[NFIELDS]{};
+  bool host_pinned[NFIELDS]{};
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  std::vector<cudaEvent_t> ev_forcing_ready, ev_slot_free;
+  std::vector<char> slot_has_data;
+  unsigned long long *d_warn = nullptr;
+  long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
+  int block = 128;
+  // measurement
+  cable_counters ctr{};
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev; size_t prof_n = 0;
+};
+
+namespace {
+
+bool is_forcing_input(const cable_handle *h, int id) {
+  const cable_field_info &f = g_fields[id];
+  if (id == FID_met_tvair || id == FID_met_tvrad) return !h->cfg.met_tv_is_tk;
+  return f.role == FORCING && !(f.flags & CABLE_FLAG_HOSTONLY);
+}
+
+void *dev_ptr(const cable_handle *h, int id, int slot) {
+  const cable_field_info &f = g_fields[id];
+  if (f.flags & CABLE_FLAG_HOSTONLY) return nullptr;
+  if (f.role == FORCING) return h->arena + h->forcing_base + (size_t)slot * h->forcing_slot_bytes + h->off[id];
+  return h->arena + h->off[id];
+}
+
+DevPtrs make_ptrs(const cable_handle *h, int slot) {
+  DevPtrs d;
+  int id = 0;
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) d.T##_##m = (ct *)dev_ptr(h, id, slot); id++;
+#include "../../include/cable_b200_fields.def"
+  // met%tvair doubles as an opt-in input: when uploaded it lives in its DIAG block (slot independent)
+  return d;
+}
+
+int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s) {
+  if (!h->host[id]) return CABLE_OK;
+  void *dp = dev_ptr(h, id, slot);
+  if (!dp) return CABLE_OK;
+  if (to_device) { CUDA_TRY(cudaMemcpyAsync(dp, h->host[id], h->bytes[id], cudaMemcpyHostToDevice, s)); h->ctr.h2d_bytes += (long long)h->bytes[id]; }
+  else { CUDA_TRY(cudaMemcpyAsync(h->host[id], dp, h->bytes[id], cudaMemcpyDeviceToHost, s)); h->ctr.d2h_bytes += (long long)h->bytes[id]; }
+  return CABLE_OK;
+}
+
+// soil%*_vec must be the spreads the default configuration builds (cable_parameters.F90:1685-1691);
+// the device promotes the per-tile scalars instead of reading them.
+int check_spreads(cable_handle *h) {
+  const int mp = h->mp;
+  struct { int vec, scal; } pairs[] = {{FID_soil_swilt_vec, FID_soil_swilt}, {FID_soil_sfc_vec, FID_soil_sfc}, {FID_soil_ssat_vec, FID_soil_ssat}};
+  for (auto &p : pairs) {
+    const double *v = (const double *)h->host[p.vec]; const float *s = (const float *)h->host[p.scal];
+    if (!v || !s) continue;
+    for (int k = 0; k < CABLE_MS; k++)
+      for (int i = 0; i < mp; i++)
+        if (v[(size_t)i + (size_t)mp * k] != (double)s[i])
+          return fail(CABLE_E_PARAM, std::string(g_fields[p.vec].name) + " is not SPREAD(" + g_fields[p.scal].name + "): per-layer soil parameters are not supported");
+  }
+  if (const double *v = (const double *)h->host[FID_soil_zse_vec])
+    for (int k = 0; k < CABLE_MS; k++)
+      for (int i = 0; i < mp; i++)
+        if (v[(size_t)i + (size_t)mp * k] != (double)h->cfg.zse[k]) return fail(CABLE_E_PARAM, "soil_zse_vec is not SPREAD(soil%zse)");
+  if (const double *v = (const double *)h->host[FID_canopy_fes_cor])
+    for (int i = 0; i < mp; i++) if (v[i] != 0.0) return fail(CABLE_E_PARAM, "canopy_fes_cor must be 0 offline (cable_serial.F90:440)");
+  return CABLE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cable_b200_abi_version(void) { return CABLE_B200_ABI_VERSION; }
+const char *cable_b200_last_error(void) { return g_err.c_str(); }
+int cable_b200_nfields(void) { return NFIELDS; }
+
+int cable_b200_field_id(const char *name) {
+  if (!name) return CABLE_E_ARG;
+  for (int i = 0; i < NFIELDS; i++) if (!strcmp(g_fields[i].name, name)) return i;
+  return fail(CABLE_E_ARG, std::string("unknown field ") + name);
+}
+
+int cable_b200_field_info(int id, cable_field_info *out) {
+  if (id < 0 || id >= NFIELDS || !out) return fail(CABLE_E_ARG, "bad field id");
+  *out = g_fields[id];
+  return CABLE_OK;
+}
+
+void cable_b200_default_cfg(cable_cfg *c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->struct_bytes = (int)sizeof(*c);
+  c->gs_switch = CABLE_GS_LEUNING;            // src/offline/cable.nml:62
+  c->fwsoil_switch = CABLE_FWSOIL_STANDARD;   // cable.nml:58
+  c->ssnow_potev = CABLE_POTEV_HDM;           // cable.nml:71
+  c->diag_soil_resp_on = 1;                   // cable.nml:63
+  c->icycle = 0;                              // cable.nml:37
+  c->mvtype = 17;
+  c->snmin = 1.0f;                            // cable_runtime_opts_mod.F90:9
+  c->max_glacier_snowd = 1100.0f; c->snow_ccnsw = 2.0f; c->max_ssdn = 750.0f;   // cable_common.F90:217-222
+  c->max_sconds = 2.51f; c->frozen_limit = 0.85f;
+  const float zse[CABLE_MS] = {.022f, .058f, .154f, .409f, 1.085f, 2.872f};      // cable_parameters.F90:1241
+  for (int k = 0; k < CABLE_MS; k++) c->zse[k] = zse[k];
+  c->zshh[0] = 0.5f * zse[0];                                                    // cable_parameters.F90:1828-1831
+  c->zshh[CABLE_MS] = 0.5f * zse[CABLE_MS - 1];
+  for (int k = 1; k < CABLE_MS; k++) c->zshh[k] = 0.5f * (zse[k - 1] + zse[k]);
+  c->ratecp[0] = 1.0f; c->ratecp[1] = 0.03f; c->ratecp[2] = 0.14f;               // pft_params.nml ratecp1-3
+  c->ratecs[0] = 2.0f; c->ratecs[1] = 0.5f;                                      // pft_params.nml ratecs1-2
+  c->met_tv_is_tk = 1; c->caller_duties = 1; c->output_level = 1; c->n_forcing_slots = 2;
+  c->threads_per_block = 0;
+}
+
+int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **out) {
+  if (!out) return fail(CABLE_E_ARG, "out is null");
+  *out = nullptr;
+  if (mp <= 0 || !cfg) return fail(CABLE_E_ARG, "mp must be > 0 and cfg non-null");
+  if (cfg->struct_bytes != (int)sizeof(cable_cfg)) return fail(CABLE_E_ARG, "cable_cfg size mismatch (ABI)");
+  // switch combinations the device path does not implement
+  if (cfg->litter || cfg->or_evap || cfg->gw_model || cfg->l_rev_corr || cfg->soil_thermal_fix ||
+      cfg->l_new_roughness_soil || cfg->call_climate || cfg->redistrb || cfg->soil_struc_sli || cfg->runtime_um)
+    return fail(CABLE_E_UNSUPPORTED, "unsupported switch: litter/or_evap/gw_model/l_rev_corr/soil_thermal_fix/"
+                                     "l_new_roughness_soil/call_climate/redistrb/soil_struc=sli/cable_runtime%um must be off");
+  if (cfg->gs_switch != CABLE_GS_LEUNING && cfg->gs_switch != CABLE_GS_MEDLYN)
+    return fail(CABLE_E_UNSUPPORTED, "gs_model_switch failed.");                 // cbl_dryLeaf.F90:436
+  if (cfg->fwsoil_switch < 0 || cfg->fwsoil_switch > CABLE_FWSOIL_LAI_KTAUL)
+    return fail(CABLE_E_UNSUPPORTED, "fwsoil_switch failed.");                   // cbl_dryLeaf.F90:179
+  if (cfg->ssnow_potev != CABLE_POTEV_HDM && cfg->ssnow_potev != CABLE_POTEV_PM) return fail(CABLE_E_UNSUPPORTED, "ssnow_potev");
+  if (cfg->output_level < 0 || cfg->output_level > 2 || cfg->n_forcing_slots < 1) return fail(CABLE_E_ARG, "output_level/n_forcing_slots");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(CABLE_E_NODEVICE, "no CUDA device visible: cable_b200 has no CPU fallback");
+  if (device < 0) { const char *lr = getenv("LOCAL_RANK"); device = lr ? atoi(lr) % ndev : 0; }
+  if (device >= ndev) return fail(CABLE_E_ARG, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+
+  cable_handle *h = new cable_handle();
+  h->mp = mp; h->device = device; h->cfg = *cfg; h->nslots = cfg->n_forcing_slots;
+  h->block = (cfg->threads_per_block == 64 || cfg->threads_per_block == 256) ? cfg->threads_per_block : 128;
+  // device-side config + host-evaluated constants
+  DevCfg &d = h->dcfg;
+  d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
+  d.diag_soil_resp_on = cfg->diag_soil_resp_on; d.l_new_runoff_speed = cfg->l_new_runoff_speed;
+  d.l_new_reduce_soilevp = cfg->l_new_reduce_soilevp; d.icycle = cfg->icycle; d.mvtype = cfg->mvtype;
+  d.met_tv_is_tk = cfg->met_tv_is_tk; d.caller_duties = cfg->caller_duties; d.output_level = cfg->output_level;
+  d.snmin = cfg->snmin; d.max_glacier_snowd = cfg->max_glacier_snowd; d.snow_ccnsw = cfg->snow_ccnsw;
+  d.max_ssdn = cfg->max_ssdn; d.max_sconds = cfg->max_sconds; d.frozen_limit = cfg->frozen_limit;
+  float zsetot = 0.f;
+  for (int k = 0; k < CABLE_MS; k++) { d.zse[k] = cfg->zse[k]; zsetot = zsetot + cfg->zse[k]; }
+  d.zsetot = zsetot;
+  for (int k = 0; k <= CABLE_MS; k++) d.zshh[k] = cfg->zshh[k];
+  for (int k = 0; k < CABLE_NCP; k++) d.ratecp[k] = cfg->ratecp[k];
+  for (int k = 0; k < CABLE_NCS; k++) d.ratecs[k] = cfg->ratecs[k];
+  const float pi180 = 3.1415927f / 180.0f, ang[3] = {15.0f, 45.0f, 75.0f};
+  for (int b = 0; b < 3; b++) d.cos3[b] = cosf(pi180 * ang[b]);
+  d.log60 = logf(60.0f); d.log250 = logf(250.0f); d.prandt_third = powf(0.71f, 1.0f / 3.0f); d.log_cccw = logf(2.0f);
+  if (cfg->icycle == 0 && !carbon_tables(cfg->mvtype, d.rw, d.tfcl, d.tvclst)) {
+    delete h;
+    return fail(CABLE_E_UNSUPPORTED, "Error! Dimension not compatible with CASA or CSIRO or IGBP types! (mvtype)");   // cable_carbon.F90:142
+  }
+  // arena layout: [PARAM][STATE][DIAG STAR][DIAG other][forcing slot 0..n-1]
+  size_t cur = 0;
+  auto place = [&](unsigned role, int star) {
+    for (int id = 0; id < NFIELDS; id++) {
+      const cable_field_info &f = g_fields[id];
+      h->bytes[id] = (size_t)mp * f.n1 * f.n2 * elem_size(f.dtype);
+      if (f.role != role || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
+      if (role == DIAG && star >= 0 && (int)((f.flags & CABLE_FLAG_STAR) != 0) != star) continue;
+      h->off[id] = cur; cur = align_up(cur + h->bytes[id], 256);
+    }
+  };
+  place(PARAM, -1); place(STATE, -1); place(DIAG, 1); place(DIAG, 0);
+  h->forcing_base = cur;
+  size_t fcur = 0;
+  for (int id = 0; id < NFIELDS; id++) {
+    const cable_field_info &f = g_fields[id];
+    if (f.role != FORCING || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
+    h->off[id] = fcur; fcur = align_up(fcur + h->bytes[id], 256);
+  }
+  h->forcing_slot_bytes = fcur;
+  h->arena_bytes = cur + fcur * (size_t)h->nslots;
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e != cudaSuccess) { delete h; return fail(CABLE_E_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
+  cudaMemset(h->arena, 0, h->arena_bytes);
+  cudaMalloc(&h->d_warn, sizeof(unsigned long long));
+  cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
+  cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
+  h->ev_forcing_ready.resize(h->nslots); h->ev_slot_free.resize(h->nslots); h->slot_has_data.assign(h->nslots, 0);
+  for (int s = 0; s < h->nslots; s++) {
+    cudaEventCreateWithFlags(&h->ev_forcing_ready[s], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_slot_free[s], cudaEventDisableTiming);
+  }
+  e = cudaMemcpyToSymbol(c_cfg, &h->dcfg, sizeof(DevCfg));
+  if (e != cudaSuccess) { cable_b200_destroy(h); return fail(CABLE_E_CUDA, std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(e)); }
+  CUDA_TRY(cudaDeviceSynchronize());
+  g_cfg_owner = h;
+  *out = h;
+  return CABLE_OK;
+}
+
+int cable_b200_destroy(cable_handle *h) {
+  if (!h) return CABLE_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (g_cfg_owner == h) g_cfg_owner = nullptr;
+  for (int id = 0; id < NFIELDS; id++) if (h->host_pinned[id]) cudaHostUnregister(h->host[id]);
+  for (auto ev : h->ev_forcing_ready) cudaEventDestroy(ev);
+  for (auto ev : h->ev_slot_free) cudaEventDestroy(ev);
+  for (auto ev : h->prof_ev) cudaEventDestroy(ev);
+  if (h->s_compute) cudaStreamDestroy(h->s_compute);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->d_warn) cudaFree(h->d_warn);
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+  return CABLE_OK;
+}
+
+int cable_b200_bind_field(cable_handle *h, int id, void *host) {
+  if (!h || id < 0 || id >= NFIELDS) return fail(CABLE_E_ARG, "bind_field: bad handle or id");
+  cudaSetDevice(h->device);
+  if (h->host_pinned[id]) { cudaHostUnregister(h->host[id]); h->host_pinned[id] = false; }
+  h->host[id] = host;
+  // pin per-step traffic in place so H2D/D2H are true async DMA; failure only costs speed
+  const cable_field_info &f = g_fields[id];
+  const bool per_step = (f.role == FORCING) || (f.role == STATE) || (f.role == DIAG && (f.flags & CABLE_FLAG_STAR));
+  if (host && per_step && !(f.flags & CABLE_FLAG_HOSTONLY)) {
+    if (cudaHostRegister(host, h->bytes[id], cudaHostRegisterDefault) == cudaSuccess) h->host_pinned[id] = true;
+    else cudaGetLastError();
+  }
+  return CABLE_OK;
+}
+
+int cable_b200_upload(cable_handle *h, unsigned role_mask) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (role_mask & PARAM) { int rc = check_spreads(h); if (rc) return rc; }
+  for (int id = 0; id < NFIELDS; id++) {
+    const cable_field_info &f = g_fields[id];
+    if (!(f.role & role_mask) || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
+    if (f.role == FORCING) continue;                       // forcing goes through set_forcing_async
+    if ((f.role & (PARAM | STATE)) && !h->host[id])
+      return fail(CABLE_E_UNBOUND, std::string("field not bound: ") + f.name);
+    int rc = copy_field(h, id, 0, true, h->s_compute); if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
+int cable_b200_download(cable_handle *h, unsigned role_mask, unsigned flag_mask) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int id = 0; id < NFIELDS; id++) {
+    const cable_field_info &f = g_fields[id];
+    if (!(f.role & role_mask) || (f.flags & CABLE_FLAG_HOSTONLY) || f.role == FORCING) continue;
+    if (f.role == DIAG && flag_mask && !(f.flags & flag_mask)) continue;
+    int rc = copy_field(h, id, 0, false, h->s_compute); if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
+int cable_b200_set_forcing_async(cable_handle *h, int slot) {
+  if (!h || slot < 0 || slot >= h->nslots) return fail(CABLE_E_ARG, "set_forcing_async: bad slot");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // do not overwrite a slot a running step still reads
+  CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_slot_free[slot], 0));
+  for (int id = 0; id < NFIELDS; id++) {
+    if (!is_forcing_input(h, id)) continue;
+    if (!h->host[id]) return fail(CABLE_E_UNBOUND, std::string("forcing field not bound: ") + g_fields[id].name);
+    int rc = copy_field(h, id, slot, true, h->s_copy); if (rc) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_forcing_ready[slot], h->s_copy));
+  h->slot_has_data[slot] = 1;
+  return CABLE_OK;
+}
+
+int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
+  (void)ktau;   // cbm only uses ktau for a diagnostic print (ktau_gl); the soil_snow SAVE counter is ours
+  if (!h || slot < 0 || slot >= h->nslots) return fail(CABLE_E_ARG, "step: bad slot");
+  if (!(dels > 0.f)) return fail(CABLE_E_ARG, "step: dels must be > 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->slot_has_data[slot]) CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_forcing_ready[slot], 0));
+  if (g_cfg_owner != h) {      // several handles (e.g. differing switches) may share the device
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->s_compute));
+    g_cfg_owner = h;
+  }
+  const DevPtrs d = make_ptrs(h, slot);
+  const int first = (h->soil_snow_calls == 0) ? 1 : 0;
+  const int grid = (h->mp + h->block - 1) / h->block;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profile) {
+    if (h->prof_n + 2 > h->prof_ev.size()) {
+      size_t old = h->prof_ev.size(); h->prof_ev.resize(old + 512);
+      for (size_t k = old; k < h->prof_ev.size(); k++) cudaEventCreate(&h->prof_ev[k]);
+    }
+    e0 = h->prof_ev[h->prof_n++]; e1 = h->prof_ev[h->prof_n++];
+    CUDA_TRY(cudaEventRecord(e0, h->s_compute));
+  }
+  switch (h->block) {
+    case 64:  cbm_kernel<64><<<grid, 64, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn); break;
+    case 256: cbm_kernel<256><<<grid, 256, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn); break;
+    default:  cbm_kernel<128><<<grid, 128, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (h->profile) CUDA_TRY(cudaEventRecord(e1, h->s_compute));
+  CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], h->s_compute));
+  h->soil_snow_calls++;
+  h->ctr.steps++; h->ctr.kernel_launches++;
+  return CABLE_OK;
+}
+
+int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  const int slot = (int)(h->ctr.steps % h->nslots);
+  int rc = cable_b200_set_forcing_async(h, slot); if (rc) return rc;
+  rc = cable_b200_step(h, ktau, dels, slot); if (rc) return rc;
+  const int lvl = h->cfg.output_level;
+  if (lvl >= 1) {
+    for (int id = 0; id < NFIELDS; id++) {
+      const cable_field_info &f = g_fields[id];
+      if (f.flags & CABLE_FLAG_HOSTONLY) continue;
+      const bool want = (f.role == STATE) || (f.role == DIAG && (lvl >= 2 || (f.flags & CABLE_FLAG_STAR)));
+      if (!want) continue;
+      rc = copy_field(h, id, 0, false, h->s_compute); if (rc) return rc;
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
+int cable_b200_sync(cable_handle *h) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
+void *cable_b200_device_ptr(cable_handle *h, int id, int slot) {
+  if (!h || id < 0 || id >= NFIELDS || slot < 0 || slot >= h->nslots) return nullptr;
+  return dev_ptr(h, id, slot);
+}
+
+void *cable_b200_compute_stream(cable_handle *h) { return h ? (void *)h->s_compute : nullptr; }
+
+int cable_b200_profile(cable_handle *h, int enable) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  h->profile = enable != 0;
+  return CABLE_OK;
+}
+
+int cable_b200_get_counters(cable_handle *h, cable_counters *out) {
+  if (!h || !out) return fail(CABLE_E_ARG, "null");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  for (size_t k = 0; k + 1 < h->prof_n; k += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[k], h->prof_ev[k + 1]) == cudaSuccess) { h->ctr.kernel_ms += ms; h->ctr.kernel_ms_count++; }
+  }
+  h->prof_n = 0;
+  unsigned long long w = 0;
+  CUDA_TRY(cudaMemcpy(&w, h->d_warn, sizeof(w), cudaMemcpyDeviceToHost));
+  h->ctr.n_dryleaf_warn = (long long)w;
+  *out = h->ctr;
+  return CABLE_OK;
+}
+
+int cable_b200_reset_counters(cable_handle *h) {
+  if (!h) return fail(CABLE_E_ARG, "null");
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->s_compute);
+  const long long steps = h->ctr.steps;       // steps also drives the forcing-slot rotation: keep it
+  h->ctr = cable_counters{}; h->ctr.steps = steps;
+  h->prof_n = 0;
+  cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
+  return CABLE_OK;
+}
+
+int cable_b200_grid_reduce(cable_handle *h, int id, int comp, const float *d_patchfrac, const int *d_cstart,
+                           const int *d_cend, int nland, float *d_out) {
+  if (!h || id < 0 || id >= NFIELDS || nland <= 0) return fail(CABLE_E_ARG, "grid_reduce: bad argument");
+  const cable_field_info &f = g_fields[id];
+  if (f.dtype != CABLE_DT_F32 || comp < 0 || comp >= f.n1 * f.n2 || (f.flags & CABLE_FLAG_HOSTONLY) || f.role == FORCING)
+    return fail(CABLE_E_ARG, "grid_reduce: field must be a resident f32 field");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const float *x = (const float *)dev_ptr(h, id, 0) + (size_t)comp * h->mp;
+  grid_reduce_kernel<<<(nland + 127) / 128, 128, 0, h->s_compute>>>(x, d_patchfrac, d_cstart, d_cend, nland, d_out);
+  CUDA_TRY(cudaGetLastError());
+  h->ctr.kernel_launches++;
+  return CABLE_OK;
+}
+
+}  // extern "C"

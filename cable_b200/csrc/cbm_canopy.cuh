@@ -1,0 +1,654 @@
+// cbm_canopy.cuh -- per-tile define_canopy (cable_canopy.F90:10-1048) and callees.
+// One thread walks one tile through the NITER=4 Monin-Obukhov stability loop and,
+// inside it, the <=MAXITER=20 coupled leaf-temperature / photosynthesis / stomata
+// iteration.  r_2 (fp64) variables of the reference stay double; everything else
+// is float with the reference's evaluation order (no FMA contraction).
+#pragma once
+#include "cbm_consts.cuh"
+
+namespace cbl {
+
+// radiation: cbl_radiation.F90:30-218
+CBL_DEV void radiation(Tile &t, bool sunlit_veg) {
+  const float lai = t.canopy_vlaiw, extkb = t.rad_extkb, extkd = t.rad_extkd;
+  const bool veg = lai > K::lai_thresh;
+  const float cf2n = expf(-t.veg_extkn * lai);
+  const float transd = veg ? expf(-extkd * lai) : 1.0f;
+  const float transb = expf(-mn(extkb * lai, 30.f));
+  t.rad_transd = transd; t.rad_transb = transb;
+  const float flpwb = K::sboltz * p4(t.met_tvrad);
+  const float flwv = K::emleaf * flpwb;
+  t.rad_flws = K::sboltz * K::emsoil * p4(t.ssnow_tss);
+  const float emair = t.met_fld / flpwb;
+  float g1 = 0.0f, g2 = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 6; q++) t.rad_qcan[q] = 0.0f;          // qcan(leaf + 2*band)
+  if (veg) {
+    g1 = (4.0f * K::emleaf / (K::capp * t.air_rho)) * flpwb / t.met_tvrad * extkd
+         * ((1.0f - transb * transd) / (extkb + extkd) + (transd - transb) / (extkb - extkd));
+    g2 = (8.0f * K::emleaf / (K::capp * t.air_rho)) * flpwb / t.met_tvrad * extkd * (1.0f - transd) / extkd - g1;
+    t.rad_qcan[0 + 2 * 2] = (t.rad_flws - flwv) * extkd * (transd - transb) / (extkb - extkd)
+                            + (emair - K::emleaf) * extkd * flpwb * (1.0f - transd * transb) / (extkb + extkd);
+    t.rad_qcan[1 + 2 * 2] = (1.0f - transd) * (t.rad_flws + t.met_fld - 2.0f * flwv) - t.rad_qcan[0 + 2 * 2];
+  }
+  g1 = t.air_cmolar * g1; g2 = t.air_cmolar * g2;
+  // MAX(1.0e-3_r_2, gradis): compared in double, stored back to float
+  t.rad_gradis[0] = ((double)g1 < 1.0e-3) ? (float)1.0e-3 : g1;
+  t.rad_gradis[1] = ((double)g2 < 1.0e-3) ? (float)1.0e-3 : g2;
+  if (sunlit_veg) {
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const float fbeam = t.rad_fbeam[b], extkdm = t.rad_extkdm[b], extkbm = t.rad_extkbm[b];
+      const float cexpkdm = t.rad_cexpkdm[b], cexpkbm = t.rad_cexpkbm[b], fsd = t.met_fsd[b];
+      const float cf1 = (1.0f - transb * cexpkdm) / (extkb + extkdm);
+      const float cf3 = (1.0f - transb * cexpkbm) / (extkb + extkbm);
+      const float dif = (1.0f - fbeam) * (1.0f - t.rad_reffdf[b]);
+      const float bem = fbeam * (1.0f - t.rad_reffbm[b]);
+      const float sct = fbeam * (1.0f - t.veg_taul[b] - t.veg_refl[b]) * extkb
+                        * ((1 - transb) / extkb - (1 - transb * transb) / (extkb + extkb));
+      t.rad_qcan[0 + 2 * b] = fsd * (dif * extkdm * cf1 + bem * extkbm * cf3 + sct);
+      t.rad_qcan[1 + 2 * b] = fsd * (dif * extkdm * ((1.0f - cexpkdm) / extkdm - cf1)
+                                     + bem * extkbm * ((1.0f - cexpkbm) / extkbm - cf3) - sct);
+    }
+    t.rad_qssabs = t.met_fsd[0] * (t.rad_fbeam[0] * (1.f - t.rad_reffbm[0]) * expf(-mn(t.rad_extkbm[0] * lai, 20.f))
+                                   + (1.f - t.rad_fbeam[0]) * (1.f - t.rad_reffdf[0]) * expf(-mn(t.rad_extkdm[0] * lai, 20.f)))
+                   + t.met_fsd[1] * (t.rad_fbeam[1] * (1.f - t.rad_reffbm[1]) * t.rad_cexpkbm[1]
+                                     + (1.f - t.rad_fbeam[1]) * (1.f - t.rad_reffdf[1]) * t.rad_cexpkdm[1]);
+    t.rad_scalex[0] = (1.0f - transb * cf2n) / (extkb + t.veg_extkn);
+    t.rad_fvlai[0] = (1.0f - transb) / extkb;
+    t.rad_fvlai[1] = lai - t.rad_fvlai[0];
+  } else {
+    t.rad_qssabs = (1.0f - t.ssnow_albsoilsn[0]) * t.met_fsd[0] + (1.0f - t.ssnow_albsoilsn[1]) * t.met_fsd[1];
+    t.rad_scalex[0] = 0.0f; t.rad_fvlai[0] = 0.0f; t.rad_fvlai[1] = lai;
+  }
+  t.rad_scalex[1] = (1.0f - cf2n) / t.veg_extkn - t.rad_scalex[0];
+#pragma unroll
+  for (int l = 0; l < 2; l++) t.rad_rniso[l] = (t.rad_qcan[l] + t.rad_qcan[l + 2]) + t.rad_qcan[l + 4];
+}
+
+// Surf_wetness_fact + initialize_wetfac: cbl_SurfaceWetness.F90:10-79, cbl_init_wetfac_mod.F90:9-116
+CBL_DEV void surf_wetness_fact(Tile &t, float cansat, float dels) {
+  const float rain = t.met_precip - t.met_precip_sn;
+  float ftemp = mn(rain, 4.0f * mn(dels, 1800.0f) / (60.0f * 1440.0f));
+  float room = mx(cansat - t.canopy_cansto, 0.0f);
+  t.canopy_wcint = (ftemp > 0.0f && t.met_tk > K::tfrz) ? mn(room, ftemp) : 0.0f;
+  t.canopy_through = t.met_precip_sn + mn(rain, mx(0.0f, rain - t.canopy_wcint));
+  t.canopy_cansto = t.canopy_cansto + t.canopy_wcint;
+  t.canopy_fwet = mx(0.0f, mn(0.9f, 0.8f * t.canopy_cansto / mx(cansat, 0.01f)));
+  t.ssnow_satfrac = (double)1.0e-8f;
+  t.ssnow_rh_srf = 1.0;
+  const float wilting_pt = t.soil_swilt / K::wilt_limitfactor;
+  float num = (float)t.ssnow_wb[0] - wilting_pt;
+  float den = mx(0.0830f, t.soil_sfc - wilting_pt);
+  float wetfac = mx(0.0f, mn(1.0f, num / den));
+  if (t.ssnow_wbice[0] > 0.0) {
+    double r = t.ssnow_wbice[0] / t.ssnow_wb[0];
+    float ice_ratio = (float)(r * r);
+    float ice_factor = (float)(1.0 - mn(0.2, (double)ice_ratio));
+    ice_factor = (float)mx(0.5, (double)ice_factor);
+    wetfac = wetfac * ice_factor;
+  }
+  if (t.ssnow_snowd > 0.1f) wetfac = 0.9f;
+  if (t.veg_iveg == K::lakes_cable) wetfac = (t.met_tk >= K::tfrz + 5.f) ? 1.0f : 0.7f;
+  t.ssnow_wetfac = 0.5f * (wetfac + t.ssnow_owetfac);
+}
+
+// soil potential evaporation: Humidity_deficit_method / Penman_Monteith (cbl_pot_evap_snow.F90)
+CBL_DEV float soil_potev(const Tile &t, const DevCfg &c, float q_air) {
+  if (c.ssnow_potev == CABLE_POTEV_PM) {
+    float sss = t.air_dsatdk;
+    float cc1 = sss / (sss + t.air_psyc), cc2 = t.air_psyc / (sss + t.air_psyc);
+    float qs = qsatf(t.met_tvair - K::tfrz, t.met_pmb);
+    return cc1 * (t.canopy_fns - t.canopy_ga) + cc2 * t.air_rho * t.air_rlam * (qs - t.met_qvair) / t.ssnow_rtsoil;
+  }
+  float dq = t.ssnow_qstss - q_air;
+  if (t.ssnow_snowd > 1.0f || t.ssnow_tgg[0] == K::tfrz) dq = mx(-0.1e-3f, dq);
+  return t.air_rho * t.air_rlam * dq / t.ssnow_rtsoil;
+}
+
+// Latent_heat_flux: cbl_latent_heat.F90:15-285
+CBL_DEV void latent_heat_flux(Tile &t, const DevCfg &c, float dels) {
+  const float rlam = t.air_rlam, potev = t.ssnow_potev, snowd = t.ssnow_snowd;
+  if (potev < 0.f) t.ssnow_wetfac = 1.0f;                                   // side effect kept (D2)
+  double fess = (double)(t.ssnow_wetfac * potev);
+  const float pwet = mx(0.f, mn(0.2f, t.ssnow_pudsto / mx(1.f, t.ssnow_pudsmx)));
+  fess = fess * (double)(1.f - pwet);
+  if (snowd < 0.1f && fess > 0.) {
+    const float frescale = c.zse[0] * K::density_liq * rlam / dels;
+    float lower = (float)t.ssnow_wb[0] - (c.l_new_reduce_soilevp ? t.soil_swilt : t.soil_swilt / 2.0f);
+    float upper = (float)mx(0., (double)(lower * frescale) - t.ssnow_evapfbl[0] * (double)rlam / (double)dels);
+    fess = mn(fess, (double)upper);
+    upper = (float)(t.ssnow_wb[0] - t.ssnow_wbice[0] / (double)c.frozen_limit) * frescale;
+    upper = mx(upper, 0.f);
+    fess = mn(fess, (double)upper);
+  }
+  float cls = 1.f;
+  if (snowd >= 0.1f) { cls = 1.1335f; fess = (double)(cls * potev); }
+  if (snowd < 0.1f && potev < 0.f && t.ssnow_tss < K::tfrz) { cls = 1.1335f; fess = (double)(cls * potev); }
+  if (snowd >= 0.1f && potev > 0.f) {
+    cls = 1.1335f;
+    fess = (double)mn((t.ssnow_wetfac * potev) * cls, snowd / dels * rlam * cls);
+  }
+  t.ssnow_cls = cls;
+  t.canopy_fess = fess;
+  t.canopy_fesp = (double)mn(t.ssnow_pudsto / dels * rlam, mx(pwet * potev, 0.f));
+  t.canopy_fes = t.canopy_fess + t.canopy_fesp;
+}
+
+// root water stress: cbl_fwsoil.F90:13-118.  soil%*_vec are spreads of the per-tile
+// scalars (cable_parameters.F90:1685-1691), so the scalars are promoted instead.
+CBL_DEV float fwsoil_calc(const Tile &t, const DevCfg &c) {
+  const double swilt = (double)t.soil_swilt, sfc = (double)t.soil_sfc, ssat = (double)t.soil_ssat;
+  if (c.fwsoil_switch == CABLE_FWSOIL_STANDARD) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K::ms; k++)
+      s = s + t.veg_froot[k] * mx(1.0e-9f, mn(1.0f, (float)((t.ssnow_wbliq[k] - swilt) / (sfc - swilt))));
+    float rwater = mx(1.0e-9f, s);
+    if (c.gs_switch == CABLE_GS_MEDLYN) return mx(1.0e-4f, mn(1.0f, rwater));
+    return mx(1.0e-9f, mn(1.0f, t.veg_vbeta * rwater));
+  } else if (c.fwsoil_switch == CABLE_FWSOIL_NONLINEAR) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < K::ms; k++) s = s + t.veg_froot[k] * mx(0.0f, mn(1.0f, (float)(t.ssnow_wbliq[k] - swilt)));
+    const float sw = t.soil_swilt, fc = t.soil_sfc;
+    float rwater = mx(1.0e-9f, s / (fc - sw));
+    rwater = sw + rwater * (fc - sw);
+    const float xi1 = sw, xi2 = sw + (fc - sw) / 2.0f, xi3 = fc;
+    float si1 = (rwater - xi2) / (xi1 - xi2) * (rwater - xi3) / (xi1 - xi3);
+    float si2 = (rwater - xi1) / (xi2 - xi1) * (rwater - xi3) / (xi2 - xi3);
+    float si3 = (rwater - xi1) / (xi3 - xi1) * (rwater - xi2) / (xi3 - xi2);
+    float fw = 1.f;
+    if (rwater < fc - 0.02f) fw = mx(0.f, mn(1.f, 0.f * si1 + 0.9f * si2 + 1.0f * si3));
+    return fw;
+  } else {  // Lai and Ktaul 2000
+    float fw = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K::ms; k++) {
+      float dummy = (float)(0.01f / mx(1.0e-3, t.ssnow_wbliq[k] - swilt));
+      float frwater = (float)mx(1.0e-4, pow((t.ssnow_wbliq[k] - swilt) / ssat, (double)dummy));
+      fw = mn(1.0f, mx(fw, frwater));
+    }
+    return fw;
+  }
+}
+
+// leaf-level response functions: cbl_dryLeaf.F90:779-877
+CBL_DEV float ejx_root(float parx, float alpha, float convex, float x) {
+  const float ap = alpha * parx;
+  return (ap + x - sqrtf(p2(ap + x) - 4.0f * convex * alpha * parx * x)) / (2.0f * convex);
+}
+CBL_DEV float xvcmxt4(float x) {
+  return powf(2.0f, 0.1f * x - 2.5f) / ((1.0f + expf(0.3f * (13.0f - x))) * (1.0f + expf(0.3f * (x - 36.0f))));
+}
+CBL_DEV float arrhenius_peaked(float x, float coef, float eha, float ehd, float entrop) {
+  float num = coef * expf((eha / (K::rgas * K::trefk)) * (1.f - K::trefk / x));
+  float den = 1.0f + expf((entrop * x - ehd) / (K::rgas * x));
+  return mx(0.0f, num / den);
+}
+
+// One root of the Ci quadratic as the reference selects it (cbl_photosynthesis.F90:78-119 etc.)
+// kind 0: Rubisco (sentinel only if |coef2|>1e-9 & |coef1|<1e-9, later overwritten),
+// kind 1: RuBP (default sentinel 99999), kind 2: sink (value is ci itself).
+CBL_DEV double an_limited(int kind, double coef2, double coef1, double coef0,
+                          float vmax, float cxa, float cxb, float v4, float rdx) {
+  const double tiny = (double)1.0e-9f;
+  double an = (kind == 1) ? (double)99999.0f : 0.0;
+  const double a2 = fabs(coef2), a1 = fabs(coef1);
+  if (kind == 2 && a2 < tiny && a1 < tiny) an = (double)99999.0f;
+  if (a2 < tiny && a1 >= tiny) {
+    double ci = -1.0f * coef0 / coef1;
+    if (kind == 2) an = ci;
+    else { ci = mx(0.0, ci); an = vmax * (ci - cxb / 2.0f) / (ci + cxa) + v4 - rdx; }
+  }
+  if (a2 >= tiny) {
+    double del = coef1 * coef1 - 4.0f * coef0 * coef2;
+    double ci = (-coef1 + sqrt(mx(0.0, del))) / (2.0f * coef2);
+    if (kind == 2) an = ci;
+    else { ci = mx(0.0, ci); an = vmax * (ci - cxb / 2.0f) / (ci + cxa) + v4 - rdx; }
+  }
+  return an;
+}
+
+// scratch that define_canopy ALLOCATEs and hands to dryLeaf / wetLeaf (cable_canopy.F90:132-175)
+struct CanopyWork {
+  float  cansat, dsx, fwsoil, tlfx, tlfy;
+  double ecy, hcy, rny;
+  double gbhu[2], gbhf[2], csx[2];
+  float  sum_rniso, sum_gradis;
+  int    warn;
+};
+
+// dryLeaf: cbl_dryLeaf.F90:10-666, one tile
+CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int iter) {
+  const float jtomol = 4.6e-6f;
+  const float cr = K::capp * K::rmair;
+  if (iter == 1) { w.fwsoil = fwsoil_calc(t, c); t.canopy_fwsoil = (double)w.fwsoil; }
+  const bool veg = t.canopy_vlaiw > K::lai_thresh;
+  const float fwsoil = w.fwsoil;
+  float gswmin[2], gh[2], ghr[2], gw[2], psycst[2], rdx[2] = {0.f, 0.f}, anx[2] = {0.f, 0.f};
+  float rdy[2] = {0.f, 0.f}, an_y[2] = {0.f, 0.f};
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    gswmin[l] = mx(1.e-6f, t.rad_scalex[l] * t.veg_gswmin);
+    gh[l] = 1.0e-3f; ghr[l] = 1.0e-3f; gw[l] = 1.0e-3f;
+    psycst[l] = t.air_psyc;
+  }
+  if (c.gs_switch == CABLE_GS_MEDLYN && veg) { gswmin[0] = t.veg_g0; gswmin[1] = t.veg_g0; }   // per-tile form of D4
+  double rnx = (double)w.sum_rniso, ecx = (double)w.sum_rniso, hcx = 0.0;
+  float abs_deltlf = 999.0f, deltlf = 0.f, tlfxx = w.tlfx;
+  w.hcy = 0.0;
+  t.canopy_fevc = 0.0;
+#pragma unroll
+  for (int k = 0; k < K::ms; k++) t.ssnow_evapfbl[k] = 0.0;
+  float oldevapfbl[K::ms];
+  if (!veg) { rnx = 0.0; ecx = 0.0; w.ecy = ecx; abs_deltlf = 0.0f; w.rny = rnx; }
+  float deltlfy = abs_deltlf;
+  const float dleaf3 = powf(t.veg_dleaf, 3.0f);
+  const float dtair = t.met_tvair - t.met_tk;
+
+  for (int k = 1; k <= K::maxiter; k++) {
+    const bool active = veg && abs_deltlf > 0.1f;
+    if (active) {
+      const float tlfx = w.tlfx;
+      // free-convection boundary-layer conductance, total conductances
+      float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - t.met_tvair) * dleaf3);
+      float gras4 = powf(gras, 0.25f);
+#pragma unroll
+      for (int l = 0; l < 2; l++) {
+        w.gbhf[l] = mx(1.e-6, (double)(t.rad_fvlai[l] * t.air_cmolar * 0.5f * K::dheat * gras4 / t.veg_dleaf));
+        gh[l] = (float)(2.0f * (w.gbhu[l] + w.gbhf[l]));
+        ghr[l] = t.rad_gradis[l] + gh[l];
+      }
+      // temperature responses of Vcmax (C3, C4) and Jmax
+      float temp3 = arrhenius_peaked(tlfx, 1.17461f, 73637.0f, 149252.0f, 486.0f) * t.veg_vcmax * (1.0f - t.veg_frac4);
+      float temp4 = xvcmxt4(tlfx - K::tfrz) * t.veg_vcmax * t.veg_frac4;
+      float tempj = arrhenius_peaked(tlfx, 1.16715f, 50300.0f, 152044.0f, 495.0f) * t.veg_ejmax * (1.0f - t.veg_frac4);
+      const float tdiff = tlfx - K::trefk;
+      const float arr = 1.0f - K::trefk / tlfx;
+      float conkct = t.veg_conkc0 * expf((t.veg_ekc / (K::rgas * K::trefk)) * arr);
+      float conkot = t.veg_conko0 * expf((t.veg_eko / (K::rgas * K::trefk)) * arr);
+      tlfxx = tlfx;
+      const float cx1 = conkct * (1.0f + 0.21f / conkot);
+      const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
+      float vsum0 = t.rad_fvlai[0] + t.rad_fvlai[1];
+#pragma unroll
+      for (int l = 0; l < 2; l++) {
+        const float vcmxt3 = t.rad_scalex[l] * temp3, vcmxt4 = t.rad_scalex[l] * temp4, ejmxt3 = t.rad_scalex[l] * tempj;
+        const float par3 = t.rad_qcan[l] * jtomol * (1.0f - t.veg_frac4);
+        const float par4 = t.rad_qcan[l] * jtomol * t.veg_frac4;
+        const float vx3 = mx(0.0f, 0.25f * ejx_root(par3, t.veg_alpha, t.veg_convex, ejmxt3));
+        const float vx4 = mx(0.0f, ejx_root(par4, t.veg_alpha, t.veg_convex, vcmxt4));
+        rdx[l] = (t.veg_cfrd * vcmxt3 + t.veg_cfrd * vcmxt4);
+        // stomatal slope coefficient
+        float gs_coeff;
+        if (c.gs_switch == CABLE_GS_LEUNING) {
+          gs_coeff = (float)(((double)fwsoil / (w.csx[l] - (double)0.0f)) * (double)(t.veg_a1gs / (1.0f + w.dsx / t.veg_d0gs)));
+        } else {
+          float vpd = (w.dsx < 50.0f) ? 0.05f : w.dsx * 1E-03f;
+          float g1 = t.veg_g1;
+          gs_coeff = (float)((double)(1.0f + (g1 * fwsoil) / sqrtf(vpd)) / w.csx[l]);
+          if (fwsoil <= 0.05f) gs_coeff = (float)((double)(fwsoil / 0.05f + (g1 * fwsoil) / sqrtf(vpd)) / w.csx[l]);
+        }
+        // photosynthesis (cbl_photosynthesis.F90:52-222) for this leaf
+        float an = 0.f;
+        if (vsum0 > K::lai_thresh && t.rad_fvlai[l] > K::lai_thresh) {
+          const double csx = w.csx[l];
+          const float g0t = gswmin[l] * fwsoil / K::rgswc;
+          const double one_m = (double)1.0f - csx * (double)gs_coeff;
+          double coef2 = (double)(g0t + gs_coeff * (vcmxt3 - (rdx[l] - vcmxt4)));
+          double coef1 = one_m * (double)(vcmxt3 + vcmxt4 - rdx[l]) + (double)g0t * ((double)cx1 - csx)
+                         - (double)(gs_coeff * (vcmxt3 * cx2 / 2.0f + cx1 * (rdx[l] - vcmxt4)));
+          double coef0 = -one_m * (double)(vcmxt3 * cx2 / 2.0f + cx1 * (rdx[l] - vcmxt4)) - (double)(g0t * cx1) * csx;
+          double anrubisco = an_limited(0, coef2, coef1, coef0, vcmxt3, cx1, cx2, vcmxt4, rdx[l]);
+          coef2 = (double)(g0t + gs_coeff * (vx3 - (rdx[l] - vx4)));
+          coef1 = one_m * (double)(vx3 + vx4 - rdx[l]) + (double)g0t * ((double)cx2 - csx)
+                  - (double)(gs_coeff * (vx3 * cx2 / 2.0f + cx2 * (rdx[l] - vx4)));
+          coef0 = -one_m * (double)(vx3 * cx2 / 2.0f + cx2 * (rdx[l] - vx4)) - (double)(g0t * cx2) * csx;
+          double anrubp = an_limited(1, coef2, coef1, coef0, vx3, cx2, cx2, vx4, rdx[l]);
+          const float effc4 = 4000.0f;
+          coef2 = (double)gs_coeff;
+          coef1 = (double)(g0t + gs_coeff * (rdx[l] - 0.5f * vcmxt3) + effc4 * vcmxt4)
+                  - (double)gs_coeff * csx * (double)effc4 * (double)vcmxt4;
+          coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)((rdx[l] - 0.5f * vcmxt3) * gswmin[l] * fwsoil / K::rgswc);
+          double ansink = an_limited(2, coef2, coef1, coef0, 0.f, 0.f, 0.f, 0.f, 0.f);
+          an = (float)mn(mn(anrubisco, anrubp), ansink);
+        }
+        anx[l] = an;
+        // leaf-surface CO2, stomatal and total water conductance (:460-485)
+        if (t.rad_fvlai[l] > K::lai_thresh) {
+          const double gb = w.gbhu[l] + w.gbhf[l];
+          w.csx[l] = mx(1.0e-4, (double)t.met_ca - (double)(K::rgbwc * an) / gb);
+          float gswx = mx(1.e-3f, gswmin[l] * fwsoil + mx(0.0f, K::rgswc * gs_coeff * an));
+          t.canopy_gswx[l] = gswx;
+          gw[l] = mx((float)(1.0f / ((double)(1.0f / gswx) + 1.0f / (1.075f * gb))), 0.00001f);
+          psycst[l] = t.air_psyc * (ghr[l] / gw[l]);
+        }
+      }
+      // big-leaf latent heat, limited by what the roots can supply (:489-536)
+      ecx = (double)((t.air_dsatdk * (t.rad_rniso[0] - cr * dtair * t.rad_gradis[0]) + cr * t.met_dva * ghr[0]) / (t.air_dsatdk + psycst[0])
+                     + (t.air_dsatdk * (t.rad_rniso[1] - cr * dtair * t.rad_gradis[1]) + cr * t.met_dva * ghr[1]) / (t.air_dsatdk + psycst[1]));
+      const double local_fevc = (double)((1.0f - t.canopy_fwet) * (float)ecx);
+      if (local_fevc > 0.0) {
+        // transp_soil_water (cbl_remove_trans.F90:43-93)
+        double diff = 0.0, s = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < K::ms; kk++) {
+          double xx = local_fevc * (double)dels / (double)K::hl * (double)t.veg_froot[kk] + diff;
+          double avail = mx(0.0, t.ssnow_wbliq[kk] - (double)1.1f * (double)t.soil_swilt) * (double)c.zse[kk] * (double)K::density_liq;
+          double xxd = xx - avail;
+          double e;
+          if (xxd > 0.0) { e = avail; diff = xxd; } else { e = xx; diff = 0.0; }
+          t.ssnow_evapfbl[kk] = e;
+          s = s + e;
+        }
+        t.canopy_fevc = s * (double)t.air_rlam / (double)dels;
+        ecx = t.canopy_fevc / (double)(1.0f - t.canopy_fwet);
+      }
+      // sensible heat, new leaf temperature, vpd at the leaf surface (:538-557)
+      const float sgh = gh[0] + gh[1], sghr = ghr[0] + ghr[1];
+      hcx = ((double)w.sum_rniso - ecx - (double)(cr * dtair * w.sum_gradis)) * (double)sgh / (double)sghr;
+      w.tlfx = t.met_tvair + (float)hcx / (cr * sgh);
+      rnx = (double)(w.sum_rniso - cr * (w.tlfx - t.met_tk) * w.sum_gradis);
+      w.dsx = mx(t.met_dva + t.air_dsatdk * (w.tlfx - t.met_tvair), 0.0f);
+      deltlf = tlfxx - w.tlfx;
+      abs_deltlf = fabsf(deltlf);
+    } else {
+      // photosynthesis() zeroes anx for tiles it skips (cbl_photosynthesis.F90:49)
+      anx[0] = 0.f; anx[1] = 0.f;
+    }
+    // keep the best iterate; damp after k > 5 (:565-606)
+    const bool better = abs_deltlf < fabsf(deltlfy);
+    if (better) deltlfy = deltlf;
+    if (better || k == 1) {
+      w.tlfy = w.tlfx; w.rny = rnx; w.hcy = hcx; w.ecy = ecx;
+      rdy[0] = rdx[0]; rdy[1] = rdx[1]; an_y[0] = anx[0]; an_y[1] = anx[1];
+#pragma unroll
+      for (int kk = 0; kk < K::ms; kk++) oldevapfbl[kk] = (float)t.ssnow_evapfbl[kk];
+    }
+    if (abs_deltlf > 0.1f) {
+      float fac = 0.5f * ((float)max(0, k - 5) / ((float)k - 4.9999f));
+      w.tlfx = fac * tlfxx + (1.0f - fac) * w.tlfx;
+    } else if (k > 1) {
+      break;    // converged: every later pass of the reference loop is a no-op for this tile
+    }
+  }
+  t.canopy_fevc = (double)(1.0f - t.canopy_fwet) * w.ecy;
+  if (w.ecy > 0.0 && t.canopy_fwet < 1.0f) {
+    if (fabs(w.ecy - ecx) > (double)1.0e-6f) {
+      float s = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < K::ms; kk++) s = s + oldevapfbl[kk];
+      if (fabs(t.canopy_fevc - (double)(s * t.air_rlam / dels)) > (double)1.0e-4f) {
+        w.warn++;                  // reference prints 'oldevapfbl not right' and carries on
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < K::ms; kk++) t.ssnow_evapfbl[kk] = (double)oldevapfbl[kk];
+      }
+    }
+  }
+  t.canopy_frday = 12.0f * (rdy[0] + rdy[1]);
+  t.canopy_fpn = mn(-12.0f * (an_y[0] + an_y[1]), t.canopy_frday);
+}
+
+// wetLeaf: cbl_wetleaf.F90:9-111
+CBL_DEV void wetLeaf(Tile &t, const CanopyWork &w, float dels) {
+  t.canopy_fevw = 0.0f; t.canopy_fhvw = 0.0f;
+  if (t.canopy_vlaiw > K::lai_thresh) {
+    const float cr = K::capp * K::rmair;
+    const float sum_gbh = (float)((w.gbhu[0] + w.gbhf[0]) + (w.gbhu[1] + w.gbhf[1]));
+    const double ghwet = (double)(2.0f * sum_gbh);
+    const float gwwet = 1.075f * sum_gbh;
+    const float ghrwet = (float)((double)w.sum_gradis + ghwet);
+    const float ccfevw = mn(t.canopy_cansto * t.air_rlam / dels, 2.0f / (1440.0f / (dels / 60.0f)) * t.air_rlam);
+    const float num = t.air_dsatdk * (w.sum_rniso - cr * (t.met_tvair - t.met_tk) * w.sum_gradis) + cr * t.met_dva * ghrwet;
+    const float den = t.air_dsatdk + t.air_psyc * ghrwet / gwwet;
+    t.canopy_fevw = mn(t.canopy_fwet * num / den, ccfevw);
+    t.canopy_fevw_pot = num / den;
+    t.canopy_fhvw = t.canopy_fwet * (w.sum_rniso - cr * (w.tlfy - t.met_tk) * w.sum_gradis) - t.canopy_fevw;
+  }
+}
+
+// within_canopy: cbl_within_canopy.F90:10-159 (no litter, no or_evap)
+CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0) {
+  if (!(t.veg_meth > 0 && t.canopy_vlaiw > K::lai_thresh && t.rough_hruff > t.rough_z0soilsn)) return;
+  const float rrbw = (float)(((w.gbhu[0] + w.gbhf[0]) + (w.gbhu[1] + w.gbhf[1])) / (double)t.air_cmolar);
+  const float rrsw = (t.canopy_gswx[0] + t.canopy_gswx[1]) / t.air_cmolar;
+  float fix_eqn = t.ssnow_cls * rt0 / (rt0 + 0.f);
+  if (t.ssnow_potev > 0.f) fix_eqn = fix_eqn * t.ssnow_wetfac;
+  const float fix_eqn2 = rt0 / (rt0 + 0.f);
+  const float epsi = t.air_epsi, rt1 = t.rough_rt1;
+  const float cond = (1.f + epsi) * rrsw + rrbw, r01 = rt0 * rt1, bs = rrbw * rrsw;
+  const float dmah = (rt0 + fix_eqn2 * rt1) * cond + epsi * r01 * bs;
+  const float dmbh = (-t.air_rlam / K::capp) * r01 * bs;
+  const float dmch = cond * rt0 * rt1 * (t.canopy_fhv + t.canopy_fhs) / (t.air_rho * K::capp);
+  const float dmae = (-epsi * K::capp / t.air_rlam) * r01 * bs;
+  const float dmbe = (rt0 + fix_eqn * rt1) * cond + r01 * bs;
+  const float dmce = (float)((double)(cond * rt0 * rt1) * ((double)t.canopy_fev + t.canopy_fes / (double)t.ssnow_cls)
+                             / (double)(t.air_rho * t.air_rlam));
+  const float det = dmah * dmbe - dmae * dmbh + 1.0e-12f;
+  float tv = t.met_tk + (dmbe * dmch - dmbh * dmce) / det;
+  tv = mx(tv, mn(t.ssnow_tss, t.met_tk) - 5.0f);
+  tv = mn(tv, mx(t.ssnow_tss, t.met_tk) + 5.0f);
+  t.met_tvair = tv;
+  float qv = t.met_qv + (dmah * dmce - dmae * dmch) / det;
+  qv = mx(0.0f, qv);
+  qv = mx(qv, mn(t.ssnow_qstss, t.met_qv));
+  qv = mn(qv, mx(t.ssnow_qstss, t.met_qv));
+  t.met_qvair = qv;
+  float qstvair = qsatf(tv - K::tfrz, t.met_pmb);
+  t.met_dva = (qstvair - qv) * K::rmair / K::rmh2o * t.met_pmb * 100.f;
+}
+
+// define_canopy: cable_canopy.F90:10-1048.  Returns number of dryLeaf soft warnings.
+CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg) {
+  CanopyWork w;
+  w.warn = 0;
+  const float cr = K::capp * K::rmair;
+  const float lai = t.canopy_vlaiw;
+  const bool veg = lai > K::lai_thresh;
+  t.canopy_cansto = t.canopy_oldcansto;
+  w.cansat = t.veg_canst1 * lai;
+  surf_wetness_fact(t, w.cansat, dels);
+  t.canopy_fevw_pot = 0.0f;
+#pragma unroll
+  for (int l = 0; l < 2; l++) { t.canopy_gswx[l] = 1e-3f; w.gbhf[l] = (double)1e-3f; w.gbhu[l] = (double)1e-3f; w.csx[l] = (double)t.met_ca; }
+#pragma unroll
+  for (int k = 0; k < K::ms; k++) { t.ssnow_evapfbl[k] = 0.0; t.ssnow_rex[k] = 0.0; }
+  t.met_tvair = t.met_tk; t.met_qvair = t.met_qv; t.canopy_tv = t.met_tvair;
+  t.canopy_fwsoil = 1.0;
+  define_air(t);
+  float qstvair = qsatf(t.met_tvair - K::tfrz, t.met_pmb);
+  t.met_dva = (qstvair - t.met_qvair) * K::rmair / K::rmh2o * t.met_pmb * 100.0f;
+  w.dsx = mx(t.met_dva, 0.0f);
+  w.tlfx = t.met_tk; w.tlfy = t.met_tk;
+  w.fwsoil = 0.f; w.ecy = 0.; w.hcy = 0.; w.rny = 0.;
+  const float ortsoil = t.ssnow_rtsoil;
+  t.ssnow_tss = (float)(1 - t.ssnow_isflag) * t.ssnow_tgg[0] + (float)t.ssnow_isflag * t.ssnow_tggsn[0];
+  const float tss4 = p4(t.ssnow_tss);
+  t.canopy_fes = 0.; t.canopy_fess = 0.; t.canopy_fesp = 0.;
+  t.ssnow_potev = 0.f;
+  radiation(t, sunlit_veg);
+  t.canopy_zetar[0] = K::zeta0; t.canopy_zetar[1] = K::zetpos + 1;
+  w.sum_rniso = t.rad_rniso[0] + t.rad_rniso[1];
+  w.sum_gradis = t.rad_gradis[0] + t.rad_gradis[1];
+
+  float rt1usc = 0.f, rt0 = 0.f;
+  const float zr = mx(t.rough_zruffs - t.rough_disp, t.rough_z0soilsn);
+  const bool above = !signbit(t.rough_zref_tq + t.rough_disp - t.rough_zruffs);   // xx = 0.5 + SIGN(0.5, .)
+  const float tvrad4 = p4(t.met_tvrad);
+  const bool dense = veg && t.rough_hruff > t.rough_z0soilsn;
+
+  float zet_cur = K::zeta0;
+#pragma unroll 1
+  for (int iter = 1; iter <= CABLE_NITER; iter++) {
+    const float zet = zet_cur;
+    // friction velocity (cbl_friction_vel.F90:19-108)
+    {
+      float psim_1 = psim(zet * t.rough_zref_uv / t.rough_zref_tq);
+      float rescale = K::vonk * mx(t.met_ua, K::umin);
+      float z_eff = t.rough_zref_uv / t.rough_z0m;
+      float psim_2 = psim(zet * t.rough_z0m / t.rough_zref_tq);
+      t.canopy_us = mn(mx(1.e-6f, rescale / (logf(z_eff) - psim_1 + psim_2)), 10.0f);
+    }
+    const float us = t.canopy_us;
+    // aerodynamic resistances (:276-363)
+    float r1c = (logf(t.rough_zref_tq / zr) - psis(zet) + psis(zet * zr / t.rough_zref_tq)) / K::vonk;
+    rt1usc = above ? 1.0f * r1c : 0.0f * r1c;
+    rt0 = mx(5.f, t.rough_rt0us / us);
+    t.rough_rt1 = mx(5.f, (t.rough_rt1usa + t.rough_rt1usb + rt1usc) / us);
+    float rtsoil = veg ? rt0 : rt0 + t.rough_rt1;
+    rtsoil = mx(5.f, rtsoil);
+    if (rtsoil > 2.f * ortsoil || rtsoil < 0.5f * ortsoil) rtsoil = mx(5.f, 0.5f * (rtsoil + ortsoil));
+    t.ssnow_rtsoil = rtsoil;
+    // forced-convection leaf boundary-layer conductances (:376-395)
+    if (veg) {
+      float gv = t.air_cmolar * K::apol * t.air_visc / K::prandt / t.veg_dleaf
+                 * sqrtf(us / mx(t.rough_usuh, 1.e-6f) * t.veg_dleaf / t.air_visc)
+                 * c.prandt_third / t.veg_shelrb;
+      const double gbvtop = mx(0.05, (double)gv);
+      const float hc = 0.5f * t.rough_coexp;
+      w.gbhu[0] = gbvtop * (double)(1.0f - expf(-mn(lai * (hc + t.rad_extkb), 20.0f))) / (double)(t.rad_extkb + hc);
+      w.gbhu[1] = (double)(2.0f / t.rough_coexp) * gbvtop * (double)(1.0f - expf(-mn(hc * lai, 20.0f))) - w.gbhu[0];
+    }
+    w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
+    dryLeaf(t, c, w, dels, iter);
+    wetLeaf(t, w, dels);
+    // vegetation fluxes and temperature (:418-456)
+    t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
+    t.canopy_fhv = (1.0f - t.canopy_fwet) * (float)w.hcy + t.canopy_fhvw;
+    t.canopy_fnv = (1.0f - t.canopy_fwet) * (float)w.rny + t.canopy_fevw + t.canopy_fhvw;
+    float tv = t.met_tvrad;
+    if (dense) {
+      t.rad_lwabv = cr * (w.tlfy - t.met_tk) * w.sum_gradis;
+      float arg = t.rad_lwabv / (2.0f * (1.0f - t.rad_transd) * K::sboltz * K::emleaf) + tvrad4;
+      if (arg > 0.0f) tv = powf(arg, 0.25f);
+    }
+    t.canopy_tv = tv;
+    t.canopy_fns = t.rad_qssabs + t.rad_transd * t.met_fld + (1.0f - t.rad_transd) * K::emleaf * K::sboltz * p4(tv)
+                   - K::emsoil * K::sboltz * tss4;
+    // soil evaporation and sensible heat, before and after the in-canopy air update (:461-610)
+    t.ssnow_qstss = qsatf(t.ssnow_tss - K::tfrz, t.met_pmb);
+    t.ssnow_potev = soil_potev(t, c, t.met_qv);
+    latent_heat_flux(t, c, dels);
+    t.canopy_fhs = t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair) / t.ssnow_rtsoil;
+    within_canopy(t, w, rt0);
+    t.ssnow_potev = soil_potev(t, c, t.met_qvair);
+    latent_heat_flux(t, c, dels);
+    t.canopy_fhs = t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair) / t.ssnow_rtsoil;
+    t.canopy_ga = (float)((double)(t.canopy_fns - t.canopy_fhs) - t.canopy_fes);
+    t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
+    t.canopy_fh = t.canopy_fhv + t.canopy_fhs;
+    t.ssnow_potev = (t.ssnow_potev >= 0.f) ? mx(0.00001f, t.ssnow_potev) : mn(-0.0002f, t.ssnow_potev);
+    t.canopy_fevw_pot = (t.canopy_fevw_pot >= 0.f) ? mx(0.000001f, t.canopy_fevw_pot) : mn(-0.002f, t.canopy_fevw_pot);
+    // update_zetar (cbl_zetar.F90:106-156): not on the last pass
+    if (iter < CABLE_NITER) {
+      float z = -(K::vonk * K::grav * t.rough_zref_tq * (t.canopy_fh + 0.07f * t.canopy_fe))
+                / (t.air_rho * K::capp * t.met_tk * p3(us));
+      zet_cur = mx(K::zetneg, mn(K::zetpos, z));
+      // static indices only: a run-time subscript would push the whole Tile into local memory
+      if (iter == 1) t.canopy_zetar[1] = zet_cur;
+      else if (iter == 2) t.canopy_zetar[2] = zet_cur;
+      else t.canopy_zetar[3] = zet_cur;
+    }
+  }
+  // diagnostics of the last pass that the loop overwrites each time (:644-669)
+  t.canopy_rnet = t.canopy_fnv + t.canopy_fns;
+  t.canopy_rniso = w.sum_rniso + t.rad_qssabs + t.rad_transd * t.met_fld
+                   + (1.0f - t.rad_transd) * K::emleaf * K::sboltz * tvrad4 - K::emsoil * K::sboltz * tvrad4;
+  t.canopy_epot = (t.canopy_fevw_pot + t.ssnow_potev / t.ssnow_cls) * dels / t.air_rlam;
+  {
+    float rlow = t.canopy_epot * t.air_rlam / dels;
+    if (rlow == 0.f) rlow = 1.e-7f;
+    float wcs = mx(0.f, mn(1.0f, t.canopy_fe / rlow));
+    if (wcs <= 0.f) wcs = mx(0.f, mn(1.f, mx(t.canopy_fev / t.canopy_fevw_pot, (float)t.canopy_fes / t.ssnow_potev)));
+    t.canopy_wetfac_cs = wcs;
+  }
+
+  const float us = t.canopy_us;
+  t.canopy_cduv = us * us / p2(mx(t.met_ua, K::umin));
+  {  // bulk surface conductance (:689-714)
+    float lai_min = mx(K::lai_thresh, lai);
+    float cc = (t.rad_fvlai[0] / lai_min) * t.canopy_gswx[0] + (t.rad_fvlai[1] / lai_min) * t.canopy_gswx[1];
+    cc = (1.f - t.rad_transd) * mx(1.e-06f, cc);
+    float rel = (float)(t.ssnow_wb[0] / (double)t.soil_sfc);
+    float sc = t.rad_transd * p2(0.01f * rel);
+    t.canopy_gswx_T = (t.soil_isoilm == K::ice_soiltype) ? 1.e6f : cc + sc;
+  }
+  const float zN = t.canopy_zetar[CABLE_NITER - 1];       // also zetar(:,iterplus): iterplus == NITER on exit
+  t.canopy_cdtq = t.canopy_cduv * (logf(t.rough_zref_uv / t.rough_z0m) - psim(zN * t.rough_zref_uv / t.rough_zref_tq)
+                                   + psim(zN * t.rough_z0m / t.rough_zref_tq))
+                  / (logf(t.rough_zref_tq / (0.1f * t.rough_z0m)) - psis(zN) + psis(zN * 0.1f * t.rough_z0m / t.rough_zref_tq));
+  // screen-level temperature and humidity (:731-878)
+  const float tstar = -t.canopy_fh / (t.air_rho * K::capp * us);
+  const float qstar = -t.canopy_fe / (t.air_rho * t.air_rlam * us * t.ssnow_cls);
+  const float zscrn = mx(t.rough_z0m, 2.0f - t.rough_disp);
+  const float ftemp = (logf(t.rough_zref_tq / zscrn) - psis(zN) + psis(zN * zscrn / t.rough_zref_tq)) / K::vonk;
+  float tscrn = t.met_tk - K::tfrz - tstar * ftemp;
+  float r_sc = 0.f;
+  const float hr = t.rough_hruff, disp = t.rough_disp, rgh = t.canopy_rghlai;
+  const bool canopy_scrn = veg && hr > 0.01f;
+  const float rsum = t.rough_rt0us + t.rough_rt1usa + t.rough_rt1usb + rt1usc;
+  if (canopy_scrn) {
+    const float zscl = mx(t.rough_z0soilsn, 2.0f);
+    float term1 = 0.f, term2 = 0.f, term5 = 0.f;
+    if (disp > 0.0f) {
+      term1 = expf(2 * K::csw * rgh * (1 - zscl / hr));
+      term2 = expf(2 * K::csw * rgh * (1 - disp / hr));
+      term5 = mx(2.f / 3.f * hr / disp, 1.f);
+    }
+    const float term3 = p2(K::a33) * K::ctl * 2 * K::csw * rgh;
+    if (zscl < disp) {
+      const float e2 = expf(2 * K::csw * rgh);
+      r_sc = term5 * logf(zscl / t.rough_z0soilsn) * (e2 - term2) / term3;
+      r_sc = r_sc + term5 * logf(disp / zscl) * (e2 - term1) / term3;
+    } else if (disp <= zscl && zscl < hr) {
+      r_sc = t.rough_rt0us + term5 * (term2 - term1) / term3;
+    } else if (hr <= zscl && zscl < t.rough_zruffs) {
+      r_sc = t.rough_rt0us + t.rough_rt1usa + term5 * (zscl - hr) / (p2(K::a33) * K::ctl * hr);
+    } else if (zscl >= t.rough_zruffs) {
+      r_sc = t.rough_rt0us + t.rough_rt1usa + t.rough_rt1usb
+             + (logf((zscl - disp) / mx(t.rough_zruffs - disp, t.rough_z0soilsn))
+                - psis((zscl - disp) * zN / t.rough_zref_tq) + psis((t.rough_zruffs - disp) * zN / t.rough_zref_tq)) / K::vonk;
+    }
+    tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, (r_sc / mx(1.f, rsum))) - K::tfrz;
+  }
+  t.canopy_tscrn = tscrn;
+  {
+    const float rsts = qsatf(tscrn, t.met_pmb);
+    const float qtgnet = rsts * t.ssnow_wetfac - t.met_qv;
+    const float qsurf = (qtgnet > 0.f) ? rsts * t.ssnow_wetfac : 0.1f * rsts * t.ssnow_wetfac + 0.9f * t.met_qv;
+    t.canopy_qmom = t.air_rho * (us * us);
+    float qscrn = t.met_qv - qstar * ftemp;
+    if (canopy_scrn) qscrn = qsurf + (t.met_qv - qsurf) * mn(1.f, (r_sc / mx(1.f, rsum)));
+    t.canopy_qscrn = qscrn;
+  }
+  // canopy water store (:881-906)
+  t.canopy_dewmm = (float)(-((double)mn(0.0f, t.canopy_fevw) + mn(0.0, t.canopy_fevc)) * (double)dels / (double)t.air_rlam);
+  t.canopy_cansto = t.canopy_cansto + t.canopy_dewmm;
+  t.canopy_cansto = mx(t.canopy_cansto - mx(0.0f, t.canopy_fevw) * dels / t.air_rlam, 0.0f);
+  t.canopy_spill = mx(0.0f, t.canopy_cansto - w.cansat);
+  t.canopy_through = t.canopy_through + t.canopy_spill;
+  t.canopy_precis = mx(0.f, t.canopy_through);
+  t.canopy_cansto = t.canopy_cansto - t.canopy_spill;
+  t.canopy_delwc = t.canopy_cansto - t.canopy_oldcansto;
+  // sensitivities for the implicit soil-temperature solve (:913-1027), default branch
+  t.ssnow_dfn_dtg = (-1.f) * 4.f * K::emsoil * K::sboltz * tss4 / t.ssnow_tss;
+  t.ssnow_dfh_dtg = t.air_rho * K::capp / t.ssnow_rtsoil;
+  t.ssnow_dfe_ddq = t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls / t.ssnow_rtsoil;
+  {
+    const float tc = t.ssnow_tss - K::tfrz;
+    t.ssnow_ddq_dtg = (K::rmh2o / K::rmair) / t.met_pmb * K::tetena * K::tetenb * K::tetenc / (p2(K::tetenc + t.ssnow_tss - K::tfrz))
+                      * expf(K::tetenb * tc / (K::tetenc + t.ssnow_tss - K::tfrz));
+  }
+  t.ssnow_dfe_dtg = t.ssnow_dfe_ddq * t.ssnow_ddq_dtg;
+  t.canopy_dgdtg = (double)(t.ssnow_dfn_dtg - t.ssnow_dfh_dtg - t.ssnow_dfe_dtg);
+  t.bal_drybal = (float)(w.ecy + w.hcy) - w.sum_rniso + cr * (w.tlfy - t.met_tk) * w.sum_gradis;
+  t.bal_wetbal = t.canopy_fevw + t.canopy_fhvw - w.sum_rniso * t.canopy_fwet + cr * (w.tlfy - t.met_tk) * w.sum_gradis * t.canopy_fwet;
+  t.rad_swnet = (t.rad_qcan[0] + t.rad_qcan[1]) + (t.rad_qcan[2] + t.rad_qcan[3]) + t.rad_qssabs;
+  t.rad_lwnet = t.met_fld - K::sboltz * K::emleaf * p4(t.canopy_tv) * (1 - t.rad_transd) - t.rad_flws * t.rad_transd;
+  t.rad_rnet = t.rad_swnet + t.rad_lwnet;
+  return w.warn;
+}
+
+}  // namespace cbl

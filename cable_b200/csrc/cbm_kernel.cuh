@@ -1,0 +1,120 @@
+// cbm_kernel.cuh -- the fused cbm() kernel: one thread per tile, one launch per timestep.
+//
+// Reference sequence (src/offline/cbl_model_driver_offline.F90:108-229):
+//   lake refill -> ruff_resist -> define_air -> masks -> init_radiation -> Albedo
+//   -> define_canopy -> soil_snow -> snow_aging -> flux sums -> simple carbon.
+// The reference runs each routine as a sweep over all mp tiles, streaming ~260 (mp)
+// arrays through cache per step; here a tile's forcing (68 B), per-tile parameters and
+// prognostic state are read once, every intermediate lives in registers, and only
+// state + requested diagnostics are written back.
+#pragma once
+#include "cbm_surface.cuh"
+#include "cbm_canopy.cuh"
+#include "cbm_soilsnow.cuh"
+
+namespace cbl {
+
+__constant__ DevCfg c_cfg;
+
+#define CBL_ROLE_FORCING CABLE_ROLE_FORCING
+#define CBL_ROLE_PARAM   CABLE_ROLE_PARAM
+#define CBL_ROLE_STATE   CABLE_ROLE_STATE
+#define CBL_ROLE_DIAG    CABLE_ROLE_DIAG
+// flag tokens used by the rows of cable_b200_fields.def
+constexpr unsigned STAR = CABLE_FLAG_STAR, COND = CABLE_FLAG_COND, HOSTONLY = CABLE_FLAG_HOSTONLY, OPTIN = CABLE_FLAG_OPTIN;
+#define CBL_FLAGS(x) ((unsigned)(x))
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+cbm_kernel(const DevPtrs d, const int mp, const float dels, const int first_call, unsigned long long *warn_counter) {
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= mp) return;
+  const DevCfg &c = c_cfg;
+  const size_t smp = (size_t)mp;
+  Tile t;
+
+  // ---- load forcing, per-tile parameters, prognostic state (coalesced SoA reads) ----
+#define CABLE_F1(T, m, ct, role, flags)                                                          \
+  if ((CBL_ROLE_##role & (CABLE_ROLE_FORCING | CABLE_ROLE_PARAM | CABLE_ROLE_STATE)) &&         \
+      !(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_OPTIN)))                            \
+    t.T##_##m = d.T##_##m[i];
+#define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
+  if ((CBL_ROLE_##role & (CABLE_ROLE_FORCING | CABLE_ROLE_PARAM | CABLE_ROLE_STATE)) &&         \
+      !(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_OPTIN))) {                          \
+    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = d.T##_##m[i + smp * k]; \
+  }
+#include "../../include/cable_b200_fields.def"
+
+  // opt-in inputs
+  if (c.met_tv_is_tk) { t.met_tvair = t.met_tk; t.met_tvrad = t.met_tk; }     // cable_input.F90:2679-2680
+  else { t.met_tvair = d.met_tvair[i]; t.met_tvrad = d.met_tvrad[i]; }
+  if (c.ssnow_potev == CABLE_POTEV_PM) t.canopy_ga = d.canopy_ga[i];           // cable_canopy.F90:487
+  if (c.caller_duties) t.canopy_oldcansto = t.canopy_cansto;                   // cable_serial.F90:573
+
+  // ---- the step ----
+  lake_refill(t, c);
+  const bool veg_branch = ruff_resist(t, c);
+  define_air(t);
+  const bool veg_mask = t.canopy_vlaiw > K::lai_thresh;                         // masks_cbl.F90:45
+  const bool sunlit_mask = (t.met_fsd[0] + t.met_fsd[1]) > K::rad_thresh;       // cbm:131 (D9)
+  const bool sunlit_veg = veg_mask && sunlit_mask;
+  init_radiation(t, c, veg_mask);
+  albedo(t, veg_mask);
+  t.rad_albedo_T = (t.rad_albedo[0] + t.rad_albedo[1]) * 0.5f;
+  t.ssnow_otss_0 = t.ssnow_otss;
+  t.ssnow_otss = t.ssnow_tss;
+  const int warn = define_canopy(t, c, dels, sunlit_veg);
+  t.ssnow_owetfac = t.ssnow_wetfac;
+  soil_snow(t, c, dels, first_call != 0);
+  snow_aging(t, dels);
+  t.ssnow_deltss = t.ssnow_tss - t.ssnow_otss;
+  t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
+  t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
+  t.canopy_rnet = t.canopy_fns + t.canopy_fnv;
+  t.rad_trad = powf((1.f - t.rad_transd) * p4(t.canopy_tv) + t.rad_transd * p4(t.ssnow_tss), 0.25f);
+  if (c.icycle == 0) simple_carbon(t, c, dels);
+  if (warn) atomicAdd(warn_counter, (unsigned long long)warn);
+
+  // ---- store state always; diagnostics by output level (coalesced SoA writes) ----
+  const int lvl = c.output_level;
+#define CABLE_F1(T, m, ct, role, flags)                                                          \
+  if (!(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_COND))) {                           \
+    if ((CBL_ROLE_##role == CABLE_ROLE_STATE) ||                                                 \
+        (CBL_ROLE_##role == CABLE_ROLE_DIAG && (lvl >= 2 || (lvl >= 1 && (CBL_FLAGS(flags) & CABLE_FLAG_STAR))))) \
+      d.T##_##m[i] = t.T##_##m;                                                                  \
+  }
+#define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
+  if (!(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_COND))) {                           \
+    if ((CBL_ROLE_##role == CABLE_ROLE_STATE) ||                                                 \
+        (CBL_ROLE_##role == CABLE_ROLE_DIAG && (lvl >= 2 || (lvl >= 1 && (CBL_FLAGS(flags) & CABLE_FLAG_STAR))))) { \
+      _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) d.T##_##m[i + smp * k] = t.T##_##m[k]; \
+    }                                                                                            \
+  }
+#include "../../include/cable_b200_fields.def"
+
+  // fields the reference writes only on some tiles: keep the device copy stale elsewhere
+  if (lvl >= 2) {
+    if (veg_branch) {                                                           // cable_roughness.F90:290-295
+      d.rough_term2[i] = t.rough_term2; d.rough_term3[i] = t.rough_term3; d.rough_term5[i] = t.rough_term5;
+      d.rough_term6[i] = t.rough_term6; d.rough_term6a[i] = t.rough_term6a;
+    }
+    if (veg_mask) { d.rad_cexpkbm[i] = t.rad_cexpkbm[0]; d.rad_cexpkbm[i + smp] = t.rad_cexpkbm[1]; }   // D1
+    d.rad_fbeam[i] = t.rad_fbeam[0]; d.rad_fbeam[i + smp] = t.rad_fbeam[1];
+    if (veg_mask && t.rough_hruff > t.rough_z0soilsn) d.rad_lwabv[i] = t.rad_lwabv;                     // cable_canopy.F90:427-431
+    d.canopy_zetash[i] = K::zeta0; d.canopy_zetash[i + smp] = K::zetpos + 1;                            // :251-252 (D5)
+  }
+}
+
+// ---- patch -> grid-cell reduction: out[l] = sum_{i=cstart[l]..cend[l]} x[i]*patchfrac[i] ----
+// (src/util/cable_grid_reductions.F90:66-73; one thread per land point, <= ~17 tiles each)
+__global__ void grid_reduce_kernel(const float *__restrict__ x, const float *__restrict__ patchfrac,
+                                   const int *__restrict__ cstart, const int *__restrict__ cend,
+                                   int nland, float *__restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= nland) return;
+  float s = 0.f;
+  for (int i = cstart[l]; i <= cend[l]; i++) s = s + x[i] * patchfrac[i];
+  out[l] = s;
+}
+
+}  // namespace cbl

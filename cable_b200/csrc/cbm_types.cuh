@@ -1,0 +1,57 @@
+// cbm_types.cuh -- device-side data model of the cbm() step.
+//
+// The reference passes 11 derived types of (mp[,k[,b]]) POINTER arrays
+// (src/offline/cable_define_types.F90:79-717).  On the device every member is
+// one structure-of-arrays allocation with the tile index fastest (identical to
+// the Fortran column-major layout), and one CUDA thread owns one tile: it pulls
+// the tile's forcing / parameters / prognostic state into the flat register
+// struct `Tile`, runs the whole step out of registers, and writes back state
+// plus the requested diagnostics.  Both structs are generated from
+// include/cable_b200_fields.def so host binding, device allocation and kernel
+// I/O can never disagree about a field.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/cable_b200.h"
+
+namespace cbl {
+
+enum FieldId {
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) FID_##T##_##m,
+#include "../../include/cable_b200_fields.def"
+  NFIELDS
+};
+
+// device pointers, one per field (HOSTONLY fields stay null)
+struct DevPtrs {
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) ct *__restrict__ T##_##m;
+#include "../../include/cable_b200_fields.def"
+};
+
+// per-thread copy of one tile
+struct Tile {
+#define CABLE_F1(T, m, ct, role, flags) ct T##_##m;
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) ct T##_##m[(n1) * (n2)];
+#include "../../include/cable_b200_fields.def"
+};
+
+// Everything cbm() reads from Fortran module scope plus a few
+// constants the reference's compiler folds at build time or evaluates once on
+// the host; they are computed once on the host at create() so that they carry
+// the host libm's correctly rounded values.
+struct DevCfg {
+  int   gs_switch, fwsoil_switch, ssnow_potev, diag_soil_resp_on;
+  int   l_new_runoff_speed, l_new_reduce_soilevp;
+  int   icycle, mvtype;
+  int   met_tv_is_tk, caller_duties, output_level;
+  float snmin, max_glacier_snowd, snow_ccnsw, max_ssdn, max_sconds, frozen_limit;
+  float zse[CABLE_MS], zshh[CABLE_MS + 1], ratecp[CABLE_NCP], ratecs[CABLE_NCS];
+  float zsetot;          // SUM(soil%zse)                   cbl_soilsnow_main.F90:66
+  float cos3[3];         // COS(pi180*[15,45,75])           cbl_init_radiation.F90:193
+  float log60, log250;   // LOG(60.0), LOG(250.0)           cbl_Oldconductivity.F90:31
+  float prandt_third;    // Cprandt**(1.0/3.0)              cable_canopy.F90:380
+  float log_cccw;        // LOG(CCCW_C)                     cable_roughness.F90:273
+  // carbon_pl per-PFT tables for this mvtype               cable_carbon.F90:94-150
+  float rw[17], tfcl[17], tvclst[17];
+};
+
+}  // namespace cbl

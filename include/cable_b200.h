@@ -1,0 +1,209 @@
+/* cable_b200.h -- C ABI of the B200-native cbm() land-surface step.
+ *
+ * This is the drop-in boundary for ONE reference interface:
+ *
+ *   SUBROUTINE cbm( ktau, dels, air, bgc, canopy, met, bal, rad, rough, soil,
+ *                   ssnow, sum_flux, veg, climate, xk, c1, rhoch )
+ *   -- reference: src/offline/cbl_model_driver_offline.F90:38-40
+ *      callers:   src/offline/cable_serial.F90:594,
+ *                 src/offline/cable_mpiworker.F90:503
+ *
+ * The reference passes eleven derived types of POINTER arrays dimensioned
+ * (mp[,k[,b]]).  Those are not C-interoperable, so the Fortran shim
+ * (fortran/cable_cbm_b200.F90) binds every member array
+ * once with cable_b200_bind_field(handle, id, C_LOC(array)) and then calls
+ * cable_b200_cbm(handle, ktau, dels) each timestep.  Field ids, dtypes and
+ * extents come from include/cable_b200_fields.def (mirror of
+ * src/offline/cable_define_types.F90:79-717).
+ *
+ * All entry points return 0 on success, a negative CABLE_E_* code otherwise;
+ * cable_b200_last_error() gives the text.  The reference has no status
+ * returns -- it STOPs (cbl_dryLeaf.F90:179,436, cable_carbon.F90:148) -- so
+ * the shim turns a non-zero status into  CALL cable_abort(...).
+ *
+ * No torch types, no C++ types: plain pointers, ints and floats only.
+ * There is no CPU fallback: without a CUDA device create() fails.
+ */
+#ifndef CABLE_B200_H
+#define CABLE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CABLE_B200_ABI_VERSION 1
+
+/* dims fixed by the reference (cable_define_types.F90:62-71) */
+#define CABLE_MS    6   /* soil layers            */
+#define CABLE_MSN   3   /* snow layers            */
+#define CABLE_MF    2   /* sunlit / shaded leaves */
+#define CABLE_NRB   3   /* radiation bands        */
+#define CABLE_SWB   2   /* shortwave bands        */
+#define CABLE_NITER 4   /* stability iterations   */
+#define CABLE_NCP   3   /* plant carbon pools     */
+#define CABLE_NCS   2   /* soil carbon pools      */
+
+/* field roles / flags (bit masks), see cable_b200_fields.def */
+#define CABLE_ROLE_FORCING 1u
+#define CABLE_ROLE_PARAM   2u
+#define CABLE_ROLE_STATE   4u
+#define CABLE_ROLE_DIAG    8u
+#define CABLE_ROLE_ALL     15u
+#define CABLE_FLAG_STAR     1u
+#define CABLE_FLAG_COND     2u
+#define CABLE_FLAG_HOSTONLY 4u
+#define CABLE_FLAG_OPTIN    8u
+
+#define CABLE_DT_F32 0
+#define CABLE_DT_F64 1
+#define CABLE_DT_I32 2
+
+/* status codes */
+#define CABLE_OK              0
+#define CABLE_E_ARG          -1   /* bad argument / unknown field          */
+#define CABLE_E_UNSUPPORTED  -2   /* switch combination not on the device  */
+#define CABLE_E_CUDA         -3   /* CUDA runtime error                    */
+#define CABLE_E_UNBOUND      -4   /* a required field has no host binding  */
+#define CABLE_E_PARAM        -5   /* parameter consistency check failed    */
+#define CABLE_E_NODEVICE     -6   /* no CUDA device: there is no fallback  */
+
+/* enumerations for cable_user switches (src/util/cable_runtime_opts_mod.F90:14-125) */
+#define CABLE_GS_LEUNING 0        /* cable_user%gs_switch = 'leuning' */
+#define CABLE_GS_MEDLYN  1        /*                      = 'medlyn'  */
+#define CABLE_FWSOIL_STANDARD   0 /* fwsoil_switch = 'standard'                 */
+#define CABLE_FWSOIL_NONLINEAR  1 /*               = 'non-linear extrapolation' */
+#define CABLE_FWSOIL_LAI_KTAUL  2 /*               = 'Lai and Ktaul 2000'       */
+#define CABLE_FWSOIL_HAVERD2013 3 /* unsupported (needs SLI)                    */
+#define CABLE_POTEV_HDM 0         /* ssnow_potev = 'HDM' or ''  */
+#define CABLE_POTEV_PM  1         /*             = 'P-M'        */
+
+/* Module-level state the reference cbm() reads implicitly:
+ * cable_user%*, cable_runtime%*, icycle, snow constants, soil%zse ...      */
+typedef struct cable_cfg {
+  int   struct_bytes;          /* = sizeof(cable_cfg), ABI check             */
+  /* cable_user switches */
+  int   gs_switch;             /* CABLE_GS_*                                 */
+  int   fwsoil_switch;         /* CABLE_FWSOIL_*                             */
+  int   ssnow_potev;           /* CABLE_POTEV_*                              */
+  int   diag_soil_resp_on;     /* 0 <=> DIAG_SOIL_RESP=='off' (cable_carbon.F90:256) */
+  int   l_new_runoff_speed;    /* cbl_smoisturev.F90:112                     */
+  int   l_new_reduce_soilevp;  /* cbl_latent_heat.F90:205                    */
+  int   litter, or_evap, gw_model, l_rev_corr, soil_thermal_fix,
+        l_new_roughness_soil, call_climate, redistrb, soil_struc_sli;
+                               /* must all be 0: CABLE_E_UNSUPPORTED otherwise */
+  /* cable_runtime, casadimension */
+  int   runtime_um;            /* must be 0 (offline path)                   */
+  int   icycle;                /* 0: simple carbon inside cbm (cbm:214)      */
+  int   mvtype;                /* 13,15,16,17 (cable_carbon.F90:94)          */
+  /* snow / soil tunables (src/util/cable_common.F90:217-222, runtime_opts:9) */
+  float snmin;
+  float max_glacier_snowd;
+  float snow_ccnsw;
+  float max_ssdn;
+  float max_sconds;
+  float frozen_limit;
+  /* non-per-tile members of the derived types */
+  float zse[CABLE_MS];         /* soil%zse                                   */
+  float zshh[CABLE_MS + 1];    /* soil%zshh                                  */
+  float ratecp[CABLE_NCP];     /* bgc%ratecp                                 */
+  float ratecs[CABLE_NCS];     /* bgc%ratecs                                 */
+  /* boundary behaviour */
+  int   met_tv_is_tk;          /* 1: met%tvair=met%tvrad=met%tk on entry, as every
+                                  offline caller sets them (cable_input.F90:2679-2680,
+                                  cable_mpiworker.F90:487-488); 0: upload both   */
+  int   caller_duties;         /* 1: device does canopy%oldcansto=canopy%cansto
+                                  before the step (cable_serial.F90:573)        */
+  int   output_level;          /* 0: state only; 1: + STAR diagnostics;
+                                  2: every DIAG field (parity / debugging)      */
+  int   n_forcing_slots;       /* device forcing ring, >= 1 (2 = double buffer) */
+  int   threads_per_block;     /* 0 = library default                           */
+} cable_cfg;
+
+typedef struct cable_field_info {
+  const char *name;            /* "<type>_<member>", e.g. "ssnow_tgg"        */
+  int   dtype;                 /* CABLE_DT_*                                 */
+  int   n1, n2;                /* trailing extents: array is (mp,n1,n2)      */
+  unsigned role;               /* CABLE_ROLE_*                               */
+  unsigned flags;              /* CABLE_FLAG_*                               */
+} cable_field_info;
+
+typedef struct cable_counters {
+  long long steps;             /* cbm steps run                              */
+  long long kernel_launches;   /* our kernels launched                       */
+  long long h2d_bytes;         /* total host->device bytes                   */
+  long long d2h_bytes;         /* total device->host bytes                   */
+  double    kernel_ms;         /* summed event time of profiled launches     */
+  long long kernel_ms_count;   /* launches in kernel_ms                      */
+  long long n_dryleaf_warn;    /* tiles that hit the 'oldevapfbl not right'
+                                  soft failure (cbl_dryLeaf.F90:630)         */
+} cable_counters;
+
+typedef struct cable_handle cable_handle;
+
+int          cable_b200_abi_version(void);
+const char  *cable_b200_last_error(void);
+
+/* registry */
+int          cable_b200_nfields(void);
+int          cable_b200_field_id(const char *name);           /* <0 if unknown */
+int          cable_b200_field_info(int id, cable_field_info *out);
+
+/* configuration: defaults = shipped src/offline/cable.nml (leuning, standard,
+ * HDM, icycle 0, snmin 1) with zse of cable_parameters.F90:1241             */
+void         cable_b200_default_cfg(cable_cfg *cfg);
+
+/* life cycle.  device < 0 => use LOCAL_RANK env var, else device 0.         */
+int          cable_b200_create(int mp, const cable_cfg *cfg, int device,
+                               cable_handle **out);
+int          cable_b200_destroy(cable_handle *h);
+
+/* bind a caller-owned column-major host array to a field (replaces passing
+ * the derived type).  The pointer must stay valid until destroy/rebind.     */
+int          cable_b200_bind_field(cable_handle *h, int field_id, void *host);
+
+/* bulk transfers of every bound field whose role is in role_mask.
+ * download() also filters on flags: a DIAG field is copied when
+ * (flags & flag_mask) != 0 or flag_mask == 0.                                */
+int          cable_b200_upload(cable_handle *h, unsigned role_mask);
+int          cable_b200_download(cable_handle *h, unsigned role_mask,
+                                 unsigned flag_mask);
+
+/* forcing: pack the bound FORCING arrays into pinned memory and start an
+ * asynchronous H2D copy into ring slot `slot` on the side stream.            */
+int          cable_b200_set_forcing_async(cable_handle *h, int slot);
+
+/* one timestep for all mp tiles from forcing slot `slot`; asynchronous on
+ * the compute stream (waits for that slot's upload event).                   */
+int          cable_b200_step(cable_handle *h, int ktau, float dels, int slot);
+
+/* The drop-in call: exactly what CALL cbm(ktau, dels, ...) does as seen from
+ * the host -- upload forcing from the bound arrays, run the step, bring back
+ * the outputs selected by cfg.output_level into the bound arrays, and
+ * synchronise.                                                              */
+int          cable_b200_cbm(cable_handle *h, int ktau, float dels);
+
+int          cable_b200_sync(cable_handle *h);
+
+/* device-side access (for device-resident drivers and for torch/NCCL plumbing
+ * via the pointer; no torch types cross this boundary)                       */
+void        *cable_b200_device_ptr(cable_handle *h, int field_id, int slot);
+void        *cable_b200_compute_stream(cable_handle *h);      /* cudaStream_t */
+
+/* measurement */
+int          cable_b200_profile(cable_handle *h, int enable); /* event-time each launch */
+int          cable_b200_get_counters(cable_handle *h, cable_counters *out);
+int          cable_b200_reset_counters(cable_handle *h);
+
+/* patch -> grid-cell area-weighted reduction of one field on the device
+ * (reference: src/util/cable_grid_reductions.F90:49-75): out[l] =
+ * sum_{i in cstart[l]..cend[l]} x[i,comp]*patchfrac[i].  Device pointers in,
+ * device pointer out; used before the per-output-interval NCCL gather.       */
+int          cable_b200_grid_reduce(cable_handle *h, int field_id, int comp,
+                                    const float *d_patchfrac,
+                                    const int *d_cstart, const int *d_cend,
+                                    int nland, float *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CABLE_B200_H */

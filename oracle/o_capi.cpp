@@ -1,0 +1,52 @@
+// oracle/o_capi.cpp -- TEST INFRASTRUCTURE (see oracle.hpp).
+// Minimal C entry points so tests/ and bench.py's cpu_baseline leg can drive
+// the restatement through ctypes.  The oracle works IN PLACE on caller-owned
+// column-major host arrays (one pointer per row of cable_b200_fields.def).
+#include "oracle.hpp"
+#include <cstdio>
+
+using namespace orc;
+
+extern "C" {
+
+int oracle_nfields(void) { return (int)NFIELDS; }
+
+const char *oracle_field_name(int id) {
+  static const char *names[] = {
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) #T "_" #m,
+#include "../include/cable_b200_fields.def"
+  };
+  return (id >= 0 && id < (int)NFIELDS) ? names[id] : nullptr;
+}
+
+// ptrs: NFIELDS host pointers in registry order (all must be non-null)
+void *oracle_create(int mp, const cable_cfg *cfg, void **ptrs) {
+  if (!cfg || cfg->struct_bytes != (int)sizeof(cable_cfg) || mp <= 0) return nullptr;
+  Oracle *o = new Oracle();
+  o->mp = mp; o->cfg = *cfg; o->ktau_soil_snow = 0; o->n_dryleaf_warn = 0;
+  int id = 0;
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) o->f.T##_##m = (ct *)ptrs[id++];
+#include "../include/cable_b200_fields.def"
+  for (int k = 0; k < (int)NFIELDS; k++) if (!ptrs[k]) { delete o; return nullptr; }
+  return o;
+}
+
+int oracle_cbm(void *h, int ktau, float dels) {
+  if (!h) return -1;
+  cbm(*(Oracle *)h, ktau, dels);
+  return 0;
+}
+
+long long oracle_dryleaf_warnings(void *h) { return ((Oracle *)h)->n_dryleaf_warn; }
+
+void oracle_destroy(void *h) { delete (Oracle *)h; }
+
+// unit-test hooks
+void oracle_trimb(int n, const double *a, const double *b, const double *c, double *rhs, int kmax) {
+  trimb(n, a, b, c, rhs, kmax, kmax);
+}
+float oracle_psim(float z) { return psim(z); }
+float oracle_psis(float z) { return psis(z); }
+float oracle_qsat(float tair_c, float pmb) { return qsatf(tair_c, pmb); }
+
+}  // extern "C"
