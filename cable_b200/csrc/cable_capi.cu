@@ -227,8 +227,10 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   for (int k = 0; k < CABLE_NCP; k++) d.ratecp[k] = cfg->ratecp[k];
   for (int k = 0; k < CABLE_NCS; k++) d.ratecs[k] = cfg->ratecs[k];
   const float pi180 = 3.1415927f / 180.0f, ang[3] = {15.0f, 45.0f, 75.0f};
-  for (int b = 0; b < 3; b++) d.cos3[b] = cosf(pi180 * ang[b]);
-  d.log60 = logf(60.0f); d.log250 = logf(250.0f); d.prandt_third = powf(0.71f, 1.0f / 3.0f); d.log_cccw = logf(2.0f);
+  // correctly rounded (fp64 evaluation, one rounding): what the reference compiler's constant folding yields
+  for (int b = 0; b < 3; b++) d.cos3[b] = (float)cos((double)(pi180 * ang[b]));
+  d.log60 = (float)log(60.0); d.log250 = (float)log(250.0);
+  d.prandt_third = (float)pow((double)0.71f, (double)(1.0f / 3.0f)); d.log_cccw = (float)log(2.0);
   if (cfg->icycle == 0 && !carbon_tables(cfg->mvtype, d.rw, d.tfcl, d.tvclst)) {
     delete h;
     return fail(CABLE_E_UNSUPPORTED, "Error! Dimension not compatible with CASA or CSIRO or IGBP types! (mvtype)");   // cable_carbon.F90:142

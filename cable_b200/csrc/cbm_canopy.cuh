@@ -12,9 +12,9 @@ namespace cbl {
 CBL_DEV void radiation(Tile &t, bool sunlit_veg) {
   const float lai = t.canopy_vlaiw, extkb = t.rad_extkb, extkd = t.rad_extkd;
   const bool veg = lai > K::lai_thresh;
-  const float cf2n = expf(-t.veg_extkn * lai);
-  const float transd = veg ? expf(-extkd * lai) : 1.0f;
-  const float transb = expf(-mn(extkb * lai, 30.f));
+  const float cf2n = m_exp(-t.veg_extkn * lai);
+  const float transd = veg ? m_exp(-extkd * lai) : 1.0f;
+  const float transb = m_exp(-mn(extkb * lai, 30.f));
   t.rad_transd = transd; t.rad_transb = transb;
   const float flpwb = K::sboltz * p4(t.met_tvrad);
   const float flwv = K::emleaf * flpwb;
@@ -50,8 +50,8 @@ CBL_DEV void radiation(Tile &t, bool sunlit_veg) {
       t.rad_qcan[1 + 2 * b] = fsd * (dif * extkdm * ((1.0f - cexpkdm) / extkdm - cf1)
                                      + bem * extkbm * ((1.0f - cexpkbm) / extkbm - cf3) - sct);
     }
-    t.rad_qssabs = t.met_fsd[0] * (t.rad_fbeam[0] * (1.f - t.rad_reffbm[0]) * expf(-mn(t.rad_extkbm[0] * lai, 20.f))
-                                   + (1.f - t.rad_fbeam[0]) * (1.f - t.rad_reffdf[0]) * expf(-mn(t.rad_extkdm[0] * lai, 20.f)))
+    t.rad_qssabs = t.met_fsd[0] * (t.rad_fbeam[0] * (1.f - t.rad_reffbm[0]) * m_exp(-mn(t.rad_extkbm[0] * lai, 20.f))
+                                   + (1.f - t.rad_fbeam[0]) * (1.f - t.rad_reffdf[0]) * m_exp(-mn(t.rad_extkdm[0] * lai, 20.f)))
                    + t.met_fsd[1] * (t.rad_fbeam[1] * (1.f - t.rad_reffbm[1]) * t.rad_cexpkbm[1]
                                      + (1.f - t.rad_fbeam[1]) * (1.f - t.rad_reffdf[1]) * t.rad_cexpkdm[1]);
     t.rad_scalex[0] = (1.0f - transb * cf2n) / (extkb + t.veg_extkn);
@@ -179,11 +179,11 @@ CBL_DEV float ejx_root(float parx, float alpha, float convex, float x) {
   return (ap + x - sqrtf(p2(ap + x) - 4.0f * convex * alpha * parx * x)) / (2.0f * convex);
 }
 CBL_DEV float xvcmxt4(float x) {
-  return powf(2.0f, 0.1f * x - 2.5f) / ((1.0f + expf(0.3f * (13.0f - x))) * (1.0f + expf(0.3f * (x - 36.0f))));
+  return m_pow(2.0f, 0.1f * x - 2.5f) / ((1.0f + m_exp(0.3f * (13.0f - x))) * (1.0f + m_exp(0.3f * (x - 36.0f))));
 }
 CBL_DEV float arrhenius_peaked(float x, float coef, float eha, float ehd, float entrop) {
-  float num = coef * expf((eha / (K::rgas * K::trefk)) * (1.f - K::trefk / x));
-  float den = 1.0f + expf((entrop * x - ehd) / (K::rgas * x));
+  float num = coef * m_exp((eha / (K::rgas * K::trefk)) * (1.f - K::trefk / x));
+  float den = 1.0f + m_exp((entrop * x - ehd) / (K::rgas * x));
   return mx(0.0f, num / den);
 }
 
@@ -244,7 +244,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
   float oldevapfbl[K::ms];
   if (!veg) { rnx = 0.0; ecx = 0.0; w.ecy = ecx; abs_deltlf = 0.0f; w.rny = rnx; }
   float deltlfy = abs_deltlf;
-  const float dleaf3 = powf(t.veg_dleaf, 3.0f);
+  const float dleaf3 = m_pow(t.veg_dleaf, 3.0f);
   const float dtair = t.met_tvair - t.met_tk;
 
   for (int k = 1; k <= K::maxiter; k++) {
@@ -253,7 +253,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
       const float tlfx = w.tlfx;
       // free-convection boundary-layer conductance, total conductances
       float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - t.met_tvair) * dleaf3);
-      float gras4 = powf(gras, 0.25f);
+      float gras4 = m_pow(gras, 0.25f);
 #pragma unroll
       for (int l = 0; l < 2; l++) {
         w.gbhf[l] = mx(1.e-6, (double)(t.rad_fvlai[l] * t.air_cmolar * 0.5f * K::dheat * gras4 / t.veg_dleaf));
@@ -266,8 +266,8 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
       float tempj = arrhenius_peaked(tlfx, 1.16715f, 50300.0f, 152044.0f, 495.0f) * t.veg_ejmax * (1.0f - t.veg_frac4);
       const float tdiff = tlfx - K::trefk;
       const float arr = 1.0f - K::trefk / tlfx;
-      float conkct = t.veg_conkc0 * expf((t.veg_ekc / (K::rgas * K::trefk)) * arr);
-      float conkot = t.veg_conko0 * expf((t.veg_eko / (K::rgas * K::trefk)) * arr);
+      float conkct = t.veg_conkc0 * m_exp((t.veg_ekc / (K::rgas * K::trefk)) * arr);
+      float conkot = t.veg_conko0 * m_exp((t.veg_eko / (K::rgas * K::trefk)) * arr);
       tlfxx = tlfx;
       const float cx1 = conkct * (1.0f + 0.21f / conkot);
       const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
@@ -489,11 +489,11 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
       float rescale = K::vonk * mx(t.met_ua, K::umin);
       float z_eff = t.rough_zref_uv / t.rough_z0m;
       float psim_2 = psim(zet * t.rough_z0m / t.rough_zref_tq);
-      t.canopy_us = mn(mx(1.e-6f, rescale / (logf(z_eff) - psim_1 + psim_2)), 10.0f);
+      t.canopy_us = mn(mx(1.e-6f, rescale / (m_log(z_eff) - psim_1 + psim_2)), 10.0f);
     }
     const float us = t.canopy_us;
     // aerodynamic resistances (:276-363)
-    float r1c = (logf(t.rough_zref_tq / zr) - psis(zet) + psis(zet * zr / t.rough_zref_tq)) / K::vonk;
+    float r1c = (m_log(t.rough_zref_tq / zr) - psis(zet) + psis(zet * zr / t.rough_zref_tq)) / K::vonk;
     rt1usc = above ? 1.0f * r1c : 0.0f * r1c;
     rt0 = mx(5.f, t.rough_rt0us / us);
     t.rough_rt1 = mx(5.f, (t.rough_rt1usa + t.rough_rt1usb + rt1usc) / us);
@@ -508,8 +508,8 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
                  * c.prandt_third / t.veg_shelrb;
       const double gbvtop = mx(0.05, (double)gv);
       const float hc = 0.5f * t.rough_coexp;
-      w.gbhu[0] = gbvtop * (double)(1.0f - expf(-mn(lai * (hc + t.rad_extkb), 20.0f))) / (double)(t.rad_extkb + hc);
-      w.gbhu[1] = (double)(2.0f / t.rough_coexp) * gbvtop * (double)(1.0f - expf(-mn(hc * lai, 20.0f))) - w.gbhu[0];
+      w.gbhu[0] = gbvtop * (double)(1.0f - m_exp(-mn(lai * (hc + t.rad_extkb), 20.0f))) / (double)(t.rad_extkb + hc);
+      w.gbhu[1] = (double)(2.0f / t.rough_coexp) * gbvtop * (double)(1.0f - m_exp(-mn(hc * lai, 20.0f))) - w.gbhu[0];
     }
     w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
     dryLeaf(t, c, w, dels, iter);
@@ -522,7 +522,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     if (dense) {
       t.rad_lwabv = cr * (w.tlfy - t.met_tk) * w.sum_gradis;
       float arg = t.rad_lwabv / (2.0f * (1.0f - t.rad_transd) * K::sboltz * K::emleaf) + tvrad4;
-      if (arg > 0.0f) tv = powf(arg, 0.25f);
+      if (arg > 0.0f) tv = m_pow(arg, 0.25f);
     }
     t.canopy_tv = tv;
     t.canopy_fns = t.rad_qssabs + t.rad_transd * t.met_fld + (1.0f - t.rad_transd) * K::emleaf * K::sboltz * p4(tv)
@@ -576,14 +576,14 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     t.canopy_gswx_T = (t.soil_isoilm == K::ice_soiltype) ? 1.e6f : cc + sc;
   }
   const float zN = t.canopy_zetar[CABLE_NITER - 1];       // also zetar(:,iterplus): iterplus == NITER on exit
-  t.canopy_cdtq = t.canopy_cduv * (logf(t.rough_zref_uv / t.rough_z0m) - psim(zN * t.rough_zref_uv / t.rough_zref_tq)
+  t.canopy_cdtq = t.canopy_cduv * (m_log(t.rough_zref_uv / t.rough_z0m) - psim(zN * t.rough_zref_uv / t.rough_zref_tq)
                                    + psim(zN * t.rough_z0m / t.rough_zref_tq))
-                  / (logf(t.rough_zref_tq / (0.1f * t.rough_z0m)) - psis(zN) + psis(zN * 0.1f * t.rough_z0m / t.rough_zref_tq));
+                  / (m_log(t.rough_zref_tq / (0.1f * t.rough_z0m)) - psis(zN) + psis(zN * 0.1f * t.rough_z0m / t.rough_zref_tq));
   // screen-level temperature and humidity (:731-878)
   const float tstar = -t.canopy_fh / (t.air_rho * K::capp * us);
   const float qstar = -t.canopy_fe / (t.air_rho * t.air_rlam * us * t.ssnow_cls);
   const float zscrn = mx(t.rough_z0m, 2.0f - t.rough_disp);
-  const float ftemp = (logf(t.rough_zref_tq / zscrn) - psis(zN) + psis(zN * zscrn / t.rough_zref_tq)) / K::vonk;
+  const float ftemp = (m_log(t.rough_zref_tq / zscrn) - psis(zN) + psis(zN * zscrn / t.rough_zref_tq)) / K::vonk;
   float tscrn = t.met_tk - K::tfrz - tstar * ftemp;
   float r_sc = 0.f;
   const float hr = t.rough_hruff, disp = t.rough_disp, rgh = t.canopy_rghlai;
@@ -593,22 +593,22 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     const float zscl = mx(t.rough_z0soilsn, 2.0f);
     float term1 = 0.f, term2 = 0.f, term5 = 0.f;
     if (disp > 0.0f) {
-      term1 = expf(2 * K::csw * rgh * (1 - zscl / hr));
-      term2 = expf(2 * K::csw * rgh * (1 - disp / hr));
+      term1 = m_exp(2 * K::csw * rgh * (1 - zscl / hr));
+      term2 = m_exp(2 * K::csw * rgh * (1 - disp / hr));
       term5 = mx(2.f / 3.f * hr / disp, 1.f);
     }
     const float term3 = p2(K::a33) * K::ctl * 2 * K::csw * rgh;
     if (zscl < disp) {
-      const float e2 = expf(2 * K::csw * rgh);
-      r_sc = term5 * logf(zscl / t.rough_z0soilsn) * (e2 - term2) / term3;
-      r_sc = r_sc + term5 * logf(disp / zscl) * (e2 - term1) / term3;
+      const float e2 = m_exp(2 * K::csw * rgh);
+      r_sc = term5 * m_log(zscl / t.rough_z0soilsn) * (e2 - term2) / term3;
+      r_sc = r_sc + term5 * m_log(disp / zscl) * (e2 - term1) / term3;
     } else if (disp <= zscl && zscl < hr) {
       r_sc = t.rough_rt0us + term5 * (term2 - term1) / term3;
     } else if (hr <= zscl && zscl < t.rough_zruffs) {
       r_sc = t.rough_rt0us + t.rough_rt1usa + term5 * (zscl - hr) / (p2(K::a33) * K::ctl * hr);
     } else if (zscl >= t.rough_zruffs) {
       r_sc = t.rough_rt0us + t.rough_rt1usa + t.rough_rt1usb
-             + (logf((zscl - disp) / mx(t.rough_zruffs - disp, t.rough_z0soilsn))
+             + (m_log((zscl - disp) / mx(t.rough_zruffs - disp, t.rough_z0soilsn))
                 - psis((zscl - disp) * zN / t.rough_zref_tq) + psis((t.rough_zruffs - disp) * zN / t.rough_zref_tq)) / K::vonk;
     }
     tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, (r_sc / mx(1.f, rsum))) - K::tfrz;
@@ -639,7 +639,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
   {
     const float tc = t.ssnow_tss - K::tfrz;
     t.ssnow_ddq_dtg = (K::rmh2o / K::rmair) / t.met_pmb * K::tetena * K::tetenb * K::tetenc / (p2(K::tetenc + t.ssnow_tss - K::tfrz))
-                      * expf(K::tetenb * tc / (K::tetenc + t.ssnow_tss - K::tfrz));
+                      * m_exp(K::tetenb * tc / (K::tetenc + t.ssnow_tss - K::tfrz));
   }
   t.ssnow_dfe_dtg = t.ssnow_dfe_ddq * t.ssnow_ddq_dtg;
   t.canopy_dgdtg = (double)(t.ssnow_dfn_dtg - t.ssnow_dfh_dtg - t.ssnow_dfe_dtg);

@@ -71,7 +71,7 @@ cbm_kernel(const DevPtrs d, const int mp, const float dels, const int first_call
   t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
   t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
   t.canopy_rnet = t.canopy_fns + t.canopy_fnv;
-  t.rad_trad = powf((1.f - t.rad_transd) * p4(t.canopy_tv) + t.rad_transd * p4(t.ssnow_tss), 0.25f);
+  t.rad_trad = m_pow((1.f - t.rad_transd) * p4(t.canopy_tv) + t.rad_transd * p4(t.ssnow_tss), 0.25f);
   if (c.icycle == 0) simple_carbon(t, c, dels);
   if (warn) atomicAdd(warn_counter, (unsigned long long)warn);
 

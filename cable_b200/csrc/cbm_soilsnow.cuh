@@ -64,10 +64,10 @@ CBL_DEV void snowcheck(Tile &t, const DevCfg &c) {
 
 // snowdensity: cbl_snowDensity.F90:9-102
 CBL_DEV float snow_settle(float s, float dels, float tsn) {
-  return s + dels * s * 3.1e-6f * expf(-0.03f * (273.15f - mn(K::tfrz, tsn)) - ((s >= 150.0f) ? 0.046f : 0.0f) * (s - 150.0f));
+  return s + dels * s * 3.1e-6f * m_exp(-0.03f * (273.15f - mn(K::tfrz, tsn)) - ((s >= 150.0f) ? 0.046f : 0.0f) * (s - 150.0f));
 }
 CBL_DEV float snow_overburden_den(float s, float tsn) {
-  return 3.0e7f * expf(0.021f * s + 0.081f * (273.15f - mn(K::tfrz, tsn)));
+  return 3.0e7f * m_exp(0.021f * s + 0.081f * (273.15f - mn(K::tfrz, tsn)));
 }
 CBL_DEV void snowdensity(Tile &t, const DevCfg &c, float dels) {
   const bool one_layer = (t.ssnow_snowd > 0.1f && t.ssnow_isflag == 0);
@@ -296,7 +296,7 @@ CBL_DEV void stempv(Tile &t, const DevCfg &c, float dels) {
       const float exp_arg = (float)((double)(ew * c.log60) + t.ssnow_wbfice[k] * (double)ssat * (double)c.log250);
       const double shape = mx(1.0, sqrt(mn(2.0, (double)(0.5f * ssat) / mn((double)ew, 0.5 * (double)ssat))));
       if (exp_arg > 30.f) ccnsw[k] = (double)1.5f * shape;
-      else ccnsw[k] = mn(t.soil_cnsd * (double)expf(exp_arg), 1.5) * shape;
+      else ccnsw[k] = mn(t.soil_cnsd * (double)m_exp(exp_arg), 1.5) * shape;
     }
   }
   // rows: 0..2 snow layers (reference indices -2..0), 3..8 soil layers (1..6)
@@ -639,7 +639,7 @@ CBL_DEV void snow_aging(Tile &t, float dels) {
     const float ar2 = 10.0f * ar1;
     float ar3 = 0.1f;
     if (t.soil_isoilm == 9) { ar3 = 0.0000001f; dnsnow = 1.0f; }
-    const float dtau = 1.0e-6f * (expf(ar1) + expf(ar2) + ar3) * dels;
+    const float dtau = 1.0e-6f * (m_exp(ar1) + m_exp(ar2) + ar3) * dels;
     t.ssnow_snage = mx(0.0f, (t.ssnow_snage + dtau) * (1.0f - dnsnow));
   }
 }
@@ -653,7 +653,7 @@ CBL_DEV void simple_carbon(Tile &t, const DevCfg &c, float dels) {
     const float poolcoef1 = s - r1, poolcoef1w = s - r1 - r3, poolcoef1r = s - r1 - r2;
     const float tmp1 = mx(3.22f - 0.046f * (t.met_tk - K::tfrz), 1e-6f);
     const float tmp2 = 0.1f * (t.met_tk - K::tfrz - 20.0f);
-    const float tmp3 = powf(tmp1, tmp2);
+    const float tmp3 = m_pow(tmp1, tmp2);
     t.canopy_frp = t.veg_rp20 * tmp3 * poolcoef1 / sec_per_year;
     t.canopy_frpw = t.veg_rp20 * tmp3 * poolcoef1w / sec_per_year;
     t.canopy_frpr = t.veg_rp20 * tmp3 * poolcoef1r / sec_per_year;
@@ -664,8 +664,8 @@ CBL_DEV void simple_carbon(Tile &t, const DevCfg &c, float dels) {
     for (int k = 0; k < K::ms; k++) { avgwrs = avgwrs + t.veg_froot[k] * (float)t.ssnow_wb[k]; avgtrs = avgtrs + t.veg_froot[k] * t.ssnow_tgg[k]; }
     avgtrs = mx(0.0f, avgtrs - K::tfrz);
     float frs = t.veg_rs20 * mn(1.0f, mx(0.0f, mn(-0.0178f + 0.2883f * avgwrs + 5.0176f * avgwrs * avgwrs - 4.5128f * avgwrs * avgwrs * avgwrs,
-                                                   0.3320f + 22.6726f * expf(-5.8184f * avgwrs))))
-                * mn(1.0f, mx(0.0f, mn(0.0104f * powf(avgtrs, 1.3053f), 5.5956f - 0.1189f * avgtrs)));
+                                                   0.3320f + 22.6726f * m_exp(-5.8184f * avgwrs))))
+                * mn(1.0f, mx(0.0f, mn(0.0104f * m_pow(avgtrs, 1.3053f), 5.5956f - 0.1189f * avgtrs)));
     frs = frs * (c.ratecs[0] * t.bgc_csoil[0] + c.ratecs[1] * t.bgc_csoil[1]) / (365.0f * 24.0f * 3600.0f);
     if (t.ssnow_snowd > 1.f) frs = frs / mx(0.001f, mn(100.f, t.ssnow_snowd));
     t.canopy_frs = frs;
@@ -684,28 +684,28 @@ CBL_DEV void simple_carbon(Tile &t, const DevCfg &c, float dels) {
     tsoil = mx(t0 + 2.f, tsoil);
     const float e0rswc = 52.4f + 285.f * rswc;
     const float ftsoil = mn(0.0015f, 1.f / (tref - t0) - 1.f / (tsoil - t0));
-    const float ftsrs = expf(mx(-15.f, mn(1.f, e0rswc * ftsoil)));
+    const float ftsrs = m_exp(mx(-15.f, mn(1.f, e0rswc * ftsoil)));
     t.canopy_frs = t.veg_vegcf * (144.0f / 44.0e6f) * 1.0f * mn(1.f, 1.4f * mx(.3f, .0278f * tsoil + .5f)) * ftsrs * rswc / (0.16f + rswc);
   }
   {  // carbon_pl
     const float beta = 0.9f, trnl = 3.17e-8f, trnr = 4.53e-9f, trnsf = 1.057e-10f, trnw = 6.342e-10f;
     const int iv = t.veg_iveg - 1;
-    const float coef_cold = expf(mn(1.f, -(t.canopy_tv - c.tvclst[iv])));
+    const float coef_cold = m_exp(mn(1.f, -(t.canopy_tv - c.tvclst[iv])));
     float wbav = 0.f;
 #pragma unroll
     for (int k = 0; k < K::ms; k++) wbav = wbav + t.veg_froot[k] * (float)t.ssnow_wb[k];
     wbav = mx(0.01f, wbav);
     const float cexp = 2.0f - t.soil_ibp2;
-    const float esw = mx(1.0f, powf(wbav, cexp) - 1.0f);
-    const float eswilt = powf(t.soil_swilt, cexp) - 1.0f;
+    const float esw = mx(1.0f, m_pow(wbav, cexp) - 1.0f);
+    const float eswilt = m_pow(t.soil_swilt, cexp) - 1.0f;
     const float rel = mn(1.0f, esw / eswilt - 1.0f);
-    const float coef_cd = (coef_cold + expf(5.0f * rel)) * 2.0e-7f;
-    const float fcl = expf(-c.tfcl[iv] * t.veg_vlai);
+    const float coef_cd = (coef_cold + m_exp(5.0f * rel)) * 2.0e-7f;
+    const float fcl = m_exp(-c.tfcl[iv] * t.veg_vlai);
     const float fpn = t.canopy_fpn;
     float cp1 = t.bgc_cplant[0], cp2 = t.bgc_cplant[1], cp3 = t.bgc_cplant[2], cs1 = t.bgc_csoil[0], cs2 = t.bgc_csoil[1];
     const float clitt = (coef_cd + trnl) * cp1;
     cp1 = cp1 - dels * (fpn * fcl + clitt);
-    const float fr = mn(1.f, expf(-c.rw[iv] * beta * 0.0001f * cp3 / mx(cp2, 0.01f)) / beta);
+    const float fr = mn(1.f, m_exp(-c.rw[iv] * beta * 0.0001f * cp3 / mx(cp2, 0.01f)) / beta);
     const float cfwd = trnw * cp2;
     cp2 = cp2 - dels * (fpn * (1.f - fcl) * (1.f - fr) + t.canopy_frpw + cfwd);
     const float cfrts = trnr * cp3;

@@ -41,7 +41,7 @@ CBL_DEV bool ruff_resist(Tile &t, const DevCfg &c) {
   const float halflai = lai * 0.5f;
   float usuh = mn(sqrtf(K::csd + K::crd * halflai), K::usuhm);
   float xx = sqrtf(K::ccd * mx(halflai, 0.0005f));
-  float dh = 1.0f - (1.0f - expf(-xx)) / xx;
+  float dh = 1.0f - (1.0f - m_exp(-xx)) / xx;
   t.rough_usuh = usuh;
   t.rough_coexp = usuh / (K::vonk * K::ccw_c * (1.0f - dh));
   const bool bare = (lai <= K::lai_thresh) || (hgt < z0sn);
@@ -51,7 +51,7 @@ CBL_DEV bool ruff_resist(Tile &t, const DevCfg &c) {
     t.rough_rt0us = 0.0f; t.rough_zruffs = 0.0f; t.rough_rt1usa = 0.0f; t.rough_rt1usb = 0.0f;
   } else {
     disp = dh * hgt;
-    z0m = ((1.0f - dh) * expf(c.log_cccw - 1.f + 1.f / K::ccw_c - K::vonk / usuh)) * hgt;
+    z0m = ((1.0f - dh) * m_exp(c.log_cccw - 1.f + 1.f / K::ccw_c - K::vonk / usuh)) * hgt;
   }
   t.rough_z0m = z0m; t.rough_disp = disp;
   float zuv = mx(3.5f + z0m, t.rough_za_uv), ztq = mx(3.5f + z0m, t.rough_za_tq);
@@ -59,14 +59,14 @@ CBL_DEV bool ruff_resist(Tile &t, const DevCfg &c) {
   t.rough_zref_uv = zuv; t.rough_zref_tq = ztq;
   if (!bare) {
     const float a33sq_ctl = p2(K::a33) * K::ctl;
-    float term2 = expf(2 * K::csw * lai * (1 - disp / hgt));
+    float term2 = m_exp(2 * K::csw * lai * (1 - disp / hgt));
     float term3 = a33sq_ctl * 2 * K::csw * lai;
     float term5 = mx((2.f / 3.f) * hgt / disp, 1.0f);
     t.rough_term2 = term2; t.rough_term3 = term3; t.rough_term5 = term5;
-    t.rough_term6 = expf(3.f * t.rough_coexp * (disp / hgt - 1.f));
-    t.rough_term6a = expf(t.rough_coexp * (0.1f * hgt / hgt - 1.f));
-    t.rough_rt0us = term5 * (K::zdlin * logf(K::zdlin * disp / z0sn) + (1 - K::zdlin))
-                    * (expf(2 * K::csw * lai) - term2) / term3;
+    t.rough_term6 = m_exp(3.f * t.rough_coexp * (disp / hgt - 1.f));
+    t.rough_term6a = m_exp(t.rough_coexp * (0.1f * hgt / hgt - 1.f));
+    t.rough_rt0us = term5 * (K::zdlin * m_log(K::zdlin * disp / z0sn) + (1 - K::zdlin))
+                    * (m_exp(2 * K::csw * lai) - term2) / term3;
     float zruffs = disp + hgt * p2(K::a33) * K::ctl / K::vonk / term5;
     t.rough_zruffs = zruffs;
     t.rough_rt1usa = term5 * (term2 - 1.0f) / term3;
@@ -79,7 +79,7 @@ CBL_DEV bool ruff_resist(Tile &t, const DevCfg &c) {
 // define_air: cable_air.F90:51-97 (from met%tvair, met%pmb)
 CBL_DEV void define_air(Tile &t) {
   const float tc = t.met_tvair - K::tfrz, pmb = t.met_pmb, tv = t.met_tvair;
-  float ex = expf(K::tetenb * tc / (K::tetenc + tc));
+  float ex = m_exp(K::tetenb * tc / (K::tetenc + tc));
   float es = K::tetena * ex;
   t.air_cmolar = pmb * 100.0f / (K::rgas * tv);
   t.air_rho = mn(1.3f, K::rmair * t.air_cmolar);
@@ -102,7 +102,7 @@ CBL_DEV float spitter(int doy, float coszen, float fsd) {
   float tmpk = (1.47f - tmpr) / 1.66f;
   float tmprat = 0.0f;
   if (coszen > 1.0e-10f && fsd > 10.0f)
-    tmprat = fsd / (solcon * (1.0f + 0.033f * cosf(2.0f * K::pi * ((float)doy - 10.0f) / 365.0f)) * coszen);
+    tmprat = fsd / (solcon * (1.0f + 0.033f * m_cos(2.0f * K::pi * ((float)doy - 10.0f) / 365.0f)) * coszen);
   if (tmprat > 0.22f) fbeam = 6.4f * p2(tmprat - 0.22f);
   if (tmprat > 0.35f) fbeam = mn(1.66f * tmprat - 0.4728f, 1.0f);
   if (tmprat > tmpk) fbeam = mx(1.0f - tmpr, 0.0f);
@@ -127,10 +127,10 @@ CBL_DEV void init_radiation(Tile &t, const DevCfg &c, bool veg_mask) {
   // extinction coefficients (:222-283)
   float extkb = 0.5f, extkd = 0.7f;
   if (veg_mask) {
-    float s = K::gauss_w0 * expf(-t.scr_xk[0] * lai);
-    s = s + K::gauss_w1 * expf(-t.scr_xk[1] * lai);
-    s = s + K::gauss_w2 * expf(-t.scr_xk[2] * lai);
-    extkd = -logf(s) / lai;
+    float s = K::gauss_w0 * m_exp(-t.scr_xk[0] * lai);
+    s = s + K::gauss_w1 * m_exp(-t.scr_xk[1] * lai);
+    s = s + K::gauss_w2 * m_exp(-t.scr_xk[2] * lai);
+    extkd = -m_log(s) / lai;
   }
   const float tols_tiny = K::coszen_tols * 1e-2f, tols_huge = K::coszen_tols * 1e2f;
   if (veg_mask && coszen > tols_tiny) extkb = xphi1 / coszen + xphi2;
@@ -189,8 +189,8 @@ CBL_DEV void albedo(Tile &t, bool veg_mask) {
     const float asn = t.ssnow_albsoilsn[b];
     t.rad_rhocbm[b] = veg_mask ? 2.0f * extkb / (extkb + extkd) * t.scr_rhoch[b] : 0.0f;
     t.rad_rhocdf[b] = t.scr_rhoch[b] * 2.0f * gsum;
-    if (veg_mask) t.rad_cexpkbm[b] = expf(-1.0f * mn(t.rad_extkbm[b] * lai, 20.0f));   // stale otherwise (D1)
-    t.rad_cexpkdm[b] = expf(-1.0f * (t.rad_extkdm[b] * lai));
+    if (veg_mask) t.rad_cexpkbm[b] = m_exp(-1.0f * mn(t.rad_extkbm[b] * lai, 20.0f));   // stale otherwise (D1)
+    t.rad_cexpkdm[b] = m_exp(-1.0f * (t.rad_extkdm[b] * lai));
     float rdf = asn, rbm = asn;
     if (veg_mask) {
       rdf = t.rad_rhocdf[b] + (asn - t.rad_rhocdf[b]) * p2(t.rad_cexpkdm[b]);

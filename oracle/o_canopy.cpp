@@ -9,24 +9,24 @@ void radiation(Oracle &o, const std::vector<char> &sunlit_veg_mask);
 float psim(float zeta) {
   const float gu = 16.0f, a = 1.0f, b = 0.667f, xc = 5.0f, d = 0.35f;
   float z = 0.5f + sign_(0.5f, zeta);
-  float stable = -a * zeta - b * (zeta - xc / d) * expf(-d * zeta) - b * xc / d;
-  float x = powf(1.0f + gu * fabsf(zeta), 0.25f);
-  float unstable = logf((1.0f + x * x) * sq(1.0f + x) / 8) - 2.0f * atanf(x) + CPI * 0.5f;
+  float stable = -a * zeta - b * (zeta - xc / d) * o_expf(-d * zeta) - b * xc / d;
+  float x = o_powf(1.0f + gu * fabsf(zeta), 0.25f);
+  float unstable = o_logf((1.0f + x * x) * sq(1.0f + x) / 8) - 2.0f * o_atanf(x) + CPI * 0.5f;
   return z * stable + (1.0f - z) * unstable;
 }
 float psis(float zeta) {
   const float gu = 16.0f, a = 1.0f, b = 0.667f, c = 5.0f, d = 0.35f;
   float z = 0.5f + sign_(0.5f, zeta);
   float stzeta = fmaxf_(0.f, zeta);
-  float stable = -powf(1.f + 2.f / 3.f * a * stzeta, 3.f / 2.f) - b * (stzeta - c / d) * expf(-d * stzeta) - b * c / d + 1.f;
-  float y = powf(1.0f + gu * fabsf(zeta), 0.5f);
-  float unstable = 2.0f * logf((1 + y) * 0.5f);
+  float stable = -o_powf(1.f + 2.f / 3.f * a * stzeta, 3.f / 2.f) - b * (stzeta - c / d) * o_expf(-d * stzeta) - b * c / d + 1.f;
+  float y = o_powf(1.0f + gu * fabsf(zeta), 0.5f);
+  float unstable = 2.0f * o_logf((1 + y) * 0.5f);
   return z * stable + (1.0f - z) * unstable;
 }
 
 // ---- qsatfjh / qsatfjh2: cbl_qsat.F90:16-85 ---------------------------------
 float qsatf(float tair, float pmb) {
-  return (CRMH2O / CRMAIR) * (CTETENA * expf(CTETENB * tair / (CTETENC + tair))) / pmb;
+  return (CRMH2O / CRMAIR) * (CTETENA * o_expf(CTETENB * tair / (CTETENC + tair))) / pmb;
 }
 
 // ---- Surf_wetness_fact: cbl_SurfaceWetness.F90:10-79
@@ -207,18 +207,18 @@ static float ej4x(float parx, float alpha, float convex, float x) {
 }
 static float xvcmxt4(float x) {
   const float q10c4 = 2.0f;
-  return powf(q10c4, 0.1f * x - 2.5f) / ((1.0f + expf(0.3f * (13.0f - x))) * (1.0f + expf(0.3f * (x - 36.0f))));
+  return o_powf(q10c4, 0.1f * x - 2.5f) / ((1.0f + o_expf(0.3f * (13.0f - x))) * (1.0f + o_expf(0.3f * (x - 36.0f))));
 }
 static float xvcmxt3(float x) {
   const float EHaVc = 73637.0f, EHdVc = 149252.0f, EntropVc = 486.0f, xVccoef = 1.17461f;
-  float xvcnum = xVccoef * expf((EHaVc / (CRGAS * CTREFK)) * (1.f - CTREFK / x));
-  float xvcden = 1.0f + expf((EntropVc * x - EHdVc) / (CRGAS * x));
+  float xvcnum = xVccoef * o_expf((EHaVc / (CRGAS * CTREFK)) * (1.f - CTREFK / x));
+  float xvcden = 1.0f + o_expf((EntropVc * x - EHdVc) / (CRGAS * x));
   return fmaxf_(0.0f, xvcnum / xvcden);
 }
 static float xejmxt3(float x) {
   const float EHaJx = 50300.0f, EHdJx = 152044.0f, EntropJx = 495.0f, xjxcoef = 1.16715f;
-  float xjxnum = xjxcoef * expf((EHaJx / (CRGAS * CTREFK)) * (1.f - CTREFK / x));
-  float xjxden = 1.0f + expf((EntropJx * x - EHdJx) / (CRGAS * x));
+  float xjxnum = xjxcoef * o_expf((EHaJx / (CRGAS * CTREFK)) * (1.f - CTREFK / x));
+  float xjxden = 1.0f + o_expf((EntropJx * x - EHdJx) / (CRGAS * x));
   return fmaxf_(0.0f, xjxnum / xjxden);
 }
 
@@ -362,9 +362,9 @@ static void dryLeaf(Oracle &o, float dels, CanopyWork &w, int iter) {
         gwwet[i] = 1.075f * sum_gbh[i];
         ghrwet[i] = (float)(w.sum_rad_gradis[i] + w.ghwet[i]);
         ccfevw[i] = fminf_(f.canopy_cansto[i] * f.air_rlam[i] / dels, 2.0f / (1440.0f / (dels / 60.0f)) * f.air_rlam[i]);
-        gras[i] = fmaxf_(1.0e-6f, 1.595E8f * fabsf(w.tlfx[i] - f.met_tvair[i]) * (powf(f.veg_dleaf[i], 3.0f)));  // :255
-        w.gbhf[i].v[0] = f.rad_fvlai[IX(i, 0)] * f.air_cmolar[i] * 0.5f * CDHEAT * (powf(gras[i], 0.25f)) / f.veg_dleaf[i];
-        w.gbhf[i].v[1] = f.rad_fvlai[IX(i, 1)] * f.air_cmolar[i] * 0.5f * CDHEAT * (powf(gras[i], 0.25f)) / f.veg_dleaf[i];
+        gras[i] = fmaxf_(1.0e-6f, 1.595E8f * fabsf(w.tlfx[i] - f.met_tvair[i]) * (o_powf(f.veg_dleaf[i], 3.0f)));  // :255
+        w.gbhf[i].v[0] = f.rad_fvlai[IX(i, 0)] * f.air_cmolar[i] * 0.5f * CDHEAT * (o_powf(gras[i], 0.25f)) / f.veg_dleaf[i];
+        w.gbhf[i].v[1] = f.rad_fvlai[IX(i, 1)] * f.air_cmolar[i] * 0.5f * CDHEAT * (o_powf(gras[i], 0.25f)) / f.veg_dleaf[i];
         for (int l = 0; l < mf; l++) {
           w.gbhf[i].v[l] = dmax_(1.e-6, w.gbhf[i].v[l]);                                  // :263
           gh[i].v[l] = (float)(2.0f * (w.gbhu[i].v[l] + w.gbhf[i].v[l]));                 // :266
@@ -380,8 +380,8 @@ static void dryLeaf(Oracle &o, float dels, CanopyWork &w, int iter) {
         ejmxt3[i].v[0] = f.rad_scalex[IX(i, 0)] * temp[i];
         ejmxt3[i].v[1] = f.rad_scalex[IX(i, 1)] * temp[i];
         tdiff[i] = w.tlfx[i] - CTREFK;
-        conkct[i] = f.veg_conkc0[i] * expf((f.veg_ekc[i] / (CRGAS * CTREFK)) * (1.0f - CTREFK / w.tlfx[i]));
-        conkot[i] = f.veg_conko0[i] * expf((f.veg_eko[i] / (CRGAS * CTREFK)) * (1.0f - CTREFK / w.tlfx[i]));
+        conkct[i] = f.veg_conkc0[i] * o_expf((f.veg_ekc[i] / (CRGAS * CTREFK)) * (1.0f - CTREFK / w.tlfx[i]));
+        conkot[i] = f.veg_conko0[i] * o_expf((f.veg_eko[i] / (CRGAS * CTREFK)) * (1.0f - CTREFK / w.tlfx[i]));
         tlfxx[i] = w.tlfx[i];                                                             // :301
         cx1[i] = conkct[i] * (1.0f + 0.21f / conkot[i]);
         cx2[i] = 2.0f * CGAM0 * (1.0f + CGAM1 * tdiff[i] + CGAM2 * tdiff[i] * tdiff[i]);
@@ -622,12 +622,12 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       float z_eff = f.rough_zref_uv[i] / f.rough_z0m[i];
       float psim_arg = zet * f.rough_z0m[i] / f.rough_zref_tq[i];
       float psim_2 = psim(psim_arg);
-      float lower_limit = rescale / (logf(z_eff) - psim_1 + psim_2);
+      float lower_limit = rescale / (o_logf(z_eff) - psim_1 + psim_2);
       f.canopy_us[i] = fminf_(fmaxf_(1.e-6f, lower_limit), 10.0f);
       // :276-284
       float xx = 0.5f + sign_(0.5f, f.rough_zref_tq[i] + f.rough_disp[i] - f.rough_zruffs[i]);
       float zr = fmaxf_(f.rough_zruffs[i] - f.rough_disp[i], f.rough_z0soilsn[i]);
-      rt1usc[i] = xx * (logf(f.rough_zref_tq[i] / zr) - psis(zet) + psis(zet * (zr) / f.rough_zref_tq[i])) / CVONK;
+      rt1usc[i] = xx * (o_logf(f.rough_zref_tq[i] / zr) - psis(zet) + psis(zet * (zr) / f.rough_zref_tq[i])) / CVONK;
       rt0[i] = fmaxf_(rt_min, f.rough_rt0us[i] / f.canopy_us[i]);                         // :333
       f.rough_rt1[i] = fmaxf_(5.f, (f.rough_rt1usa[i] + f.rough_rt1usb[i] + rt1usc[i]) / f.canopy_us[i]);   // :339
       if (f.canopy_vlaiw[i] > CLAI_THRESH) f.ssnow_rtsoil[i] = rt0[i];
@@ -637,13 +637,13 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
         f.ssnow_rtsoil[i] = fmaxf_(rt_min, 0.5f * (f.ssnow_rtsoil[i] + ortsoil[i]));      // :356-361
       if (f.canopy_vlaiw[i] > CLAI_THRESH) {                                              // :376-395
         w.gbvtop[i] = f.air_cmolar[i] * CAPOL * f.air_visc[i] / CPRANDT / f.veg_dleaf[i]
-                      * powf(f.canopy_us[i] / fmaxf_(f.rough_usuh[i], 1.e-6f) * f.veg_dleaf[i] / f.air_visc[i], 0.5f)
-                      * powf(CPRANDT, 1.0f / 3.0f) / f.veg_shelrb[i];
+                      * o_powf(f.canopy_us[i] / fmaxf_(f.rough_usuh[i], 1.e-6f) * f.veg_dleaf[i] / f.air_visc[i], 0.5f)
+                      * o_powf(CPRANDT, 1.0f / 3.0f) / f.veg_shelrb[i];
         w.gbvtop[i] = dmax_(0.05, w.gbvtop[i]);
-        w.gbhu[i].v[0] = w.gbvtop[i] * (1.0f - expf(-fminf_(f.canopy_vlaiw[i] * (0.5f * f.rough_coexp[i] + f.rad_extkb[i]), 20.0f)))
+        w.gbhu[i].v[0] = w.gbvtop[i] * (1.0f - o_expf(-fminf_(f.canopy_vlaiw[i] * (0.5f * f.rough_coexp[i] + f.rad_extkb[i]), 20.0f)))
                          / (f.rad_extkb[i] + 0.5f * f.rough_coexp[i]);
         w.gbhu[i].v[1] = (2.0f / f.rough_coexp[i]) * w.gbvtop[i]
-                         * (1.0f - expf(-fminf_(0.5f * f.rough_coexp[i] * f.canopy_vlaiw[i], 20.0f))) - w.gbhu[i].v[0];
+                         * (1.0f - o_expf(-fminf_(0.5f * f.rough_coexp[i] * f.canopy_vlaiw[i], 20.0f))) - w.gbhu[i].v[0];
       }
       w.rny[i] = w.sum_rad_rniso[i];                                                      // :400-402
       w.hcy[i] = 0.0;
@@ -660,7 +660,7 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       if (f.canopy_vlaiw[j] > CLAI_THRESH && f.rough_hruff[j] > f.rough_z0soilsn[j]) {    // :427
         f.rad_lwabv[j] = CCAPP * CRMAIR * (w.tlfy[j] - f.met_tk[j]) * w.sum_rad_gradis[j];
         float arg = f.rad_lwabv[j] / (2.0f * (1.0f - f.rad_transd[j]) * CSBOLTZ * CEMLEAF) + pow4(f.met_tvrad[j]);
-        if (arg > 0.0f) f.canopy_tv[j] = powf(arg, 0.25f);
+        if (arg > 0.0f) f.canopy_tv[j] = o_powf(arg, 0.25f);
         else f.canopy_tv[j] = f.met_tvrad[j];
       } else {
         f.canopy_tv[j] = f.met_tvrad[j];
@@ -724,37 +724,37 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
     if (f.soil_isoilm[j] == ICE_SOILTYPE) Surf_conductance = 1.e6f;
     f.canopy_gswx_T[j] = Surf_conductance;
     float zN = f.canopy_zetar[IX(j, niter - 1)];
-    f.canopy_cdtq[j] = f.canopy_cduv[j] * (logf(f.rough_zref_uv[j] / f.rough_z0m[j])
+    f.canopy_cdtq[j] = f.canopy_cduv[j] * (o_logf(f.rough_zref_uv[j] / f.rough_z0m[j])
                          - psim(zN * f.rough_zref_uv[j] / f.rough_zref_tq[j])
                          + psim(zN * f.rough_z0m[j] / f.rough_zref_tq[j]))
-                       / (logf(f.rough_zref_tq[j] / (0.1f * f.rough_z0m[j])) - psis(zN)
+                       / (o_logf(f.rough_zref_tq[j] / (0.1f * f.rough_z0m[j])) - psis(zN)
                           + psis(zN * 0.1f * f.rough_z0m[j] / f.rough_zref_tq[j]));       // :716
     float zP = f.canopy_zetar[IX(j, iterplus - 1)];
     float tstar = -f.canopy_fh[j] / (f.air_rho[j] * CCAPP * f.canopy_us[j]);              // :731
     float qstar = -f.canopy_fe[j] / (f.air_rho[j] * f.air_rlam[j] * f.canopy_us[j] * f.ssnow_cls[j]);
     float zscrn = fmaxf_(f.rough_z0m[j], 2.0f - f.rough_disp[j]);
-    float ftemp = (logf(f.rough_zref_tq[j] / zscrn) - psis(zP) + psis(zP * zscrn / f.rough_zref_tq[j])) / CVONK;
+    float ftemp = (o_logf(f.rough_zref_tq[j] / zscrn) - psis(zP) + psis(zP * zscrn / f.rough_zref_tq[j])) / CVONK;
     f.canopy_tscrn[j] = f.met_tk[j] - CTFRZ - tstar * ftemp;                              // :738
     float term1 = 0.f, term2 = 0.f, term5 = 0.f, term3 = 0.f, r_sc = 0.f;
     float zscl = fmaxf_(f.rough_z0soilsn[j], 2.0f);
     float rgh = f.canopy_rghlai[j], hr = f.rough_hruff[j], disp = f.rough_disp[j];
     if (f.canopy_vlaiw[j] > CLAI_THRESH && hr > 0.01f) {                                  // :754
       if (disp > 0.0f) {
-        term1 = expf(2 * CCSW * rgh * (1 - zscl / hr));
-        term2 = expf(2 * CCSW * rgh * (1 - disp / hr));
+        term1 = o_expf(2 * CCSW * rgh * (1 - zscl / hr));
+        term2 = o_expf(2 * CCSW * rgh * (1 - disp / hr));
         term5 = fmaxf_(2.f / 3.f * hr / disp, 1.f);
       }
       term3 = sq(CA33) * CCTL * 2 * CCSW * rgh;
       if (zscl < disp) {
-        r_sc = term5 * logf(zscl / f.rough_z0soilsn[j]) * (expf(2 * CCSW * rgh) - term2) / term3;
-        r_sc = r_sc + term5 * logf(disp / zscl) * (expf(2 * CCSW * rgh) - term1) / term3;
+        r_sc = term5 * o_logf(zscl / f.rough_z0soilsn[j]) * (o_expf(2 * CCSW * rgh) - term2) / term3;
+        r_sc = r_sc + term5 * o_logf(disp / zscl) * (o_expf(2 * CCSW * rgh) - term1) / term3;
       } else if (disp <= zscl && zscl < hr) {
         r_sc = f.rough_rt0us[j] + term5 * (term2 - term1) / term3;
       } else if (hr <= zscl && zscl < f.rough_zruffs[j]) {
         r_sc = f.rough_rt0us[j] + f.rough_rt1usa[j] + term5 * (zscl - hr) / (sq(CA33) * CCTL * hr);
       } else if (zscl >= f.rough_zruffs[j]) {
         r_sc = f.rough_rt0us[j] + f.rough_rt1usa[j] + f.rough_rt1usb[j]
-               + (logf((zscl - disp) / fmaxf_(f.rough_zruffs[j] - disp, f.rough_z0soilsn[j]))
+               + (o_logf((zscl - disp) / fmaxf_(f.rough_zruffs[j] - disp, f.rough_z0soilsn[j]))
                   - psis((zscl - disp) * zP / f.rough_zref_tq[j])
                   + psis((f.rough_zruffs[j] - disp) * zP / f.rough_zref_tq[j])) / CVONK;
       }
@@ -786,7 +786,7 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
     f.ssnow_dfe_ddq[j] = f.ssnow_wetfac[j] * f.air_rho[j] * f.air_rlam[j] * f.ssnow_cls[j] / rttsoil;
     f.ssnow_ddq_dtg[j] = (CRMH2O / CRMAIR) / f.met_pmb[j] * CTETENA * CTETENB * CTETENC
                          / (sq(CTETENC + f.ssnow_tss[j] - CTFRZ))
-                         * expf(CTETENB * (f.ssnow_tss[j] - CTFRZ) / (CTETENC + f.ssnow_tss[j] - CTFRZ));   // :1018
+                         * o_expf(CTETENB * (f.ssnow_tss[j] - CTFRZ) / (CTETENC + f.ssnow_tss[j] - CTFRZ));   // :1018
     f.ssnow_dfe_dtg[j] = f.ssnow_dfe_ddq[j] * f.ssnow_ddq_dtg[j];
     f.canopy_dgdtg[j] = f.ssnow_dfn_dtg[j] - f.ssnow_dfh_dtg[j] - f.ssnow_dfe_dtg[j];     // :1027
     f.bal_drybal[j] = (float)(w.ecy[j] + w.hcy[j]) - w.sum_rad_rniso[j]

@@ -45,28 +45,28 @@ void ruff_resist(Oracle &o) {
       f.rough_rt1usb[i] = 0.0f;
       f.rough_usuh[i] = fminf_(sqrtf(CCSD + CCRD * (f.canopy_vlaiw[i] * 0.5f)), CUSUHM);
       xx = sqrtf(CCCD * fmaxf_((f.canopy_vlaiw[i] * 0.5f), 0.0005f));
-      dh = 1.0f - (1.0f - expf(-xx)) / xx;
+      dh = 1.0f - (1.0f - o_expf(-xx)) / xx;
       f.rough_coexp[i] = f.rough_usuh[i] / (CVONK * CCCW_C * (1.0f - dh));
     } else {
       f.rough_usuh[i] = fminf_(sqrtf(CCSD + CCRD * (f.canopy_rghlai[i] * 0.5f)), CUSUHM);
       xx = sqrtf(CCCD * fmaxf_((f.canopy_rghlai[i] * 0.5f), 0.0005f));
-      dh = 1.0f - (1.0f - expf(-xx)) / xx;
+      dh = 1.0f - (1.0f - o_expf(-xx)) / xx;
       f.rough_disp[i] = dh * f.rough_hruff[i];
-      f.rough_z0m[i] = ((1.0f - dh) * expf(logf(CCCW_C) - 1.f + 1.f / CCCW_C - CVONK / f.rough_usuh[i]))
+      f.rough_z0m[i] = ((1.0f - dh) * o_expf(o_logf(CCCW_C) - 1.f + 1.f / CCCW_C - CVONK / f.rough_usuh[i]))
                        * f.rough_hruff[i];
       f.rough_zref_uv[i] = fmaxf_(3.5f + f.rough_z0m[i], f.rough_za_uv[i]);
       f.rough_zref_tq[i] = fmaxf_(3.5f + f.rough_z0m[i], f.rough_za_tq[i]);
       f.rough_zref_uv[i] = fmaxf_(f.rough_zref_uv[i], f.rough_hruff[i] - f.rough_disp[i]);
       f.rough_zref_tq[i] = fmaxf_(f.rough_zref_tq[i], f.rough_hruff[i] - f.rough_disp[i]);
       f.rough_coexp[i] = f.rough_usuh[i] / (CVONK * CCCW_C * (1.0f - dh));
-      f.rough_term2[i] = expf(2 * CCSW * f.canopy_rghlai[i] * (1 - f.rough_disp[i] / f.rough_hruff[i]));
+      f.rough_term2[i] = o_expf(2 * CCSW * f.canopy_rghlai[i] * (1 - f.rough_disp[i] / f.rough_hruff[i]));
       f.rough_term3[i] = sq(CA33) * CCTL * 2 * CCSW * f.canopy_rghlai[i];
       f.rough_term5[i] = fmaxf_((2.f / 3.f) * f.rough_hruff[i] / f.rough_disp[i], 1.0f);
-      f.rough_term6[i] = expf(3.f * f.rough_coexp[i] * (f.rough_disp[i] / f.rough_hruff[i] - 1.f));
-      f.rough_term6a[i] = expf(f.rough_coexp[i] * (0.1f * f.rough_hruff[i] / f.rough_hruff[i] - 1.f));
-      f.rough_rt0us[i] = f.rough_term5[i] * (CZDLIN * logf(CZDLIN * f.rough_disp[i] / f.rough_z0soilsn[i])
+      f.rough_term6[i] = o_expf(3.f * f.rough_coexp[i] * (f.rough_disp[i] / f.rough_hruff[i] - 1.f));
+      f.rough_term6a[i] = o_expf(f.rough_coexp[i] * (0.1f * f.rough_hruff[i] / f.rough_hruff[i] - 1.f));
+      f.rough_rt0us[i] = f.rough_term5[i] * (CZDLIN * o_logf(CZDLIN * f.rough_disp[i] / f.rough_z0soilsn[i])
                          + (1 - CZDLIN))
-                         * (expf(2 * CCSW * f.canopy_rghlai[i]) - f.rough_term2[i]) / f.rough_term3[i];
+                         * (o_expf(2 * CCSW * f.canopy_rghlai[i]) - f.rough_term2[i]) / f.rough_term3[i];
       f.rough_zruffs[i] = f.rough_disp[i] + f.rough_hruff[i] * sq(CA33) * CCTL / CVONK / f.rough_term5[i];
       f.rough_rt1usa[i] = f.rough_term5[i] * (f.rough_term2[i] - 1.0f) / f.rough_term3[i];
       f.rough_rt1usb[i] = f.rough_term5[i] * (fminf_(f.rough_zref_tq[i] + f.rough_disp[i], f.rough_zruffs[i])
@@ -81,7 +81,7 @@ void define_air(Oracle &o) {
   const int mp = o.mp; Fields &f = o.f;
   for (int i = 0; i < mp; i++) {
     float tv = f.met_tvair[i], pmb = f.met_pmb[i];
-    float es = CTETENA * expf(CTETENB * (tv - CTFRZ) / (CTETENC + (tv - CTFRZ)));        // :64
+    float es = CTETENA * o_expf(CTETENB * (tv - CTFRZ) / (CTETENC + (tv - CTFRZ)));        // :64
     f.air_cmolar[i] = pmb * 100.0f / (CRGAS * (tv));                                      // :68
     f.air_rho[i] = fminf_(1.3f, CRMAIR * f.air_cmolar[i]);                                // :71
     f.air_volm[i] = CRGAS * (tv) / (100.0f * pmb);                                        // :74
@@ -92,7 +92,7 @@ void define_air(Oracle &o) {
     f.air_visc[i] = 1e-5f * fmaxf_(1.0f, 1.35f + 0.0092f * (tv - CTFRZ));                 // :87
     f.air_psyc[i] = pmb * 100.0f * CCAPP * CRMAIR / f.air_rlam[i] / CRMH2O;               // :90
     f.air_dsatdk[i] = 100.0f * (CTETENA * CTETENB * CTETENC) / sq((tv - CTFRZ) + CTETENC)
-                      * expf(CTETENB * (tv - CTFRZ) / ((tv - CTFRZ) + CTETENC));          // :93
+                      * o_expf(CTETENB * (tv - CTFRZ) / ((tv - CTFRZ) + CTETENC));          // :93
   }
 }
 
@@ -109,7 +109,7 @@ void plantcarb(Oracle &o) {
     float poolcoef1r = (s - ratecp[0] * f.bgc_cplant[IX(i, 0)] - ratecp[1] * f.bgc_cplant[IX(i, 1)]);
     float tmp1 = fmaxf_(3.22f - 0.046f * (f.met_tk[i] - CTFRZ), 1e-6f);
     float tmp2 = 0.1f * (f.met_tk[i] - CTFRZ - 20.0f);
-    float tmp3 = powf(tmp1, tmp2);
+    float tmp3 = o_powf(tmp1, tmp2);
     f.canopy_frp[i] = f.veg_rp20[i] * tmp3 * poolcoef1 / sec_per_year;
     f.canopy_frpw[i] = f.veg_rp20[i] * tmp3 * poolcoef1w / sec_per_year;
     f.canopy_frpr[i] = f.veg_rp20[i] * tmp3 * poolcoef1r / sec_per_year;
@@ -128,8 +128,8 @@ void soilcarb(Oracle &o) {
       avgtrs = fmaxf_(0.0f, avgtrs - CTFRZ);
       float frs = f.veg_rs20[i] * fminf_(1.0f, fmaxf_(0.0f, fminf_(
                      -0.0178f + 0.2883f * avgwrs + 5.0176f * avgwrs * avgwrs - 4.5128f * avgwrs * avgwrs * avgwrs,
-                     0.3320f + 22.6726f * expf(-5.8184f * avgwrs))))
-                 * fminf_(1.0f, fmaxf_(0.0f, fminf_(0.0104f * (powf(avgtrs, 1.3053f)), 5.5956f - 0.1189f * avgtrs)));
+                     0.3320f + 22.6726f * o_expf(-5.8184f * avgwrs))))
+                 * fminf_(1.0f, fmaxf_(0.0f, fminf_(0.0104f * (o_powf(avgtrs, 1.3053f)), 5.5956f - 0.1189f * avgtrs)));
       float s = o.cfg.ratecs[0] * f.bgc_csoil[IX(i, 0)];
       s = s + o.cfg.ratecs[1] * f.bgc_csoil[IX(i, 1)];
       frs = frs * s / (365.0f * 24.0f * 3600.0f);
@@ -150,7 +150,7 @@ void soilcarb(Oracle &o) {
       float e0rswc = 52.4f + 285.f * rswc;
       float ftsoil = fminf_(0.0015f, 1.f / (tref - t0) - 1.f / (tsoil - t0));
       float sss = fmaxf_(-15.f, fminf_(1.f, e0rswc * ftsoil));
-      float ftsrs = expf(sss);
+      float ftsrs = o_expf(sss);
       f.canopy_frs[i] = f.veg_vegcf[i] * (144.0f / 44.0e6f) * soilcf
                         * fminf_(1.f, 1.4f * fmaxf_(.3f, .0278f * tsoil + .5f)) * ftsrs * rswc / (rswch + rswc);
     }
@@ -188,22 +188,22 @@ void carbon_pl(Oracle &o, float dels) {
   if (!carbon_tables(o.cfg.mvtype, rw, tfcl, tvclst)) return;  // reference STOPs (:142-148); create() rejects
   for (int i = 0; i < mp; i++) {
     int iv = f.veg_iveg[i] - 1;
-    float coef_cold = expf(fminf_(1.f, -(f.canopy_tv[i] - tvclst[iv])));                  // :153
+    float coef_cold = o_expf(fminf_(1.f, -(f.canopy_tv[i] - tvclst[iv])));                  // :153
     float wbav = 0.f;
     for (int k = 0; k < ms; k++) wbav = wbav + f.veg_froot[IX(i, k)] * (float)f.ssnow_wb[IX(i, k)];
     wbav = fmaxf_(0.01f, wbav);
     float CampbellExp = 2.0f - f.soil_ibp2[i];
-    float EffStressIndexWater = powf(wbav, CampbellExp) - 1.0f;
+    float EffStressIndexWater = o_powf(wbav, CampbellExp) - 1.0f;
     EffStressIndexWater = fmaxf_(1.0f, EffStressIndexWater);
-    float EffStressIndexWilting = powf(f.soil_swilt[i], CampbellExp) - 1.0f;
+    float EffStressIndexWilting = o_powf(f.soil_swilt[i], CampbellExp) - 1.0f;
     float RelativeStress = EffStressIndexWater / EffStressIndexWilting - 1.0f;
     RelativeStress = fminf_(1.0f, RelativeStress);
-    float coef_drght = expf(5.0f * RelativeStress);
+    float coef_drght = o_expf(5.0f * RelativeStress);
     float coef_cd = (coef_cold + coef_drght) * 2.0e-7f;
-    float fcl = expf(-tfcl[iv] * f.veg_vlai[i]);                                          // :173
+    float fcl = o_expf(-tfcl[iv] * f.veg_vlai[i]);                                          // :173
     float clitt = (coef_cd + trnl) * f.bgc_cplant[IX(i, 0)];
     f.bgc_cplant[IX(i, 0)] = f.bgc_cplant[IX(i, 0)] - dels * (f.canopy_fpn[i] * fcl + clitt);
-    float fr = fminf_(1.f, expf(-rw[iv] * beta * 0.0001f * f.bgc_cplant[IX(i, 2)]
+    float fr = fminf_(1.f, o_expf(-rw[iv] * beta * 0.0001f * f.bgc_cplant[IX(i, 2)]
                                 / fmaxf_(f.bgc_cplant[IX(i, 1)], 0.01f)) / beta);          // :184
     float cfwd = trnw * f.bgc_cplant[IX(i, 1)];
     f.bgc_cplant[IX(i, 1)] = f.bgc_cplant[IX(i, 1)] - dels * (f.canopy_fpn[i] * (1.f - fcl) * (1.f - fr)
@@ -265,7 +265,7 @@ void cbm(Oracle &o, int ktau, float dels) {
     f.canopy_fev[i] = (float)(f.canopy_fevc[i] + f.canopy_fevw[i]);                       // :203
     f.canopy_fe[i] = (float)(f.canopy_fev[i] + f.canopy_fes[i]);                          // :206
     f.canopy_rnet[i] = f.canopy_fns[i] + f.canopy_fnv[i];                                 // :209
-    f.rad_trad[i] = powf((1.f - f.rad_transd[i]) * pow4(f.canopy_tv[i])
+    f.rad_trad[i] = o_powf((1.f - f.rad_transd[i]) * pow4(f.canopy_tv[i])
                          + f.rad_transd[i] * pow4(f.ssnow_tss[i]), 0.25f);                // :212
   }
   if (o.cfg.icycle == 0) {                                                                // :214-229

@@ -12,7 +12,7 @@ static float spitter(int doy, float coszen, float fsd) {
   float tmpk = (1.47f - tmpr) / 1.66f;
   float tmprat;
   if (coszen > 1.0e-10f && fsd > 10.0f)
-    tmprat = fsd / (solcon * (1.0f + 0.033f * cosf(2.0f * CPI * ((float)doy - 10.0f) / 365.0f)) * coszen);
+    tmprat = fsd / (solcon * (1.0f + 0.033f * o_cosf(2.0f * CPI * ((float)doy - 10.0f) / 365.0f)) * coszen);
   else
     tmprat = 0.0f;
   if (tmprat > 0.22f) fbeam = 6.4f * sq(tmprat - 0.22f);
@@ -27,7 +27,7 @@ void init_radiation(Oracle &o, const std::vector<char> &veg_mask) {
   // Common_InitRad_Scalings (:132-218)
   float cos3[3];
   const float ang[3] = {15.0f, 45.0f, 75.0f};
-  for (int b = 0; b < 3; b++) cos3[b] = cosf(CPI180 * ang[b]);                            // :193
+  for (int b = 0; b < 3; b++) cos3[b] = o_cosf(CPI180 * ang[b]);                            // :193
   const float Ccoszen_tols_huge = CCOSZEN_TOLS * 1e2f;                                    // :104
   const float Ccoszen_tols_tiny = CCOSZEN_TOLS * 1e-2f;                                   // :105
   for (int i = 0; i < mp; i++) {
@@ -50,8 +50,8 @@ void init_radiation(Oracle &o, const std::vector<char> &veg_mask) {
     float extkb = 0.5f, extkd = 0.7f;
     if (veg_mask[i]) {
       float s = 0.f;
-      for (int b = 0; b < 3; b++) s = s + CGAUSS_W[b] * expf(-f.scr_xk[IX(i, b)] * xvlai2);
-      extkd = -logf(s) / f.canopy_vlaiw[i];
+      for (int b = 0; b < 3; b++) s = s + CGAUSS_W[b] * o_expf(-f.scr_xk[IX(i, b)] * xvlai2);
+      extkd = -o_logf(s) / f.canopy_vlaiw[i];
     }
     if (veg_mask[i] && f.met_coszen[i] > Ccoszen_tols_tiny) extkb = xphi1 / f.met_coszen[i] + xphi2;
     if (f.met_coszen[i] < Ccoszen_tols_tiny) extkb = 1.0e5f;
@@ -127,12 +127,12 @@ void albedo(Oracle &o, const std::vector<char> &veg_mask) {
     for (int b = 0; b < 2; b++) {
       if (veg_mask[i]) {
         float dummy = fminf_(f.rad_extkbm[IX(i, b)] * f.canopy_vlaiw[i], 20.0f);
-        f.rad_cexpkbm[IX(i, b)] = expf(-1.0f * dummy);
+        f.rad_cexpkbm[IX(i, b)] = o_expf(-1.0f * dummy);
       }
     }
     for (int b = 0; b < 2; b++) {
       float dummy = f.rad_extkdm[IX(i, b)] * f.canopy_vlaiw[i];
-      f.rad_cexpkdm[IX(i, b)] = expf(-1.0f * dummy);
+      f.rad_cexpkdm[IX(i, b)] = o_expf(-1.0f * dummy);
     }
     // EffectiveSurfaceReflectance (:175-181, :287-350)
     for (int b = 0; b < 3; b++) {
@@ -161,11 +161,11 @@ void radiation(Oracle &o, const std::vector<char> &sunlit_veg_mask) {
 #define QCAN(i, l, b) f.rad_qcan[(size_t)(i) + (size_t)mp * ((l) + 2 * (b))]
   for (int i = 0; i < mp; i++) {
     float vlaiw = f.canopy_vlaiw[i];
-    float cf2n = expf(-f.veg_extkn[i] * vlaiw);                                           // :74
+    float cf2n = o_expf(-f.veg_extkn[i] * vlaiw);                                           // :74
     f.rad_transd[i] = 1.0f;
-    if (vlaiw > CLAI_THRESH) f.rad_transd[i] = expf(-f.rad_extkd[i] * vlaiw);             // :78-85
+    if (vlaiw > CLAI_THRESH) f.rad_transd[i] = o_expf(-f.rad_extkd[i] * vlaiw);             // :78-85
     float dummy2 = fminf_(f.rad_extkb[i] * vlaiw, 30.f);
-    float dummy = expf(-dummy2);
+    float dummy = o_expf(-dummy2);
     f.rad_transb[i] = dummy;
     float flpwb = CSBOLTZ * pow4(f.met_tvrad[i]);                                         // :97
     float flwv = CEMLEAF * flpwb;
@@ -208,9 +208,9 @@ void radiation(Oracle &o, const std::vector<char> &sunlit_veg_mask) {
     f.rad_qssabs[i] = 0.f;
     if (sunlit_veg_mask[i]) {                                                             // :181-199
       f.rad_qssabs[i] = f.met_fsd[IX(i, 0)] * (f.rad_fbeam[IX(i, 0)] * (1.f - f.rad_reffbm[IX(i, 0)])
-                          * expf(-fminf_(f.rad_extkbm[IX(i, 0)] * vlaiw, 20.f))
+                          * o_expf(-fminf_(f.rad_extkbm[IX(i, 0)] * vlaiw, 20.f))
                           + (1.f - f.rad_fbeam[IX(i, 0)]) * (1.f - f.rad_reffdf[IX(i, 0)])
-                          * expf(-fminf_(f.rad_extkdm[IX(i, 0)] * vlaiw, 20.f)))
+                          * o_expf(-fminf_(f.rad_extkdm[IX(i, 0)] * vlaiw, 20.f)))
                         + f.met_fsd[IX(i, 1)] * (f.rad_fbeam[IX(i, 1)] * (1.f - f.rad_reffbm[IX(i, 1)])
                           * f.rad_cexpkbm[IX(i, 1)] + (1.f - f.rad_fbeam[IX(i, 1)])
                           * (1.f - f.rad_reffdf[IX(i, 1)]) * f.rad_cexpkdm[IX(i, 1)]);

@@ -84,9 +84,9 @@ static void snowdensity(Oracle &o, float dels) {
     if (m1) {                                                                             // :23-50
       float s1 = sd[IX(i, 0)];
       s1 = fminf_(max_ssdn, fmaxf_(120.0f, s1 + dels * s1 * 3.1e-6f
-             * expf(-0.03f * (273.15f - tgg_min1) - ((s1 >= 150.0f) ? 0.046f : 0.0f) * (s1 - 150.0f))));
+             * o_expf(-0.03f * (273.15f - tgg_min1) - ((s1 >= 150.0f) ? 0.046f : 0.0f) * (s1 - 150.0f))));
       s1 = fminf_(max_ssdn, s1 + dels * 9.806f * s1 * 0.75f * f.ssnow_snowd[i]
-             / (3.0e7f * expf(0.021f * s1 + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tgg[IX(i, 0)])))));
+             / (3.0e7f * o_expf(0.021f * s1 + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tgg[IX(i, 0)])))));
       if (f.soil_isoilm[i] != 9) s1 = fminf_(450.0f, s1);
       sd[IX(i, 0)] = s1;
       f.ssnow_sconds[IX(i, 0)] = fmaxf_(0.2f, fminf_(2.876e-6f * sq(s1) + 0.074f, max_sconds));
@@ -99,16 +99,16 @@ static void snowdensity(Oracle &o, float dels) {
       for (int k = 0; k < 3; k++) {
         float s = sd[IX(i, k)];
         sd[IX(i, k)] = s + dels * s * 3.1e-6f
-            * expf(-0.03f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, k)])) - ((s >= 150.0f) ? 0.046f : 0.0f) * (s - 150.0f));
+            * o_expf(-0.03f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, k)])) - ((s >= 150.0f) ? 0.046f : 0.0f) * (s - 150.0f));
       }
       float t = f.ssnow_t_snwlr[i];
       sd[IX(i, 0)] = sd[IX(i, 0)] + dels * 9.806f * sd[IX(i, 0)] * t * sd[IX(i, 0)]
-          / (3.0e7f * expf(.021f * sd[IX(i, 0)] + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, 0)]))));
+          / (3.0e7f * o_expf(.021f * sd[IX(i, 0)] + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, 0)]))));
       sd[IX(i, 1)] = sd[IX(i, 1)] + dels * 9.806f * sd[IX(i, 1)] * (t * sd[IX(i, 0)] + 0.5f * f.ssnow_smass[IX(i, 1)])
-          / (3.0e7f * expf(.021f * sd[IX(i, 1)] + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, 1)]))));
+          / (3.0e7f * o_expf(.021f * sd[IX(i, 1)] + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, 1)]))));
       sd[IX(i, 2)] = sd[IX(i, 2)] + dels * 9.806f * sd[IX(i, 2)]
           * (t * sd[IX(i, 0)] + f.ssnow_smass[IX(i, 1)] + 0.5f * f.ssnow_smass[IX(i, 2)])
-          / (3.0e7f * expf(.021f * sd[IX(i, 2)] + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, 2)]))));
+          / (3.0e7f * o_expf(.021f * sd[IX(i, 2)] + 0.081f * (273.15f - fminf_(CTFRZ, f.ssnow_tggsn[IX(i, 2)]))));
       for (int k = 0; k < 3; k++) f.ssnow_sdepth[IX(i, k)] = f.ssnow_smass[IX(i, k)] / sd[IX(i, k)];
       f.ssnow_ssdnn[i] = (sd[IX(i, 0)] * f.ssnow_smass[IX(i, 0)] + sd[IX(i, 1)] * f.ssnow_smass[IX(i, 1)]
                           + sd[IX(i, 2)] * f.ssnow_smass[IX(i, 2)]) / f.ssnow_snowd[i];
@@ -311,13 +311,13 @@ static void old_soil_conductivity(Oracle &o, std::vector<double> &ccnsw) {
       } else {
         float ssat = f.soil_ssat[j];
         float ew = (float)(f.ssnow_wblf[IX(j, k)] * ssat);
-        float exp_arg = (float)((ew * logf(60.0f)) + (f.ssnow_wbfice[IX(j, k)] * ssat * logf(250.0f)));
+        float exp_arg = (float)((ew * o_logf(60.0f)) + (f.ssnow_wbfice[IX(j, k)] * ssat * o_logf(250.0f)));
         bool direct2min = false;
         if (exp_arg > 30) direct2min = true;
         if (direct2min)
           ccnsw[IX(j, k)] = 1.5f * dmax_(1.0, std::sqrt(dmin_(2.0, 0.5f * ssat / dmin_((double)ew, 0.5 * ssat))));
         else
-          ccnsw[IX(j, k)] = dmin_(f.soil_cnsd[j] * expf(exp_arg), 1.5)
+          ccnsw[IX(j, k)] = dmin_(f.soil_cnsd[j] * o_expf(exp_arg), 1.5)
                             * dmax_(1.0, std::sqrt(dmin_(2.0, 0.5f * ssat / dmin_((double)ew, 0.5 * ssat))));
       }
     }
@@ -709,7 +709,7 @@ void snow_aging(Oracle &o, float dels) {
       float ar3;
       if (f.soil_isoilm[i] == 9) { ar3 = 0.0000001f; dnsnow = 1.0f; }
       else ar3 = 0.1f;
-      float dtau = 1.0e-6f * (expf(ar1) + expf(ar2) + ar3) * dels;
+      float dtau = 1.0e-6f * (o_expf(ar1) + o_expf(ar2) + ar3) * dels;
       f.ssnow_snage[i] = fmaxf_(0.0f, (f.ssnow_snage[i] + dtau) * (1.0f - dnsnow));
     }
   }

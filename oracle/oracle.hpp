@@ -78,6 +78,23 @@ constexpr int EVERGREEN_NEEDLELEAF = 1, EVERGREEN_BROADLEAF = 2, DECIDUOUS_NEEDL
 
 constexpr int ms = CABLE_MS, msn = CABLE_MSN, mf = CABLE_MF, nrb = CABLE_NRB, niter = CABLE_NITER;
 
+// REAL (fp32) transcendental intrinsics.  Default build: the host libm's float routines, i.e. what
+// a gfortran build of the reference links.  -DORACLE_CR_MATH: evaluated in double and rounded once
+// (correctly rounded); used to separate "logic differs" from "libm differs" in the parity tests.
+#ifdef ORACLE_CR_MATH
+static inline float o_expf(float x) { return (float)std::exp((double)x); }
+static inline float o_logf(float x) { return (float)std::log((double)x); }
+static inline float o_powf(float x, float y) { return (float)std::pow((double)x, (double)y); }
+static inline float o_atanf(float x) { return (float)std::atan((double)x); }
+static inline float o_cosf(float x) { return (float)std::cos((double)x); }
+#else
+static inline float o_expf(float x) { return ::expf(x); }
+static inline float o_logf(float x) { return ::logf(x); }
+static inline float o_powf(float x, float y) { return ::powf(x, y); }
+static inline float o_atanf(float x) { return ::atanf(x); }
+static inline float o_cosf(float x) { return ::cosf(x); }
+#endif
+
 // Fortran intrinsics
 static inline float  fmaxf_(float a, float b) { return a > b ? a : b; }   // MAX
 static inline float  fminf_(float a, float b) { return a < b ? a : b; }   // MIN

@@ -10,19 +10,23 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
-_lib = None
+LIB_CR_PATH = os.path.join(_HERE, "liboracle_cr.so")
+_libs = {}
 
 
 def build() -> None:
     subprocess.check_call(["make", "-s", "-C", _HERE, "-j8"])
 
 
-def load() -> C.CDLL:
-    global _lib
+def load(cr_math: bool = False) -> C.CDLL:
+    """cr_math=False: host libm float intrinsics (a gfortran build's semantics);
+    cr_math=True: correctly rounded fp32 intrinsics (isolates logic from libm differences)."""
+    path = LIB_CR_PATH if cr_math else LIB_PATH
+    _lib = _libs.get(path)
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if not os.path.exists(path):
             build()
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         lib.oracle_nfields.restype = C.c_int
         lib.oracle_field_name.restype = C.c_char_p
         lib.oracle_field_name.argtypes = [C.c_int]
@@ -40,15 +44,15 @@ def load() -> C.CDLL:
             fn.argtypes = [C.c_float]
         lib.oracle_qsat.restype = C.c_float
         lib.oracle_qsat.argtypes = [C.c_float, C.c_float]
-        _lib = lib
+        _libs[path] = _lib = lib
     return _lib
 
 
 class Oracle:
     """Runs the restated cbm() in place on a dict of (ncomp, mp) arrays (registry layout)."""
 
-    def __init__(self, tiles: dict[str, np.ndarray], cfg):
-        lib = load()
+    def __init__(self, tiles: dict[str, np.ndarray], cfg, cr_math: bool = False):
+        lib = load(cr_math)
         n = lib.oracle_nfields()
         names = [lib.oracle_field_name(i).decode() for i in range(n)]
         self.tiles = tiles
