@@ -80,7 +80,7 @@ struct cable_handle {
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
-  int block = 128;
+  int block = 128, split = 1, minb_a = 8, minb_b = 8;
   // measurement
   cable_counters ctr{};
   bool profile = false;
@@ -211,7 +211,11 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
 
   cable_handle *h = new cable_handle();
   h->mp = mp; h->device = device; h->cfg = *cfg; h->nslots = cfg->n_forcing_slots;
-  h->block = (cfg->threads_per_block == 64 || cfg->threads_per_block == 256) ? cfg->threads_per_block : 128;
+  h->block = 128;
+  // tuning knobs (DESIGN.md 'Kernel'): split step into kernels A/B, min resident blocks per SM of each
+  if (const char *e = getenv("CABLE_B200_SPLIT")) h->split = atoi(e);
+  if (const char *e = getenv("CABLE_B200_MINB_A")) h->minb_a = atoi(e);
+  if (const char *e = getenv("CABLE_B200_MINB_B")) h->minb_b = atoi(e);
   // device-side config + host-evaluated constants
   DevCfg &d = h->dcfg;
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
@@ -302,8 +306,13 @@ int cable_b200_bind_field(cable_handle *h, int id, void *host) {
   const cable_field_info &f = g_fields[id];
   const bool per_step = (f.role == FORCING) || (f.role == STATE) || (f.role == DIAG && (f.flags & CABLE_FLAG_STAR));
   if (host && per_step && !(f.flags & CABLE_FLAG_HOSTONLY)) {
-    if (cudaHostRegister(host, h->bytes[id], cudaHostRegisterDefault) == cudaSuccess) h->host_pinned[id] = true;
-    else cudaGetLastError();
+    cudaPointerAttributes attr{};
+    const bool already = (cudaPointerGetAttributes(&attr, host) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!already) {       // caller-pinned buffers (cudaHostAlloc / registered elsewhere) are used as they are
+      if (cudaHostRegister(host, h->bytes[id], cudaHostRegisterDefault) == cudaSuccess) h->host_pinned[id] = true;
+      else cudaGetLastError();
+    }
   }
   return CABLE_OK;
 }
@@ -374,11 +383,22 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
     e0 = h->prof_ev[h->prof_n++]; e1 = h->prof_ev[h->prof_n++];
     CUDA_TRY(cudaEventRecord(e0, h->s_compute));
   }
-  switch (h->block) {
-    case 64:  cbm_kernel<64><<<grid, 64, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn); break;
-    case 256: cbm_kernel<256><<<grid, 256, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn); break;
-    default:  cbm_kernel<128><<<grid, 128, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn); break;
+  // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
+  // MINB = resident 128-thread blocks per SM the compiler must allow (register cap 65536 / (128*MINB)).
+#define CBL_LAUNCH(PH, MB) cbm_kernel<PH, 128, MB><<<grid, 128, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn)
+#define CBL_DISPATCH(PH, mb)                                                     \
+  switch (mb) { case 3: CBL_LAUNCH(PH, 3); break; case 4: CBL_LAUNCH(PH, 4); break; \
+                case 6: CBL_LAUNCH(PH, 6); break; default: CBL_LAUNCH(PH, 8); break; }
+  if (h->split) {
+    CBL_DISPATCH(1, h->minb_a);
+    CUDA_TRY(cudaGetLastError());
+    CBL_DISPATCH(2, h->minb_b);
+    h->ctr.kernel_launches++;
+  } else {
+    CBL_DISPATCH(3, h->minb_a);
   }
+#undef CBL_DISPATCH
+#undef CBL_LAUNCH
   CUDA_TRY(cudaGetLastError());
   if (h->profile) CUDA_TRY(cudaEventRecord(e1, h->s_compute));
   CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], h->s_compute));

@@ -166,7 +166,7 @@ CBL_DEV float fwsoil_calc(const Tile &t, const DevCfg &c) {
 #pragma unroll
     for (int k = 0; k < K::ms; k++) {
       float dummy = (float)(0.01f / mx(1.0e-3, t.ssnow_wbliq[k] - swilt));
-      float frwater = (float)mx(1.0e-4, pow((t.ssnow_wbliq[k] - swilt) / ssat, (double)dummy));
+      float frwater = (float)mx(1.0e-4, d_pow((t.ssnow_wbliq[k] - swilt) / ssat, (double)dummy));
       fw = mn(1.0f, mx(fw, frwater));
     }
     return fw;
@@ -179,7 +179,7 @@ CBL_DEV float ejx_root(float parx, float alpha, float convex, float x) {
   return (ap + x - sqrtf(p2(ap + x) - 4.0f * convex * alpha * parx * x)) / (2.0f * convex);
 }
 CBL_DEV float xvcmxt4(float x) {
-  return m_pow(2.0f, 0.1f * x - 2.5f) / ((1.0f + m_exp(0.3f * (13.0f - x))) * (1.0f + m_exp(0.3f * (x - 36.0f))));
+  return m_exp2(0.1f * x - 2.5f) / ((1.0f + m_exp(0.3f * (13.0f - x))) * (1.0f + m_exp(0.3f * (x - 36.0f))));
 }
 CBL_DEV float arrhenius_peaked(float x, float coef, float eha, float ehd, float entrop) {
   float num = coef * m_exp((eha / (K::rgas * K::trefk)) * (1.f - K::trefk / x));
@@ -190,7 +190,7 @@ CBL_DEV float arrhenius_peaked(float x, float coef, float eha, float ehd, float 
 // One root of the Ci quadratic as the reference selects it (cbl_photosynthesis.F90:78-119 etc.)
 // kind 0: Rubisco (sentinel only if |coef2|>1e-9 & |coef1|<1e-9, later overwritten),
 // kind 1: RuBP (default sentinel 99999), kind 2: sink (value is ci itself).
-CBL_DEV double an_limited(int kind, double coef2, double coef1, double coef0,
+CBL_NOINLINE double an_limited(int kind, double coef2, double coef1, double coef0,
                           float vmax, float cxa, float cxb, float v4, float rdx) {
   const double tiny = (double)1.0e-9f;
   double an = (kind == 1) ? (double)99999.0f : 0.0;
@@ -253,7 +253,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
       const float tlfx = w.tlfx;
       // free-convection boundary-layer conductance, total conductances
       float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - t.met_tvair) * dleaf3);
-      float gras4 = m_pow(gras, 0.25f);
+      float gras4 = m_pow025(gras);
 #pragma unroll
       for (int l = 0; l < 2; l++) {
         w.gbhf[l] = mx(1.e-6, (double)(t.rad_fvlai[l] * t.air_cmolar * 0.5f * K::dheat * gras4 / t.veg_dleaf));
@@ -522,7 +522,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     if (dense) {
       t.rad_lwabv = cr * (w.tlfy - t.met_tk) * w.sum_gradis;
       float arg = t.rad_lwabv / (2.0f * (1.0f - t.rad_transd) * K::sboltz * K::emleaf) + tvrad4;
-      if (arg > 0.0f) tv = m_pow(arg, 0.25f);
+      if (arg > 0.0f) tv = m_pow025(arg);
     }
     t.canopy_tv = tv;
     t.canopy_fns = t.rad_qssabs + t.rad_transd * t.met_fld + (1.0f - t.rad_transd) * K::emleaf * K::sboltz * p4(tv)

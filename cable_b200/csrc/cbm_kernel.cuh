@@ -21,11 +21,35 @@ __constant__ DevCfg c_cfg;
 #define CBL_ROLE_STATE   CABLE_ROLE_STATE
 #define CBL_ROLE_DIAG    CABLE_ROLE_DIAG
 // flag tokens used by the rows of cable_b200_fields.def
-constexpr unsigned STAR = CABLE_FLAG_STAR, COND = CABLE_FLAG_COND, HOSTONLY = CABLE_FLAG_HOSTONLY, OPTIN = CABLE_FLAG_OPTIN;
+constexpr unsigned STAR = CABLE_FLAG_STAR, COND = CABLE_FLAG_COND, HOSTONLY = CABLE_FLAG_HOSTONLY, OPTIN = CABLE_FLAG_OPTIN,
+                   XCH = CABLE_FLAG_XCH, PHB = CABLE_FLAG_PHB, STA = CABLE_FLAG_STA;
 #define CBL_FLAGS(x) ((unsigned)(x))
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+// PHASE 1 = kernel A: lake refill .. define_canopy (surface + canopy energy/water balance)
+// PHASE 2 = kernel B: soil_snow, snow_aging, flux sums, simple carbon
+// PHASE 3 = both in one launch.
+// The step is split because the fused program is ~370 KB of SASS: with every warp of an SM somewhere else in
+// it the instruction cache thrashes (ncu: stall_no_instruction ~20 per issue, profiles/).  Each half keeps the
+// SM's warps inside one ~100-150 KB region and needs fewer live registers; the price is ~130 B/tile of
+// exchange fields (flag XCH) through HBM, which is noise against the arithmetic.
+__host__ __device__ constexpr bool load_in_phase(int phase, unsigned role, unsigned flags) {
+  if (flags & CABLE_FLAG_HOSTONLY) return false;
+  if (phase == 2 && (flags & CABLE_FLAG_XCH)) return true;      // e.g. canopy%ga: OPTIN for kernel A, exchange for B
+  if (flags & CABLE_FLAG_OPTIN) return false;
+  return (role & (CABLE_ROLE_FORCING | CABLE_ROLE_PARAM | CABLE_ROLE_STATE)) != 0;
+}
+// 0 = never, 1 = always, 2 = when the output level asks for it
+__host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsigned flags) {
+  if (flags & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_COND)) return 0;
+  if (role == CABLE_ROLE_STATE) return (phase != 1 || (flags & CABLE_FLAG_STA)) ? 1 : 0;
+  if (role != CABLE_ROLE_DIAG) return 0;
+  if (phase == 3) return 2;
+  if (phase == 1) return (flags & CABLE_FLAG_XCH) ? 1 : ((flags & CABLE_FLAG_PHB) ? 0 : 2);
+  return (flags & CABLE_FLAG_PHB) ? 2 : 0;
+}
+
+template <int PHASE, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 cbm_kernel(const DevPtrs d, const int mp, const float dels, const int first_call, unsigned long long *warn_counter) {
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= mp) return;
@@ -33,67 +57,65 @@ cbm_kernel(const DevPtrs d, const int mp, const float dels, const int first_call
   const size_t smp = (size_t)mp;
   Tile t;
 
-  // ---- load forcing, per-tile parameters, prognostic state (coalesced SoA reads) ----
+  // ---- load forcing, per-tile parameters, prognostic state (+ exchange fields in kernel B): coalesced SoA reads ----
 #define CABLE_F1(T, m, ct, role, flags)                                                          \
-  if ((CBL_ROLE_##role & (CABLE_ROLE_FORCING | CABLE_ROLE_PARAM | CABLE_ROLE_STATE)) &&         \
-      !(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_OPTIN)))                            \
-    t.T##_##m = d.T##_##m[i];
+  if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) t.T##_##m = d.T##_##m[i];
 #define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
-  if ((CBL_ROLE_##role & (CABLE_ROLE_FORCING | CABLE_ROLE_PARAM | CABLE_ROLE_STATE)) &&         \
-      !(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_OPTIN))) {                          \
+  if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) {                                 \
     _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = d.T##_##m[i + smp * k]; \
   }
 #include "../../include/cable_b200_fields.def"
 
-  // opt-in inputs
-  if (c.met_tv_is_tk) { t.met_tvair = t.met_tk; t.met_tvrad = t.met_tk; }     // cable_input.F90:2679-2680
-  else { t.met_tvair = d.met_tvair[i]; t.met_tvrad = d.met_tvrad[i]; }
-  if (c.ssnow_potev == CABLE_POTEV_PM) t.canopy_ga = d.canopy_ga[i];           // cable_canopy.F90:487
-  if (c.caller_duties) t.canopy_oldcansto = t.canopy_cansto;                   // cable_serial.F90:573
+  bool veg_branch = false, veg_mask = false;
+  if (PHASE & 1) {
+    // opt-in inputs
+    if (c.met_tv_is_tk) { t.met_tvair = t.met_tk; t.met_tvrad = t.met_tk; }     // cable_input.F90:2679-2680
+    else { t.met_tvair = d.met_tvair[i]; t.met_tvrad = d.met_tvrad[i]; }
+    if (c.ssnow_potev == CABLE_POTEV_PM) t.canopy_ga = d.canopy_ga[i];           // cable_canopy.F90:487
+    if (c.caller_duties) t.canopy_oldcansto = t.canopy_cansto;                   // cable_serial.F90:573
 
-  // ---- the step ----
-  lake_refill(t, c);
-  const bool veg_branch = ruff_resist(t, c);
-  define_air(t);
-  const bool veg_mask = t.canopy_vlaiw > K::lai_thresh;                         // masks_cbl.F90:45
-  const bool sunlit_mask = (t.met_fsd[0] + t.met_fsd[1]) > K::rad_thresh;       // cbm:131 (D9)
-  const bool sunlit_veg = veg_mask && sunlit_mask;
-  init_radiation(t, c, veg_mask);
-  albedo(t, veg_mask);
-  t.rad_albedo_T = (t.rad_albedo[0] + t.rad_albedo[1]) * 0.5f;
-  t.ssnow_otss_0 = t.ssnow_otss;
-  t.ssnow_otss = t.ssnow_tss;
-  const int warn = define_canopy(t, c, dels, sunlit_veg);
-  t.ssnow_owetfac = t.ssnow_wetfac;
-  soil_snow(t, c, dels, first_call != 0);
-  snow_aging(t, dels);
-  t.ssnow_deltss = t.ssnow_tss - t.ssnow_otss;
-  t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
-  t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
-  t.canopy_rnet = t.canopy_fns + t.canopy_fnv;
-  t.rad_trad = m_pow((1.f - t.rad_transd) * p4(t.canopy_tv) + t.rad_transd * p4(t.ssnow_tss), 0.25f);
-  if (c.icycle == 0) simple_carbon(t, c, dels);
-  if (warn) atomicAdd(warn_counter, (unsigned long long)warn);
-
-  // ---- store state always; diagnostics by output level (coalesced SoA writes) ----
-  const int lvl = c.output_level;
-#define CABLE_F1(T, m, ct, role, flags)                                                          \
-  if (!(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_COND))) {                           \
-    if ((CBL_ROLE_##role == CABLE_ROLE_STATE) ||                                                 \
-        (CBL_ROLE_##role == CABLE_ROLE_DIAG && (lvl >= 2 || (lvl >= 1 && (CBL_FLAGS(flags) & CABLE_FLAG_STAR))))) \
-      d.T##_##m[i] = t.T##_##m;                                                                  \
+    lake_refill(t, c);
+    veg_branch = ruff_resist(t, c);
+    define_air(t);
+    veg_mask = t.canopy_vlaiw > K::lai_thresh;                                    // masks_cbl.F90:45
+    const bool sunlit_mask = (t.met_fsd[0] + t.met_fsd[1]) > K::rad_thresh;       // cbm:131 (D9)
+    const bool sunlit_veg = veg_mask && sunlit_mask;
+    init_radiation(t, c, veg_mask);
+    albedo(t, veg_mask);
+    t.rad_albedo_T = (t.rad_albedo[0] + t.rad_albedo[1]) * 0.5f;
+    t.ssnow_otss_0 = t.ssnow_otss;
+    t.ssnow_otss = t.ssnow_tss;
+    const int warn = define_canopy(t, c, dels, sunlit_veg);
+    t.ssnow_owetfac = t.ssnow_wetfac;
+    if (warn) atomicAdd(warn_counter, (unsigned long long)warn);
   }
+  if (PHASE & 2) {
+    soil_snow(t, c, dels, first_call != 0);
+    snow_aging(t, dels);
+    t.ssnow_deltss = t.ssnow_tss - t.ssnow_otss;
+    t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
+    t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
+    t.canopy_rnet = t.canopy_fns + t.canopy_fnv;
+    t.rad_trad = m_pow025((1.f - t.rad_transd) * p4(t.canopy_tv) + t.rad_transd * p4(t.ssnow_tss));
+    if (c.icycle == 0) simple_carbon(t, c, dels);
+  }
+
+  // ---- store: state, exchange fields, and diagnostics by output level (coalesced SoA writes) ----
+  const int lvl = c.output_level;
+#define CBL_WANT(role, flags)                                                                    \
+  (store_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags)) == 1 ||                              \
+   (store_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags)) == 2 &&                             \
+    (lvl >= 2 || (lvl >= 1 && (CBL_FLAGS(flags) & CABLE_FLAG_STAR)))))
+#define CABLE_F1(T, m, ct, role, flags) if (CBL_WANT(role, flags)) d.T##_##m[i] = t.T##_##m;
 #define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
-  if (!(CBL_FLAGS(flags) & (CABLE_FLAG_HOSTONLY | CABLE_FLAG_COND))) {                           \
-    if ((CBL_ROLE_##role == CABLE_ROLE_STATE) ||                                                 \
-        (CBL_ROLE_##role == CABLE_ROLE_DIAG && (lvl >= 2 || (lvl >= 1 && (CBL_FLAGS(flags) & CABLE_FLAG_STAR))))) { \
-      _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) d.T##_##m[i + smp * k] = t.T##_##m[k]; \
-    }                                                                                            \
+  if (CBL_WANT(role, flags)) {                                                                   \
+    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) d.T##_##m[i + smp * k] = t.T##_##m[k]; \
   }
 #include "../../include/cable_b200_fields.def"
+#undef CBL_WANT
 
-  // fields the reference writes only on some tiles: keep the device copy stale elsewhere
-  if (lvl >= 2) {
+  // fields the reference writes only on some tiles: keep the device copy stale elsewhere (all belong to kernel A)
+  if ((PHASE & 1) && lvl >= 2) {
     if (veg_branch) {                                                           // cable_roughness.F90:290-295
       d.rough_term2[i] = t.rough_term2; d.rough_term3[i] = t.rough_term3; d.rough_term5[i] = t.rough_term5;
       d.rough_term6[i] = t.rough_term6; d.rough_term6a[i] = t.rough_term6a;

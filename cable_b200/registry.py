@@ -13,7 +13,7 @@ from dataclasses import dataclass
 import numpy as np
 
 ROLE = {"FORCING": 1, "PARAM": 2, "STATE": 4, "DIAG": 8}
-FLAG = {"STAR": 1, "COND": 2, "HOSTONLY": 4, "OPTIN": 8}
+FLAG = {"STAR": 1, "COND": 2, "HOSTONLY": 4, "OPTIN": 8, "XCH": 16, "PHB": 32, "STA": 64}
 DTYPE = {"float": np.float32, "double": np.float64, "int": np.int32}
 
 _DEF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "cable_b200_fields.def")

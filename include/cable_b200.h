@@ -53,6 +53,9 @@ extern "C" {
 #define CABLE_FLAG_COND     2u
 #define CABLE_FLAG_HOSTONLY 4u
 #define CABLE_FLAG_OPTIN    8u
+#define CABLE_FLAG_XCH     16u   /* device routing: kernel A -> kernel B exchange   */
+#define CABLE_FLAG_PHB     32u   /* device routing: DIAG finalised by kernel B      */
+#define CABLE_FLAG_STA     64u   /* device routing: STATE modified by kernel A      */
 
 #define CABLE_DT_F32 0
 #define CABLE_DT_F64 1
