@@ -80,7 +80,7 @@ struct cable_handle {
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
-  int block = 128, split = 1, minb_a = 8, minb_b = 8;
+  int block = 128, split = 1, minb_a = 6, minb_b = 6;
   // measurement
   cable_counters ctr{};
   bool profile = false;
@@ -387,15 +387,14 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
   // MINB = resident 128-thread blocks per SM the compiler must allow (register cap 65536 / (128*MINB)).
 #define CBL_LAUNCH(PH, MB) cbm_kernel<PH, 128, MB><<<grid, 128, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn)
 #define CBL_DISPATCH(PH, mb)                                                     \
-  switch (mb) { case 3: CBL_LAUNCH(PH, 3); break; case 4: CBL_LAUNCH(PH, 4); break; \
-                case 6: CBL_LAUNCH(PH, 6); break; default: CBL_LAUNCH(PH, 8); break; }
+  switch (mb) { case 4: CBL_LAUNCH(PH, 4); break; case 8: CBL_LAUNCH(PH, 8); break; default: CBL_LAUNCH(PH, 6); break; }
   if (h->split) {
     CBL_DISPATCH(1, h->minb_a);
     CUDA_TRY(cudaGetLastError());
     CBL_DISPATCH(2, h->minb_b);
     h->ctr.kernel_launches++;
   } else {
-    CBL_DISPATCH(3, h->minb_a);
+    CBL_LAUNCH(3, 8);
   }
 #undef CBL_DISPATCH
 #undef CBL_LAUNCH

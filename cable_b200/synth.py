@@ -125,7 +125,16 @@ def make_grid(nland: int, nap: int = 5, seed: int = SEED, site_lat: float | None
         s0, s1 = np.sin(np.deg2rad(-56.0)), np.sin(np.deg2rad(84.0))
         lat = np.rad2deg(np.arcsin(rng.uniform(s0, s1, nland))).astype(np.float32)
     lon = rng.uniform(-180, 180, nland).astype(np.float32)
-    elev = rng.uniform(0, 2500, nland).astype(np.float32)
+    # land points in raster order of the land mask (rows of `dlat` degrees from the north, west -> east inside
+    # a row), the order in which the reference numbers land points from its gridinfo mask
+    # (src/offline/cable_parameters.F90 countLandPoints / landpt): neighbours in memory are neighbours in space.
+    if site_lat is None and nland > 1:
+        dlat = 0.5
+        order = np.lexsort((lon, -np.floor((lat + 90.0) / dlat)))
+        lat, lon = lat[order], lon[order]
+    # terrain height: smooth in space plus local roughness
+    elev = (1250.0 + 900.0 * np.sin(np.deg2rad(3.0 * lon)) * np.cos(np.deg2rad(2.0 * lat))
+            + rng.uniform(-350, 350, nland)).clip(0, 2500).astype(np.float32)
     mp = nland * nap
     tile2land = np.repeat(np.arange(nland, dtype=np.int32), nap)
     cstart = (np.arange(nland, dtype=np.int32) * nap)
@@ -301,9 +310,16 @@ class Forcing:
         rd = np.random.default_rng([g.seed, 3, day])        # per-day draws
         rs = np.random.default_rng([g.seed, 4, step])       # per-step draws
         n = g.nland
-        tau = rd.uniform(0.25, 0.75, n).astype(np.float32)
-        emis = rd.uniform(0.70, 0.95, n).astype(np.float32)
-        rh = np.clip(rd.uniform(0.3, 0.95, n) + rs.normal(0, 0.03, n), 0.2, 0.98).astype(np.float32)
+        # synoptic-scale weather: a few random planetary waves per day (spatially coherent, as real forcing is),
+        # plus small per-point noise
+        ph = rd.uniform(0, 2 * np.pi, 6)
+        lonr, latr = np.deg2rad(g.lon.astype(np.float64)), np.deg2rad(g.lat.astype(np.float64))
+        wave = (np.sin(3 * lonr + ph[0]) * np.cos(2 * latr + ph[1]) + np.sin(5 * lonr + ph[2]) * np.cos(4 * latr + ph[3])
+                + 0.5 * np.sin(9 * lonr + ph[4]) * np.cos(7 * latr + ph[5])) / 2.5        # in [-1, 1]
+        cloud = np.clip(0.5 + 0.5 * wave + rd.normal(0, 0.05, n), 0.0, 1.0)
+        tau = (0.75 - 0.5 * cloud).astype(np.float32)                                   # 0.25 .. 0.75
+        emis = (0.70 + 0.25 * cloud).astype(np.float32)                                 # 0.70 .. 0.95
+        rh = np.clip(0.3 + 0.65 * cloud + rs.normal(0, 0.03, n), 0.2, 0.98).astype(np.float32)
         lst = (f(hod) + self.lon_shift) % f(24.0)
         coszen = sinbet(doy, g.lat, lst)
         sw = f(1370.0) * coszen * tau
@@ -317,7 +333,7 @@ class Forcing:
         qv = (rh * qsat).astype(np.float32)
         ua = np.clip(rs.lognormal(np.log(3.0), 0.5, n), 0.1, 20.0).astype(np.float32)
         fld = (emis * f(5.67e-8) * tair ** 4).astype(np.float32)
-        wet = rs.random(n) < 0.12
+        wet = rs.random(n) < 0.30 * cloud ** 2                                          # ~0.12 on average, under cloud
         precip = np.where(wet, rs.exponential(0.5 * self.dels / 1800.0, n), 0.0).astype(np.float32)
         precip_sn = np.where(tair <= TFRZ, precip, f(0.0)).astype(np.float32)    # cable_input.F90:2666-2671
         t2l = g.tile2land

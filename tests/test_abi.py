@@ -1,0 +1,96 @@
+"""CPU: the C-ABI library loads, exports every symbol include/cable_b200.h declares, and agrees with the
+registry file.  No compute calls (there is no GPU here, and no CPU fallback to call)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from cable_b200 import lib
+from cable_b200.registry import FIELDS, DTYPE
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cable_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cable_b200_\w+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    L = lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/cable_b200.h but not exported"
+    assert sorted(lib.EXPORTS) == declared
+    assert L.cable_b200_abi_version() == 1
+
+
+def test_registry_matches_def_file():
+    L = lib.load()
+    assert L.cable_b200_nfields() == len(FIELDS)
+    codes = {np.float32: 0, np.float64: 1, np.int32: 2}
+    for f in FIELDS:
+        info = lib.FieldInfo()
+        assert L.cable_b200_field_info(f.id, C.byref(info)) == 0
+        assert info.name.decode() == f.name
+        assert (info.dtype, info.n1, info.n2, info.role, info.flags) == (codes[f.dtype], f.n1, f.n2, f.role, f.flags)
+        assert L.cable_b200_field_id(f.name.encode()) == f.id
+    assert L.cable_b200_field_id(b"no_such_field") < 0
+
+
+def test_registry_covers_reference_interface():
+    names = {f.name for f in FIELDS}
+    # the reference's own per-step forcing message (cable_mpiworker.F90:3449-3609) ...
+    for n in ("met_fsd", "met_tk", "met_pmb", "met_qv", "met_ua", "met_precip", "met_precip_sn", "met_fld", "met_ca",
+              "met_coszen", "veg_vlai", "met_doy"):
+        assert n in names
+    # ... and its restart set = prognostic state
+    for n in ("ssnow_tgg", "ssnow_wb", "ssnow_wbice", "ssnow_gammzz", "ssnow_tss", "ssnow_ssdnn", "ssnow_ssdn", "ssnow_snowd",
+              "ssnow_smass", "ssnow_sdepth", "ssnow_tggsn", "ssnow_snage", "ssnow_rtsoil", "ssnow_isflag", "canopy_cansto",
+              "bgc_cplant", "bgc_csoil"):
+        assert n in names
+
+
+def test_default_cfg_is_shipped_namelist():
+    cfg = lib.default_cfg()
+    assert cfg.struct_bytes == C.sizeof(lib.CableCfg)
+    assert (cfg.gs_switch, cfg.fwsoil_switch, cfg.ssnow_potev, cfg.icycle) == (0, 0, 0, 0)   # cable.nml:58-71,37
+    assert cfg.snmin == 1.0 and abs(cfg.frozen_limit - 0.85) < 1e-7 and cfg.max_glacier_snowd == 1100.0
+    assert [round(z, 3) for z in cfg.zse] == [0.022, 0.058, 0.154, 0.409, 1.085, 2.872]      # cable_parameters.F90:1241
+    assert abs(cfg.zshh[0] - 0.011) < 1e-7 and abs(cfg.zshh[6] - 1.436) < 1e-6               # :1828-1831
+
+
+def test_create_error_behaviour_without_compute():
+    L = lib.load()
+    h = C.c_void_p()
+    cfg = lib.default_cfg()
+    # unsupported switches are rejected before any device work (reference: STOP 'fwsoil_switch failed.')
+    cfg.litter = 1
+    assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -2
+    assert b"unsupported" in L.cable_b200_last_error()
+    cfg = lib.default_cfg()
+    cfg.fwsoil_switch = 3                      # Haverd2013
+    assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -2
+    cfg = lib.default_cfg()
+    cfg.struct_bytes = 4
+    assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -1
+    cfg = lib.default_cfg()
+    assert L.cable_b200_create(0, C.byref(cfg), 0, C.byref(h)) == -1
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        # no device: loud failure, never a CPU fallback
+        assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -6
+        assert b"no CPU fallback" in L.cable_b200_last_error()
+        assert not h.value
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "cable_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, fn

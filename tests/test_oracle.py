@@ -1,0 +1,139 @@
+"""CPU: pin the oracle -- analytic known answers, the reference's own closure invariants, and the frozen
+golden vectors.  (The reference ships no cbm() vectors and cannot be built here: 'parity unpinned' in the
+strict sense; these are the strongest pins available, see DESIGN.md.)"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cable_b200 import lib, synth
+from oracle import pyoracle
+from oracle.pyoracle import Oracle
+from util import DELS, make_case, output_fields, water_balance, energy_balances, field_errors
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_cr_v1.npz")
+
+
+def test_trimb_matches_dense_solve():
+    """cbl_trimb.F90:17-53 (Thomas) against numpy.linalg.solve for the 9- and 6-unknown systems."""
+    L = pyoracle.load()
+    rng = np.random.default_rng(7)
+    for kmax in (9, 6):
+        n = 50
+        a = -rng.uniform(0.01, 0.5, (kmax, n)); c = -rng.uniform(0.01, 0.5, (kmax, n))
+        a[0] = 0.0; c[-1] = 0.0
+        b = 1.0 - a - c
+        rhs = rng.uniform(250, 310, (kmax, n))
+        x = rhs.copy()
+        L.oracle_trimb(n, a.ctypes.data, b.ctypes.data, c.ctypes.data, x.ctypes.data, kmax)
+        for i in range(n):
+            A = np.diag(b[:, i]) + np.diag(a[1:, i], -1) + np.diag(c[:-1, i], 1)
+            np.testing.assert_allclose(x[:, i], np.linalg.solve(A, rhs[:, i]), rtol=1e-12)
+
+
+def test_stability_functions_and_teten():
+    L = pyoracle.load()
+    assert abs(L.oracle_psim(0.0)) < 1e-6 and abs(L.oracle_psis(0.0)) < 1e-6          # psi(0) = 0
+    assert L.oracle_psim(0.5) < 0 and L.oracle_psis(0.5) < 0                           # stable: negative
+    assert L.oracle_psim(-0.5) > 0 and L.oracle_psis(-0.5) > 0                         # unstable: positive
+    # Teten at 20 C, 1000 hPa in float64: q = (rmh2o/rmair) * 6.106*exp(17.27*20/257.3) / p  (cbl_qsat.F90:48)
+    q64 = (0.018016 / 0.02897) * 6.106 * np.exp(17.27 * 20.0 / (237.3 + 20.0)) / 1000.0
+    assert abs(L.oracle_qsat(20.0, 1000.0) - q64) < 1e-8 and 0.0144 < q64 < 0.0147
+    # Businger-Dyer continuity across zeta = 0
+    assert abs(L.oracle_psim(1e-6) - L.oracle_psim(-1e-6)) < 1e-4
+
+
+def test_synthetic_forcing_inside_reference_ranges():
+    """ranges_type of the reference (cable_checks.F90:60-70)."""
+    cfg, grid, T, F = make_case(500)
+    for k in (0, 3, 5, 11):
+        F.fill(T, k)
+        assert 0 <= T["met_fsd"].min() and (T["met_fsd"][0] + T["met_fsd"][1]).max() <= 1360.0   # SWdown
+        assert 200.0 <= T["met_tk"].min() and T["met_tk"].max() <= 333.0                           # Tair
+        assert 500.0 <= T["met_pmb"].min() and T["met_pmb"].max() <= 1100.0                        # PSurf
+        assert 0 <= T["met_qv"].min() and T["met_qv"].max() <= 0.1                                 # Qair
+        assert 0 <= T["met_ua"].min() and T["met_ua"].max() <= 75.0                                # Wind
+        assert 0.0 <= T["met_fld"].min() and T["met_fld"].max() <= 750.0                           # LWdown
+        assert np.all(T["met_precip_sn"] <= T["met_precip"])
+        assert np.all(T["veg_vlai"][0][T["veg_iveg"][0] >= 14] == 0)
+    np.testing.assert_allclose(T["veg_froot"].sum(axis=0), 1.0, atol=2e-6)                          # cable_parameters.F90:3333-3343
+
+
+@pytest.mark.parametrize("gs", [0, 1])
+def test_reference_closure_invariants(gs):
+    """bal%wbal / Radbal / EbalSoil / Ebalveg / Ebal of the reference's own checks close on the oracle output
+    (src/offline/cable_checks.F90:521-523, 585-604)."""
+    cfg = lib.default_cfg(); cfg.gs_switch = gs
+    cfg, grid, T, F = make_case(600, cfg=cfg)
+    o = Oracle(T, cfg)
+    for k in range(12):
+        F.fill(T, k)
+        wb_prev = T["ssnow_wbtot"][0].copy()
+        o.cbm(k + 1, DELS)
+        if k == 0:
+            continue
+        for name in ("canopy_fe", "canopy_fh", "ssnow_tgg", "ssnow_wb", "canopy_fpn"):
+            assert np.all(np.isfinite(T[name]))
+        radbal, ebalsoil, ebalveg, ebal = energy_balances(T)
+        assert np.abs(radbal).max() < 5e-3 and np.abs(ebalsoil).max() < 1e-3          # W/m2, fp32 rounding level
+        assert np.abs(ebalveg).max() < 5e-3 and np.abs(ebal).max() < 5e-3
+        wbal = water_balance(T, DELS, wb_prev)
+        normal = T["veg_iveg"][0] < 16                 # lakes refill (cbm:116-121) and glaciers shed snow: real sources
+        assert np.abs(wbal[normal]).max() < 2e-2       # mm per 3-hour step
+        assert abs(wbal[normal].mean()) < 2e-3
+    assert o.warnings() == 0
+
+
+@pytest.mark.parametrize("tag,gs", [("leuning", 0), ("medlyn", 1)])
+def test_oracle_reproduces_golden_vectors(tag, gs):
+    gold = np.load(GOLD)
+    cfg = lib.default_cfg(); cfg.gs_switch = gs
+    cfg, grid, T, F = make_case(24, cfg=cfg, start_doy=100)
+    o = Oracle(T, cfg, cr_math=True)
+    sums = {}
+    for k in range(16):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        for n in ("canopy_fe", "canopy_fh", "canopy_fpn", "ssnow_runoff", "canopy_fes", "rad_swnet"):
+            sums[n] = sums.get(n, 0.0) + T[n].astype(np.float64)
+    for f in output_fields():
+        ref = gold[f"{tag}/final/{f.name}"]
+        mx, tol, _ = field_errors(ref, T[f.name], f.dtype)
+        assert mx <= 1e-6, (f.name, mx)        # the CR build is meant to be bit-reproducible; allow libm(fp64) last-bit noise
+    for n, a in sums.items():
+        np.testing.assert_allclose(a, gold[f"{tag}/sum/{n}"], rtol=1e-6, atol=1e-9)
+
+
+def test_libm_and_cr_builds_agree_within_tolerance():
+    """The default (host libm) oracle vs the correctly rounded build: same logic, intrinsics differ by <= 1 ulp.
+    Iterative thresholds can flip for a few tiles (SURVEY.md hard part 1), so the criterion is the fraction of
+    elements inside the north-star tolerance."""
+    cfg, grid, Ta, F = make_case(400)
+    Tb = {k: v.copy() for k, v in Ta.items()}
+    oa, ob = Oracle(Ta, cfg, cr_math=False), Oracle(Tb, cfg, cr_math=True)
+    for k in range(6):
+        F.fill(Ta, k)
+        for n in synth.FORCING_FIELDS:
+            Tb[n][...] = Ta[n]
+        oa.cbm(k + 1, DELS); ob.cbm(k + 1, DELS)
+    for f in output_fields():
+        if f.name in ("bal_drybal", "bal_wetbal"):
+            continue                                    # residuals of cancelling terms
+        mx, tol, rel = field_errors(Ta[f.name], Tb[f.name], f.dtype)
+        frac = float(np.mean(rel <= max(tol, 1e-4)))
+        assert frac >= 0.97, (f.name, frac, mx)
+
+
+def test_oracle_single_tile_site_config():
+    """BASELINE config 1 shape: one tile, half-hourly, a day of steps stays finite and physical."""
+    cfg = lib.default_cfg()
+    grid = synth.make_grid(1, 1, site_lat=-35.66)          # Tumbarumba latitude
+    T = synth.make_tiles(grid, cfg, single_pft=2)
+    F = synth.Forcing(grid, T, 1800.0, start_doy=15)
+    o = Oracle(T, cfg)
+    for k in range(48):
+        F.fill(T, k)
+        o.cbm(k + 1, 1800.0)
+        assert np.isfinite(T["canopy_fe"][0, 0]) and 200 < T["ssnow_tss"][0, 0] < 340
+    assert -100 < T["canopy_fh"][0, 0] < 700

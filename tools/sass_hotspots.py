@@ -8,7 +8,12 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capt
 cubin = glob.glob(tmp + "/*.cubin")[0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(sass)))
+allrows = list(csv.reader(io.StringIO(sass)))
+# the page concatenates kernels: "Kernel Name" row, header row, instruction rows ...
+starts = [k for k, r in enumerate(allrows) if r and r[0] == "Kernel Name"]
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+k0 = starts[which]; k1 = starts[which + 1] if which + 1 < len(starts) else len(allrows)
+rows = allrows[k0:k1]
 kname = rows[0][1]
 hdr = rows[1]; body = rows[2:]
 i_s, i_ex, i_ni, i_src = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("stall_no_inst"), hdr.index("Source")
