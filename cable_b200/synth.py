@@ -180,7 +180,10 @@ def make_tiles(grid: Grid, cfg=None, single_pft: int | None = None) -> dict[str,
         iveg = _pick_pft(rng, lat_t)
         iveg[rng.random(mp) < 0.01] = 16                                     # lakes
         isoilm = rng.integers(1, 9, mp).astype(np.int32)
-        ice_pt = (np.abs(grid.lat) > 65) & (rng.random(nland) < 0.08)
+        polar = np.abs(grid.lat) > 65
+        ice_pt = polar & (rng.random(nland) < 0.08)
+        if polar.any() and not ice_pt.any():                                  # always cover the glacier path
+            ice_pt[np.flatnonzero(polar)[0]] = True
         ice_t = ice_pt[grid.tile2land]
         iveg[ice_t] = 17
         isoilm[ice_t] = 9
