@@ -134,7 +134,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nland_w = 400                                       # 2 000 tiles per worker per step
+    nland_w = 2000                                      # 10 000 tiles per worker per step
     t0 = time.perf_counter()
     rate, tmax = cpu_oracle_rate(nland_w, args.steps, cores, warm=args.warmup)
     ms = tmax / max(args.steps, 1) * 1e3
@@ -287,7 +287,7 @@ def run_b200(args) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        nland_w, nst = 400, 24
+        nland_w, nst = 2000, 160                        # ~10-20 s of CPU work per core
         rate, tmax = cpu_oracle_rate(nland_w, nst, cores)
         cpu = {"value": rate, "unit": "tile-timesteps/s", "cores": cores, "kind": "port",
                "sample": f"{cores} workers x {nland_w} land points x {NAP} tiles x {nst} steps ({tmax:.1f} s), C++ restatement "
