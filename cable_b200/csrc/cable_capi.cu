@@ -11,6 +11,8 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <unordered_map>
+#include <cstdint>
 #include "cbm_kernel.cuh"
 
 using namespace cbl;
@@ -75,7 +77,17 @@ struct cable_handle {
   int nslots = 2;
   void *host[NFIELDS]{};
   bool host_pinned[NFIELDS]{};
-  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaStream_t s_compute = nullptr, s_compute2 = nullptr, s_copy = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_join_c2 = nullptr;
+  int chunk_tiles = 0;
+  std::vector<cudaEvent_t> ev_chunk_in, ev_chunk_done;   // pipelined cable_b200_cbm()
+  int nchunks = 1;
+  // CUDA graphs of the pipelined drop-in step, keyed by (slot, dels, bound host pointers)
+  std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
+  cudaEvent_t ev_fork = nullptr, ev_join_copy = nullptr, ev_join_d2h = nullptr;
+  int use_graph = 1, trace = 0;
+  std::vector<cudaEvent_t> tr;     // CABLE_B200_TRACE=1: timing events of one pipelined step (debug aid)
+  long long graph_launches = 0, graph_h2d = 0, graph_d2h = 0;
   std::vector<cudaEvent_t> ev_forcing_ready, ev_slot_free;
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
@@ -111,6 +123,20 @@ DevPtrs make_ptrs(const cable_handle *h, int slot) {
   return d;
 }
 
+// copy tiles [i0, i1) of one field: every component is a contiguous run, the components are mp elements apart
+int copy_field_range(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s, int i0, int i1) {
+  if (!h->host[id] || i1 <= i0) return CABLE_OK;
+  char *dp = (char *)dev_ptr(h, id, slot);
+  if (!dp) return CABLE_OK;
+  const cable_field_info &f = g_fields[id];
+  const size_t es = elem_size(f.dtype), pitch = (size_t)h->mp * es, width = (size_t)(i1 - i0) * es, rows = (size_t)f.n1 * f.n2;
+  char *hp = (char *)h->host[id] + (size_t)i0 * es;
+  dp += (size_t)i0 * es;
+  if (to_device) { CUDA_TRY(cudaMemcpy2DAsync(dp, pitch, hp, pitch, width, rows, cudaMemcpyHostToDevice, s)); h->ctr.h2d_bytes += (long long)(width * rows); }
+  else { CUDA_TRY(cudaMemcpy2DAsync(hp, pitch, dp, pitch, width, rows, cudaMemcpyDeviceToHost, s)); h->ctr.d2h_bytes += (long long)(width * rows); }
+  return CABLE_OK;
+}
+
 int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s) {
   if (!h->host[id]) return CABLE_OK;
   void *dp = dev_ptr(h, id, slot);
@@ -118,6 +144,38 @@ int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s
   if (to_device) { CUDA_TRY(cudaMemcpyAsync(dp, h->host[id], h->bytes[id], cudaMemcpyHostToDevice, s)); h->ctr.h2d_bytes += (long long)h->bytes[id]; }
   else { CUDA_TRY(cudaMemcpyAsync(h->host[id], dp, h->bytes[id], cudaMemcpyDeviceToHost, s)); h->ctr.d2h_bytes += (long long)h->bytes[id]; }
   return CABLE_OK;
+}
+
+// launch the step kernels for tiles [i0, i1) on the compute stream
+int launch_range(cable_handle *h, const DevPtrs &d, float dels, int first, int i0, int i1, cudaStream_t st) {
+  const int grid = (i1 - i0 + 127) / 128;
+  if (grid <= 0) return CABLE_OK;
+  // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
+  // MINB = resident 128-thread blocks per SM the compiler must allow (register cap 65536 / (128*MINB)).
+#define CBL_LAUNCH(PH, MB) cbm_kernel<PH, 128, MB><<<grid, 128, 0, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn)
+#define CBL_DISPATCH(PH, mb)                                                     \
+  switch (mb) { case 4: CBL_LAUNCH(PH, 4); break; case 8: CBL_LAUNCH(PH, 8); break; default: CBL_LAUNCH(PH, 6); break; }
+  if (h->split) {
+    CBL_DISPATCH(1, h->minb_a);
+    CUDA_TRY(cudaGetLastError());
+    CBL_DISPATCH(2, h->minb_b);
+    h->ctr.kernel_launches++;
+  } else {
+    CBL_LAUNCH(3, 8);
+  }
+#undef CBL_DISPATCH
+#undef CBL_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  h->ctr.kernel_launches++;
+  return CABLE_OK;
+}
+
+bool wanted_output(const cable_handle *h, int id) {
+  const cable_field_info &f = g_fields[id];
+  if (f.flags & CABLE_FLAG_HOSTONLY) return false;
+  const int lvl = h->cfg.output_level;
+  if (lvl < 1) return false;
+  return (f.role == STATE) || (f.role == DIAG && (lvl >= 2 || (f.flags & CABLE_FLAG_STAR)));
 }
 
 // soil%*_vec must be the spreads the default configuration builds (cable_parameters.F90:1685-1691);
@@ -267,6 +325,36 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
   cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&h->s_compute2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_join_c2, cudaEventDisableTiming);
+  // drop-in call pipelining: tiles are cut into chunks so that forcing H2D, the kernels and the D2H of results of
+  // different chunks overlap (PCIe is full duplex); tiny shards are not worth cutting
+  // A chunk is a whole number of full waves (148 SMs x resident blocks x 128 tiles), so cutting the shard does not
+  // add partial waves; chunks alternate between two compute streams so one chunk's tail overlaps the next one's head.
+  {
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int wave = sms * h->minb_a * 128;
+    int waves_per_chunk = 1;
+    if (const char *e = getenv("CABLE_B200_CHUNK_WAVES")) waves_per_chunk = atoi(e) > 0 ? atoi(e) : 1;
+    h->chunk_tiles = wave * waves_per_chunk;
+    h->nchunks = (mp + h->chunk_tiles - 1) / h->chunk_tiles;
+  }
+  if (const char *e = getenv("CABLE_B200_CHUNKS")) {        // explicit override: equal chunks
+    h->nchunks = atoi(e) > 0 ? atoi(e) : 1;
+    h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + 127) / 128 * 128;
+  }
+  if (h->nchunks > 64) { h->nchunks = 64; h->chunk_tiles = ((mp + 63) / 64 + 127) / 128 * 128; }
+  if (const char *e = getenv("CABLE_B200_GRAPH")) h->use_graph = atoi(e);
+  if (const char *e = getenv("CABLE_B200_TRACE")) { h->trace = atoi(e); if (h->trace) h->use_graph = 0; }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join_copy, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_join_d2h, cudaEventDisableTiming);
+  h->ev_chunk_in.resize(h->nchunks); h->ev_chunk_done.resize(h->nchunks);
+  for (int c = 0; c < h->nchunks; c++) {
+    cudaEventCreateWithFlags(&h->ev_chunk_in[c], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_chunk_done[c], cudaEventDisableTiming);
+  }
   h->ev_forcing_ready.resize(h->nslots); h->ev_slot_free.resize(h->nslots); h->slot_has_data.assign(h->nslots, 0);
   for (int s = 0; s < h->nslots; s++) {
     cudaEventCreateWithFlags(&h->ev_forcing_ready[s], cudaEventDisableTiming);
@@ -291,6 +379,13 @@ int cable_b200_destroy(cable_handle *h) {
   for (auto ev : h->prof_ev) cudaEventDestroy(ev);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  if (h->s_compute2) cudaStreamDestroy(h->s_compute2);
+  if (h->ev_join_c2) cudaEventDestroy(h->ev_join_c2);
+  for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+  if (h->ev_fork) { cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join_copy); cudaEventDestroy(h->ev_join_d2h); }
+  for (auto ev : h->ev_chunk_in) cudaEventDestroy(ev);
+  for (auto ev : h->ev_chunk_done) cudaEventDestroy(ev);
   if (h->d_warn) cudaFree(h->d_warn);
   if (h->arena) cudaFree(h->arena);
   delete h;
@@ -373,7 +468,6 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
   }
   const DevPtrs d = make_ptrs(h, slot);
   const int first = (h->soil_snow_calls == 0) ? 1 : 0;
-  const int grid = (h->mp + h->block - 1) / h->block;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profile) {
     if (h->prof_n + 2 > h->prof_ev.size()) {
@@ -383,45 +477,138 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
     e0 = h->prof_ev[h->prof_n++]; e1 = h->prof_ev[h->prof_n++];
     CUDA_TRY(cudaEventRecord(e0, h->s_compute));
   }
-  // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
-  // MINB = resident 128-thread blocks per SM the compiler must allow (register cap 65536 / (128*MINB)).
-#define CBL_LAUNCH(PH, MB) cbm_kernel<PH, 128, MB><<<grid, 128, 0, h->s_compute>>>(d, h->mp, dels, first, h->d_warn)
-#define CBL_DISPATCH(PH, mb)                                                     \
-  switch (mb) { case 4: CBL_LAUNCH(PH, 4); break; case 8: CBL_LAUNCH(PH, 8); break; default: CBL_LAUNCH(PH, 6); break; }
-  if (h->split) {
-    CBL_DISPATCH(1, h->minb_a);
-    CUDA_TRY(cudaGetLastError());
-    CBL_DISPATCH(2, h->minb_b);
-    h->ctr.kernel_launches++;
-  } else {
-    CBL_LAUNCH(3, 8);
-  }
-#undef CBL_DISPATCH
-#undef CBL_LAUNCH
-  CUDA_TRY(cudaGetLastError());
+  { int rc = launch_range(h, d, dels, first, 0, h->mp, h->s_compute); if (rc) return rc; }
   if (h->profile) CUDA_TRY(cudaEventRecord(e1, h->s_compute));
   CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], h->s_compute));
   h->soil_snow_calls++;
-  h->ctr.steps++; h->ctr.kernel_launches++;
+  h->ctr.steps++;
   return CABLE_OK;
 }
 
-int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
-  if (!h) return fail(CABLE_E_ARG, "null handle");
-  const int slot = (int)(h->ctr.steps % h->nslots);
-  int rc = cable_b200_set_forcing_async(h, slot); if (rc) return rc;
-  rc = cable_b200_step(h, ktau, dels, slot); if (rc) return rc;
-  const int lvl = h->cfg.output_level;
-  if (lvl >= 1) {
-    for (int id = 0; id < NFIELDS; id++) {
-      const cable_field_info &f = g_fields[id];
-      if (f.flags & CABLE_FLAG_HOSTONLY) continue;
-      const bool want = (f.role == STATE) || (f.role == DIAG && (lvl >= 2 || (f.flags & CABLE_FLAG_STAR)));
-      if (!want) continue;
-      rc = copy_field(h, id, 0, false, h->s_compute); if (rc) return rc;
-    }
+namespace {
+
+// Enqueue one pipelined step over tile chunks on the three streams:
+//   [H2D forcing c] (s_copy) -> [kernel A c, kernel B c] (s_compute) -> [D2H results c] (s_d2h)
+// so the PCIe transfers of one chunk hide behind the arithmetic of its neighbours (PCIe is full duplex).
+// Chunk edges are multiples of 128.  Used directly, or under stream capture to build a CUDA graph.
+int enqueue_pipelined_step(cable_handle *h, const DevPtrs &d, float dels, int first, int slot) {
+  const int nch = h->nchunks, per = h->chunk_tiles;
+  const bool tr = h->trace && (h->trace++ == 4);      // the 4th pipelined call after start-up
+  if (tr) { h->tr.resize(1 + 3 * nch); for (auto &e : h->tr) cudaEventCreate(&e); cudaEventRecord(h->tr[0], h->s_copy); }
+  for (int c = 0; c < nch; c++) {
+    const int i0 = c * per, i1 = (i0 + per < h->mp) ? i0 + per : h->mp;
+    if (i0 >= i1) break;
+    for (int id = 0; id < NFIELDS; id++)
+      if (is_forcing_input(h, id)) { int rc = copy_field_range(h, id, slot, true, h->s_copy, i0, i1); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(h->ev_chunk_in[c], h->s_copy));
+    if (tr) cudaEventRecord(h->tr[1 + 3 * c], h->s_copy);
   }
+  for (int c = 0; c < nch; c++) {
+    const int i0 = c * per, i1 = (i0 + per < h->mp) ? i0 + per : h->mp;
+    if (i0 >= i1) break;
+    cudaStream_t st = (c & 1) ? h->s_compute2 : h->s_compute;
+    CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk_in[c], 0));
+    { int rc = launch_range(h, d, dels, first, i0, i1, st); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(h->ev_chunk_done[c], st));
+    if (tr) cudaEventRecord(h->tr[2 + 3 * c], st);
+    if (h->cfg.output_level >= 1) {
+      CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_chunk_done[c], 0));
+      for (int id = 0; id < NFIELDS; id++)
+        if (wanted_output(h, id)) { int rc = copy_field_range(h, id, 0, false, h->s_d2h, i0, i1); if (rc) return rc; }
+    }
+    if (tr) cudaEventRecord(h->tr[3 + 3 * c], h->s_d2h);
+  }
+  if (tr) {
+    cudaDeviceSynchronize();
+    for (int c = 0; c < nch; c++) {
+      float a = 0, b = 0, d2 = 0;
+      cudaEventElapsedTime(&a, h->tr[0], h->tr[1 + 3 * c]); cudaEventElapsedTime(&b, h->tr[0], h->tr[2 + 3 * c]);
+      cudaEventElapsedTime(&d2, h->tr[0], h->tr[3 + 3 * c]);
+      fprintf(stderr, "[trace] chunk %d tiles [%d,%d): h2d done %.3f ms, kernels done %.3f ms, d2h done %.3f ms\n", c, c * per,
+              (c * per + per < h->mp) ? c * per + per : h->mp, a, b, d2);
+    }
+    for (auto &e : h->tr) cudaEventDestroy(e);
+    h->tr.clear();
+  }
+  return CABLE_OK;
+}
+
+uint64_t step_key(const cable_handle *h, int slot, float dels) {
+  uint64_t k = 1469598103934665603ull;
+  auto mix = [&k](uint64_t v) { k ^= v; k *= 1099511628211ull; };
+  uint32_t db; memcpy(&db, &dels, 4);
+  mix((uint64_t)slot); mix(db); mix((uint64_t)h->cfg.output_level); mix((uint64_t)h->nchunks); mix((uint64_t)h->split);
+  for (int id = 0; id < NFIELDS; id++)
+    if (is_forcing_input(h, id) || wanted_output(h, id)) mix((uint64_t)(uintptr_t)h->host[id]);
+  return k;
+}
+
+}  // namespace
+
+int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
+  (void)ktau;
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  if (!(dels > 0.f)) return fail(CABLE_E_ARG, "cbm: dels must be > 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int slot = (int)(h->ctr.steps % h->nslots);
+  for (int id = 0; id < NFIELDS; id++)
+    if (is_forcing_input(h, id) && !h->host[id]) return fail(CABLE_E_UNBOUND, std::string("forcing field not bound: ") + g_fields[id].name);
+  if (g_cfg_owner != h) {
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->s_compute));
+    g_cfg_owner = h;
+  }
+  const DevPtrs d = make_ptrs(h, slot);
+  const int first = (h->soil_snow_calls == 0) ? 1 : 0;
+  // a previous asynchronous user of this slot (set_forcing_async/step) must have drained
+  CUDA_TRY(cudaStreamSynchronize(h->s_copy));
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  const long long launches0 = h->ctr.kernel_launches, h2d0 = h->ctr.h2d_bytes, d2h0 = h->ctr.d2h_bytes;
+  if (h->use_graph && !first) {
+    // The whole pipeline (hundreds of strided copies + kernels) is replayed as ONE graph launch: the per-call
+    // enqueue cost of the copies would otherwise exceed the transfer time it is meant to hide.
+    const uint64_t key = step_key(h, slot, dels);
+    auto it = h->graphs.find(key);
+    if (it == h->graphs.end()) {
+      cudaGraph_t g = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(h->s_compute, cudaStreamCaptureModeThreadLocal));
+      int rc = CABLE_OK;
+      cudaError_t e = cudaEventRecord(h->ev_fork, h->s_compute);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_copy, h->ev_fork, 0);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_d2h, h->ev_fork, 0);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_compute2, h->ev_fork, 0);
+      if (e == cudaSuccess) rc = enqueue_pipelined_step(h, d, dels, 0, slot);
+      if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_join_copy, h->s_copy);
+      if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_join_d2h, h->s_d2h);
+      if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_join_c2, h->s_compute2);
+      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->s_compute, h->ev_join_c2, 0);
+      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->s_compute, h->ev_join_copy, 0);
+      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->s_compute, h->ev_join_d2h, 0);
+      cudaError_t e2 = cudaStreamEndCapture(h->s_compute, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess || e2 != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(CABLE_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2)); }
+      cudaGraphExec_t ge = nullptr;
+      e = cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) return fail(CABLE_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      if (h->graphs.size() >= 64) { for (auto &x : h->graphs) cudaGraphExecDestroy(x.second); h->graphs.clear(); }
+      it = h->graphs.emplace(key, ge).first;
+      // capture only recorded the work: remember what one replay moves / launches
+      h->graph_launches = h->ctr.kernel_launches - launches0;
+      h->graph_h2d = h->ctr.h2d_bytes - h2d0; h->graph_d2h = h->ctr.d2h_bytes - d2h0;
+    }
+    h->ctr.kernel_launches = launches0 + h->graph_launches;
+    h->ctr.h2d_bytes = h2d0 + h->graph_h2d; h->ctr.d2h_bytes = d2h0 + h->graph_d2h;
+    CUDA_TRY(cudaGraphLaunch(it->second, h->s_compute));
+  } else {
+    int rc = enqueue_pipelined_step(h, d, dels, first, slot); if (rc) return rc;
+  }
+  h->slot_has_data[slot] = 0;
+  h->soil_snow_calls++;
+  h->ctr.steps++;
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute2));
+  CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+  CUDA_TRY(cudaStreamSynchronize(h->s_copy));
   return CABLE_OK;
 }
 
@@ -430,6 +617,7 @@ int cable_b200_sync(cable_handle *h) {
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
   return CABLE_OK;
 }
 

@@ -50,9 +50,11 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
 
 template <int PHASE, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-cbm_kernel(const DevPtrs d, const int mp, const float dels, const int first_call, unsigned long long *warn_counter) {
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  if (i >= mp) return;
+cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const float dels, const int first_call,
+           unsigned long long *warn_counter) {
+  // tiles [i0, i1) of this launch (a whole shard, or one chunk of the pipelined drop-in call)
+  const int i = i0 + blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= i1) return;
   const DevCfg &c = c_cfg;
   const size_t smp = (size_t)mp;
   Tile t;

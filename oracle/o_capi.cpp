@@ -37,6 +37,14 @@ int oracle_cbm(void *h, int ktau, float dels) {
   return 0;
 }
 
+// profiling aid: enable / read / reset the per-tile count of dryLeaf passes
+void oracle_debug_kiter(void *h, int *out) {
+  Oracle *o = (Oracle *)h;
+  if (o->dbg_kiter.empty()) { o->dbg_kiter.assign(o->mp, 0); return; }
+  if (out) for (int i = 0; i < o->mp; i++) out[i] = o->dbg_kiter[i];
+  std::fill(o->dbg_kiter.begin(), o->dbg_kiter.end(), 0);
+}
+
 long long oracle_dryleaf_warnings(void *h) { return ((Oracle *)h)->n_dryleaf_warn; }
 
 void oracle_destroy(void *h) { delete (Oracle *)h; }
