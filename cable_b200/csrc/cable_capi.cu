@@ -17,6 +17,25 @@
 
 using namespace cbl;
 
+// occupancy targets of the three kernel variants (tuned on B200); build-time so that only the
+// variants that ship are compiled
+#ifndef CBL_MINB_A
+#define CBL_MINB_A 1
+#endif
+#ifndef CBL_MINB_B
+#define CBL_MINB_B 6
+#endif
+#ifndef CBL_MINB_FUSED
+#define CBL_MINB_FUSED 8
+#endif
+// threads per block of kernel A / B (A's phase barriers make its block the unit that shares instruction fetches)
+#ifndef CBL_BLOCK_A
+#define CBL_BLOCK_A 768
+#endif
+#ifndef CBL_BLOCK_B
+#define CBL_BLOCK_B 128
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -92,7 +111,7 @@ struct cable_handle {
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
-  int block = 128, split = 1, minb_a = 6, minb_b = 6;
+  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B;
   // measurement
   cable_counters ctr{};
   bool profile = false;
@@ -148,20 +167,19 @@ int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s
 
 // launch the step kernels for tiles [i0, i1) on the compute stream
 int launch_range(cable_handle *h, const DevPtrs &d, float dels, int first, int i0, int i1, cudaStream_t st) {
-  const int grid = (i1 - i0 + 127) / 128;
-  if (grid <= 0) return CABLE_OK;
+  if (i1 <= i0) return CABLE_OK;
   // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
-  // MINB = resident 128-thread blocks per SM the compiler must allow (register cap 65536 / (128*MINB)).
-#define CBL_LAUNCH(PH, MB) cbm_kernel<PH, 128, MB><<<grid, 128, 0, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn)
-#define CBL_DISPATCH(PH, mb)                                                     \
-  switch (mb) { case 4: CBL_LAUNCH(PH, 4); break; case 8: CBL_LAUNCH(PH, 8); break; default: CBL_LAUNCH(PH, 6); break; }
+  // CBL_MINB_x = resident blocks per SM the compiler must allow (register cap 65536 / (BLOCK*MINB)).
+#define CBL_LAUNCH(PH, BL, MB, LV) cbm_kernel<PH, BL, MB, LV><<<(i1 - i0 + (BL) - 1) / (BL), BL, 0, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn)
+#define CBL_DISPATCH(PH, BL, MB)                                                     \
+  switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
   if (h->split) {
-    CBL_DISPATCH(1, h->minb_a);
+    CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A);
     CUDA_TRY(cudaGetLastError());
-    CBL_DISPATCH(2, h->minb_b);
+    CBL_DISPATCH(2, CBL_BLOCK_B, CBL_MINB_B);
     h->ctr.kernel_launches++;
   } else {
-    CBL_LAUNCH(3, 8);
+    CBL_DISPATCH(3, 128, CBL_MINB_FUSED);
   }
 #undef CBL_DISPATCH
 #undef CBL_LAUNCH
@@ -272,8 +290,6 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   h->block = 128;
   // tuning knobs (DESIGN.md 'Kernel'): split step into kernels A/B, min resident blocks per SM of each
   if (const char *e = getenv("CABLE_B200_SPLIT")) h->split = atoi(e);
-  if (const char *e = getenv("CABLE_B200_MINB_A")) h->minb_a = atoi(e);
-  if (const char *e = getenv("CABLE_B200_MINB_B")) h->minb_b = atoi(e);
   // device-side config + host-evaluated constants
   DevCfg &d = h->dcfg;
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
@@ -334,7 +350,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   // add partial waves; chunks alternate between two compute streams so one chunk's tail overlaps the next one's head.
   {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int wave = sms * h->minb_a * 128;
+    const int wave = sms * CBL_MINB_A * CBL_BLOCK_A;
     int waves_per_chunk = 1;
     if (const char *e = getenv("CABLE_B200_CHUNK_WAVES")) waves_per_chunk = atoi(e) > 0 ? atoi(e) : 1;
     h->chunk_tiles = wave * waves_per_chunk;

@@ -19,16 +19,16 @@ CBL_DEV void radiation(Tile &t, bool sunlit_veg) {
   const float flpwb = K::sboltz * p4(t.met_tvrad);
   const float flwv = K::emleaf * flpwb;
   t.rad_flws = K::sboltz * K::emsoil * p4(t.ssnow_tss);
-  const float emair = t.met_fld / flpwb;
+  const float emair = dv(t.met_fld, flpwb);
   float g1 = 0.0f, g2 = 0.0f;
 #pragma unroll
   for (int q = 0; q < 6; q++) t.rad_qcan[q] = 0.0f;          // qcan(leaf + 2*band)
   if (veg) {
-    g1 = (4.0f * K::emleaf / (K::capp * t.air_rho)) * flpwb / t.met_tvrad * extkd
-         * ((1.0f - transb * transd) / (extkb + extkd) + (transd - transb) / (extkb - extkd));
-    g2 = (8.0f * K::emleaf / (K::capp * t.air_rho)) * flpwb / t.met_tvrad * extkd * (1.0f - transd) / extkd - g1;
-    t.rad_qcan[0 + 2 * 2] = (t.rad_flws - flwv) * extkd * (transd - transb) / (extkb - extkd)
-                            + (emair - K::emleaf) * extkd * flpwb * (1.0f - transd * transb) / (extkb + extkd);
+    g1 = dv(dv(4.0f * K::emleaf, K::capp * t.air_rho) * flpwb, t.met_tvrad) * extkd
+         * (dv(1.0f - transb * transd, extkb + extkd) + dv(transd - transb, extkb - extkd));
+    g2 = dv(dv(dv(8.0f * K::emleaf, K::capp * t.air_rho) * flpwb, t.met_tvrad) * extkd * (1.0f - transd), extkd) - g1;
+    t.rad_qcan[0 + 2 * 2] = dv((t.rad_flws - flwv) * extkd * (transd - transb), extkb - extkd)
+                            + dv((emair - K::emleaf) * extkd * flpwb * (1.0f - transd * transb), extkb + extkd);
     t.rad_qcan[1 + 2 * 2] = (1.0f - transd) * (t.rad_flws + t.met_fld - 2.0f * flwv) - t.rad_qcan[0 + 2 * 2];
   }
   g1 = t.air_cmolar * g1; g2 = t.air_cmolar * g2;
@@ -40,28 +40,28 @@ CBL_DEV void radiation(Tile &t, bool sunlit_veg) {
     for (int b = 0; b < 2; b++) {
       const float fbeam = t.rad_fbeam[b], extkdm = t.rad_extkdm[b], extkbm = t.rad_extkbm[b];
       const float cexpkdm = t.rad_cexpkdm[b], cexpkbm = t.rad_cexpkbm[b], fsd = t.met_fsd[b];
-      const float cf1 = (1.0f - transb * cexpkdm) / (extkb + extkdm);
-      const float cf3 = (1.0f - transb * cexpkbm) / (extkb + extkbm);
+      const float cf1 = dv(1.0f - transb * cexpkdm, extkb + extkdm);
+      const float cf3 = dv(1.0f - transb * cexpkbm, extkb + extkbm);
       const float dif = (1.0f - fbeam) * (1.0f - t.rad_reffdf[b]);
       const float bem = fbeam * (1.0f - t.rad_reffbm[b]);
       const float sct = fbeam * (1.0f - t.veg_taul[b] - t.veg_refl[b]) * extkb
-                        * ((1 - transb) / extkb - (1 - transb * transb) / (extkb + extkb));
+                        * (dv(1 - transb, extkb) - dv(1 - transb * transb, extkb + extkb));
       t.rad_qcan[0 + 2 * b] = fsd * (dif * extkdm * cf1 + bem * extkbm * cf3 + sct);
-      t.rad_qcan[1 + 2 * b] = fsd * (dif * extkdm * ((1.0f - cexpkdm) / extkdm - cf1)
-                                     + bem * extkbm * ((1.0f - cexpkbm) / extkbm - cf3) - sct);
+      t.rad_qcan[1 + 2 * b] = fsd * (dif * extkdm * (dv(1.0f - cexpkdm, extkdm) - cf1)
+                                     + bem * extkbm * (dv(1.0f - cexpkbm, extkbm) - cf3) - sct);
     }
     t.rad_qssabs = t.met_fsd[0] * (t.rad_fbeam[0] * (1.f - t.rad_reffbm[0]) * m_exp(-mn(t.rad_extkbm[0] * lai, 20.f))
                                    + (1.f - t.rad_fbeam[0]) * (1.f - t.rad_reffdf[0]) * m_exp(-mn(t.rad_extkdm[0] * lai, 20.f)))
                    + t.met_fsd[1] * (t.rad_fbeam[1] * (1.f - t.rad_reffbm[1]) * t.rad_cexpkbm[1]
                                      + (1.f - t.rad_fbeam[1]) * (1.f - t.rad_reffdf[1]) * t.rad_cexpkdm[1]);
-    t.rad_scalex[0] = (1.0f - transb * cf2n) / (extkb + t.veg_extkn);
-    t.rad_fvlai[0] = (1.0f - transb) / extkb;
+    t.rad_scalex[0] = dv(1.0f - transb * cf2n, extkb + t.veg_extkn);
+    t.rad_fvlai[0] = dv(1.0f - transb, extkb);
     t.rad_fvlai[1] = lai - t.rad_fvlai[0];
   } else {
     t.rad_qssabs = (1.0f - t.ssnow_albsoilsn[0]) * t.met_fsd[0] + (1.0f - t.ssnow_albsoilsn[1]) * t.met_fsd[1];
     t.rad_scalex[0] = 0.0f; t.rad_fvlai[0] = 0.0f; t.rad_fvlai[1] = lai;
   }
-  t.rad_scalex[1] = (1.0f - cf2n) / t.veg_extkn - t.rad_scalex[0];
+  t.rad_scalex[1] = dv(1.0f - cf2n, t.veg_extkn) - t.rad_scalex[0];
 #pragma unroll
   for (int l = 0; l < 2; l++) t.rad_rniso[l] = (t.rad_qcan[l] + t.rad_qcan[l + 2]) + t.rad_qcan[l + 4];
 }
@@ -74,15 +74,15 @@ CBL_DEV void surf_wetness_fact(Tile &t, float cansat, float dels) {
   t.canopy_wcint = (ftemp > 0.0f && t.met_tk > K::tfrz) ? mn(room, ftemp) : 0.0f;
   t.canopy_through = t.met_precip_sn + mn(rain, mx(0.0f, rain - t.canopy_wcint));
   t.canopy_cansto = t.canopy_cansto + t.canopy_wcint;
-  t.canopy_fwet = mx(0.0f, mn(0.9f, 0.8f * t.canopy_cansto / mx(cansat, 0.01f)));
+  t.canopy_fwet = mx(0.0f, mn(0.9f, dv(0.8f * t.canopy_cansto, mx(cansat, 0.01f))));
   t.ssnow_satfrac = (double)1.0e-8f;
   t.ssnow_rh_srf = 1.0;
   const float wilting_pt = t.soil_swilt / K::wilt_limitfactor;
   float num = (float)t.ssnow_wb[0] - wilting_pt;
   float den = mx(0.0830f, t.soil_sfc - wilting_pt);
-  float wetfac = mx(0.0f, mn(1.0f, num / den));
+  float wetfac = mx(0.0f, mn(1.0f, dv(num, den)));
   if (t.ssnow_wbice[0] > 0.0) {
-    double r = t.ssnow_wbice[0] / t.ssnow_wb[0];
+    double r = dv(t.ssnow_wbice[0], t.ssnow_wb[0]);
     float ice_ratio = (float)(r * r);
     float ice_factor = (float)(1.0 - mn(0.2, (double)ice_ratio));
     ice_factor = (float)mx(0.5, (double)ice_factor);
@@ -99,11 +99,11 @@ CBL_DEV float soil_potev(const Tile &t, const DevCfg &c, float q_air) {
     float sss = t.air_dsatdk;
     float cc1 = sss / (sss + t.air_psyc), cc2 = t.air_psyc / (sss + t.air_psyc);
     float qs = qsatf(t.met_tvair - K::tfrz, t.met_pmb);
-    return cc1 * (t.canopy_fns - t.canopy_ga) + cc2 * t.air_rho * t.air_rlam * (qs - t.met_qvair) / t.ssnow_rtsoil;
+    return cc1 * (t.canopy_fns - t.canopy_ga) + dv(cc2 * t.air_rho * t.air_rlam * (qs - t.met_qvair), t.ssnow_rtsoil);
   }
   float dq = t.ssnow_qstss - q_air;
   if (t.ssnow_snowd > 1.0f || t.ssnow_tgg[0] == K::tfrz) dq = mx(-0.1e-3f, dq);
-  return t.air_rho * t.air_rlam * dq / t.ssnow_rtsoil;
+  return dv(t.air_rho * t.air_rlam * dq, t.ssnow_rtsoil);
 }
 
 // Latent_heat_flux: cbl_latent_heat.F90:15-285
@@ -111,14 +111,14 @@ CBL_DEV void latent_heat_flux(Tile &t, const DevCfg &c, float dels) {
   const float rlam = t.air_rlam, potev = t.ssnow_potev, snowd = t.ssnow_snowd;
   if (potev < 0.f) t.ssnow_wetfac = 1.0f;                                   // side effect kept (D2)
   double fess = (double)(t.ssnow_wetfac * potev);
-  const float pwet = mx(0.f, mn(0.2f, t.ssnow_pudsto / mx(1.f, t.ssnow_pudsmx)));
+  const float pwet = mx(0.f, mn(0.2f, dv(t.ssnow_pudsto, mx(1.f, t.ssnow_pudsmx))));
   fess = fess * (double)(1.f - pwet);
   if (snowd < 0.1f && fess > 0.) {
-    const float frescale = c.zse[0] * K::density_liq * rlam / dels;
+    const float frescale = dv(c.zse[0] * K::density_liq * rlam, dels);
     float lower = (float)t.ssnow_wb[0] - (c.l_new_reduce_soilevp ? t.soil_swilt : t.soil_swilt / 2.0f);
-    float upper = (float)mx(0., (double)(lower * frescale) - t.ssnow_evapfbl[0] * (double)rlam / (double)dels);
+    float upper = (float)mx(0., (double)(lower * frescale) - dv(t.ssnow_evapfbl[0] * (double)rlam, (double)dels));
     fess = mn(fess, (double)upper);
-    upper = (float)(t.ssnow_wb[0] - t.ssnow_wbice[0] / (double)c.frozen_limit) * frescale;
+    upper = (float)(t.ssnow_wb[0] - dv(t.ssnow_wbice[0], (double)c.frozen_limit)) * frescale;
     upper = mx(upper, 0.f);
     fess = mn(fess, (double)upper);
   }
@@ -127,11 +127,11 @@ CBL_DEV void latent_heat_flux(Tile &t, const DevCfg &c, float dels) {
   if (snowd < 0.1f && potev < 0.f && t.ssnow_tss < K::tfrz) { cls = 1.1335f; fess = (double)(cls * potev); }
   if (snowd >= 0.1f && potev > 0.f) {
     cls = 1.1335f;
-    fess = (double)mn((t.ssnow_wetfac * potev) * cls, snowd / dels * rlam * cls);
+    fess = (double)mn((t.ssnow_wetfac * potev) * cls, dv(snowd, dels) * rlam * cls);
   }
   t.ssnow_cls = cls;
   t.canopy_fess = fess;
-  t.canopy_fesp = (double)mn(t.ssnow_pudsto / dels * rlam, mx(pwet * potev, 0.f));
+  t.canopy_fesp = (double)mn(dv(t.ssnow_pudsto, dels) * rlam, mx(pwet * potev, 0.f));
   t.canopy_fes = t.canopy_fess + t.canopy_fesp;
 }
 
@@ -143,7 +143,7 @@ CBL_DEV float fwsoil_calc(const Tile &t, const DevCfg &c) {
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < K::ms; k++)
-      s = s + t.veg_froot[k] * mx(1.0e-9f, mn(1.0f, (float)((t.ssnow_wbliq[k] - swilt) / (sfc - swilt))));
+      s = s + t.veg_froot[k] * mx(1.0e-9f, mn(1.0f, (float)dv(t.ssnow_wbliq[k] - swilt, sfc - swilt)));
     float rwater = mx(1.0e-9f, s);
     if (c.gs_switch == CABLE_GS_MEDLYN) return mx(1.0e-4f, mn(1.0f, rwater));
     return mx(1.0e-9f, mn(1.0f, t.veg_vbeta * rwater));
@@ -174,17 +174,19 @@ CBL_DEV float fwsoil_calc(const Tile &t, const DevCfg &c) {
 }
 
 // leaf-level response functions: cbl_dryLeaf.F90:779-877
-CBL_DEV float ejx_root(float parx, float alpha, float convex, float x) {
+// (divisions and square roots in everything the iteration loops execute go through dv()/f_sqrt()/d_sqrt():
+//  one shared out-of-line copy instead of an inline expansion per use -- see cbm_consts.cuh)
+CBL_NOINLINE float ejx_root(float parx, float alpha, float convex, float x) {
   const float ap = alpha * parx;
-  return (ap + x - sqrtf(p2(ap + x) - 4.0f * convex * alpha * parx * x)) / (2.0f * convex);
+  return dv(ap + x - f_sqrt(p2(ap + x) - 4.0f * convex * alpha * parx * x), 2.0f * convex);
 }
 CBL_DEV float xvcmxt4(float x) {
-  return m_exp2(0.1f * x - 2.5f) / ((1.0f + m_exp(0.3f * (13.0f - x))) * (1.0f + m_exp(0.3f * (x - 36.0f))));
+  return dv(m_exp2(0.1f * x - 2.5f), (1.0f + m_exp(0.3f * (13.0f - x))) * (1.0f + m_exp(0.3f * (x - 36.0f))));
 }
-CBL_DEV float arrhenius_peaked(float x, float coef, float eha, float ehd, float entrop) {
-  float num = coef * m_exp((eha / (K::rgas * K::trefk)) * (1.f - K::trefk / x));
-  float den = 1.0f + m_exp((entrop * x - ehd) / (K::rgas * x));
-  return mx(0.0f, num / den);
+CBL_NOINLINE float arrhenius_peaked(float x, float coef, float eha, float ehd, float entrop) {
+  float num = coef * m_exp((eha / (K::rgas * K::trefk)) * (1.f - dv(K::trefk, x)));
+  float den = 1.0f + m_exp(dv(entrop * x - ehd, K::rgas * x));
+  return mx(0.0f, dv(num, den));
 }
 
 // One root of the Ci quadratic as the reference selects it (cbl_photosynthesis.F90:78-119 etc.)
@@ -196,16 +198,18 @@ CBL_NOINLINE double an_limited(int kind, double coef2, double coef1, double coef
   double an = (kind == 1) ? (double)99999.0f : 0.0;
   const double a2 = fabs(coef2), a1 = fabs(coef1);
   if (kind == 2 && a2 < tiny && a1 < tiny) an = (double)99999.0f;
-  if (a2 < tiny && a1 >= tiny) {
-    double ci = -1.0f * coef0 / coef1;
-    if (kind == 2) an = ci;
-    else { ci = mx(0.0, ci); an = vmax * (ci - cxb / 2.0f) / (ci + cxa) + v4 - rdx; }
-  }
+  // the two solvable cases are exclusive (a2 < tiny / a2 >= tiny): pick ci first, then one copy of the flux formula
+  double ci = 0.0;
+  bool have = false;
+  if (a2 < tiny && a1 >= tiny) { ci = dv(-1.0f * coef0, coef1); have = true; }
   if (a2 >= tiny) {
-    double del = coef1 * coef1 - 4.0f * coef0 * coef2;
-    double ci = (-coef1 + sqrt(mx(0.0, del))) / (2.0f * coef2);
+    const double del = coef1 * coef1 - 4.0f * coef0 * coef2;
+    ci = dv(-coef1 + d_sqrt(mx(0.0, del)), 2.0f * coef2);
+    have = true;
+  }
+  if (have) {
     if (kind == 2) an = ci;
-    else { ci = mx(0.0, ci); an = vmax * (ci - cxb / 2.0f) / (ci + cxa) + v4 - rdx; }
+    else { ci = mx(0.0, ci); an = dv(vmax * (ci - cxb / 2.0f), ci + cxa) + v4 - rdx; }
   }
   return an;
 }
@@ -216,6 +220,7 @@ struct CanopyWork {
   double ecy, hcy, rny;
   double gbhu[2], gbhf[2], csx[2];
   float  sum_rniso, sum_gradis;
+  float  dleaf3;            // veg%dleaf**3.0, the same every pass
   int    warn;
 };
 
@@ -244,97 +249,124 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
   float oldevapfbl[K::ms];
   if (!veg) { rnx = 0.0; ecx = 0.0; w.ecy = ecx; abs_deltlf = 0.0f; w.rny = rnx; }
   float deltlfy = abs_deltlf;
-  const float dleaf3 = m_pow(t.veg_dleaf, 3.0f);
+  const float dleaf3 = w.dleaf3;
   const float dtair = t.met_tvair - t.met_tk;
 
+#if CBL_SYNC_A >= 2
+  bool done = false;
+#endif
   for (int k = 1; k <= K::maxiter; k++) {
+#if CBL_SYNC_A >= 2
+    // per-pass barrier: the block's warps take pass k together; a warp whose tiles have all converged only votes
+    if (!__syncthreads_or(!done)) break;
+    if (done) continue;
+#endif
     const bool active = veg && abs_deltlf > 0.1f;
     if (active) {
       const float tlfx = w.tlfx;
       // free-convection boundary-layer conductance, total conductances
       float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - t.met_tvair) * dleaf3);
       float gras4 = m_pow025(gras);
-#pragma unroll
-      for (int l = 0; l < 2; l++) {
-        w.gbhf[l] = mx(1.e-6, (double)(t.rad_fvlai[l] * t.air_cmolar * 0.5f * K::dheat * gras4 / t.veg_dleaf));
-        gh[l] = (float)(2.0f * (w.gbhu[l] + w.gbhf[l]));
-        ghr[l] = t.rad_gradis[l] + gh[l];
-      }
       // temperature responses of Vcmax (C3, C4) and Jmax
       float temp3 = arrhenius_peaked(tlfx, 1.17461f, 73637.0f, 149252.0f, 486.0f) * t.veg_vcmax * (1.0f - t.veg_frac4);
       float temp4 = xvcmxt4(tlfx - K::tfrz) * t.veg_vcmax * t.veg_frac4;
       float tempj = arrhenius_peaked(tlfx, 1.16715f, 50300.0f, 152044.0f, 495.0f) * t.veg_ejmax * (1.0f - t.veg_frac4);
       const float tdiff = tlfx - K::trefk;
-      const float arr = 1.0f - K::trefk / tlfx;
+      const float arr = 1.0f - dv(K::trefk, tlfx);
       float conkct = t.veg_conkc0 * m_exp((t.veg_ekc / (K::rgas * K::trefk)) * arr);
       float conkot = t.veg_conko0 * m_exp((t.veg_eko / (K::rgas * K::trefk)) * arr);
       tlfxx = tlfx;
-      const float cx1 = conkct * (1.0f + 0.21f / conkot);
+      const float cx1 = conkct * (1.0f + dv(0.21f, conkot));
       const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
       float vsum0 = t.rad_fvlai[0] + t.rad_fvlai[1];
-#pragma unroll
+      // stomatal-slope factors that do not depend on the leaf
+      float gs_shared;
+      if (c.gs_switch == CABLE_GS_LEUNING) {
+        gs_shared = dv(t.veg_a1gs, 1.0f + dv(w.dsx, t.veg_d0gs));
+      } else {
+        float vpd = (w.dsx < 50.0f) ? 0.05f : w.dsx * 1E-03f;
+        gs_shared = dv(t.veg_g1 * fwsoil, f_sqrt(vpd));
+      }
+      // sunlit (l = 0) and shaded (l = 1) big leaf: ONE copy of the code, the per-leaf operands are selected on l
+      // (a rolled loop over register arrays; unrolling it doubled the footprint of the hottest loop of the step)
+#pragma unroll 1
       for (int l = 0; l < 2; l++) {
-        const float vcmxt3 = t.rad_scalex[l] * temp3, vcmxt4 = t.rad_scalex[l] * temp4, ejmxt3 = t.rad_scalex[l] * tempj;
-        const float par3 = t.rad_qcan[l] * jtomol * (1.0f - t.veg_frac4);
-        const float par4 = t.rad_qcan[l] * jtomol * t.veg_frac4;
+        const float fvlai_l = l ? t.rad_fvlai[1] : t.rad_fvlai[0];
+        const float scalex_l = l ? t.rad_scalex[1] : t.rad_scalex[0];
+        const float qcan_l = l ? t.rad_qcan[1] : t.rad_qcan[0];
+        const float gradis_l = l ? t.rad_gradis[1] : t.rad_gradis[0];
+        const float gswmin_l = l ? gswmin[1] : gswmin[0];
+        const double gbhu_l = l ? w.gbhu[1] : w.gbhu[0];
+        const double csx_l = l ? w.csx[1] : w.csx[0];
+        const double gbhf_l = mx(1.e-6, (double)dv(fvlai_l * t.air_cmolar * 0.5f * K::dheat * gras4, t.veg_dleaf));
+        const float gh_l = (float)(2.0f * (gbhu_l + gbhf_l));
+        const float ghr_l = gradis_l + gh_l;
+        const float vcmxt3 = scalex_l * temp3, vcmxt4 = scalex_l * temp4, ejmxt3 = scalex_l * tempj;
+        const float par3 = qcan_l * jtomol * (1.0f - t.veg_frac4);
+        const float par4 = qcan_l * jtomol * t.veg_frac4;
         const float vx3 = mx(0.0f, 0.25f * ejx_root(par3, t.veg_alpha, t.veg_convex, ejmxt3));
         const float vx4 = mx(0.0f, ejx_root(par4, t.veg_alpha, t.veg_convex, vcmxt4));
-        rdx[l] = (t.veg_cfrd * vcmxt3 + t.veg_cfrd * vcmxt4);
+        const float rdx_l = (t.veg_cfrd * vcmxt3 + t.veg_cfrd * vcmxt4);
         // stomatal slope coefficient
         float gs_coeff;
         if (c.gs_switch == CABLE_GS_LEUNING) {
-          gs_coeff = (float)(((double)fwsoil / (w.csx[l] - (double)0.0f)) * (double)(t.veg_a1gs / (1.0f + w.dsx / t.veg_d0gs)));
+          gs_coeff = (float)(dv((double)fwsoil, csx_l - (double)0.0f) * (double)gs_shared);
         } else {
-          float vpd = (w.dsx < 50.0f) ? 0.05f : w.dsx * 1E-03f;
-          float g1 = t.veg_g1;
-          gs_coeff = (float)((double)(1.0f + (g1 * fwsoil) / sqrtf(vpd)) / w.csx[l]);
-          if (fwsoil <= 0.05f) gs_coeff = (float)((double)(fwsoil / 0.05f + (g1 * fwsoil) / sqrtf(vpd)) / w.csx[l]);
+          gs_coeff = (float)dv((double)(1.0f + gs_shared), csx_l);
+          if (fwsoil <= 0.05f) gs_coeff = (float)dv((double)(dv(fwsoil, 0.05f) + gs_shared), csx_l);
         }
         // photosynthesis (cbl_photosynthesis.F90:52-222) for this leaf
         float an = 0.f;
-        if (vsum0 > K::lai_thresh && t.rad_fvlai[l] > K::lai_thresh) {
-          const double csx = w.csx[l];
-          const float g0t = gswmin[l] * fwsoil / K::rgswc;
+        if (vsum0 > K::lai_thresh && fvlai_l > K::lai_thresh) {
+          const double csx = csx_l;
+          const float g0t = dv(gswmin_l * fwsoil, K::rgswc);
           const double one_m = (double)1.0f - csx * (double)gs_coeff;
-          double coef2 = (double)(g0t + gs_coeff * (vcmxt3 - (rdx[l] - vcmxt4)));
-          double coef1 = one_m * (double)(vcmxt3 + vcmxt4 - rdx[l]) + (double)g0t * ((double)cx1 - csx)
-                         - (double)(gs_coeff * (vcmxt3 * cx2 / 2.0f + cx1 * (rdx[l] - vcmxt4)));
-          double coef0 = -one_m * (double)(vcmxt3 * cx2 / 2.0f + cx1 * (rdx[l] - vcmxt4)) - (double)(g0t * cx1) * csx;
-          double anrubisco = an_limited(0, coef2, coef1, coef0, vcmxt3, cx1, cx2, vcmxt4, rdx[l]);
-          coef2 = (double)(g0t + gs_coeff * (vx3 - (rdx[l] - vx4)));
-          coef1 = one_m * (double)(vx3 + vx4 - rdx[l]) + (double)g0t * ((double)cx2 - csx)
-                  - (double)(gs_coeff * (vx3 * cx2 / 2.0f + cx2 * (rdx[l] - vx4)));
-          coef0 = -one_m * (double)(vx3 * cx2 / 2.0f + cx2 * (rdx[l] - vx4)) - (double)(g0t * cx2) * csx;
-          double anrubp = an_limited(1, coef2, coef1, coef0, vx3, cx2, cx2, vx4, rdx[l]);
+          double coef2 = (double)(g0t + gs_coeff * (vcmxt3 - (rdx_l - vcmxt4)));
+          double coef1 = one_m * (double)(vcmxt3 + vcmxt4 - rdx_l) + (double)g0t * ((double)cx1 - csx)
+                         - (double)(gs_coeff * (vcmxt3 * cx2 / 2.0f + cx1 * (rdx_l - vcmxt4)));
+          double coef0 = -one_m * (double)(vcmxt3 * cx2 / 2.0f + cx1 * (rdx_l - vcmxt4)) - (double)(g0t * cx1) * csx;
+          double anrubisco = an_limited(0, coef2, coef1, coef0, vcmxt3, cx1, cx2, vcmxt4, rdx_l);
+          coef2 = (double)(g0t + gs_coeff * (vx3 - (rdx_l - vx4)));
+          coef1 = one_m * (double)(vx3 + vx4 - rdx_l) + (double)g0t * ((double)cx2 - csx)
+                  - (double)(gs_coeff * (vx3 * cx2 / 2.0f + cx2 * (rdx_l - vx4)));
+          coef0 = -one_m * (double)(vx3 * cx2 / 2.0f + cx2 * (rdx_l - vx4)) - (double)(g0t * cx2) * csx;
+          double anrubp = an_limited(1, coef2, coef1, coef0, vx3, cx2, cx2, vx4, rdx_l);
           const float effc4 = 4000.0f;
           coef2 = (double)gs_coeff;
-          coef1 = (double)(g0t + gs_coeff * (rdx[l] - 0.5f * vcmxt3) + effc4 * vcmxt4)
+          coef1 = (double)(g0t + gs_coeff * (rdx_l - 0.5f * vcmxt3) + effc4 * vcmxt4)
                   - (double)gs_coeff * csx * (double)effc4 * (double)vcmxt4;
-          coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)((rdx[l] - 0.5f * vcmxt3) * gswmin[l] * fwsoil / K::rgswc);
+          coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)dv((rdx_l - 0.5f * vcmxt3) * gswmin_l * fwsoil, K::rgswc);
           double ansink = an_limited(2, coef2, coef1, coef0, 0.f, 0.f, 0.f, 0.f, 0.f);
           an = (float)mn(mn(anrubisco, anrubp), ansink);
         }
-        anx[l] = an;
         // leaf-surface CO2, stomatal and total water conductance (:460-485)
-        if (t.rad_fvlai[l] > K::lai_thresh) {
-          const double gb = w.gbhu[l] + w.gbhf[l];
-          w.csx[l] = mx(1.0e-4, (double)t.met_ca - (double)(K::rgbwc * an) / gb);
-          float gswx = mx(1.e-3f, gswmin[l] * fwsoil + mx(0.0f, K::rgswc * gs_coeff * an));
-          t.canopy_gswx[l] = gswx;
-          gw[l] = mx((float)(1.0f / ((double)(1.0f / gswx) + 1.0f / (1.075f * gb))), 0.00001f);
-          psycst[l] = t.air_psyc * (ghr[l] / gw[l]);
+        double csx_n = csx_l;
+        float gswx_n = l ? t.canopy_gswx[1] : t.canopy_gswx[0];
+        float gw_l = l ? gw[1] : gw[0];
+        float psycst_l = l ? psycst[1] : psycst[0];
+        if (fvlai_l > K::lai_thresh) {
+          const double gb = gbhu_l + gbhf_l;
+          csx_n = mx(1.0e-4, (double)t.met_ca - dv((double)(K::rgbwc * an), gb));
+          gswx_n = mx(1.e-3f, gswmin_l * fwsoil + mx(0.0f, K::rgswc * gs_coeff * an));
+          gw_l = mx((float)dv(1.0f, (double)dv(1.0f, gswx_n) + dv(1.0f, 1.075f * gb)), 0.00001f);
+          psycst_l = t.air_psyc * dv(ghr_l, gw_l);
         }
+        if (l == 0) { w.gbhf[0] = gbhf_l; gh[0] = gh_l; ghr[0] = ghr_l; rdx[0] = rdx_l; anx[0] = an; w.csx[0] = csx_n;
+                      t.canopy_gswx[0] = gswx_n; gw[0] = gw_l; psycst[0] = psycst_l; }
+        else        { w.gbhf[1] = gbhf_l; gh[1] = gh_l; ghr[1] = ghr_l; rdx[1] = rdx_l; anx[1] = an; w.csx[1] = csx_n;
+                      t.canopy_gswx[1] = gswx_n; gw[1] = gw_l; psycst[1] = psycst_l; }
       }
       // big-leaf latent heat, limited by what the roots can supply (:489-536)
-      ecx = (double)((t.air_dsatdk * (t.rad_rniso[0] - cr * dtair * t.rad_gradis[0]) + cr * t.met_dva * ghr[0]) / (t.air_dsatdk + psycst[0])
-                     + (t.air_dsatdk * (t.rad_rniso[1] - cr * dtair * t.rad_gradis[1]) + cr * t.met_dva * ghr[1]) / (t.air_dsatdk + psycst[1]));
+      ecx = (double)(dv(t.air_dsatdk * (t.rad_rniso[0] - cr * dtair * t.rad_gradis[0]) + cr * t.met_dva * ghr[0], t.air_dsatdk + psycst[0])
+                     + dv(t.air_dsatdk * (t.rad_rniso[1] - cr * dtair * t.rad_gradis[1]) + cr * t.met_dva * ghr[1], t.air_dsatdk + psycst[1]));
       const double local_fevc = (double)((1.0f - t.canopy_fwet) * (float)ecx);
       if (local_fevc > 0.0) {
         // transp_soil_water (cbl_remove_trans.F90:43-93)
         double diff = 0.0, s = 0.0;
+        const double demand = dv(local_fevc * (double)dels, (double)K::hl);
 #pragma unroll
         for (int kk = 0; kk < K::ms; kk++) {
-          double xx = local_fevc * (double)dels / (double)K::hl * (double)t.veg_froot[kk] + diff;
+          double xx = demand * (double)t.veg_froot[kk] + diff;
           double avail = mx(0.0, t.ssnow_wbliq[kk] - (double)1.1f * (double)t.soil_swilt) * (double)c.zse[kk] * (double)K::density_liq;
           double xxd = xx - avail;
           double e;
@@ -342,13 +374,13 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
           t.ssnow_evapfbl[kk] = e;
           s = s + e;
         }
-        t.canopy_fevc = s * (double)t.air_rlam / (double)dels;
-        ecx = t.canopy_fevc / (double)(1.0f - t.canopy_fwet);
+        t.canopy_fevc = dv(s * (double)t.air_rlam, (double)dels);
+        ecx = dv(t.canopy_fevc, (double)(1.0f - t.canopy_fwet));
       }
       // sensible heat, new leaf temperature, vpd at the leaf surface (:538-557)
       const float sgh = gh[0] + gh[1], sghr = ghr[0] + ghr[1];
-      hcx = ((double)w.sum_rniso - ecx - (double)(cr * dtair * w.sum_gradis)) * (double)sgh / (double)sghr;
-      w.tlfx = t.met_tvair + (float)hcx / (cr * sgh);
+      hcx = dv(((double)w.sum_rniso - ecx - (double)(cr * dtair * w.sum_gradis)) * (double)sgh, (double)sghr);
+      w.tlfx = t.met_tvair + dv((float)hcx, cr * sgh);
       rnx = (double)(w.sum_rniso - cr * (w.tlfx - t.met_tk) * w.sum_gradis);
       w.dsx = mx(t.met_dva + t.air_dsatdk * (w.tlfx - t.met_tvair), 0.0f);
       deltlf = tlfxx - w.tlfx;
@@ -367,10 +399,15 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
       for (int kk = 0; kk < K::ms; kk++) oldevapfbl[kk] = (float)t.ssnow_evapfbl[kk];
     }
     if (abs_deltlf > 0.1f) {
-      float fac = 0.5f * ((float)max(0, k - 5) / ((float)k - 4.9999f));
+      float fac = 0.5f * dv((float)max(0, k - 5), (float)k - 4.9999f);
       w.tlfx = fac * tlfxx + (1.0f - fac) * w.tlfx;
     } else if (k > 1) {
-      break;    // converged: every later pass of the reference loop is a no-op for this tile
+      // converged: every later pass of the reference loop is a no-op for this tile
+#if CBL_SYNC_A >= 2
+      done = true;
+#else
+      break;
+#endif
     }
   }
   t.canopy_fevc = (double)(1.0f - t.canopy_fwet) * w.ecy;
@@ -379,7 +416,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
       float s = 0.f;
 #pragma unroll
       for (int kk = 0; kk < K::ms; kk++) s = s + oldevapfbl[kk];
-      if (fabs(t.canopy_fevc - (double)(s * t.air_rlam / dels)) > (double)1.0e-4f) {
+      if (fabs(t.canopy_fevc - (double)dv(s * t.air_rlam, dels)) > (double)1.0e-4f) {
         w.warn++;                  // reference prints 'oldevapfbl not right' and carries on
       } else {
 #pragma unroll
@@ -400,11 +437,11 @@ CBL_DEV void wetLeaf(Tile &t, const CanopyWork &w, float dels) {
     const double ghwet = (double)(2.0f * sum_gbh);
     const float gwwet = 1.075f * sum_gbh;
     const float ghrwet = (float)((double)w.sum_gradis + ghwet);
-    const float ccfevw = mn(t.canopy_cansto * t.air_rlam / dels, 2.0f / (1440.0f / (dels / 60.0f)) * t.air_rlam);
+    const float ccfevw = mn(dv(t.canopy_cansto * t.air_rlam, dels), dv(2.0f, dv(1440.0f, dv(dels, 60.0f))) * t.air_rlam);
     const float num = t.air_dsatdk * (w.sum_rniso - cr * (t.met_tvair - t.met_tk) * w.sum_gradis) + cr * t.met_dva * ghrwet;
-    const float den = t.air_dsatdk + t.air_psyc * ghrwet / gwwet;
-    t.canopy_fevw = mn(t.canopy_fwet * num / den, ccfevw);
-    t.canopy_fevw_pot = num / den;
+    const float den = t.air_dsatdk + dv(t.air_psyc * ghrwet, gwwet);
+    t.canopy_fevw = mn(dv(t.canopy_fwet * num, den), ccfevw);
+    t.canopy_fevw_pot = dv(num, den);
     t.canopy_fhvw = t.canopy_fwet * (w.sum_rniso - cr * (w.tlfy - t.met_tk) * w.sum_gradis) - t.canopy_fevw;
   }
 }
@@ -412,32 +449,32 @@ CBL_DEV void wetLeaf(Tile &t, const CanopyWork &w, float dels) {
 // within_canopy: cbl_within_canopy.F90:10-159 (no litter, no or_evap)
 CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0) {
   if (!(t.veg_meth > 0 && t.canopy_vlaiw > K::lai_thresh && t.rough_hruff > t.rough_z0soilsn)) return;
-  const float rrbw = (float)(((w.gbhu[0] + w.gbhf[0]) + (w.gbhu[1] + w.gbhf[1])) / (double)t.air_cmolar);
-  const float rrsw = (t.canopy_gswx[0] + t.canopy_gswx[1]) / t.air_cmolar;
-  float fix_eqn = t.ssnow_cls * rt0 / (rt0 + 0.f);
+  const float rrbw = (float)dv((w.gbhu[0] + w.gbhf[0]) + (w.gbhu[1] + w.gbhf[1]), (double)t.air_cmolar);
+  const float rrsw = dv(t.canopy_gswx[0] + t.canopy_gswx[1], t.air_cmolar);
+  float fix_eqn = dv(t.ssnow_cls * rt0, rt0 + 0.f);
   if (t.ssnow_potev > 0.f) fix_eqn = fix_eqn * t.ssnow_wetfac;
-  const float fix_eqn2 = rt0 / (rt0 + 0.f);
+  const float fix_eqn2 = dv(rt0, rt0 + 0.f);
   const float epsi = t.air_epsi, rt1 = t.rough_rt1;
   const float cond = (1.f + epsi) * rrsw + rrbw, r01 = rt0 * rt1, bs = rrbw * rrsw;
   const float dmah = (rt0 + fix_eqn2 * rt1) * cond + epsi * r01 * bs;
-  const float dmbh = (-t.air_rlam / K::capp) * r01 * bs;
-  const float dmch = cond * rt0 * rt1 * (t.canopy_fhv + t.canopy_fhs) / (t.air_rho * K::capp);
-  const float dmae = (-epsi * K::capp / t.air_rlam) * r01 * bs;
+  const float dmbh = dv(-t.air_rlam, K::capp) * r01 * bs;
+  const float dmch = dv(cond * rt0 * rt1 * (t.canopy_fhv + t.canopy_fhs), t.air_rho * K::capp);
+  const float dmae = dv(-epsi * K::capp, t.air_rlam) * r01 * bs;
   const float dmbe = (rt0 + fix_eqn * rt1) * cond + r01 * bs;
-  const float dmce = (float)((double)(cond * rt0 * rt1) * ((double)t.canopy_fev + t.canopy_fes / (double)t.ssnow_cls)
-                             / (double)(t.air_rho * t.air_rlam));
+  const float dmce = (float)dv((double)(cond * rt0 * rt1) * ((double)t.canopy_fev + dv(t.canopy_fes, (double)t.ssnow_cls)),
+                               (double)(t.air_rho * t.air_rlam));
   const float det = dmah * dmbe - dmae * dmbh + 1.0e-12f;
-  float tv = t.met_tk + (dmbe * dmch - dmbh * dmce) / det;
+  float tv = t.met_tk + dv(dmbe * dmch - dmbh * dmce, det);
   tv = mx(tv, mn(t.ssnow_tss, t.met_tk) - 5.0f);
   tv = mn(tv, mx(t.ssnow_tss, t.met_tk) + 5.0f);
   t.met_tvair = tv;
-  float qv = t.met_qv + (dmah * dmce - dmae * dmch) / det;
+  float qv = t.met_qv + dv(dmah * dmce - dmae * dmch, det);
   qv = mx(0.0f, qv);
   qv = mx(qv, mn(t.ssnow_qstss, t.met_qv));
   qv = mn(qv, mx(t.ssnow_qstss, t.met_qv));
   t.met_qvair = qv;
   float qstvair = qsatf(tv - K::tfrz, t.met_pmb);
-  t.met_dva = (qstvair - qv) * K::rmair / K::rmh2o * t.met_pmb * 100.f;
+  t.met_dva = dv((qstvair - qv) * K::rmair, K::rmh2o) * t.met_pmb * 100.f;
 }
 
 // define_canopy: cable_canopy.F90:10-1048.  Returns number of dryLeaf soft warnings.
@@ -459,10 +496,11 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
   t.canopy_fwsoil = 1.0;
   define_air(t);
   float qstvair = qsatf(t.met_tvair - K::tfrz, t.met_pmb);
-  t.met_dva = (qstvair - t.met_qvair) * K::rmair / K::rmh2o * t.met_pmb * 100.0f;
+  t.met_dva = dv((qstvair - t.met_qvair) * K::rmair, K::rmh2o) * t.met_pmb * 100.0f;
   w.dsx = mx(t.met_dva, 0.0f);
   w.tlfx = t.met_tk; w.tlfy = t.met_tk;
   w.fwsoil = 0.f; w.ecy = 0.; w.hcy = 0.; w.rny = 0.;
+  w.dleaf3 = m_pow(t.veg_dleaf, 3.0f);
   const float ortsoil = t.ssnow_rtsoil;
   t.ssnow_tss = (float)(1 - t.ssnow_isflag) * t.ssnow_tgg[0] + (float)t.ssnow_isflag * t.ssnow_tggsn[0];
   const float tss4 = p4(t.ssnow_tss);
@@ -482,37 +520,39 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
   float zet_cur = K::zeta0;
 #pragma unroll 1
   for (int iter = 1; iter <= CABLE_NITER; iter++) {
+    CBL_PHASE_BARRIER(CBL_SYNC_A);     // the block's warps walk the loop body together (cbm_consts.cuh)
     const float zet = zet_cur;
     // friction velocity (cbl_friction_vel.F90:19-108)
     {
-      float psim_1 = psim(zet * t.rough_zref_uv / t.rough_zref_tq);
+      float psim_1 = psim(dv(zet * t.rough_zref_uv, t.rough_zref_tq));
       float rescale = K::vonk * mx(t.met_ua, K::umin);
-      float z_eff = t.rough_zref_uv / t.rough_z0m;
-      float psim_2 = psim(zet * t.rough_z0m / t.rough_zref_tq);
-      t.canopy_us = mn(mx(1.e-6f, rescale / (m_log(z_eff) - psim_1 + psim_2)), 10.0f);
+      float z_eff = dv(t.rough_zref_uv, t.rough_z0m);
+      float psim_2 = psim(dv(zet * t.rough_z0m, t.rough_zref_tq));
+      t.canopy_us = mn(mx(1.e-6f, dv(rescale, m_log(z_eff) - psim_1 + psim_2)), 10.0f);
     }
     const float us = t.canopy_us;
     // aerodynamic resistances (:276-363)
-    float r1c = (m_log(t.rough_zref_tq / zr) - psis(zet) + psis(zet * zr / t.rough_zref_tq)) / K::vonk;
+    float r1c = dv(m_log(dv(t.rough_zref_tq, zr)) - psis(zet) + psis(dv(zet * zr, t.rough_zref_tq)), K::vonk);
     rt1usc = above ? 1.0f * r1c : 0.0f * r1c;
-    rt0 = mx(5.f, t.rough_rt0us / us);
-    t.rough_rt1 = mx(5.f, (t.rough_rt1usa + t.rough_rt1usb + rt1usc) / us);
+    rt0 = mx(5.f, dv(t.rough_rt0us, us));
+    t.rough_rt1 = mx(5.f, dv(t.rough_rt1usa + t.rough_rt1usb + rt1usc, us));
     float rtsoil = veg ? rt0 : rt0 + t.rough_rt1;
     rtsoil = mx(5.f, rtsoil);
     if (rtsoil > 2.f * ortsoil || rtsoil < 0.5f * ortsoil) rtsoil = mx(5.f, 0.5f * (rtsoil + ortsoil));
     t.ssnow_rtsoil = rtsoil;
     // forced-convection leaf boundary-layer conductances (:376-395)
     if (veg) {
-      float gv = t.air_cmolar * K::apol * t.air_visc / K::prandt / t.veg_dleaf
-                 * sqrtf(us / mx(t.rough_usuh, 1.e-6f) * t.veg_dleaf / t.air_visc)
-                 * c.prandt_third / t.veg_shelrb;
+      float gv = dv(dv(dv(t.air_cmolar * K::apol * t.air_visc, K::prandt), t.veg_dleaf)
+                    * f_sqrt(dv(dv(us, mx(t.rough_usuh, 1.e-6f)) * t.veg_dleaf, t.air_visc))
+                    * c.prandt_third, t.veg_shelrb);
       const double gbvtop = mx(0.05, (double)gv);
       const float hc = 0.5f * t.rough_coexp;
-      w.gbhu[0] = gbvtop * (double)(1.0f - m_exp(-mn(lai * (hc + t.rad_extkb), 20.0f))) / (double)(t.rad_extkb + hc);
-      w.gbhu[1] = (double)(2.0f / t.rough_coexp) * gbvtop * (double)(1.0f - m_exp(-mn(hc * lai, 20.0f))) - w.gbhu[0];
+      w.gbhu[0] = dv(gbvtop * (double)(1.0f - m_exp(-mn(lai * (hc + t.rad_extkb), 20.0f))), (double)(t.rad_extkb + hc));
+      w.gbhu[1] = (double)dv(2.0f, t.rough_coexp) * gbvtop * (double)(1.0f - m_exp(-mn(hc * lai, 20.0f))) - w.gbhu[0];
     }
     w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
     dryLeaf(t, c, w, dels, iter);
+    CBL_PHASE_BARRIER(CBL_SYNC_A);     // re-align after the data-dependent number of dryLeaf passes
     wetLeaf(t, w, dels);
     // vegetation fluxes and temperature (:418-456)
     t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
@@ -521,7 +561,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     float tv = t.met_tvrad;
     if (dense) {
       t.rad_lwabv = cr * (w.tlfy - t.met_tk) * w.sum_gradis;
-      float arg = t.rad_lwabv / (2.0f * (1.0f - t.rad_transd) * K::sboltz * K::emleaf) + tvrad4;
+      float arg = dv(t.rad_lwabv, 2.0f * (1.0f - t.rad_transd) * K::sboltz * K::emleaf) + tvrad4;
       if (arg > 0.0f) tv = m_pow025(arg);
     }
     t.canopy_tv = tv;
@@ -531,11 +571,11 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     t.ssnow_qstss = qsatf(t.ssnow_tss - K::tfrz, t.met_pmb);
     t.ssnow_potev = soil_potev(t, c, t.met_qv);
     latent_heat_flux(t, c, dels);
-    t.canopy_fhs = t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair) / t.ssnow_rtsoil;
+    t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil);
     within_canopy(t, w, rt0);
     t.ssnow_potev = soil_potev(t, c, t.met_qvair);
     latent_heat_flux(t, c, dels);
-    t.canopy_fhs = t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair) / t.ssnow_rtsoil;
+    t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil);
     t.canopy_ga = (float)((double)(t.canopy_fns - t.canopy_fhs) - t.canopy_fes);
     t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
     t.canopy_fh = t.canopy_fhv + t.canopy_fhs;
@@ -543,8 +583,8 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     t.canopy_fevw_pot = (t.canopy_fevw_pot >= 0.f) ? mx(0.000001f, t.canopy_fevw_pot) : mn(-0.002f, t.canopy_fevw_pot);
     // update_zetar (cbl_zetar.F90:106-156): not on the last pass
     if (iter < CABLE_NITER) {
-      float z = -(K::vonk * K::grav * t.rough_zref_tq * (t.canopy_fh + 0.07f * t.canopy_fe))
-                / (t.air_rho * K::capp * t.met_tk * p3(us));
+      float z = dv(-(K::vonk * K::grav * t.rough_zref_tq * (t.canopy_fh + 0.07f * t.canopy_fe)),
+                   t.air_rho * K::capp * t.met_tk * p3(us));
       zet_cur = mx(K::zetneg, mn(K::zetpos, z));
       // static indices only: a run-time subscript would push the whole Tile into local memory
       if (iter == 1) t.canopy_zetar[1] = zet_cur;
@@ -556,34 +596,34 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
   t.canopy_rnet = t.canopy_fnv + t.canopy_fns;
   t.canopy_rniso = w.sum_rniso + t.rad_qssabs + t.rad_transd * t.met_fld
                    + (1.0f - t.rad_transd) * K::emleaf * K::sboltz * tvrad4 - K::emsoil * K::sboltz * tvrad4;
-  t.canopy_epot = (t.canopy_fevw_pot + t.ssnow_potev / t.ssnow_cls) * dels / t.air_rlam;
+  t.canopy_epot = dv((t.canopy_fevw_pot + dv(t.ssnow_potev, t.ssnow_cls)) * dels, t.air_rlam);
   {
-    float rlow = t.canopy_epot * t.air_rlam / dels;
+    float rlow = dv(t.canopy_epot * t.air_rlam, dels);
     if (rlow == 0.f) rlow = 1.e-7f;
-    float wcs = mx(0.f, mn(1.0f, t.canopy_fe / rlow));
-    if (wcs <= 0.f) wcs = mx(0.f, mn(1.f, mx(t.canopy_fev / t.canopy_fevw_pot, (float)t.canopy_fes / t.ssnow_potev)));
+    float wcs = mx(0.f, mn(1.0f, dv(t.canopy_fe, rlow)));
+    if (wcs <= 0.f) wcs = mx(0.f, mn(1.f, mx(dv(t.canopy_fev, t.canopy_fevw_pot), dv((float)t.canopy_fes, t.ssnow_potev))));
     t.canopy_wetfac_cs = wcs;
   }
 
   const float us = t.canopy_us;
-  t.canopy_cduv = us * us / p2(mx(t.met_ua, K::umin));
+  t.canopy_cduv = dv(us * us, p2(mx(t.met_ua, K::umin)));
   {  // bulk surface conductance (:689-714)
     float lai_min = mx(K::lai_thresh, lai);
-    float cc = (t.rad_fvlai[0] / lai_min) * t.canopy_gswx[0] + (t.rad_fvlai[1] / lai_min) * t.canopy_gswx[1];
+    float cc = dv(t.rad_fvlai[0], lai_min) * t.canopy_gswx[0] + dv(t.rad_fvlai[1], lai_min) * t.canopy_gswx[1];
     cc = (1.f - t.rad_transd) * mx(1.e-06f, cc);
-    float rel = (float)(t.ssnow_wb[0] / (double)t.soil_sfc);
+    float rel = (float)dv(t.ssnow_wb[0], (double)t.soil_sfc);
     float sc = t.rad_transd * p2(0.01f * rel);
     t.canopy_gswx_T = (t.soil_isoilm == K::ice_soiltype) ? 1.e6f : cc + sc;
   }
   const float zN = t.canopy_zetar[CABLE_NITER - 1];       // also zetar(:,iterplus): iterplus == NITER on exit
-  t.canopy_cdtq = t.canopy_cduv * (m_log(t.rough_zref_uv / t.rough_z0m) - psim(zN * t.rough_zref_uv / t.rough_zref_tq)
-                                   + psim(zN * t.rough_z0m / t.rough_zref_tq))
-                  / (m_log(t.rough_zref_tq / (0.1f * t.rough_z0m)) - psis(zN) + psis(zN * 0.1f * t.rough_z0m / t.rough_zref_tq));
+  t.canopy_cdtq = dv(t.canopy_cduv * (m_log(dv(t.rough_zref_uv, t.rough_z0m)) - psim(dv(zN * t.rough_zref_uv, t.rough_zref_tq))
+                                      + psim(dv(zN * t.rough_z0m, t.rough_zref_tq))),
+                     m_log(dv(t.rough_zref_tq, 0.1f * t.rough_z0m)) - psis(zN) + psis(dv(zN * 0.1f * t.rough_z0m, t.rough_zref_tq)));
   // screen-level temperature and humidity (:731-878)
-  const float tstar = -t.canopy_fh / (t.air_rho * K::capp * us);
-  const float qstar = -t.canopy_fe / (t.air_rho * t.air_rlam * us * t.ssnow_cls);
+  const float tstar = dv(-t.canopy_fh, t.air_rho * K::capp * us);
+  const float qstar = dv(-t.canopy_fe, t.air_rho * t.air_rlam * us * t.ssnow_cls);
   const float zscrn = mx(t.rough_z0m, 2.0f - t.rough_disp);
-  const float ftemp = (m_log(t.rough_zref_tq / zscrn) - psis(zN) + psis(zN * zscrn / t.rough_zref_tq)) / K::vonk;
+  const float ftemp = dv(m_log(dv(t.rough_zref_tq, zscrn)) - psis(zN) + psis(dv(zN * zscrn, t.rough_zref_tq)), K::vonk);
   float tscrn = t.met_tk - K::tfrz - tstar * ftemp;
   float r_sc = 0.f;
   const float hr = t.rough_hruff, disp = t.rough_disp, rgh = t.canopy_rghlai;
@@ -593,25 +633,25 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     const float zscl = mx(t.rough_z0soilsn, 2.0f);
     float term1 = 0.f, term2 = 0.f, term5 = 0.f;
     if (disp > 0.0f) {
-      term1 = m_exp(2 * K::csw * rgh * (1 - zscl / hr));
-      term2 = m_exp(2 * K::csw * rgh * (1 - disp / hr));
-      term5 = mx(2.f / 3.f * hr / disp, 1.f);
+      term1 = m_exp(2 * K::csw * rgh * (1 - dv(zscl, hr)));
+      term2 = m_exp(2 * K::csw * rgh * (1 - dv(disp, hr)));
+      term5 = mx(dv(2.f / 3.f * hr, disp), 1.f);
     }
     const float term3 = p2(K::a33) * K::ctl * 2 * K::csw * rgh;
     if (zscl < disp) {
       const float e2 = m_exp(2 * K::csw * rgh);
-      r_sc = term5 * m_log(zscl / t.rough_z0soilsn) * (e2 - term2) / term3;
-      r_sc = r_sc + term5 * m_log(disp / zscl) * (e2 - term1) / term3;
+      r_sc = dv(term5 * m_log(dv(zscl, t.rough_z0soilsn)) * (e2 - term2), term3);
+      r_sc = r_sc + dv(term5 * m_log(dv(disp, zscl)) * (e2 - term1), term3);
     } else if (disp <= zscl && zscl < hr) {
-      r_sc = t.rough_rt0us + term5 * (term2 - term1) / term3;
+      r_sc = t.rough_rt0us + dv(term5 * (term2 - term1), term3);
     } else if (hr <= zscl && zscl < t.rough_zruffs) {
-      r_sc = t.rough_rt0us + t.rough_rt1usa + term5 * (zscl - hr) / (p2(K::a33) * K::ctl * hr);
+      r_sc = t.rough_rt0us + t.rough_rt1usa + dv(term5 * (zscl - hr), p2(K::a33) * K::ctl * hr);
     } else if (zscl >= t.rough_zruffs) {
       r_sc = t.rough_rt0us + t.rough_rt1usa + t.rough_rt1usb
-             + (m_log((zscl - disp) / mx(t.rough_zruffs - disp, t.rough_z0soilsn))
-                - psis((zscl - disp) * zN / t.rough_zref_tq) + psis((t.rough_zruffs - disp) * zN / t.rough_zref_tq)) / K::vonk;
+             + dv(m_log(dv(zscl - disp, mx(t.rough_zruffs - disp, t.rough_z0soilsn)))
+                  - psis(dv((zscl - disp) * zN, t.rough_zref_tq)) + psis(dv((t.rough_zruffs - disp) * zN, t.rough_zref_tq)), K::vonk);
     }
-    tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, (r_sc / mx(1.f, rsum))) - K::tfrz;
+    tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, dv(r_sc, mx(1.f, rsum))) - K::tfrz;
   }
   t.canopy_tscrn = tscrn;
   {
@@ -620,26 +660,26 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
     const float qsurf = (qtgnet > 0.f) ? rsts * t.ssnow_wetfac : 0.1f * rsts * t.ssnow_wetfac + 0.9f * t.met_qv;
     t.canopy_qmom = t.air_rho * (us * us);
     float qscrn = t.met_qv - qstar * ftemp;
-    if (canopy_scrn) qscrn = qsurf + (t.met_qv - qsurf) * mn(1.f, (r_sc / mx(1.f, rsum)));
+    if (canopy_scrn) qscrn = qsurf + (t.met_qv - qsurf) * mn(1.f, dv(r_sc, mx(1.f, rsum)));
     t.canopy_qscrn = qscrn;
   }
   // canopy water store (:881-906)
-  t.canopy_dewmm = (float)(-((double)mn(0.0f, t.canopy_fevw) + mn(0.0, t.canopy_fevc)) * (double)dels / (double)t.air_rlam);
+  t.canopy_dewmm = (float)dv(-((double)mn(0.0f, t.canopy_fevw) + mn(0.0, t.canopy_fevc)) * (double)dels, (double)t.air_rlam);
   t.canopy_cansto = t.canopy_cansto + t.canopy_dewmm;
-  t.canopy_cansto = mx(t.canopy_cansto - mx(0.0f, t.canopy_fevw) * dels / t.air_rlam, 0.0f);
+  t.canopy_cansto = mx(t.canopy_cansto - dv(mx(0.0f, t.canopy_fevw) * dels, t.air_rlam), 0.0f);
   t.canopy_spill = mx(0.0f, t.canopy_cansto - w.cansat);
   t.canopy_through = t.canopy_through + t.canopy_spill;
   t.canopy_precis = mx(0.f, t.canopy_through);
   t.canopy_cansto = t.canopy_cansto - t.canopy_spill;
   t.canopy_delwc = t.canopy_cansto - t.canopy_oldcansto;
   // sensitivities for the implicit soil-temperature solve (:913-1027), default branch
-  t.ssnow_dfn_dtg = (-1.f) * 4.f * K::emsoil * K::sboltz * tss4 / t.ssnow_tss;
-  t.ssnow_dfh_dtg = t.air_rho * K::capp / t.ssnow_rtsoil;
-  t.ssnow_dfe_ddq = t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls / t.ssnow_rtsoil;
+  t.ssnow_dfn_dtg = dv((-1.f) * 4.f * K::emsoil * K::sboltz * tss4, t.ssnow_tss);
+  t.ssnow_dfh_dtg = dv(t.air_rho * K::capp, t.ssnow_rtsoil);
+  t.ssnow_dfe_ddq = dv(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, t.ssnow_rtsoil);
   {
     const float tc = t.ssnow_tss - K::tfrz;
-    t.ssnow_ddq_dtg = (K::rmh2o / K::rmair) / t.met_pmb * K::tetena * K::tetenb * K::tetenc / (p2(K::tetenc + t.ssnow_tss - K::tfrz))
-                      * m_exp(K::tetenb * tc / (K::tetenc + t.ssnow_tss - K::tfrz));
+    t.ssnow_ddq_dtg = dv(dv(K::rmh2o / K::rmair, t.met_pmb) * K::tetena * K::tetenb * K::tetenc, p2(K::tetenc + t.ssnow_tss - K::tfrz))
+                      * m_exp(dv(K::tetenb * tc, K::tetenc + t.ssnow_tss - K::tfrz));
   }
   t.ssnow_dfe_dtg = t.ssnow_dfe_ddq * t.ssnow_ddq_dtg;
   t.canopy_dgdtg = (double)(t.ssnow_dfn_dtg - t.ssnow_dfh_dtg - t.ssnow_dfe_dtg);

@@ -48,13 +48,18 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
   return (flags & CABLE_FLAG_PHB) ? 2 : 0;
 }
 
-template <int PHASE, int BLOCK, int MINB>
+// LVL = cfg.output_level as a compile-time constant: at levels 0/1 the ~110 non-STAR diagnostics are dead code, so
+// they cost neither registers/spill slots for the whole step nor store instructions (at level 2 they are all kept).
+template <int PHASE, int BLOCK, int MINB, int LVL>
 __global__ void __launch_bounds__(BLOCK, MINB)
 cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const float dels, const int first_call,
            unsigned long long *warn_counter) {
   // tiles [i0, i1) of this launch (a whole shard, or one chunk of the pipelined drop-in call)
-  const int i = i0 + blockIdx.x * BLOCK + threadIdx.x;
-  if (i >= i1) return;
+  // A thread past the end of the range shadows the last tile (its stores are suppressed) instead of leaving:
+  // kernel A's block-wide phase barriers (define_canopy) need every thread of the block.
+  const int i_raw = i0 + blockIdx.x * BLOCK + threadIdx.x;
+  const bool valid = i_raw < i1;
+  const int i = valid ? i_raw : i1 - 1;
   const DevCfg &c = c_cfg;
   const size_t smp = (size_t)mp;
   Tile t;
@@ -89,7 +94,7 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
     t.ssnow_otss = t.ssnow_tss;
     const int warn = define_canopy(t, c, dels, sunlit_veg);
     t.ssnow_owetfac = t.ssnow_wetfac;
-    if (warn) atomicAdd(warn_counter, (unsigned long long)warn);
+    if (warn && valid) atomicAdd(warn_counter, (unsigned long long)warn);
   }
   if (PHASE & 2) {
     soil_snow(t, c, dels, first_call != 0);
@@ -103,7 +108,8 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
   }
 
   // ---- store: state, exchange fields, and diagnostics by output level (coalesced SoA writes) ----
-  const int lvl = c.output_level;
+  if (!valid) return;
+  constexpr int lvl = LVL;
 #define CBL_WANT(role, flags)                                                                    \
   (store_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags)) == 1 ||                              \
    (store_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags)) == 2 &&                             \

@@ -10,6 +10,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcable_b200.so")
+# tuning aid: CABLE_B200_LIB points at a variant build of the same library (cable_b200/csrc/Makefile, OUT=...)
+if os.environ.get("CABLE_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["CABLE_B200_LIB"])
 
 MS, MSN, MF, NRB, NCP, NCS = 6, 3, 2, 3, 3, 2
 

@@ -1,0 +1,67 @@
+// Host check of cable_b200/csrc/cbm_math.cuh (the identical source the kernels compile):
+// exp_cr / exp2_cr / log_cr_pos must equal (float)exp((double)x) etc. -- what the CR oracle evaluates --
+// on every sampled fp32 argument; a handful of 1-ulp differences per 10^9 are the documented limit.
+//   usage: test_lean_math [stride]      (stride 1 = every fp32 bit pattern in range; default 97)
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <thread>
+#include <vector>
+#include <atomic>
+#include "../../cable_b200/csrc/cbm_math.cuh"
+
+static float f_of(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static uint32_t b_of(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+
+struct Result { unsigned long long n = 0, bad = 0; float worst_arg = 0; };
+
+template <class F, class G>
+static Result sweep(uint32_t b0, uint32_t b1, uint32_t stride, F lean, G ref) {
+  const unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+  std::vector<Result> part(nt);
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      Result r;
+      for (uint64_t b = (uint64_t)b0 + (uint64_t)t * stride; b <= b1; b += (uint64_t)nt * stride) {
+        const float x = f_of((uint32_t)b);
+        const float a = lean(x), c = ref(x);
+        r.n++;
+        if (b_of(a) != b_of(c) && !(a != a && c != c)) { r.bad++; r.worst_arg = x; }
+      }
+      part[t] = r;
+    });
+  for (auto &t : th) t.join();
+  Result r;
+  for (auto &p : part) { r.n += p.n; r.bad += p.bad; if (p.bad) r.worst_arg = p.worst_arg; }
+  return r;
+}
+
+int main(int argc, char **argv) {
+  const uint32_t stride = argc > 1 ? (uint32_t)atoi(argv[1]) : 97;
+  using namespace cbl::lean;
+  int rc = 0;
+  auto report = [&](const char *name, Result r) {
+    printf("%-28s n=%llu mismatches=%llu (last arg %.9g)\n", name, r.n, r.bad, r.worst_arg);
+    // documented limit: ~1e-8 of arguments may round the other way
+    if ((double)r.bad > 2.0 + 1e-7 * (double)r.n) rc = 1;
+  };
+  auto e_ref = [](float x) { return (float)std::exp((double)x); };
+  auto e2_ref = [](float x) { return (float)std::exp2((double)x); };
+  auto l_ref = [](float x) { return (float)std::log((double)x); };
+  // exp: positive arguments 0 .. 200, negative 0 .. -200 (sign bit set), incl. over/underflow clamps
+  report("exp_cr  x in [0, 200]", sweep(0x00000000u, b_of(200.f), stride, exp_cr, e_ref));
+  report("exp_cr  x in [-200, -0]", sweep(0x80000000u, b_of(-200.f), stride, exp_cr, e_ref));
+  report("exp2_cr y in [0, 300]", sweep(0x00000000u, b_of(300.f), stride, exp2_cr, e2_ref));
+  report("exp2_cr y in [-300, -0]", sweep(0x80000000u, b_of(-300.f), stride, exp2_cr, e2_ref));
+  // log: every positive finite fp32 incl. subnormals
+  report("log_cr_pos x in (0, FLT_MAX]", sweep(0x00000001u, 0x7f7fffffu, stride, log_cr_pos, l_ref));
+  // special values of exp
+  const float inf = INFINITY;
+  if (exp_cr(inf) != inf || exp_cr(-inf) != 0.f || !(exp_cr(NAN) != exp_cr(NAN)) || exp_cr(0.f) != 1.f) { printf("exp specials FAILED\n"); rc = 1; }
+  if (exp2_cr(inf) != inf || exp2_cr(-inf) != 0.f || exp2_cr(0.f) != 1.f || exp2_cr(10.f) != 1024.f) { printf("exp2 specials FAILED\n"); rc = 1; }
+  printf(rc ? "FAILED\n" : "ok\n");
+  return rc;
+}
