@@ -111,7 +111,7 @@ struct cable_handle {
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
-  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B;
+  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148;
   // measurement
   cable_counters ctr{};
   bool profile = false;
@@ -174,7 +174,10 @@ int launch_range(cable_handle *h, const DevPtrs &d, float dels, int first, int i
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
   switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
   if (h->split) {
-    CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A);
+    // kernel A: one 768-thread block per SM when the range fills the chip that way; small ranges (a shard of an
+    // 8-GPU run, a pipeline chunk) take 256-thread blocks, three per SM, so that every SM still gets work
+    if (i1 - i0 >= h->sms * CBL_BLOCK_A) { CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A); }
+    else { CBL_DISPATCH(1, 256, 3); }
     CUDA_TRY(cudaGetLastError());
     CBL_DISPATCH(2, CBL_BLOCK_B, CBL_MINB_B);
     h->ctr.kernel_launches++;
@@ -349,7 +352,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   // A chunk is a whole number of full waves (148 SMs x resident blocks x 128 tiles), so cutting the shard does not
   // add partial waves; chunks alternate between two compute streams so one chunk's tail overlaps the next one's head.
   {
-    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->sms = sms;
     const int wave = sms * CBL_MINB_A * CBL_BLOCK_A;
     int waves_per_chunk = 1;
     if (const char *e = getenv("CABLE_B200_CHUNK_WAVES")) waves_per_chunk = atoi(e) > 0 ? atoi(e) : 1;

@@ -50,26 +50,41 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
 
 // LVL = cfg.output_level as a compile-time constant: at levels 0/1 the ~110 non-STAR diagnostics are dead code, so
 // they cost neither registers/spill slots for the whole step nor store instructions (at level 2 they are all kept).
+// Every field is read once and written once per step: stream it past L1 (evict-first) so that L1 keeps the
+// per-thread spill slots, which are what the loops re-read (CBL_STREAM=0: default caching).
+#ifndef CBL_STREAM
+#define CBL_STREAM 1
+#endif
+#if CBL_STREAM
+#define CBL_LD(p) __ldcs(p)
+#define CBL_ST(p, v) __stcs(p, v)
+#else
+#define CBL_LD(p) (*(p))
+#define CBL_ST(p, v) (*(p) = (v))
+#endif
+
 template <int PHASE, int BLOCK, int MINB, int LVL>
 __global__ void __launch_bounds__(BLOCK, MINB)
 cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const float dels, const int first_call,
            unsigned long long *warn_counter) {
-  // tiles [i0, i1) of this launch (a whole shard, or one chunk of the pipelined drop-in call)
+  // Tiles [i0, i1) of this launch (a whole shard, or one chunk of the pipelined drop-in call), BLOCK per block.
+  // Blocks are handed out by the hardware scheduler on purpose: the cost of a tile varies with time of day and
+  // vegetation (1-20 dryLeaf passes), and a static even split of the range over the SMs measured 35 % slower.
   // A thread past the end of the range shadows the last tile (its stores are suppressed) instead of leaving:
   // kernel A's block-wide phase barriers (define_canopy) need every thread of the block.
+  const DevCfg &c = c_cfg;
+  const size_t smp = (size_t)mp;
   const int i_raw = i0 + blockIdx.x * BLOCK + threadIdx.x;
   const bool valid = i_raw < i1;
   const int i = valid ? i_raw : i1 - 1;
-  const DevCfg &c = c_cfg;
-  const size_t smp = (size_t)mp;
   Tile t;
 
   // ---- load forcing, per-tile parameters, prognostic state (+ exchange fields in kernel B): coalesced SoA reads ----
 #define CABLE_F1(T, m, ct, role, flags)                                                          \
-  if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) t.T##_##m = d.T##_##m[i];
+  if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) t.T##_##m = CBL_LD(&d.T##_##m[i]);
 #define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
   if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) {                                 \
-    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = d.T##_##m[i + smp * k]; \
+    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = CBL_LD(&d.T##_##m[i + smp * k]); \
   }
 #include "../../include/cable_b200_fields.def"
 
@@ -114,10 +129,10 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
   (store_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags)) == 1 ||                              \
    (store_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags)) == 2 &&                             \
     (lvl >= 2 || (lvl >= 1 && (CBL_FLAGS(flags) & CABLE_FLAG_STAR)))))
-#define CABLE_F1(T, m, ct, role, flags) if (CBL_WANT(role, flags)) d.T##_##m[i] = t.T##_##m;
+#define CABLE_F1(T, m, ct, role, flags) if (CBL_WANT(role, flags)) CBL_ST(&d.T##_##m[i], t.T##_##m);
 #define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
   if (CBL_WANT(role, flags)) {                                                                   \
-    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) d.T##_##m[i + smp * k] = t.T##_##m[k]; \
+    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) CBL_ST(&d.T##_##m[i + smp * k], t.T##_##m[k]); \
   }
 #include "../../include/cable_b200_fields.def"
 #undef CBL_WANT
