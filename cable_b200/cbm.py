@@ -129,6 +129,60 @@ class CableB200:
         _lib.check(self._lib.cable_b200_grid_reduce(self._h, BY_NAME[name].id, comp, d_patchfrac, d_cstart, d_cend, nland, d_out))
 
 
+    # -- driver stages either side of cbm ---------------------------------------------
+    def driver_init(self, cstart: np.ndarray, cend: np.ndarray, patchfrac: np.ndarray, latitude: np.ndarray) -> None:
+        """landpt(:)%cstart-1 / %cend-1 (0-based, inclusive), patch(:)%frac, rad%latitude (per tile)."""
+        cs, ce = np.ascontiguousarray(cstart, np.int32), np.ascontiguousarray(cend, np.int32)
+        pf, la = np.ascontiguousarray(patchfrac, np.float32).ravel(), np.ascontiguousarray(latitude, np.float32).ravel()
+        self.nland = int(cs.size)
+        _lib.check(self._lib.cable_b200_driver_init(self._h, self.nland, cs.ctypes.data, ce.ctypes.data, pf.ctypes.data, la.ctypes.data))
+
+    def set_met_async(self, slot: int, met_land: np.ndarray, convert: _lib.MetConvert) -> None:
+        """met_land: float32 [len(MET_ROWS), nland], C-contiguous; must stay alive until the copy has run."""
+        assert met_land.dtype == np.float32 and met_land.shape == (len(_lib.MET_ROWS), self.nland) and met_land.flags["C_CONTIGUOUS"]
+        _lib.check(self._lib.cable_b200_set_met_async(self._h, slot, met_land.ctypes.data, C.byref(convert)))
+
+    def upload_lai(self) -> None:
+        _lib.check(self._lib.cable_b200_upload_lai(self._h))
+
+    def post_step(self, ktau: int, kstart: int, dels: float, mass_bal: bool = True, energy_bal: bool = True) -> None:
+        _lib.check(self._lib.cable_b200_post_step(self._h, int(ktau), int(kstart), float(dels), int(mass_bal), int(energy_bal)))
+
+    def output_plan(self, rows) -> None:
+        """rows: iterable of (name, comp, method[, scale, div, offset]); name is a registry field or a driver array."""
+        ids, comps, meth, sc, dv, off = [], [], [], [], [], []
+        for r in rows:
+            name, comp, method = r[0], r[1], r[2]
+            if name in BY_NAME:
+                ids.append(BY_NAME[name].id)
+            else:
+                k = self._lib.cable_b200_driver_field_id(name.encode())
+                if k < 0:
+                    raise KeyError(name)
+                ids.append(-(1 + k))
+            comps.append(comp); meth.append(_lib.AGG[method] if isinstance(method, str) else int(method))
+            sc.append(r[3] if len(r) > 3 else 1.0); dv.append(r[4] if len(r) > 4 else 1.0); off.append(r[5] if len(r) > 5 else 0.0)
+        a = [np.asarray(ids, np.int32), np.asarray(comps, np.int32), np.asarray(meth, np.int32),
+             np.asarray(sc, np.float32), np.asarray(dv, np.float32), np.asarray(off, np.float32)]
+        self.nrows = len(ids)
+        _lib.check(self._lib.cable_b200_output_plan(self._h, self.nrows, *[x.ctypes.data for x in a]))
+
+    def output_accumulate(self) -> None:
+        _lib.check(self._lib.cable_b200_output_accumulate(self._h))
+
+    def output_fetch_async(self, host_out: np.ndarray) -> None:
+        assert host_out.dtype == np.float32 and host_out.size == self.nrows * self.nland and host_out.flags["C_CONTIGUOUS"]
+        _lib.check(self._lib.cable_b200_output_fetch_async(self._h, host_out.ctypes.data))
+
+    def output_wait(self) -> None:
+        _lib.check(self._lib.cable_b200_output_wait(self._h))
+
+    def driver_download(self, name: str) -> np.ndarray:
+        out = np.empty(self.mp, np.float64 if name == "bal_owb" else np.float32)
+        _lib.check(self._lib.cable_b200_driver_download(self._h, name.encode(), out.ctypes.data))
+        return out
+
+
 _HANDLES: dict[int, CableB200] = {}
 
 

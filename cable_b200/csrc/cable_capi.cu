@@ -14,6 +14,7 @@
 #include <unordered_map>
 #include <cstdint>
 #include "cbm_kernel.cuh"
+#include "cbm_driver.cuh"
 
 using namespace cbl;
 
@@ -111,7 +112,22 @@ struct cable_handle {
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
+  int last_slot = 0;                   // forcing slot of the most recent step
   int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148;
+  // driver stages (cbm_driver.cuh); allocated by cable_b200_driver_init
+  struct Driver {
+    bool on = false;
+    int nland = 0;
+    int *d_cstart = nullptr, *d_cend = nullptr, *d_tile_land = nullptr;
+    float *d_patchfrac = nullptr, *d_latitude = nullptr;
+    std::vector<float *> d_met_land;            // one per forcing slot: [CABLE_MET_NROWS][nland]
+    char *arr_block = nullptr;                  // backing store of `arr`
+    DriverArrays arr{};
+    std::vector<OutRow> rows; OutRow *d_rows = nullptr;
+    double *d_agg = nullptr; int agg_counter = 0;
+    float *d_out[2] = {nullptr, nullptr}; cudaEvent_t ev_out_free[2] = {nullptr, nullptr}; int out_buf = 0;
+    cudaEvent_t ev_reduced = nullptr;
+  } drv;
   // measurement
   cable_counters ctr{};
   bool profile = false;
@@ -119,6 +135,8 @@ struct cable_handle {
 };
 
 namespace {
+
+void driver_free(cable_handle *h);      // driver stages, end of this file
 
 bool is_forcing_input(const cable_handle *h, int id) {
   const cable_field_info &f = g_fields[id];
@@ -405,6 +423,7 @@ int cable_b200_destroy(cable_handle *h) {
   if (h->ev_fork) { cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join_copy); cudaEventDestroy(h->ev_join_d2h); }
   for (auto ev : h->ev_chunk_in) cudaEventDestroy(ev);
   for (auto ev : h->ev_chunk_done) cudaEventDestroy(ev);
+  if (h->drv.on) driver_free(h);
   if (h->d_warn) cudaFree(h->d_warn);
   if (h->arena) cudaFree(h->arena);
   delete h;
@@ -501,6 +520,7 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
   CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], h->s_compute));
   h->soil_snow_calls++;
   h->ctr.steps++;
+  h->last_slot = slot;
   return CABLE_OK;
 }
 
@@ -624,6 +644,7 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
   h->slot_has_data[slot] = 0;
   h->soil_snow_calls++;
   h->ctr.steps++;
+  h->last_slot = slot;
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
   CUDA_TRY(cudaStreamSynchronize(h->s_compute2));
   CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
@@ -691,6 +712,256 @@ int cable_b200_grid_reduce(cable_handle *h, int id, int comp, const float *d_pat
   grid_reduce_kernel<<<(nland + 127) / 128, 128, 0, h->s_compute>>>(x, d_patchfrac, d_cstart, d_cend, nland, d_out);
   CUDA_TRY(cudaGetLastError());
   h->ctr.kernel_launches++;
+  return CABLE_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Driver stages either side of cbm() (include/cable_b200.h, second half; kernels in cbm_driver.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct DrvName { const char *name; size_t off; bool f64; };
+#define DRV(n) {#n, offsetof(DriverArrays, n), false}
+const DrvName g_drv_names[] = {
+  {"canopy_tscrn_max_daily", offsetof(DriverArrays, tscrn_max_daily), false},
+  {"canopy_tscrn_min_daily", offsetof(DriverArrays, tscrn_min_daily), false},
+  {"sum_flux_sumpn", offsetof(DriverArrays, sumpn), false}, {"sum_flux_sumrp", offsetof(DriverArrays, sumrp), false},
+  {"sum_flux_sumrpw", offsetof(DriverArrays, sumrpw), false}, {"sum_flux_sumrpr", offsetof(DriverArrays, sumrpr), false},
+  {"sum_flux_sumrs", offsetof(DriverArrays, sumrs), false}, {"sum_flux_sumrd", offsetof(DriverArrays, sumrd), false},
+  {"sum_flux_dsumpn", offsetof(DriverArrays, dsumpn), false}, {"sum_flux_dsumrp", offsetof(DriverArrays, dsumrp), false},
+  {"sum_flux_dsumrd", offsetof(DriverArrays, dsumrd), false},
+  {"bal_owb", offsetof(DriverArrays, owb), true},
+  {"bal_wbal", offsetof(DriverArrays, wbal), false}, {"bal_wbal_tot", offsetof(DriverArrays, wbal_tot), false},
+  {"bal_precip_tot", offsetof(DriverArrays, precip_tot), false}, {"bal_rnoff_tot", offsetof(DriverArrays, rnoff_tot), false},
+  {"bal_evap_tot", offsetof(DriverArrays, evap_tot), false},
+  {"bal_Radbal", offsetof(DriverArrays, radbal), false}, {"bal_EbalSoil", offsetof(DriverArrays, ebalsoil), false},
+  {"bal_Ebalveg", offsetof(DriverArrays, ebalveg), false}, {"bal_ebal", offsetof(DriverArrays, ebal), false},
+  {"bal_ebal_tot", offsetof(DriverArrays, ebal_tot), false}, {"bal_Radbalsum", offsetof(DriverArrays, radbalsum), false},
+};
+#undef DRV
+constexpr int N_DRV = (int)(sizeof(g_drv_names) / sizeof(g_drv_names[0]));
+
+void *drv_ptr(const cable_handle *h, int k) { return *(void *const *)((const char *)&h->drv.arr + g_drv_names[k].off); }
+
+void driver_free(cable_handle *h) {
+  auto &v = h->drv;
+  cudaFree(v.d_cstart); cudaFree(v.d_cend); cudaFree(v.d_tile_land); cudaFree(v.d_patchfrac); cudaFree(v.d_latitude);
+  for (auto p : v.d_met_land) cudaFree(p);
+  cudaFree(v.arr_block); cudaFree(v.d_rows); cudaFree(v.d_agg); cudaFree(v.d_out[0]); cudaFree(v.d_out[1]);
+  for (int b = 0; b < 2; b++) if (v.ev_out_free[b]) cudaEventDestroy(v.ev_out_free[b]);
+  if (v.ev_reduced) cudaEventDestroy(v.ev_reduced);
+  v = cable_handle::Driver{};
+}
+
+}  // namespace
+
+extern "C" {
+
+int cable_b200_driver_field_id(const char *name) {
+  if (!name) return -1;
+  for (int k = 0; k < N_DRV; k++) if (!strcmp(name, g_drv_names[k].name)) return k;
+  return -1;
+}
+
+int cable_b200_driver_init(cable_handle *h, int nland, const int *cstart, const int *cend, const float *patchfrac,
+                           const float *latitude) {
+  if (!h || nland <= 0 || !cstart || !cend || !patchfrac || !latitude) return fail(CABLE_E_ARG, "driver_init: null/empty argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // the land points must tile [0, mp) in order: landpt(l)%cstart..%cend (cable_input.F90:158-160)
+  std::vector<int> tile_land(h->mp, -1);
+  int expect = 0;
+  for (int l = 0; l < nland; l++) {
+    if (cstart[l] != expect || cend[l] < cstart[l] || cend[l] >= h->mp) return fail(CABLE_E_ARG, "driver_init: cstart/cend must partition [0, mp) in order");
+    for (int i = cstart[l]; i <= cend[l]; i++) tile_land[i] = l;
+    expect = cend[l] + 1;
+  }
+  if (expect != h->mp) return fail(CABLE_E_ARG, "driver_init: land points do not cover all mp tiles");
+  if (h->drv.on) driver_free(h);
+  auto &v = h->drv;
+  v.nland = nland;
+  const size_t mp = (size_t)h->mp;
+  CUDA_TRY(cudaMalloc(&v.d_cstart, nland * sizeof(int))); CUDA_TRY(cudaMalloc(&v.d_cend, nland * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&v.d_tile_land, mp * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&v.d_patchfrac, mp * sizeof(float))); CUDA_TRY(cudaMalloc(&v.d_latitude, mp * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(v.d_cstart, cstart, nland * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.d_cend, cend, nland * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.d_tile_land, tile_land.data(), mp * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.d_patchfrac, patchfrac, mp * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(v.d_latitude, latitude, mp * sizeof(float), cudaMemcpyHostToDevice));
+  v.d_met_land.assign(h->nslots, nullptr);
+  for (int s = 0; s < h->nslots; s++) CUDA_TRY(cudaMalloc(&v.d_met_land[s], (size_t)CABLE_MET_NROWS * nland * sizeof(float)));
+  // driver-owned per-tile arrays: one block, 8 bytes per element so the double array fits anywhere
+  CUDA_TRY(cudaMalloc(&v.arr_block, (size_t)N_DRV * mp * 8));
+  CUDA_TRY(cudaMemset(v.arr_block, 0, (size_t)N_DRV * mp * 8));
+  for (int k = 0; k < N_DRV; k++) *(void **)((char *)&v.arr + g_drv_names[k].off) = v.arr_block + (size_t)k * mp * 8;
+  // aggregator initial values: max -> -huge, min -> +huge (aggregator.F90:1015-1119)
+  {
+    std::vector<float> hi(mp, 3.402823466e38f), lo(mp, -3.402823466e38f);
+    CUDA_TRY(cudaMemcpy(v.arr.tscrn_min_daily, hi.data(), mp * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(v.arr.tscrn_max_daily, lo.data(), mp * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&v.ev_out_free[b], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&v.ev_reduced, cudaEventDisableTiming));
+  v.on = true;
+  return CABLE_OK;
+}
+
+int cable_b200_set_met_async(cable_handle *h, int slot, const float *met_land, const cable_met_convert *cv) {
+  if (!h || !h->drv.on) return fail(CABLE_E_ARG, "set_met_async: call cable_b200_driver_init first");
+  if (slot < 0 || slot >= h->nslots || !met_land || !cv) return fail(CABLE_E_ARG, "set_met_async: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  auto &v = h->drv;
+  CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_slot_free[slot], 0));     // a running step may still read the slot
+  const size_t bytes = (size_t)CABLE_MET_NROWS * v.nland * sizeof(float);
+  CUDA_TRY(cudaMemcpyAsync(v.d_met_land[slot], met_land, bytes, cudaMemcpyHostToDevice, h->s_copy));
+  h->ctr.h2d_bytes += (long long)bytes;
+  MetConvert c{cv->tair_offset, cv->psurf_scale, cv->rainf_scale, cv->co2_scale, cv->snowf_from_tair,
+               (float)sin((double)(23.45f * (3.1415927f / 180.0f)))};
+  MetOut o{(float *)dev_ptr(h, FID_met_fsd, slot), (float *)dev_ptr(h, FID_met_tk, slot), (float *)dev_ptr(h, FID_met_pmb, slot),
+           (float *)dev_ptr(h, FID_met_qv, slot), (float *)dev_ptr(h, FID_met_ua, slot), (float *)dev_ptr(h, FID_met_precip, slot),
+           (float *)dev_ptr(h, FID_met_precip_sn, slot), (float *)dev_ptr(h, FID_met_fld, slot), (float *)dev_ptr(h, FID_met_ca, slot),
+           (float *)dev_ptr(h, FID_met_coszen, slot), (float *)dev_ptr(h, FID_met_doy, slot)};
+  met_expand_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_copy>>>(v.d_met_land[slot], v.nland, v.d_tile_land, v.d_latitude, c, o, h->mp);
+  CUDA_TRY(cudaGetLastError());
+  h->ctr.kernel_launches++;
+  CUDA_TRY(cudaEventRecord(h->ev_forcing_ready[slot], h->s_copy));
+  h->slot_has_data[slot] = 1;
+  return CABLE_OK;
+}
+
+int cable_b200_upload_lai(cable_handle *h) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  if (!h->host[FID_veg_vlai]) return fail(CABLE_E_UNBOUND, "forcing field not bound: veg_vlai");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (int s = 0; s < h->nslots; s++) {
+    CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_slot_free[s], 0));
+    int rc = copy_field(h, FID_veg_vlai, s, true, h->s_copy); if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+  return CABLE_OK;
+}
+
+int cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels, int do_mass_bal, int do_energy_bal) {
+  if (!h || !h->drv.on) return fail(CABLE_E_ARG, "post_step: call cable_b200_driver_init first");
+  if (h->cfg.icycle > 1) return fail(CABLE_E_UNSUPPORTED, "post_step: sumcflux with icycle > 1 needs CASA-CNP (out of scope)");
+  if (h->ctr.steps <= 0) return fail(CABLE_E_ARG, "post_step: no step has run");
+  CUDA_TRY(cudaSetDevice(h->device));
+  // met%* live in the forcing slot of the step just enqueued; dev_ptr ignores the slot for resident fields
+  auto F = [&](int id) { return (float *)dev_ptr(h, id, h->last_slot); };
+  PostIn p{};
+  p.smelt = F(FID_ssnow_smelt); p.rnof1 = F(FID_ssnow_rnof1); p.rnof2 = F(FID_ssnow_rnof2); p.runoff = F(FID_ssnow_runoff);
+  p.tscrn = F(FID_canopy_tscrn); p.fpn = F(FID_canopy_fpn); p.frday = F(FID_canopy_frday); p.frp = F(FID_canopy_frp);
+  p.frpw = F(FID_canopy_frpw); p.frpr = F(FID_canopy_frpr); p.frs = F(FID_canopy_frs); p.fnee = F(FID_canopy_fnee);
+  p.precip = F(FID_met_precip); p.delwc = F(FID_canopy_delwc); p.snowd = F(FID_ssnow_snowd); p.osnowd = F(FID_ssnow_osnowd);
+  p.fevw = F(FID_canopy_fevw); p.fev = F(FID_canopy_fev); p.cls = F(FID_ssnow_cls); p.rlam = F(FID_air_rlam);
+  p.fsd = F(FID_met_fsd); p.fld = F(FID_met_fld); p.albedo = F(FID_rad_albedo); p.transd = F(FID_rad_transd);
+  p.otss = F(FID_ssnow_otss); p.tv = F(FID_canopy_tv); p.fnv = F(FID_canopy_fnv); p.fns = F(FID_canopy_fns);
+  p.fhs = F(FID_canopy_fhs); p.ga = F(FID_canopy_ga); p.fhv = F(FID_canopy_fhv); p.fh = F(FID_canopy_fh);
+  p.qcan = F(FID_rad_qcan); p.qssabs = F(FID_rad_qssabs); p.flws = F(FID_rad_flws);
+  p.wbtot = (const double *)dev_ptr(h, FID_ssnow_wbtot, 0); p.fevc = (const double *)dev_ptr(h, FID_canopy_fevc, 0);
+  p.fes = (const double *)dev_ptr(h, FID_canopy_fes, 0);
+  post_step_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(p, h->drv.arr, h->mp, ktau, kstart, dels, do_mass_bal, do_energy_bal);
+  CUDA_TRY(cudaGetLastError());
+  h->ctr.kernel_launches++;
+  return CABLE_OK;
+}
+
+int cable_b200_output_plan(cable_handle *h, int nrows, const int *field_id, const int *comp, const int *method,
+                           const float *scale, const float *div, const float *offset) {
+  if (!h || !h->drv.on) return fail(CABLE_E_ARG, "output_plan: call cable_b200_driver_init first");
+  if (nrows <= 0 || !field_id || !comp || !method) return fail(CABLE_E_ARG, "output_plan: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  auto &v = h->drv;
+  std::vector<OutRow> rows(nrows);
+  for (int r = 0; r < nrows; r++) {
+    OutRow &o = rows[r];
+    if (method[r] < CABLE_AGG_POINT || method[r] > CABLE_AGG_MAX) return fail(CABLE_E_ARG, "output_plan: unknown aggregation method");
+    o.method = method[r]; o.scale = scale ? scale[r] : 1.0f; o.div = div ? div[r] : 1.0f; o.offset = offset ? offset[r] : 0.0f;
+    if (field_id[r] >= 0) {
+      if (field_id[r] >= NFIELDS) return fail(CABLE_E_ARG, "output_plan: unknown field");
+      const cable_field_info &f = g_fields[field_id[r]];
+      if ((f.flags & CABLE_FLAG_HOSTONLY) || f.role == FORCING || comp[r] < 0 || comp[r] >= f.n1 * f.n2)
+        return fail(CABLE_E_ARG, std::string("output_plan: not a resident field component: ") + f.name);
+      if (f.role == DIAG && !(f.flags & CABLE_FLAG_STAR) && h->cfg.output_level < 2)
+        return fail(CABLE_E_ARG, std::string("output_plan: ") + f.name + " is only written at output_level 2");
+      o.dtype = f.dtype;
+      o.src = (const char *)dev_ptr(h, field_id[r], 0) + (size_t)comp[r] * h->mp * elem_size(f.dtype);
+    } else {
+      const int k = -field_id[r] - 1;
+      if (k >= N_DRV || comp[r] != 0) return fail(CABLE_E_ARG, "output_plan: unknown driver array");
+      o.dtype = g_drv_names[k].f64 ? CABLE_DT_F64 : CABLE_DT_F32;
+      o.src = drv_ptr(h, k);
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute)); CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+  cudaFree(v.d_rows); cudaFree(v.d_agg); cudaFree(v.d_out[0]); cudaFree(v.d_out[1]);
+  v.d_rows = nullptr; v.d_agg = nullptr; v.d_out[0] = v.d_out[1] = nullptr;
+  CUDA_TRY(cudaMalloc(&v.d_rows, nrows * sizeof(OutRow)));
+  CUDA_TRY(cudaMemcpy(v.d_rows, rows.data(), nrows * sizeof(OutRow), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&v.d_agg, (size_t)nrows * h->mp * sizeof(double)));
+  for (int b = 0; b < 2; b++) CUDA_TRY(cudaMalloc(&v.d_out[b], (size_t)nrows * v.nland * sizeof(float)));
+  v.rows = rows; v.agg_counter = 0; v.out_buf = 0;
+  aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, h->mp);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
+int cable_b200_output_accumulate(cable_handle *h) {
+  if (!h || !h->drv.on || h->drv.rows.empty()) return fail(CABLE_E_ARG, "output_accumulate: no output plan");
+  CUDA_TRY(cudaSetDevice(h->device));
+  auto &v = h->drv;
+  aggregate_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, (int)v.rows.size(), v.d_agg, h->mp, v.agg_counter);
+  CUDA_TRY(cudaGetLastError());
+  v.agg_counter++;
+  h->ctr.kernel_launches++;
+  return CABLE_OK;
+}
+
+int cable_b200_output_fetch_async(cable_handle *h, float *host_out) {
+  if (!h || !h->drv.on || h->drv.rows.empty() || !host_out) return fail(CABLE_E_ARG, "output_fetch_async: no output plan / null buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  auto &v = h->drv;
+  const int nrows = (int)v.rows.size(), b = v.out_buf;
+  // the D2H that last used this staging buffer must have drained
+  CUDA_TRY(cudaStreamWaitEvent(h->s_compute, v.ev_out_free[b], 0));
+  const dim3 grid((v.nland + 127) / 128, nrows);
+  output_reduce_kernel<<<grid, 128, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, v.agg_counter > 0 ? 1 : 0, v.d_patchfrac,
+                                                       v.d_cstart, v.d_cend, v.nland, h->mp, v.d_out[b]);
+  CUDA_TRY(cudaGetLastError());
+  h->ctr.kernel_launches++;
+  if (v.agg_counter > 0) {
+    aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, h->mp);
+    CUDA_TRY(cudaGetLastError());
+    h->ctr.kernel_launches++;
+    v.agg_counter = 0;
+  }
+  CUDA_TRY(cudaEventRecord(v.ev_reduced, h->s_compute));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, v.ev_reduced, 0));
+  const size_t bytes = (size_t)nrows * v.nland * sizeof(float);
+  CUDA_TRY(cudaMemcpyAsync(host_out, v.d_out[b], bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+  CUDA_TRY(cudaEventRecord(v.ev_out_free[b], h->s_d2h));
+  h->ctr.d2h_bytes += (long long)bytes;
+  v.out_buf ^= 1;
+  return CABLE_OK;
+}
+
+int cable_b200_output_wait(cable_handle *h) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+  return CABLE_OK;
+}
+
+int cable_b200_driver_download(cable_handle *h, const char *name, void *host) {
+  if (!h || !h->drv.on || !host) return fail(CABLE_E_ARG, "driver_download: bad argument");
+  const int k = cable_b200_driver_field_id(name);
+  if (k < 0) return fail(CABLE_E_ARG, std::string("driver_download: unknown driver array ") + (name ? name : "(null)"));
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaMemcpy(host, drv_ptr(h, k), (size_t)h->mp * (g_drv_names[k].f64 ? 8 : 4), cudaMemcpyDeviceToHost));
   return CABLE_OK;
 }
 

@@ -4,7 +4,7 @@
 // path evaluates them in fp64 to <= ~2 ulp(fp64) and rounds ONCE to fp32, i.e. the correctly rounded fp32
 // result except when the exact value lies within ~1e-16 (relative) of an fp32 rounding boundary -- about
 // one argument in 10^8.  These are the same values (float)exp((double)x) etc. give, which is how the CR
-// build of the oracle evaluates them (oracle/oracle.hpp), at ~1/3 of the instructions of CUDA's general fp64
+// build of the test oracle evaluates them, at ~1/3 of the instructions of CUDA's general fp64
 // routines: the arguments are fp32, so no fp64 overflow/denormal/huge-argument paths are needed, and the
 // kernels' instruction footprint (they are instruction-cache bound) shrinks accordingly.
 //

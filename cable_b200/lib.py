@@ -54,7 +54,20 @@ EXPORTS = [
     "cable_b200_step", "cable_b200_cbm", "cable_b200_sync", "cable_b200_device_ptr",
     "cable_b200_compute_stream", "cable_b200_profile", "cable_b200_get_counters",
     "cable_b200_reset_counters", "cable_b200_grid_reduce",
+    # driver stages either side of cbm()
+    "cable_b200_driver_init", "cable_b200_set_met_async", "cable_b200_upload_lai", "cable_b200_post_step",
+    "cable_b200_output_plan", "cable_b200_driver_field_id", "cable_b200_output_accumulate",
+    "cable_b200_output_fetch_async", "cable_b200_output_wait", "cable_b200_driver_download",
 ]
+
+MET_ROWS = ("SWdown", "Tair", "Qair", "PSurf", "Wind", "Rainf", "Snowf", "LWdown", "CO2air", "hod", "doy")
+AGG = {"point": 0, "mean": 1, "sum": 2, "min": 3, "max": 4}
+
+
+class MetConvert(C.Structure):
+    """Mirror of `struct cable_met_convert` (cable_input.F90:1053-1209 convert%*)."""
+    _fields_ = [("tair_offset", C.c_float), ("psurf_scale", C.c_float), ("rainf_scale", C.c_float),
+                ("co2_scale", C.c_float), ("snowf_from_tair", C.c_int)]
 
 _lib = None
 
@@ -94,6 +107,16 @@ def load() -> C.CDLL:
     lib.cable_b200_get_counters.argtypes = [H, C.POINTER(Counters)]
     lib.cable_b200_reset_counters.argtypes = [H]
     lib.cable_b200_grid_reduce.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.cable_b200_driver_init.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cable_b200_set_met_async.argtypes = [H, C.c_int, C.c_void_p, C.POINTER(MetConvert)]
+    lib.cable_b200_upload_lai.argtypes = [H]
+    lib.cable_b200_post_step.argtypes = [H, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int]
+    lib.cable_b200_output_plan.argtypes = [H, C.c_int] + [C.c_void_p] * 6
+    lib.cable_b200_driver_field_id.argtypes = [C.c_char_p]
+    lib.cable_b200_output_accumulate.argtypes = [H]
+    lib.cable_b200_output_fetch_async.argtypes = [H, C.c_void_p]
+    lib.cable_b200_output_wait.argtypes = [H]
+    lib.cable_b200_driver_download.argtypes = [H, C.c_char_p, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is None and name != "cable_b200_default_cfg":

@@ -306,7 +306,8 @@ class Forcing:
         hod = (sub + 0.5) * self.dels / 3600.0
         return doy, hod
 
-    def fill(self, T: dict[str, np.ndarray], step: int) -> None:
+    def _land(self, step: int) -> dict[str, np.ndarray]:
+        """Per-land-point forcing of step `step` (what one time slice of a gridded met file holds)."""
         g, f = self.g, np.float32
         doy, hod = self.time_of(step)
         day = step // self.steps_per_day
@@ -339,6 +340,33 @@ class Forcing:
         wet = rs.random(n) < 0.30 * cloud ** 2                                          # ~0.12 on average, under cloud
         precip = np.where(wet, rs.exponential(0.5 * self.dels / 1800.0, n), 0.0).astype(np.float32)
         precip_sn = np.where(tair <= TFRZ, precip, f(0.0)).astype(np.float32)    # cable_input.F90:2666-2671
+        return dict(sw=sw, tair=tair, pmb=pmb, qv=qv, ua=ua, precip=precip, precip_sn=precip_sn, fld=fld, coszen=coszen,
+                    doy=doy, lst=lst)
+
+    def land_slice(self, step: int, out: np.ndarray | None = None) -> np.ndarray:
+        """One time slice in met-file (ALMA) units, rows = cable_b200.lib.MET_ROWS: the input of
+        cable_b200_set_met_async.  PSurf in Pa, Rainf in kg/m2/s, no Snowf variable (derived from Tair), CO2 in ppm."""
+        L = self._land(step)
+        f = np.float32
+        if out is None:
+            out = np.empty((11, self.g.nland), np.float32)
+        out[0] = L["sw"]; out[1] = L["tair"]; out[2] = L["qv"]; out[3] = L["pmb"] * f(100.0); out[4] = L["ua"]
+        out[5] = L["precip"] / f(self.dels); out[6] = 0.0; out[7] = L["fld"]; out[8] = f(350.0); out[9] = L["lst"]
+        out[10] = f(L["doy"])
+        return out
+
+    def lai(self, step: int) -> np.ndarray:
+        f = np.float32
+        doy, _ = self.time_of(step)
+        lai = self.laimax * (f(0.55) + f(0.45) * np.cos(f(2 * np.pi) * (f(doy) - self.peak) / f(365.0)))
+        lai[self.iveg >= 14] = 0.0                                                # cable_serial.F90:575
+        return lai.astype(np.float32)
+
+    def fill(self, T: dict[str, np.ndarray], step: int) -> None:
+        g, f = self.g, np.float32
+        L = self._land(step)
+        sw, tair, pmb, qv, ua, precip, precip_sn, fld, coszen, doy = (L[k] for k in
+            ("sw", "tair", "pmb", "qv", "ua", "precip", "precip_sn", "fld", "coszen", "doy"))
         t2l = g.tile2land
         T["met_fsd"][0] = (f(0.5) * sw)[t2l]                                      # cable_input.F90:1880-1883
         T["met_fsd"][1] = (f(0.5) * sw)[t2l]
@@ -353,9 +381,7 @@ class Forcing:
         T["met_coszen"][0] = coszen[t2l]
         T["met_doy"][0] = f(doy)
         T["met_tvrad"][0] = T["met_tk"][0]
-        lai = self.laimax * (f(0.55) + f(0.45) * np.cos(f(2 * np.pi) * (f(doy) - self.peak) / f(365.0)))
-        lai[self.iveg >= 14] = 0.0                                                # cable_serial.F90:575
-        T["veg_vlai"][0] = lai.astype(np.float32)
+        T["veg_vlai"][0] = self.lai(step)
 
 
 FORCING_FIELDS = [f.name for f in FIELDS if f.role == 1 and not (f.flags & 8)]

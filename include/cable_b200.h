@@ -206,6 +206,99 @@ int          cable_b200_grid_reduce(cable_handle *h, int field_id, int comp,
                                     const int *d_cstart, const int *d_cend,
                                     int nland, float *d_out);
 
+/* ---------------------------------------------------------------------------
+ * Driver stages either side of cbm(), kept on the device.
+ * They replace, for a caller that wants them, the per-tile host loops of the
+ * offline drivers; cbm()'s own interface above is unchanged.
+ *
+ *   before the step  get_met_data's tile expansion + unit conversion + sinbet
+ *                    (src/offline/cable_input.F90:1880-1883, 2139-2213,
+ *                    2666-2680; src/science/radiation/cbl_sinbet.F90:12-28)
+ *   after the step   cable_serial.F90:602-608 (runoff*dels, daily tscrn max/min),
+ *                    sumcflux (src/science/casa-cnp/casa_sumcflux.F90:76-102),
+ *                    mass_balance / energy_balance (src/offline/cable_checks.F90:
+ *                    472-618), the output module's time aggregators
+ *                    (src/util/aggregator.F90:585-1172) and patch -> grid-cell
+ *                    reduction (src/util/cable_grid_reductions.F90:49-75).
+ * ------------------------------------------------------------------------- */
+
+/* rows of the per-land-point forcing block: float met_land[CABLE_MET_NROWS][nland],
+ * in the units of the met file (ALMA): SWdown W/m2, Tair K or degC, Qair kg/kg,
+ * PSurf Pa|hPa|kPa, Wind m/s, Rainf and Snowf kg/m2/s or mm/h, LWdown W/m2,
+ * CO2air ppm, then local hour of day and day of year of the land point
+ * (met%hod, met%doy -- the calendar itself stays on the host).               */
+#define CABLE_MET_SWDOWN 0
+#define CABLE_MET_TAIR   1
+#define CABLE_MET_QAIR   2
+#define CABLE_MET_PSURF  3
+#define CABLE_MET_WIND   4
+#define CABLE_MET_RAINF  5
+#define CABLE_MET_SNOWF  6
+#define CABLE_MET_LWDOWN 7
+#define CABLE_MET_CO2    8
+#define CABLE_MET_HOD    9
+#define CABLE_MET_DOY    10
+#define CABLE_MET_NROWS  11
+
+typedef struct cable_met_convert {   /* cable_input.F90:1053-1209: convert%*     */
+  float tair_offset;                 /* 0 (K) or 273.16 (degC)                   */
+  float psurf_scale;                 /* 0.01 (Pa), 1 (hPa), 10 (kPa)             */
+  float rainf_scale;                 /* dels (kg/m2/s) or dels/3600 (mm/h)       */
+  float co2_scale;                   /* 1e-6: ppm -> mol/mol                     */
+  int   snowf_from_tair;             /* 1: file has no (or an all-zero) Snowf:
+                                        precip_sn = precip where tk <= tfrz      */
+} cable_met_convert;
+
+/* aggregation methods of the output module (aggregator.F90) */
+#define CABLE_AGG_POINT 0
+#define CABLE_AGG_MEAN  1
+#define CABLE_AGG_SUM   2
+#define CABLE_AGG_MIN   3
+#define CABLE_AGG_MAX   4
+
+/* Decomposition of this shard: tiles of land point l are cstart[l]..cend[l]
+ * (0-based, inclusive; landpt(l)%cstart-1 / %cend-1), patchfrac = patch(:)%frac,
+ * latitude = rad%latitude (per tile).  Allocates the driver-owned arrays
+ * (bal%*, sum_flux%*, canopy%tscrn_{max,min}_daily).                          */
+int          cable_b200_driver_init(cable_handle *h, int nland, const int *cstart,
+                                    const int *cend, const float *patchfrac,
+                                    const float *latitude);
+
+/* Asynchronous H2D of one time slice of per-land-point forcing (pinned host
+ * memory recommended) into ring slot `slot`, expanded to the tiles' met%* and
+ * coszen on the device; replaces set_forcing_async for that slot.  veg%vlai
+ * is not part of the slice: cable_b200_upload_lai copies the bound veg%vlai
+ * to every slot (monthly, cable_input.F90:2377).                             */
+int          cable_b200_set_met_async(cable_handle *h, int slot, const float *met_land,
+                                      const cable_met_convert *cv);
+int          cable_b200_upload_lai(cable_handle *h);
+
+/* The statements between CALL cbm and the output module, for the step just
+ * enqueued (stream ordered after it).  ktau/kstart as in cable_serial;
+ * do_mass_bal / do_energy_bal = check%mass_bal / check%energy_bal.            */
+int          cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels,
+                                  int do_mass_bal, int do_energy_bal);
+
+/* Output plan: nrows rows, each one component of a field sampled as
+ * scale*x/div + offset and aggregated in time with `method`.  field_id >= 0 is
+ * a registry field; field_id = -(1+k) is driver array k (cable_b200_driver_field_id). */
+int          cable_b200_output_plan(cable_handle *h, int nrows, const int *field_id,
+                                    const int *comp, const int *method,
+                                    const float *scale, const float *div,
+                                    const float *offset);
+int          cable_b200_driver_field_id(const char *name);   /* k >= 0, or < 0 */
+/* sample the plan's sources once (aggregator%accumulate of every row) */
+int          cable_b200_output_accumulate(cable_handle *h);
+/* end of an output interval: reduce every row patch -> grid cell on the device,
+ * start the D2H of the [nrows][nland] float block into host_out (async, own
+ * stream, double buffered) and reset the aggregators.  With exactly one sample
+ * per interval (output%averaging='all') call it WITHOUT output_accumulate: the
+ * rows are sampled and reduced in one pass.                                    */
+int          cable_b200_output_fetch_async(cable_handle *h, float *host_out);
+int          cable_b200_output_wait(cable_handle *h);
+/* copy a driver array (float, or double for "bal_owb") to the host; synchronous */
+int          cable_b200_driver_download(cable_handle *h, const char *name, void *host);
+
 #ifdef __cplusplus
 }
 #endif

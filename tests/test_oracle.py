@@ -137,3 +137,86 @@ def test_oracle_single_tile_site_config():
         o.cbm(k + 1, 1800.0)
         assert np.isfinite(T["canopy_fe"][0, 0]) and 200 < T["ssnow_tss"][0, 0] < 340
     assert -100 < T["canopy_fh"][0, 0] < 700
+
+
+# ---- driver stages (oracle/o_driver.cpp) ---------------------------------------------------------------------------
+def test_sinbet_known_answers():
+    """cbl_sinbet.F90:12-28: equinox noon at the equator ~ 1, polar night clamps to 1e-8, symmetric about noon."""
+    from oracle import pyoracle
+    assert abs(pyoracle.sinbet(81.0, 0.0, 12.0) - 1.0) < 2e-3          # ~21 March: declination ~ 0
+    assert pyoracle.sinbet(355.0, 80.0, 12.0) == np.float32(1e-8)      # polar night
+    assert pyoracle.sinbet(172.0, 23.45, 12.0) > 0.9999                # solstice, sun overhead the tropic
+    assert abs(pyoracle.sinbet(100.0, -35.0, 9.0) - pyoracle.sinbet(100.0, -35.0, 15.0)) < 1e-6
+    # the numpy generator used for the synthetic forcing implements the same formula
+    for doy, lat, hod in ((1.0, -60.0, 3.0), (200.0, 45.0, 17.5), (300.0, 10.0, 11.0)):
+        assert abs(pyoracle.sinbet(doy, lat, hod) - float(synth.sinbet(doy, np.float32(lat), np.float32(hod)))) < 2e-6
+
+
+def test_met_expand_reproduces_per_tile_forcing_and_snow_rule():
+    from oracle import pyoracle
+    cfg, grid, T, F = make_case(400)
+    land = F.land_slice(5)
+    names = ("met_fsd", "met_tk", "met_pmb", "met_qv", "met_ua", "met_precip", "met_precip_sn", "met_fld", "met_ca", "met_coszen", "met_doy")
+    out = {k: np.zeros_like(T[k]) for k in names}
+    pyoracle.met_expand(out, land, grid.cstart, grid.cend, grid.lat[grid.tile2land], 0.0, 0.01, DELS, 1e-6, True)
+    F.fill(T, 5)
+    assert np.array_equal(out["met_tk"], T["met_tk"]) and np.array_equal(out["met_fsd"], T["met_fsd"])
+    np.testing.assert_allclose(out["met_precip"], T["met_precip"], rtol=2e-7)
+    np.testing.assert_allclose(out["met_coszen"], T["met_coszen"], rtol=2e-6, atol=1e-7)
+    cold = out["met_tk"][0] <= 273.16                                   # cable_input.F90:2666-2673
+    assert np.array_equal(out["met_precip_sn"][0][cold], out["met_precip"][0][cold]) and not out["met_precip_sn"][0][~cold].any()
+    # a file that carries Snowf: Rainf + Snowf is the total, Snowf is honoured
+    land2 = land.copy(); land2[6] = 0.25 * land[5]
+    pyoracle.met_expand(out, land2, grid.cstart, grid.cend, grid.lat[grid.tile2land], 0.0, 0.01, DELS, 1e-6, False)
+    l0 = int(np.argmax(land[5] > 0))
+    i0 = int(grid.cstart[l0])
+    assert out["met_precip"][0][i0] == np.float32((land2[5][l0] + land2[6][l0]) * np.float32(DELS))
+    assert out["met_precip_sn"][0][i0] == np.float32(land2[6][l0] * np.float32(DELS))
+
+
+def test_aggregators_and_grid_reduce_known_answers():
+    """aggregator.F90: mean of a constant is the constant, running mean == arithmetic mean, min/max/sum/point;
+    grid reduce of ones is the sum of patch fractions (= 1)."""
+    from oracle import pyoracle
+    rng = np.random.default_rng(7)
+    xs = [rng.normal(10.0, 3.0, 1000).astype(np.float32) for _ in range(8)]
+    for method, ref in ((1, np.mean(xs, axis=0)), (2, np.sum(xs, axis=0)), (3, np.min(xs, axis=0)), (4, np.max(xs, axis=0)), (0, xs[-1])):
+        agg = np.zeros(1000)
+        if method == 3: agg[:] = np.finfo(np.float32).max
+        if method == 4: agg[:] = -np.finfo(np.float32).max
+        for k, x in enumerate(xs):
+            pyoracle.aggregate(x, method, agg, k)
+        np.testing.assert_allclose(agg, ref, rtol=1e-5)
+    agg = np.zeros(10); c = np.full(10, 3.25, np.float64)
+    for k in range(5):
+        pyoracle.aggregate(c, 1, agg, k, scale=2.0, div=4.0, offset=1.0)
+    assert np.all(agg == 3.25 * 2.0 / 4.0 + 1.0)
+    grid = synth.make_grid(50, 5)
+    ones = pyoracle.grid_reduce(np.ones(grid.mp, np.float32), grid.patchfrac, grid.cstart, grid.cend)
+    np.testing.assert_allclose(ones, 1.0, rtol=3e-7)
+
+
+def test_post_step_closure_and_bookkeeping():
+    """mass_balance / energy_balance (cable_checks.F90:472-618) on oracle output: per-step closure is small, the
+    cumulative sums start after ktau > 10, sum_flux accumulates fpn*dels, runoff is scaled by dels exactly once."""
+    from oracle.pyoracle import Oracle, OracleDriver
+    cfg, grid, T, F = make_case(300)
+    o = Oracle(T, cfg, cr_math=True)
+    d = OracleDriver(o)
+    sumpn = np.zeros(grid.mp, np.float32)
+    for k in range(14):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        runoff_rate = T["ssnow_runoff"][0].copy()
+        d.post_step(k + 1, 1, DELS)
+        assert np.array_equal(T["ssnow_runoff"][0], runoff_rate * np.float32(DELS))
+        sumpn = T["canopy_fpn"][0] * np.float32(DELS) if k == 0 else sumpn + T["canopy_fpn"][0] * np.float32(DELS)
+        assert np.array_equal(d.arrays["sumpn"], sumpn)
+        ok = T["veg_iveg"][0] < 16
+        assert np.abs(d.arrays["ebal"]).max() < 5e-3 and np.abs(d.arrays["radbal"]).max() < 5e-3
+        if k > 0:       # ktau == 1 sets owb = wbtot AFTER the step (cable_checks.F90:503-507): delwb = 0, wbal is not a balance
+            assert np.abs(d.arrays["wbal"][ok]).max() < 2e-2
+        if k + 1 <= 10:
+            assert not d.arrays["wbal_tot"].any() and not d.arrays["precip_tot"].any()
+    assert d.arrays["precip_tot"].any()
+    assert np.array_equal(T["canopy_fnee"][0], T["canopy_fpn"][0] + T["canopy_frs"][0] + T["canopy_frp"][0])
