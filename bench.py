@@ -61,6 +61,26 @@ def measured_peak_hbm() -> tuple[float, str]:
         return 6650.0, "fallback"
 
 
+def profiled_metrics() -> dict | None:
+    """Per-launch DRAM traffic and pipe utilisation of the two step kernels from the committed `ncu --set full`
+    capture (profiles/, written by tools/ncu_metrics_json.py) -- attached to the roofline object, never measured here."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as fh:
+            m = json.load(fh)
+        ks = m["kernels"]
+        return {"file": os.path.relpath(files[-1], ROOT), "tiles": m.get("tiles"),
+                "traffic_bytes_per_step": sum(k["dram_bytes"] for k in ks),
+                "kernels": [{k2: k[k2] for k2 in ("kernel", "duration_ms", "dram_bytes", "issue_active_pct", "pipe_fp64_pct",
+                                                    "pipe_fma_fp32_pct", "pipe_alu_pct", "pipe_xu_pct", "dram_pct_of_peak",
+                                                    "active_threads_per_warp_inst", "icache_hit_pct")} for k in ks]}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
@@ -181,6 +201,8 @@ def run_b200(args) -> None:
         raise SystemExit("bench.py needs a CUDA device: cable_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, max(args.warmup, 3)
 
@@ -371,6 +393,10 @@ def run_b200(args) -> None:
     if rank == 0:
         peak, which = measured_peak_hbm()
         achieved = ALGO_BYTES_PER_TILE_STEP * mp / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+        prof = profiled_metrics()
+        traffic = None
+        if prof and prof.get("tiles") == mp:
+            traffic = prof["traffic_bytes_per_step"]
         line = {
             "metric": "tile-timesteps/sec for cbm()", "value": value, "unit": "tile-timesteps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": t_res / K * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -381,10 +407,18 @@ def run_b200(args) -> None:
                        "l2": "per-step working set (state+params+forcing ~ 0.2 GB) exceeds the 126 MB L2; no flush needed",
                        "forcing_ring_steps": RING, "outputs_finite": finite},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "kernel_ms": kern_ms,
+                         "traffic": traffic, "peak_source": which, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_tile_step": ALGO_BYTES_PER_TILE_STEP,
-                         "note": "arithmetic/latency-bound kernel (fp64 islands + ~300 transcendentals per tile-step); "
-                                 "HBM fraction is reported because it is the official denominator"},
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_TILE_STEP * mp,
+                         "launch": "one step = kernel A (surface+canopy) + kernel B (soil/snow/carbon) over all tiles; kernel_ms is "
+                                   "the pair, timed with CUDA events on the library's compute stream",
+                         "ncu": prof,
+                         "note": "instruction-issue / latency-bound step (fp64 islands, ~300 correctly rounded transcendentals "
+                                 "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 46 %, FP64 pipe 18-26 %, "
+                                 "DRAM 5-22 % in the ncu capture; the HBM fraction is reported because it is the official "
+                                 "denominator.  traffic > algorithmic bytes: per-tile parameter arrays of the reference "
+                                 "interface (230 B/tile), driver-visible diagnostics (336 B/tile at output_level=1), the A->B "
+                                 "exchange (132 B/tile) and register-spill write-backs"},
             "e2e": {"value": e2e, "unit": "tile-timesteps/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "steps": Ke, "gpu_launches": e2e_launches, "outputs_finite": e2e_finite, "output_rows": len(rows),
                     "api": "offline driver loop through the C ABI, host buffers: cable_b200_set_met_async (met slice H2D + "

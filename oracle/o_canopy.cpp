@@ -358,7 +358,7 @@ static void dryLeaf(Oracle &o, float dels, CanopyWork &w, int iter) {
     float g0_last = 0.f; bool g0_set = false;
     for (int i = 0; i < mp; i++) {
       if (f.canopy_vlaiw[i] > CLAI_THRESH && abs_deltlf[i] > 0.1f) {                      // :243
-        if (!o.dbg_kiter.empty()) o.dbg_kiter[i]++;
+        if (!o.dbg_kiter.empty()) o.dbg_kiter[(size_t)i + (size_t)mp * (iter - 1)]++;   // passes of tile i in stability iteration `iter`
         w.ghwet[i] = 2.0f * sum_gbh[i];
         gwwet[i] = 1.075f * sum_gbh[i];
         ghrwet[i] = (float)(w.sum_rad_gradis[i] + w.ghwet[i]);

@@ -37,11 +37,12 @@ int oracle_cbm(void *h, int ktau, float dels) {
   return 0;
 }
 
-// profiling aid: enable / read / reset the per-tile count of dryLeaf passes
+// profiling aid: enable / read / reset the per-tile count of dryLeaf passes, one row per stability iteration: out[NITER][mp]
 void oracle_debug_kiter(void *h, int *out) {
   Oracle *o = (Oracle *)h;
-  if (o->dbg_kiter.empty()) { o->dbg_kiter.assign(o->mp, 0); return; }
-  if (out) for (int i = 0; i < o->mp; i++) out[i] = o->dbg_kiter[i];
+  const size_t n = (size_t)o->mp * CABLE_NITER;
+  if (o->dbg_kiter.empty()) { o->dbg_kiter.assign(n, 0); return; }
+  if (out) for (size_t i = 0; i < n; i++) out[i] = o->dbg_kiter[i];
   std::fill(o->dbg_kiter.begin(), o->dbg_kiter.end(), 0);
 }
 

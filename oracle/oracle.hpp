@@ -48,7 +48,7 @@ struct Oracle {
   Fields f;
   int ktau_soil_snow;   // INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   long long n_dryleaf_warn;
-  std::vector<int> dbg_kiter;   // per tile: dryLeaf passes executed in the last step (profiling aid for the device design)
+  std::vector<int> dbg_kiter;   // [NITER][mp]: dryLeaf passes executed in the last step (profiling aid for the device design)
 };
 
 // ---- constants: src/params/cable_phys_constants_mod.F90:24-86 ---------------

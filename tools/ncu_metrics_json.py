@@ -1,0 +1,35 @@
+"""ncu report -> profiles/<tag>_ncu_metrics.json (what bench.py attaches to its roofline object).
+usage: python tools/ncu_metrics_json.py rep.ncu-rep profiles/r01_ncu_metrics.json"""
+import csv, io, json, subprocess, sys
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, data = rows[0], rows[2:]
+def col(r, name):
+    try: return float(r[hdr.index(name)].replace(",", ""))
+    except Exception: return None
+U = hdr.index
+kernels = []
+for r in data:
+    unit = {n: rows[1][U(n)] for n in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum")}
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    tscale = {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0, "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9, "second": 1.0}
+    kernels.append({
+        "kernel": r[U("Kernel Name")][:48],
+        "duration_ms": col(r, "gpu__time_duration.sum") * tscale.get(unit["gpu__time_duration.sum"], 1e-3) * 1e3,
+        "dram_bytes": col(r, "dram__bytes_read.sum") * scale[unit["dram__bytes_read.sum"]] + col(r, "dram__bytes_write.sum") * scale[unit["dram__bytes_write.sum"]],
+        "issue_active_pct": col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "pipe_fp64_pct": col(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        "pipe_fma_fp32_pct": col(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "pipe_alu_pct": col(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+        "pipe_xu_pct": col(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+        "dram_pct_of_peak": col(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "warp_inst_executed": col(r, "smsp__inst_executed.sum"),
+        "active_threads_per_warp_inst": col(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "icache_hit_pct": col(r, "sm__icc_request_hit_rate.pct"),
+        "registers_per_thread": col(r, "launch__registers_per_thread"),
+        "block_size": col(r, "launch__block_size"), "grid_size": col(r, "launch__grid_size"),
+    })
+json.dump({"source": rep.split("/")[-1], "command": "ncu --set full --clock-control none -k regex:cbm_kernel -s 20 -c 2 python tools/quick_perf.py 62000 12",
+           "tiles": 310000, "kernels": kernels}, open(out, "w"), indent=1)
+print(open(out).read()[:1500])
