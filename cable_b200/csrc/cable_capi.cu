@@ -18,6 +18,15 @@
 
 using namespace cbl;
 
+// scratch rows / shared memory of kernel A's dryLeaf pass pool (0 when the pool is compiled out)
+#if CBL_COMPACT
+constexpr int SD_ROWS = SD_ND, SF_ROWS = SF_NF;
+constexpr size_t pool_smem_bytes(int block) { return leaf_pool_smem_bytes(block); }
+#else
+constexpr int SD_ROWS = 1, SF_ROWS = 1;
+constexpr size_t pool_smem_bytes(int) { return 0; }
+#endif
+
 // occupancy targets of the three kernel variants (tuned on B200); build-time so that only the
 // variants that ship are compiled
 #ifndef CBL_MINB_A
@@ -111,6 +120,7 @@ struct cable_handle {
   std::vector<cudaEvent_t> ev_forcing_ready, ev_slot_free;
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
+  double *leaf_scr_d = nullptr; float *leaf_scr_f = nullptr;   // dryLeaf pass-pool scratch (kernel A)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
   int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148;
@@ -157,6 +167,7 @@ DevPtrs make_ptrs(const cable_handle *h, int slot) {
 #define CABLE_FA(T, m, ct, n1, n2, role, flags) d.T##_##m = (ct *)dev_ptr(h, id, slot); id++;
 #include "../../include/cable_b200_fields.def"
   // met%tvair doubles as an opt-in input: when uploaded it lives in its DIAG block (slot independent)
+  d.leaf_scr_d = h->leaf_scr_d; d.leaf_scr_f = h->leaf_scr_f;
   return d;
 }
 
@@ -188,7 +199,13 @@ int launch_range(cable_handle *h, const DevPtrs &d, float dels, int first, int i
   if (i1 <= i0) return CABLE_OK;
   // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
   // CBL_MINB_x = resident blocks per SM the compiler must allow (register cap 65536 / (BLOCK*MINB)).
-#define CBL_LAUNCH(PH, BL, MB, LV) cbm_kernel<PH, BL, MB, LV><<<(i1 - i0 + (BL) - 1) / (BL), BL, 0, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn)
+#define CBL_LAUNCH(PH, BL, MB, LV) {                                                                                        \
+    const size_t sm_ = ((PH) & 1) ? pool_smem_bytes(BL) : 0;                                                                 \
+    if (sm_ > 48 * 1024) {                                                                                                     \
+      static bool once_ = false;   /* per instantiation */                                                                    \
+      if (!once_) { CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); once_ = true; } \
+    }                                                                                                                          \
+    cbm_kernel<PH, BL, MB, LV><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn); }
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
   switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
   if (h->split) {
@@ -358,6 +375,10 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
   if (e != cudaSuccess) { delete h; return fail(CABLE_E_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   cudaMemset(h->arena, 0, h->arena_bytes);
+  cudaMalloc(&h->leaf_scr_d, (size_t)mp * SD_ROWS * sizeof(double));
+  cudaMalloc(&h->leaf_scr_f, (size_t)mp * SF_ROWS * sizeof(float));
+  cudaMemset(h->leaf_scr_d, 0, (size_t)mp * SD_ROWS * sizeof(double));
+  cudaMemset(h->leaf_scr_f, 0, (size_t)mp * SF_ROWS * sizeof(float));
   cudaMalloc(&h->d_warn, sizeof(unsigned long long));
   cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
   cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking);
@@ -425,6 +446,7 @@ int cable_b200_destroy(cable_handle *h) {
   for (auto ev : h->ev_chunk_done) cudaEventDestroy(ev);
   if (h->drv.on) driver_free(h);
   if (h->d_warn) cudaFree(h->d_warn);
+  cudaFree(h->leaf_scr_d); cudaFree(h->leaf_scr_f);
   if (h->arena) cudaFree(h->arena);
   delete h;
   return CABLE_OK;

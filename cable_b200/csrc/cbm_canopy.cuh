@@ -222,210 +222,380 @@ struct CanopyWork {
   float  sum_rniso, sum_gradis;
   float  dleaf3;            // veg%dleaf**3.0, the same every pass
   int    warn;
+  bool   valid;             // false: this thread only shadows a tile (range tail), it must not publish anything
 };
 
-// dryLeaf: cbl_dryLeaf.F90:10-666, one tile
-CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int iter) {
+// ---- dryLeaf: cbl_dryLeaf.F90:10-666 -----------------------------------------------------------------------------
+// Everything one pass of the coupled leaf-temperature / photosynthesis / stomata iteration reads and writes for ONE
+// tile.  Keeping it in one struct lets the same pass code run on the owning thread's registers (CBL_COMPACT=0) or on
+// a record fetched from shared/global memory by whichever thread the block's pass pool hands the tile to (=1).
+struct LeafPass {
+  // constant during one dryLeaf call
+  float tvair, tk, dva, ca, cmolar, psyc, dsatdk, rlam, fwsoil, fwet, dleaf3, dleaf;
+  float vcmax, frac4, ejmax, conkc0, conko0, ekc, eko, a1gs, d0gs, g1, alpha, convex, cfrd, swilt;
+  float fvlai[2], scalex[2], qcan[2], gradis[2], rniso[2], gswmin[2];
+  double gbhu[2];
+  float froot[K::ms];
+  double wbliq[K::ms];
+  // state carried from pass to pass
+  float tlfx, dsx, abs_deltlf, deltlfy;
+  double csx[2];
+  float gw[2], psycst[2], gswx[2];
+  double evapfbl[K::ms];
+  // results of the latest pass
+  double gbhf[2], ecx;
+  // best iterate so far (:565-582)
+  float tlfy;
+  double rny, hcy, ecy;
+  float rdy[2], an_y[2], oldevapfbl[K::ms];
+};
+
+// One ACTIVE pass k (the reference's loop body for a tile with vlaiw > thresh and |deltlf| > 0.1, :243-560), then the
+// bookkeeping every pass ends with (keep the best iterate, damp after k > 5, :565-606).
+// Returns true while the tile needs another pass; `captured` tells whether the best iterate was replaced.
+CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int k, bool &captured) {
   const float jtomol = 4.6e-6f;
   const float cr = K::capp * K::rmair;
+  const float sum_rniso = p.rniso[0] + p.rniso[1], sum_gradis = p.gradis[0] + p.gradis[1];
+  const float dtair = p.tvair - p.tk;
+  const float fwsoil = p.fwsoil;
+  float gh[2], ghr[2], rdx[2], anx[2];
+  const float tlfx = p.tlfx;
+  // free-convection boundary-layer conductance, total conductances
+  float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - p.tvair) * p.dleaf3);
+  float gras4 = m_pow025(gras);
+  // temperature responses of Vcmax (C3, C4) and Jmax
+  float temp3 = arrhenius_peaked(tlfx, 1.17461f, 73637.0f, 149252.0f, 486.0f) * p.vcmax * (1.0f - p.frac4);
+  float temp4 = xvcmxt4(tlfx - K::tfrz) * p.vcmax * p.frac4;
+  float tempj = arrhenius_peaked(tlfx, 1.16715f, 50300.0f, 152044.0f, 495.0f) * p.ejmax * (1.0f - p.frac4);
+  const float tdiff = tlfx - K::trefk;
+  const float arr = 1.0f - dv(K::trefk, tlfx);
+  float conkct = p.conkc0 * m_exp((p.ekc / (K::rgas * K::trefk)) * arr);
+  float conkot = p.conko0 * m_exp((p.eko / (K::rgas * K::trefk)) * arr);
+  const float tlfxx = tlfx;
+  const float cx1 = conkct * (1.0f + dv(0.21f, conkot));
+  const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
+  float vsum0 = p.fvlai[0] + p.fvlai[1];
+  // stomatal-slope factors that do not depend on the leaf
+  float gs_shared;
+  if (c.gs_switch == CABLE_GS_LEUNING) {
+    gs_shared = dv(p.a1gs, 1.0f + dv(p.dsx, p.d0gs));
+  } else {
+    float vpd = (p.dsx < 50.0f) ? 0.05f : p.dsx * 1E-03f;
+    gs_shared = dv(p.g1 * fwsoil, f_sqrt(vpd));
+  }
+  // sunlit (l = 0) and shaded (l = 1) big leaf: ONE copy of the code, the per-leaf operands are selected on l
+  // (a rolled loop over register arrays; unrolling it doubled the footprint of the hottest loop of the step)
+#pragma unroll 1
+  for (int l = 0; l < 2; l++) {
+    const float fvlai_l = l ? p.fvlai[1] : p.fvlai[0];
+    const float scalex_l = l ? p.scalex[1] : p.scalex[0];
+    const float qcan_l = l ? p.qcan[1] : p.qcan[0];
+    const float gradis_l = l ? p.gradis[1] : p.gradis[0];
+    const float gswmin_l = l ? p.gswmin[1] : p.gswmin[0];
+    const double gbhu_l = l ? p.gbhu[1] : p.gbhu[0];
+    const double csx_l = l ? p.csx[1] : p.csx[0];
+    const double gbhf_l = mx(1.e-6, (double)dv(fvlai_l * p.cmolar * 0.5f * K::dheat * gras4, p.dleaf));
+    const float gh_l = (float)(2.0f * (gbhu_l + gbhf_l));
+    const float ghr_l = gradis_l + gh_l;
+    const float vcmxt3 = scalex_l * temp3, vcmxt4 = scalex_l * temp4, ejmxt3 = scalex_l * tempj;
+    const float par3 = qcan_l * jtomol * (1.0f - p.frac4);
+    const float par4 = qcan_l * jtomol * p.frac4;
+    const float vx3 = mx(0.0f, 0.25f * ejx_root(par3, p.alpha, p.convex, ejmxt3));
+    const float vx4 = mx(0.0f, ejx_root(par4, p.alpha, p.convex, vcmxt4));
+    const float rdx_l = (p.cfrd * vcmxt3 + p.cfrd * vcmxt4);
+    // stomatal slope coefficient
+    float gs_coeff;
+    if (c.gs_switch == CABLE_GS_LEUNING) {
+      gs_coeff = (float)(dv((double)fwsoil, csx_l - (double)0.0f) * (double)gs_shared);
+    } else {
+      gs_coeff = (float)dv((double)(1.0f + gs_shared), csx_l);
+      if (fwsoil <= 0.05f) gs_coeff = (float)dv((double)(dv(fwsoil, 0.05f) + gs_shared), csx_l);
+    }
+    // photosynthesis (cbl_photosynthesis.F90:52-222) for this leaf
+    float an = 0.f;
+    if (vsum0 > K::lai_thresh && fvlai_l > K::lai_thresh) {
+      const double csx = csx_l;
+      const float g0t = dv(gswmin_l * fwsoil, K::rgswc);
+      const double one_m = (double)1.0f - csx * (double)gs_coeff;
+      double coef2 = (double)(g0t + gs_coeff * (vcmxt3 - (rdx_l - vcmxt4)));
+      double coef1 = one_m * (double)(vcmxt3 + vcmxt4 - rdx_l) + (double)g0t * ((double)cx1 - csx)
+                     - (double)(gs_coeff * (vcmxt3 * cx2 / 2.0f + cx1 * (rdx_l - vcmxt4)));
+      double coef0 = -one_m * (double)(vcmxt3 * cx2 / 2.0f + cx1 * (rdx_l - vcmxt4)) - (double)(g0t * cx1) * csx;
+      double anrubisco = an_limited(0, coef2, coef1, coef0, vcmxt3, cx1, cx2, vcmxt4, rdx_l);
+      coef2 = (double)(g0t + gs_coeff * (vx3 - (rdx_l - vx4)));
+      coef1 = one_m * (double)(vx3 + vx4 - rdx_l) + (double)g0t * ((double)cx2 - csx)
+              - (double)(gs_coeff * (vx3 * cx2 / 2.0f + cx2 * (rdx_l - vx4)));
+      coef0 = -one_m * (double)(vx3 * cx2 / 2.0f + cx2 * (rdx_l - vx4)) - (double)(g0t * cx2) * csx;
+      double anrubp = an_limited(1, coef2, coef1, coef0, vx3, cx2, cx2, vx4, rdx_l);
+      const float effc4 = 4000.0f;
+      coef2 = (double)gs_coeff;
+      coef1 = (double)(g0t + gs_coeff * (rdx_l - 0.5f * vcmxt3) + effc4 * vcmxt4)
+              - (double)gs_coeff * csx * (double)effc4 * (double)vcmxt4;
+      coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)dv((rdx_l - 0.5f * vcmxt3) * gswmin_l * fwsoil, K::rgswc);
+      double ansink = an_limited(2, coef2, coef1, coef0, 0.f, 0.f, 0.f, 0.f, 0.f);
+      an = (float)mn(mn(anrubisco, anrubp), ansink);
+    }
+    // leaf-surface CO2, stomatal and total water conductance (:460-485)
+    double csx_n = csx_l;
+    float gswx_n = l ? p.gswx[1] : p.gswx[0];
+    float gw_l = l ? p.gw[1] : p.gw[0];
+    float psycst_l = l ? p.psycst[1] : p.psycst[0];
+    if (fvlai_l > K::lai_thresh) {
+      const double gb = gbhu_l + gbhf_l;
+      csx_n = mx(1.0e-4, (double)p.ca - dv((double)(K::rgbwc * an), gb));
+      gswx_n = mx(1.e-3f, gswmin_l * fwsoil + mx(0.0f, K::rgswc * gs_coeff * an));
+      gw_l = mx((float)dv(1.0f, (double)dv(1.0f, gswx_n) + dv(1.0f, 1.075f * gb)), 0.00001f);
+      psycst_l = p.psyc * dv(ghr_l, gw_l);
+    }
+    if (l == 0) { p.gbhf[0] = gbhf_l; gh[0] = gh_l; ghr[0] = ghr_l; rdx[0] = rdx_l; anx[0] = an; p.csx[0] = csx_n;
+                  p.gswx[0] = gswx_n; p.gw[0] = gw_l; p.psycst[0] = psycst_l; }
+    else        { p.gbhf[1] = gbhf_l; gh[1] = gh_l; ghr[1] = ghr_l; rdx[1] = rdx_l; anx[1] = an; p.csx[1] = csx_n;
+                  p.gswx[1] = gswx_n; p.gw[1] = gw_l; p.psycst[1] = psycst_l; }
+  }
+  // big-leaf latent heat, limited by what the roots can supply (:489-536)
+  double ecx = (double)(dv(p.dsatdk * (p.rniso[0] - cr * dtair * p.gradis[0]) + cr * p.dva * ghr[0], p.dsatdk + p.psycst[0])
+                        + dv(p.dsatdk * (p.rniso[1] - cr * dtair * p.gradis[1]) + cr * p.dva * ghr[1], p.dsatdk + p.psycst[1]));
+  const double local_fevc = (double)((1.0f - p.fwet) * (float)ecx);
+  if (local_fevc > 0.0) {
+    // transp_soil_water (cbl_remove_trans.F90:43-93)
+    double diff = 0.0, s = 0.0;
+    const double demand = dv(local_fevc * (double)dels, (double)K::hl);
+#pragma unroll
+    for (int kk = 0; kk < K::ms; kk++) {
+      double xx = demand * (double)p.froot[kk] + diff;
+      double avail = mx(0.0, p.wbliq[kk] - (double)1.1f * (double)p.swilt) * (double)c.zse[kk] * (double)K::density_liq;
+      double xxd = xx - avail;
+      double e;
+      if (xxd > 0.0) { e = avail; diff = xxd; } else { e = xx; diff = 0.0; }
+      p.evapfbl[kk] = e;
+      s = s + e;
+    }
+    const double fevc = dv(s * (double)p.rlam, (double)dels);
+    ecx = dv(fevc, (double)(1.0f - p.fwet));
+  }
+  p.ecx = ecx;
+  // sensible heat, new leaf temperature, vpd at the leaf surface (:538-557)
+  const float sgh = gh[0] + gh[1], sghr = ghr[0] + ghr[1];
+  const double hcx = dv(((double)sum_rniso - ecx - (double)(cr * dtair * sum_gradis)) * (double)sgh, (double)sghr);
+  p.tlfx = p.tvair + dv((float)hcx, cr * sgh);
+  const double rnx = (double)(sum_rniso - cr * (p.tlfx - p.tk) * sum_gradis);
+  p.dsx = mx(p.dva + p.dsatdk * (p.tlfx - p.tvair), 0.0f);
+  const float deltlf = tlfxx - p.tlfx;
+  p.abs_deltlf = fabsf(deltlf);
+  // keep the best iterate; damp after k > 5 (:565-606)
+  const bool better = p.abs_deltlf < fabsf(p.deltlfy);
+  if (better) p.deltlfy = deltlf;
+  captured = better || k == 1;
+  if (captured) {
+    p.tlfy = p.tlfx; p.rny = rnx; p.hcy = hcx; p.ecy = ecx;
+    p.rdy[0] = rdx[0]; p.rdy[1] = rdx[1]; p.an_y[0] = anx[0]; p.an_y[1] = anx[1];
+#pragma unroll
+    for (int kk = 0; kk < K::ms; kk++) p.oldevapfbl[kk] = (float)p.evapfbl[kk];
+  }
+  if (p.abs_deltlf > 0.1f) {
+    float fac = 0.5f * dv((float)max(0, k - 5), (float)k - 4.9999f);
+    p.tlfx = fac * tlfxx + (1.0f - fac) * p.tlfx;
+    return true;
+  }
+  // converged: every later pass of the reference loop is a no-op for this tile (at k = 1 as well: pass 2 would find
+  // it inactive, not better, and leave)
+  return false;
+}
+
+#ifndef CBL_COMPACT
+#define CBL_COMPACT 0
+#endif
+#if CBL_COMPACT
+// Shared-memory record of a tile in the block's pass pool: what a pass needs that is neither in global memory nor
+// recomputable (values of THIS stability iteration) + the pass-to-pass state.  SoA over the block's slots.
+enum { LR_TVAIR = 0, LR_DVA, LR_CMOLAR, LR_PSYC, LR_DSATDK, LR_FWSOIL, LR_FWET, LR_DLEAF3, LR_FVLAI0, LR_FVLAI1, LR_SCALEX0,
+       LR_SCALEX1, LR_QCAN0, LR_QCAN1, LR_GRADIS0, LR_GRADIS1, LR_RNISO0, LR_RNISO1,
+       LR_TLFX, LR_DSX, LR_ABSD, LR_DELTLFY, LR_GW0, LR_GW1, LR_PSYCST0, LR_PSYCST1, LR_GSWX0, LR_GSWX1, LR_NF };
+enum { LD_GBHU0 = 0, LD_GBHU1, LD_CSX0, LD_CSX1, LD_ND };
+// global scratch rows (per tile): best iterate and latest-pass results that the owner reads back after the loop
+enum { SD_RNY = 0, SD_HCY, SD_ECY, SD_ECX, SD_GBHF0, SD_GBHF1, SD_ND };
+enum { SF_TLFY = 0, SF_RDY0, SF_RDY1, SF_ANY0, SF_ANY1, SF_OLDEV0, SF_NF = SF_OLDEV0 + K::ms };
+__host__ __device__ constexpr size_t leaf_pool_smem_bytes(int block) {
+  return (size_t)block * (LD_ND * sizeof(double) + LR_NF * sizeof(float) + sizeof(int)) + 32 * sizeof(int);
+}
+#endif
+
+// dryLeaf for the calling thread's tile.  `d`, `tile`, `smp`: global arrays / this thread's tile / mp (pool mode only).
+CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int iter, const DevPtrs &d, const int tile,
+                     const size_t smp) {
   if (iter == 1) { w.fwsoil = fwsoil_calc(t, c); t.canopy_fwsoil = (double)w.fwsoil; }
   const bool veg = t.canopy_vlaiw > K::lai_thresh;
-  const float fwsoil = w.fwsoil;
-  float gswmin[2], gh[2], ghr[2], gw[2], psycst[2], rdx[2] = {0.f, 0.f}, anx[2] = {0.f, 0.f};
-  float rdy[2] = {0.f, 0.f}, an_y[2] = {0.f, 0.f};
+  LeafPass p;
+  p.tvair = t.met_tvair; p.tk = t.met_tk; p.dva = t.met_dva; p.ca = t.met_ca; p.cmolar = t.air_cmolar; p.psyc = t.air_psyc;
+  p.dsatdk = t.air_dsatdk; p.rlam = t.air_rlam; p.fwsoil = w.fwsoil; p.fwet = t.canopy_fwet; p.dleaf3 = w.dleaf3; p.dleaf = t.veg_dleaf;
+  p.vcmax = t.veg_vcmax; p.frac4 = t.veg_frac4; p.ejmax = t.veg_ejmax; p.conkc0 = t.veg_conkc0; p.conko0 = t.veg_conko0;
+  p.ekc = t.veg_ekc; p.eko = t.veg_eko; p.a1gs = t.veg_a1gs; p.d0gs = t.veg_d0gs; p.g1 = t.veg_g1; p.alpha = t.veg_alpha;
+  p.convex = t.veg_convex; p.cfrd = t.veg_cfrd; p.swilt = t.soil_swilt;
 #pragma unroll
   for (int l = 0; l < 2; l++) {
-    gswmin[l] = mx(1.e-6f, t.rad_scalex[l] * t.veg_gswmin);
-    gh[l] = 1.0e-3f; ghr[l] = 1.0e-3f; gw[l] = 1.0e-3f;
-    psycst[l] = t.air_psyc;
+    p.fvlai[l] = t.rad_fvlai[l]; p.scalex[l] = t.rad_scalex[l]; p.qcan[l] = t.rad_qcan[l]; p.gradis[l] = t.rad_gradis[l];
+    p.rniso[l] = t.rad_rniso[l]; p.gbhu[l] = w.gbhu[l];
+    p.gswmin[l] = mx(1.e-6f, t.rad_scalex[l] * t.veg_gswmin);
+    p.gw[l] = 1.0e-3f; p.psycst[l] = t.air_psyc; p.gswx[l] = t.canopy_gswx[l]; p.csx[l] = w.csx[l]; p.gbhf[l] = w.gbhf[l];
+    p.rdy[l] = 0.f; p.an_y[l] = 0.f;
   }
-  if (c.gs_switch == CABLE_GS_MEDLYN && veg) { gswmin[0] = t.veg_g0; gswmin[1] = t.veg_g0; }   // per-tile form of D4
-  double rnx = (double)w.sum_rniso, ecx = (double)w.sum_rniso, hcx = 0.0;
-  float abs_deltlf = 999.0f, deltlf = 0.f, tlfxx = w.tlfx;
-  w.hcy = 0.0;
-  t.canopy_fevc = 0.0;
+  if (c.gs_switch == CABLE_GS_MEDLYN && veg) { p.gswmin[0] = t.veg_g0; p.gswmin[1] = t.veg_g0; }   // per-tile form of D4
 #pragma unroll
-  for (int k = 0; k < K::ms; k++) t.ssnow_evapfbl[k] = 0.0;
-  float oldevapfbl[K::ms];
-  if (!veg) { rnx = 0.0; ecx = 0.0; w.ecy = ecx; abs_deltlf = 0.0f; w.rny = rnx; }
-  float deltlfy = abs_deltlf;
-  const float dleaf3 = w.dleaf3;
-  const float dtair = t.met_tvair - t.met_tk;
+  for (int k = 0; k < K::ms; k++) { p.froot[k] = t.veg_froot[k]; p.wbliq[k] = t.ssnow_wbliq[k]; p.evapfbl[k] = 0.0; p.oldevapfbl[k] = 0.f; }
+  p.tlfx = w.tlfx; p.dsx = w.dsx;
+  p.abs_deltlf = 999.0f;
+  p.ecx = (double)w.sum_rniso;
+  p.tlfy = w.tlfy; p.rny = (double)w.sum_rniso; p.hcy = 0.0; p.ecy = w.ecy;
+  if (!veg) {
+    // never active: pass 1 of the reference loop only records the (zero) iterate, pass 2 leaves (:243, :565-582)
+    p.abs_deltlf = 0.0f; p.ecx = 0.0;
+    p.tlfy = w.tlfx; p.rny = 0.0; p.hcy = 0.0; p.ecy = 0.0;
+  }
+  p.deltlfy = p.abs_deltlf;
 
+#if !CBL_COMPACT
+  (void)d; (void)tile; (void)smp;
+  if (veg) {
+    for (int k = 1; k <= K::maxiter; k++) {
 #if CBL_SYNC_A >= 2
-  bool done = false;
+      __syncthreads();      // (debug variant: needs block-uniform trip counts; not used with the default barriers)
 #endif
-  for (int k = 1; k <= K::maxiter; k++) {
-#if CBL_SYNC_A >= 2
-    // per-pass barrier: the block's warps take pass k together; a warp whose tiles have all converged only votes
-    if (!__syncthreads_or(!done)) break;
-    if (done) continue;
-#endif
-    const bool active = veg && abs_deltlf > 0.1f;
-    if (active) {
-      const float tlfx = w.tlfx;
-      // free-convection boundary-layer conductance, total conductances
-      float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - t.met_tvair) * dleaf3);
-      float gras4 = m_pow025(gras);
-      // temperature responses of Vcmax (C3, C4) and Jmax
-      float temp3 = arrhenius_peaked(tlfx, 1.17461f, 73637.0f, 149252.0f, 486.0f) * t.veg_vcmax * (1.0f - t.veg_frac4);
-      float temp4 = xvcmxt4(tlfx - K::tfrz) * t.veg_vcmax * t.veg_frac4;
-      float tempj = arrhenius_peaked(tlfx, 1.16715f, 50300.0f, 152044.0f, 495.0f) * t.veg_ejmax * (1.0f - t.veg_frac4);
-      const float tdiff = tlfx - K::trefk;
-      const float arr = 1.0f - dv(K::trefk, tlfx);
-      float conkct = t.veg_conkc0 * m_exp((t.veg_ekc / (K::rgas * K::trefk)) * arr);
-      float conkot = t.veg_conko0 * m_exp((t.veg_eko / (K::rgas * K::trefk)) * arr);
-      tlfxx = tlfx;
-      const float cx1 = conkct * (1.0f + dv(0.21f, conkot));
-      const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
-      float vsum0 = t.rad_fvlai[0] + t.rad_fvlai[1];
-      // stomatal-slope factors that do not depend on the leaf
-      float gs_shared;
-      if (c.gs_switch == CABLE_GS_LEUNING) {
-        gs_shared = dv(t.veg_a1gs, 1.0f + dv(w.dsx, t.veg_d0gs));
-      } else {
-        float vpd = (w.dsx < 50.0f) ? 0.05f : w.dsx * 1E-03f;
-        gs_shared = dv(t.veg_g1 * fwsoil, f_sqrt(vpd));
-      }
-      // sunlit (l = 0) and shaded (l = 1) big leaf: ONE copy of the code, the per-leaf operands are selected on l
-      // (a rolled loop over register arrays; unrolling it doubled the footprint of the hottest loop of the step)
-#pragma unroll 1
-      for (int l = 0; l < 2; l++) {
-        const float fvlai_l = l ? t.rad_fvlai[1] : t.rad_fvlai[0];
-        const float scalex_l = l ? t.rad_scalex[1] : t.rad_scalex[0];
-        const float qcan_l = l ? t.rad_qcan[1] : t.rad_qcan[0];
-        const float gradis_l = l ? t.rad_gradis[1] : t.rad_gradis[0];
-        const float gswmin_l = l ? gswmin[1] : gswmin[0];
-        const double gbhu_l = l ? w.gbhu[1] : w.gbhu[0];
-        const double csx_l = l ? w.csx[1] : w.csx[0];
-        const double gbhf_l = mx(1.e-6, (double)dv(fvlai_l * t.air_cmolar * 0.5f * K::dheat * gras4, t.veg_dleaf));
-        const float gh_l = (float)(2.0f * (gbhu_l + gbhf_l));
-        const float ghr_l = gradis_l + gh_l;
-        const float vcmxt3 = scalex_l * temp3, vcmxt4 = scalex_l * temp4, ejmxt3 = scalex_l * tempj;
-        const float par3 = qcan_l * jtomol * (1.0f - t.veg_frac4);
-        const float par4 = qcan_l * jtomol * t.veg_frac4;
-        const float vx3 = mx(0.0f, 0.25f * ejx_root(par3, t.veg_alpha, t.veg_convex, ejmxt3));
-        const float vx4 = mx(0.0f, ejx_root(par4, t.veg_alpha, t.veg_convex, vcmxt4));
-        const float rdx_l = (t.veg_cfrd * vcmxt3 + t.veg_cfrd * vcmxt4);
-        // stomatal slope coefficient
-        float gs_coeff;
-        if (c.gs_switch == CABLE_GS_LEUNING) {
-          gs_coeff = (float)(dv((double)fwsoil, csx_l - (double)0.0f) * (double)gs_shared);
-        } else {
-          gs_coeff = (float)dv((double)(1.0f + gs_shared), csx_l);
-          if (fwsoil <= 0.05f) gs_coeff = (float)dv((double)(dv(fwsoil, 0.05f) + gs_shared), csx_l);
-        }
-        // photosynthesis (cbl_photosynthesis.F90:52-222) for this leaf
-        float an = 0.f;
-        if (vsum0 > K::lai_thresh && fvlai_l > K::lai_thresh) {
-          const double csx = csx_l;
-          const float g0t = dv(gswmin_l * fwsoil, K::rgswc);
-          const double one_m = (double)1.0f - csx * (double)gs_coeff;
-          double coef2 = (double)(g0t + gs_coeff * (vcmxt3 - (rdx_l - vcmxt4)));
-          double coef1 = one_m * (double)(vcmxt3 + vcmxt4 - rdx_l) + (double)g0t * ((double)cx1 - csx)
-                         - (double)(gs_coeff * (vcmxt3 * cx2 / 2.0f + cx1 * (rdx_l - vcmxt4)));
-          double coef0 = -one_m * (double)(vcmxt3 * cx2 / 2.0f + cx1 * (rdx_l - vcmxt4)) - (double)(g0t * cx1) * csx;
-          double anrubisco = an_limited(0, coef2, coef1, coef0, vcmxt3, cx1, cx2, vcmxt4, rdx_l);
-          coef2 = (double)(g0t + gs_coeff * (vx3 - (rdx_l - vx4)));
-          coef1 = one_m * (double)(vx3 + vx4 - rdx_l) + (double)g0t * ((double)cx2 - csx)
-                  - (double)(gs_coeff * (vx3 * cx2 / 2.0f + cx2 * (rdx_l - vx4)));
-          coef0 = -one_m * (double)(vx3 * cx2 / 2.0f + cx2 * (rdx_l - vx4)) - (double)(g0t * cx2) * csx;
-          double anrubp = an_limited(1, coef2, coef1, coef0, vx3, cx2, cx2, vx4, rdx_l);
-          const float effc4 = 4000.0f;
-          coef2 = (double)gs_coeff;
-          coef1 = (double)(g0t + gs_coeff * (rdx_l - 0.5f * vcmxt3) + effc4 * vcmxt4)
-                  - (double)gs_coeff * csx * (double)effc4 * (double)vcmxt4;
-          coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)dv((rdx_l - 0.5f * vcmxt3) * gswmin_l * fwsoil, K::rgswc);
-          double ansink = an_limited(2, coef2, coef1, coef0, 0.f, 0.f, 0.f, 0.f, 0.f);
-          an = (float)mn(mn(anrubisco, anrubp), ansink);
-        }
-        // leaf-surface CO2, stomatal and total water conductance (:460-485)
-        double csx_n = csx_l;
-        float gswx_n = l ? t.canopy_gswx[1] : t.canopy_gswx[0];
-        float gw_l = l ? gw[1] : gw[0];
-        float psycst_l = l ? psycst[1] : psycst[0];
-        if (fvlai_l > K::lai_thresh) {
-          const double gb = gbhu_l + gbhf_l;
-          csx_n = mx(1.0e-4, (double)t.met_ca - dv((double)(K::rgbwc * an), gb));
-          gswx_n = mx(1.e-3f, gswmin_l * fwsoil + mx(0.0f, K::rgswc * gs_coeff * an));
-          gw_l = mx((float)dv(1.0f, (double)dv(1.0f, gswx_n) + dv(1.0f, 1.075f * gb)), 0.00001f);
-          psycst_l = t.air_psyc * dv(ghr_l, gw_l);
-        }
-        if (l == 0) { w.gbhf[0] = gbhf_l; gh[0] = gh_l; ghr[0] = ghr_l; rdx[0] = rdx_l; anx[0] = an; w.csx[0] = csx_n;
-                      t.canopy_gswx[0] = gswx_n; gw[0] = gw_l; psycst[0] = psycst_l; }
-        else        { w.gbhf[1] = gbhf_l; gh[1] = gh_l; ghr[1] = ghr_l; rdx[1] = rdx_l; anx[1] = an; w.csx[1] = csx_n;
-                      t.canopy_gswx[1] = gswx_n; gw[1] = gw_l; psycst[1] = psycst_l; }
-      }
-      // big-leaf latent heat, limited by what the roots can supply (:489-536)
-      ecx = (double)(dv(t.air_dsatdk * (t.rad_rniso[0] - cr * dtair * t.rad_gradis[0]) + cr * t.met_dva * ghr[0], t.air_dsatdk + psycst[0])
-                     + dv(t.air_dsatdk * (t.rad_rniso[1] - cr * dtair * t.rad_gradis[1]) + cr * t.met_dva * ghr[1], t.air_dsatdk + psycst[1]));
-      const double local_fevc = (double)((1.0f - t.canopy_fwet) * (float)ecx);
-      if (local_fevc > 0.0) {
-        // transp_soil_water (cbl_remove_trans.F90:43-93)
-        double diff = 0.0, s = 0.0;
-        const double demand = dv(local_fevc * (double)dels, (double)K::hl);
-#pragma unroll
-        for (int kk = 0; kk < K::ms; kk++) {
-          double xx = demand * (double)t.veg_froot[kk] + diff;
-          double avail = mx(0.0, t.ssnow_wbliq[kk] - (double)1.1f * (double)t.soil_swilt) * (double)c.zse[kk] * (double)K::density_liq;
-          double xxd = xx - avail;
-          double e;
-          if (xxd > 0.0) { e = avail; diff = xxd; } else { e = xx; diff = 0.0; }
-          t.ssnow_evapfbl[kk] = e;
-          s = s + e;
-        }
-        t.canopy_fevc = dv(s * (double)t.air_rlam, (double)dels);
-        ecx = dv(t.canopy_fevc, (double)(1.0f - t.canopy_fwet));
-      }
-      // sensible heat, new leaf temperature, vpd at the leaf surface (:538-557)
-      const float sgh = gh[0] + gh[1], sghr = ghr[0] + ghr[1];
-      hcx = dv(((double)w.sum_rniso - ecx - (double)(cr * dtair * w.sum_gradis)) * (double)sgh, (double)sghr);
-      w.tlfx = t.met_tvair + dv((float)hcx, cr * sgh);
-      rnx = (double)(w.sum_rniso - cr * (w.tlfx - t.met_tk) * w.sum_gradis);
-      w.dsx = mx(t.met_dva + t.air_dsatdk * (w.tlfx - t.met_tvair), 0.0f);
-      deltlf = tlfxx - w.tlfx;
-      abs_deltlf = fabsf(deltlf);
-    } else {
-      // photosynthesis() zeroes anx for tiles it skips (cbl_photosynthesis.F90:49)
-      anx[0] = 0.f; anx[1] = 0.f;
-    }
-    // keep the best iterate; damp after k > 5 (:565-606)
-    const bool better = abs_deltlf < fabsf(deltlfy);
-    if (better) deltlfy = deltlf;
-    if (better || k == 1) {
-      w.tlfy = w.tlfx; w.rny = rnx; w.hcy = hcx; w.ecy = ecx;
-      rdy[0] = rdx[0]; rdy[1] = rdx[1]; an_y[0] = anx[0]; an_y[1] = anx[1];
-#pragma unroll
-      for (int kk = 0; kk < K::ms; kk++) oldevapfbl[kk] = (float)t.ssnow_evapfbl[kk];
-    }
-    if (abs_deltlf > 0.1f) {
-      float fac = 0.5f * dv((float)max(0, k - 5), (float)k - 4.9999f);
-      w.tlfx = fac * tlfxx + (1.0f - fac) * w.tlfx;
-    } else if (k > 1) {
-      // converged: every later pass of the reference loop is a no-op for this tile
-#if CBL_SYNC_A >= 2
-      done = true;
-#else
-      break;
-#endif
+      bool captured;
+      if (!leaf_pass(p, c, dels, k, captured)) break;
     }
   }
+#else
+  // ---- the block's pass pool: every pass, the tiles that still iterate are re-packed onto the lowest-numbered
+  // threads, so a pass costs ceil(active/32) warps instead of every warp that still owns one active tile, and no
+  // warp waits at the barrier behind another warp's stragglers.  A tile's arithmetic is unchanged; only the thread
+  // that executes it varies, so results are bit-identical to the per-owner loop.
+  extern __shared__ __align__(16) unsigned char leaf_smem[];
+  const int nslot = (int)blockDim.x, me = (int)threadIdx.x, lane = me & 31, wid = me >> 5;
+  double *rd = reinterpret_cast<double *>(leaf_smem);
+  float *rf = reinterpret_cast<float *>(rd + (size_t)LD_ND * nslot);
+  int *s_list = reinterpret_cast<int *>(rf + (size_t)LR_NF * nslot);
+  int *s_wtot = s_list + nslot;
+  const int tile0 = tile - me;                      // first tile of this block (shadow threads never enter the pool)
+  bool act = veg && w.valid;
+  if (act) {
+    rf[LR_TVAIR * nslot + me] = p.tvair; rf[LR_DVA * nslot + me] = p.dva; rf[LR_CMOLAR * nslot + me] = p.cmolar;
+    rf[LR_PSYC * nslot + me] = p.psyc; rf[LR_DSATDK * nslot + me] = p.dsatdk; rf[LR_FWSOIL * nslot + me] = p.fwsoil;
+    rf[LR_FWET * nslot + me] = p.fwet; rf[LR_DLEAF3 * nslot + me] = p.dleaf3;
+    rf[LR_FVLAI0 * nslot + me] = p.fvlai[0]; rf[LR_FVLAI1 * nslot + me] = p.fvlai[1];
+    rf[LR_SCALEX0 * nslot + me] = p.scalex[0]; rf[LR_SCALEX1 * nslot + me] = p.scalex[1];
+    rf[LR_QCAN0 * nslot + me] = p.qcan[0]; rf[LR_QCAN1 * nslot + me] = p.qcan[1];
+    rf[LR_GRADIS0 * nslot + me] = p.gradis[0]; rf[LR_GRADIS1 * nslot + me] = p.gradis[1];
+    rf[LR_RNISO0 * nslot + me] = p.rniso[0]; rf[LR_RNISO1 * nslot + me] = p.rniso[1];
+    rf[LR_TLFX * nslot + me] = p.tlfx; rf[LR_DSX * nslot + me] = p.dsx; rf[LR_ABSD * nslot + me] = p.abs_deltlf;
+    rf[LR_DELTLFY * nslot + me] = p.deltlfy;
+    rf[LR_GW0 * nslot + me] = p.gw[0]; rf[LR_GW1 * nslot + me] = p.gw[1];
+    rf[LR_PSYCST0 * nslot + me] = p.psycst[0]; rf[LR_PSYCST1 * nslot + me] = p.psycst[1];
+    rf[LR_GSWX0 * nslot + me] = p.gswx[0]; rf[LR_GSWX1 * nslot + me] = p.gswx[1];
+    rd[LD_GBHU0 * nslot + me] = p.gbhu[0]; rd[LD_GBHU1 * nslot + me] = p.gbhu[1];
+    rd[LD_CSX0 * nslot + me] = p.csx[0]; rd[LD_CSX1 * nslot + me] = p.csx[1];
+#pragma unroll
+    for (int kk = 0; kk < K::ms; kk++) d.ssnow_evapfbl[tile + smp * kk] = 0.0;     // pass-to-pass state lives in its own array
+  }
+  for (int k = 1; k <= K::maxiter; k++) {
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) s_wtot[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w2 = 0; w2 < (nslot >> 5); w2++) { const int n = s_wtot[w2]; base += (w2 < wid) ? n : 0; total += n; }
+    if (total == 0) break;                            // block-uniform
+    if (act) s_list[base + __popc(bal & ((1u << lane) - 1u))] = me;
+    __syncthreads();
+    if (me < total) {
+      const int s = s_list[me], ti = tile0 + s;
+      LeafPass q;
+      q.tvair = rf[LR_TVAIR * nslot + s]; q.dva = rf[LR_DVA * nslot + s]; q.cmolar = rf[LR_CMOLAR * nslot + s];
+      q.psyc = rf[LR_PSYC * nslot + s]; q.dsatdk = rf[LR_DSATDK * nslot + s]; q.fwsoil = rf[LR_FWSOIL * nslot + s];
+      q.fwet = rf[LR_FWET * nslot + s]; q.dleaf3 = rf[LR_DLEAF3 * nslot + s];
+      q.fvlai[0] = rf[LR_FVLAI0 * nslot + s]; q.fvlai[1] = rf[LR_FVLAI1 * nslot + s];
+      q.scalex[0] = rf[LR_SCALEX0 * nslot + s]; q.scalex[1] = rf[LR_SCALEX1 * nslot + s];
+      q.qcan[0] = rf[LR_QCAN0 * nslot + s]; q.qcan[1] = rf[LR_QCAN1 * nslot + s];
+      q.gradis[0] = rf[LR_GRADIS0 * nslot + s]; q.gradis[1] = rf[LR_GRADIS1 * nslot + s];
+      q.rniso[0] = rf[LR_RNISO0 * nslot + s]; q.rniso[1] = rf[LR_RNISO1 * nslot + s];
+      q.tlfx = rf[LR_TLFX * nslot + s]; q.dsx = rf[LR_DSX * nslot + s]; q.abs_deltlf = rf[LR_ABSD * nslot + s];
+      q.deltlfy = rf[LR_DELTLFY * nslot + s];
+      q.gw[0] = rf[LR_GW0 * nslot + s]; q.gw[1] = rf[LR_GW1 * nslot + s];
+      q.psycst[0] = rf[LR_PSYCST0 * nslot + s]; q.psycst[1] = rf[LR_PSYCST1 * nslot + s];
+      q.gswx[0] = rf[LR_GSWX0 * nslot + s]; q.gswx[1] = rf[LR_GSWX1 * nslot + s];
+      q.gbhu[0] = rd[LD_GBHU0 * nslot + s]; q.gbhu[1] = rd[LD_GBHU1 * nslot + s];
+      q.csx[0] = rd[LD_CSX0 * nslot + s]; q.csx[1] = rd[LD_CSX1 * nslot + s];
+      // per-tile constants straight from the arrays this kernel loaded them from (L1/L2 resident)
+      q.tk = __ldg(&d.met_tk[ti]); q.ca = __ldg(&d.met_ca[ti]); q.rlam = K::hl; q.dleaf = __ldg(&d.veg_dleaf[ti]);
+      q.vcmax = __ldg(&d.veg_vcmax[ti]); q.frac4 = __ldg(&d.veg_frac4[ti]); q.ejmax = __ldg(&d.veg_ejmax[ti]);
+      q.conkc0 = __ldg(&d.veg_conkc0[ti]); q.conko0 = __ldg(&d.veg_conko0[ti]); q.ekc = __ldg(&d.veg_ekc[ti]);
+      q.eko = __ldg(&d.veg_eko[ti]); q.a1gs = __ldg(&d.veg_a1gs[ti]); q.d0gs = __ldg(&d.veg_d0gs[ti]); q.g1 = __ldg(&d.veg_g1[ti]);
+      q.alpha = __ldg(&d.veg_alpha[ti]); q.convex = __ldg(&d.veg_convex[ti]); q.cfrd = __ldg(&d.veg_cfrd[ti]);
+      q.swilt = __ldg(&d.soil_swilt[ti]);
+      if (c.gs_switch == CABLE_GS_MEDLYN) { q.gswmin[0] = q.gswmin[1] = __ldg(&d.veg_g0[ti]); }
+      else { const float gm = __ldg(&d.veg_gswmin[ti]); q.gswmin[0] = mx(1.e-6f, q.scalex[0] * gm); q.gswmin[1] = mx(1.e-6f, q.scalex[1] * gm); }
+#pragma unroll
+      for (int kk = 0; kk < K::ms; kk++) {
+        q.froot[kk] = __ldg(&d.veg_froot[ti + smp * kk]); q.wbliq[kk] = __ldg(&d.ssnow_wbliq[ti + smp * kk]);
+        q.evapfbl[kk] = d.ssnow_evapfbl[ti + smp * kk];
+      }
+      bool captured;
+      leaf_pass(q, c, dels, k, captured);
+      rf[LR_TLFX * nslot + s] = q.tlfx; rf[LR_DSX * nslot + s] = q.dsx; rf[LR_ABSD * nslot + s] = q.abs_deltlf;
+      rf[LR_DELTLFY * nslot + s] = q.deltlfy;
+      rf[LR_GW0 * nslot + s] = q.gw[0]; rf[LR_GW1 * nslot + s] = q.gw[1];
+      rf[LR_PSYCST0 * nslot + s] = q.psycst[0]; rf[LR_PSYCST1 * nslot + s] = q.psycst[1];
+      rf[LR_GSWX0 * nslot + s] = q.gswx[0]; rf[LR_GSWX1 * nslot + s] = q.gswx[1];
+      rd[LD_CSX0 * nslot + s] = q.csx[0]; rd[LD_CSX1 * nslot + s] = q.csx[1];
+#pragma unroll
+      for (int kk = 0; kk < K::ms; kk++) d.ssnow_evapfbl[ti + smp * kk] = q.evapfbl[kk];
+      d.leaf_scr_d[ti + smp * SD_ECX] = q.ecx; d.leaf_scr_d[ti + smp * SD_GBHF0] = q.gbhf[0]; d.leaf_scr_d[ti + smp * SD_GBHF1] = q.gbhf[1];
+      if (captured) {
+        d.leaf_scr_d[ti + smp * SD_RNY] = q.rny; d.leaf_scr_d[ti + smp * SD_HCY] = q.hcy; d.leaf_scr_d[ti + smp * SD_ECY] = q.ecy;
+        d.leaf_scr_f[ti + smp * SF_TLFY] = q.tlfy; d.leaf_scr_f[ti + smp * SF_RDY0] = q.rdy[0]; d.leaf_scr_f[ti + smp * SF_RDY1] = q.rdy[1];
+        d.leaf_scr_f[ti + smp * SF_ANY0] = q.an_y[0]; d.leaf_scr_f[ti + smp * SF_ANY1] = q.an_y[1];
+#pragma unroll
+        for (int kk = 0; kk < K::ms; kk++) d.leaf_scr_f[ti + smp * (SF_OLDEV0 + kk)] = q.oldevapfbl[kk];
+      }
+    }
+    __syncthreads();
+    if (act) act = rf[LR_ABSD * nslot + me] > 0.1f;
+  }
+  if (veg && w.valid) {      // the owner takes its tile back
+    p.tlfx = rf[LR_TLFX * nslot + me]; p.dsx = rf[LR_DSX * nslot + me];
+    p.gswx[0] = rf[LR_GSWX0 * nslot + me]; p.gswx[1] = rf[LR_GSWX1 * nslot + me];
+    p.csx[0] = rd[LD_CSX0 * nslot + me]; p.csx[1] = rd[LD_CSX1 * nslot + me];
+    p.ecx = d.leaf_scr_d[tile + smp * SD_ECX]; p.gbhf[0] = d.leaf_scr_d[tile + smp * SD_GBHF0]; p.gbhf[1] = d.leaf_scr_d[tile + smp * SD_GBHF1];
+    p.rny = d.leaf_scr_d[tile + smp * SD_RNY]; p.hcy = d.leaf_scr_d[tile + smp * SD_HCY]; p.ecy = d.leaf_scr_d[tile + smp * SD_ECY];
+    p.tlfy = d.leaf_scr_f[tile + smp * SF_TLFY]; p.rdy[0] = d.leaf_scr_f[tile + smp * SF_RDY0]; p.rdy[1] = d.leaf_scr_f[tile + smp * SF_RDY1];
+    p.an_y[0] = d.leaf_scr_f[tile + smp * SF_ANY0]; p.an_y[1] = d.leaf_scr_f[tile + smp * SF_ANY1];
+#pragma unroll
+    for (int kk = 0; kk < K::ms; kk++) { p.oldevapfbl[kk] = d.leaf_scr_f[tile + smp * (SF_OLDEV0 + kk)]; p.evapfbl[kk] = d.ssnow_evapfbl[tile + smp * kk]; }
+  }
+  __syncthreads();           // the records are free for the next stability iteration
+#endif
+
+  // hand the results back to the tile (:608-666)
+  w.tlfx = p.tlfx; w.dsx = p.dsx; w.tlfy = p.tlfy; w.rny = p.rny; w.hcy = p.hcy; w.ecy = p.ecy;
+#pragma unroll
+  for (int l = 0; l < 2; l++) { w.csx[l] = p.csx[l]; w.gbhf[l] = p.gbhf[l]; t.canopy_gswx[l] = p.gswx[l]; }
+#pragma unroll
+  for (int kk = 0; kk < K::ms; kk++) t.ssnow_evapfbl[kk] = p.evapfbl[kk];
   t.canopy_fevc = (double)(1.0f - t.canopy_fwet) * w.ecy;
   if (w.ecy > 0.0 && t.canopy_fwet < 1.0f) {
-    if (fabs(w.ecy - ecx) > (double)1.0e-6f) {
+    if (fabs(w.ecy - p.ecx) > (double)1.0e-6f) {
       float s = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < K::ms; kk++) s = s + oldevapfbl[kk];
+      for (int kk = 0; kk < K::ms; kk++) s = s + p.oldevapfbl[kk];
       if (fabs(t.canopy_fevc - (double)dv(s * t.air_rlam, dels)) > (double)1.0e-4f) {
         w.warn++;                  // reference prints 'oldevapfbl not right' and carries on
       } else {
 #pragma unroll
-        for (int kk = 0; kk < K::ms; kk++) t.ssnow_evapfbl[kk] = (double)oldevapfbl[kk];
+        for (int kk = 0; kk < K::ms; kk++) t.ssnow_evapfbl[kk] = (double)p.oldevapfbl[kk];
       }
     }
   }
-  t.canopy_frday = 12.0f * (rdy[0] + rdy[1]);
-  t.canopy_fpn = mn(-12.0f * (an_y[0] + an_y[1]), t.canopy_frday);
+  t.canopy_frday = 12.0f * (p.rdy[0] + p.rdy[1]);
+  t.canopy_fpn = mn(-12.0f * (p.an_y[0] + p.an_y[1]), t.canopy_frday);
 }
 
 // wetLeaf: cbl_wetleaf.F90:9-111
@@ -478,9 +648,10 @@ CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0) {
 }
 
 // define_canopy: cable_canopy.F90:10-1048.  Returns number of dryLeaf soft warnings.
-CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg) {
+CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg, const DevPtrs &d, const int tile,
+                          const size_t smp, const bool valid) {
   CanopyWork w;
-  w.warn = 0;
+  w.warn = 0; w.valid = valid;
   const float cr = K::capp * K::rmair;
   const float lai = t.canopy_vlaiw;
   const bool veg = lai > K::lai_thresh;
@@ -551,7 +722,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg)
       w.gbhu[1] = (double)dv(2.0f, t.rough_coexp) * gbvtop * (double)(1.0f - m_exp(-mn(hc * lai, 20.0f))) - w.gbhu[0];
     }
     w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
-    dryLeaf(t, c, w, dels, iter);
+    dryLeaf(t, c, w, dels, iter, d, tile, smp);
     CBL_PHASE_BARRIER(CBL_SYNC_A);     // re-align after the data-dependent number of dryLeaf passes
     wetLeaf(t, w, dels);
     // vegetation fluxes and temperature (:418-456)

@@ -107,7 +107,7 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
     t.rad_albedo_T = (t.rad_albedo[0] + t.rad_albedo[1]) * 0.5f;
     t.ssnow_otss_0 = t.ssnow_otss;
     t.ssnow_otss = t.ssnow_tss;
-    const int warn = define_canopy(t, c, dels, sunlit_veg);
+    const int warn = define_canopy(t, c, dels, sunlit_veg, d, i, smp, valid);
     t.ssnow_owetfac = t.ssnow_wetfac;
     if (warn && valid) atomicAdd(warn_counter, (unsigned long long)warn);
   }

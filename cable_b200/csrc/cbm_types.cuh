@@ -25,6 +25,9 @@ enum FieldId {
 struct DevPtrs {
 #define CABLE_FA(T, m, ct, n1, n2, role, flags) ct *__restrict__ T##_##m;
 #include "../../include/cable_b200_fields.def"
+  // per-tile scratch of kernel A's dryLeaf pass pool (cbm_canopy.cuh): best iterate / latest-pass results in flight
+  double *leaf_scr_d;
+  float *leaf_scr_f;
 };
 
 // per-thread copy of one tile
