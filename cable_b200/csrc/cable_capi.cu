@@ -123,7 +123,7 @@ struct cable_handle {
   double *leaf_scr_d = nullptr; float *leaf_scr_f = nullptr;   // dryLeaf pass-pool scratch (kernel A)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
-  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148;
+  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148, max_l1 = 1;
   // driver stages (cbm_driver.cuh); allocated by cable_b200_driver_init
   struct Driver {
     bool on = false;
@@ -201,9 +201,15 @@ int launch_range(cable_handle *h, const DevPtrs &d, float dels, int first, int i
   // CBL_MINB_x = resident blocks per SM the compiler must allow (register cap 65536 / (BLOCK*MINB)).
 #define CBL_LAUNCH(PH, BL, MB, LV) {                                                                                        \
     const size_t sm_ = ((PH) & 1) ? pool_smem_bytes(BL) : 0;                                                                 \
-    if (sm_ > 48 * 1024) {                                                                                                     \
+    {                                                                                                                          \
       static bool once_ = false;   /* per instantiation */                                                                    \
-      if (!once_) { CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); once_ = true; } \
+      if (!once_) {                                                                                                            \
+        if (sm_ > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+        /* no shared memory in the default build: give the whole unified array to L1, which holds the spill slots */          \
+        if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); \
+        cudaGetLastError();                                                                                                    \
+        once_ = true;                                                                                                          \
+      }                                                                                                                        \
     }                                                                                                                          \
     cbm_kernel<PH, BL, MB, LV><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn); }
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
@@ -328,6 +334,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   h->block = 128;
   // tuning knobs (DESIGN.md 'Kernel'): split step into kernels A/B, min resident blocks per SM of each
   if (const char *e = getenv("CABLE_B200_SPLIT")) h->split = atoi(e);
+  if (const char *e = getenv("CABLE_B200_MAXL1")) h->max_l1 = atoi(e);
   // device-side config + host-evaluated constants
   DevCfg &d = h->dcfg;
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;

@@ -23,6 +23,34 @@
 namespace cbl {
 namespace lean {
 
+// fp64 constants of the three routines.  On the device they live in __constant__ memory so that DFMA takes them as a
+// constant-bank operand: as immediates every 64-bit coefficient costs two extra UMOV issue slots per use (they were 9 %
+// of kernel A's issued instructions).  The host build (tests/cpp/test_lean_math.cpp) reads the same initialisers.
+#define CBL_LEAN_EXP_TAB { /* 1/12! ... 1/3! */                                                                          \
+  2.08767569878680989792e-09, 2.50521083854417187751e-08, 2.75573192239858906526e-07, 2.75573192239858906526e-06,       \
+  2.48015873015873015873e-05, 1.98412698412698412698e-04, 1.38888888888888888889e-03, 8.33333333333333333333e-03,       \
+  4.16666666666666666667e-02, 1.66666666666666666667e-01,                                                               \
+  /* 10: 1.5*2^52, 11: log2(e), 12: ln2 hi, 13: ln2 lo (fdlibm split), 14: ln2 */                                       \
+  6755399441055744.0, 1.44269504088896340736, 6.93147180369123816490e-01, 1.90821492927058770002e-10,                   \
+  6.93147180559945309417e-01 }
+#define CBL_LEAN_LOG_TAB { /* 1/21, 1/19, ... 1/3 */                                                                     \
+  4.76190476190476190476e-02, 5.26315789473684210526e-02, 5.88235294117647058824e-02, 6.66666666666666666667e-02,       \
+  7.69230769230769230769e-02, 9.09090909090909090909e-02, 1.11111111111111111111e-01, 1.42857142857142857143e-01,       \
+  2.00000000000000000000e-01, 3.33333333333333333333e-01 }
+#if defined(__CUDACC__)
+__constant__ double c_lean_exp[15] = CBL_LEAN_EXP_TAB;
+__constant__ double c_lean_log[10] = CBL_LEAN_LOG_TAB;
+#endif
+static const double h_lean_exp[15] = CBL_LEAN_EXP_TAB;
+static const double h_lean_log[10] = CBL_LEAN_LOG_TAB;
+#if defined(__CUDA_ARCH__)
+#define CBL_KE(i) c_lean_exp[i]
+#define CBL_KL(i) c_lean_log[i]
+#else
+#define CBL_KE(i) h_lean_exp[i]
+#define CBL_KL(i) h_lean_log[i]
+#endif
+
 CBL_HD int d_hi(double x) {
 #if defined(__CUDA_ARCH__)
   return __double2hiint(x);
@@ -55,16 +83,16 @@ CBL_HD double rcp_seed(double d) {
 
 // e^r for |r| <= 0.35 (Taylor to r^12: truncation 1.7e-16), times 2^k by exponent arithmetic; k in [-160, 130]
 CBL_HD double exp_reduced(double r, int k) {
-  double p = 2.08767569878680989792e-09;          // 1/12!
-  p = fma(p, r, 2.50521083854417187751e-08);      // 1/11!
-  p = fma(p, r, 2.75573192239858906526e-07);      // 1/10!
-  p = fma(p, r, 2.75573192239858906526e-06);      // 1/9!
-  p = fma(p, r, 2.48015873015873015873e-05);      // 1/8!
-  p = fma(p, r, 1.98412698412698412698e-04);      // 1/7!
-  p = fma(p, r, 1.38888888888888888889e-03);      // 1/6!
-  p = fma(p, r, 8.33333333333333333333e-03);      // 1/5!
-  p = fma(p, r, 4.16666666666666666667e-02);      // 1/4!
-  p = fma(p, r, 1.66666666666666666667e-01);      // 1/3!
+  double p = CBL_KE(0);                           // 1/12!
+  p = fma(p, r, CBL_KE(1));                       // 1/11!
+  p = fma(p, r, CBL_KE(2));                       // 1/10!
+  p = fma(p, r, CBL_KE(3));                       // 1/9!
+  p = fma(p, r, CBL_KE(4));                       // 1/8!
+  p = fma(p, r, CBL_KE(5));                       // 1/7!
+  p = fma(p, r, CBL_KE(6));                       // 1/6!
+  p = fma(p, r, CBL_KE(7));                       // 1/5!
+  p = fma(p, r, CBL_KE(8));                       // 1/4!
+  p = fma(p, r, CBL_KE(9));                       // 1/3!
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
@@ -76,12 +104,12 @@ CBL_HD float exp_cr(float x) {
   double xd = (double)x;
   xd = xd < -105.0 ? -105.0 : xd;                 // e^-105 = 2.5e-46 rounds to +0 in fp32 (min subnormal 1.4e-45)
   xd = xd > 89.0 ? 89.0 : xd;                     // e^89 = 4.5e38 rounds to +Inf in fp32
-  const double magic = 6755399441055744.0;        // 1.5 * 2^52: adds with round-to-nearest-integer
-  const double t = fma(xd, 1.44269504088896340736, magic);
+  const double magic = CBL_KE(10);                // 1.5 * 2^52: adds with round-to-nearest-integer
+  const double t = fma(xd, CBL_KE(11), magic);
   const int k = d_lo(t);
   const double kd = t - magic;
-  double r = fma(kd, -6.93147180369123816490e-01, xd);     // ln2 split hi/lo (fdlibm)
-  r = fma(kd, -1.90821492927058770002e-10, r);
+  double r = fma(-kd, CBL_KE(12), xd);            // ln2 split hi/lo (fdlibm)
+  r = fma(-kd, CBL_KE(13), r);
   return (float)exp_reduced(r, k);                // NaN in -> NaN out (comparisons are false, k = 0)
 }
 
@@ -90,11 +118,11 @@ CBL_HD float exp2_cr(float y) {
   double yd = (double)y;
   yd = yd < -152.0 ? -152.0 : yd;
   yd = yd > 129.0 ? 129.0 : yd;
-  const double magic = 6755399441055744.0;
+  const double magic = CBL_KE(10);
   const double t = yd + magic;
   const int k = d_lo(t);
   const double f = yd - (t - magic);              // exact, |f| <= 0.5
-  return (float)exp_reduced(f * 6.93147180559945309417e-01, k);
+  return (float)exp_reduced(f * CBL_KE(14), k);
 }
 
 // LOG(x) / ALOG(x), x default REAL, for finite x > 0 (callers route everything else to the general routine)
@@ -112,20 +140,60 @@ CBL_HD float log_cr_pos(float x) {
   double s = f * rc;
   s = fma(fma(-s, den, f), rc, s);                // s = f/den to < 1 ulp
   const double z = s * s;                         // <= 0.02944
-  double q = 4.76190476190476190476e-02;          // 1/21
-  q = fma(q, z, 5.26315789473684210526e-02);      // 1/19
-  q = fma(q, z, 5.88235294117647058824e-02);      // 1/17
-  q = fma(q, z, 6.66666666666666666667e-02);      // 1/15
-  q = fma(q, z, 7.69230769230769230769e-02);      // 1/13
-  q = fma(q, z, 9.09090909090909090909e-02);      // 1/11
-  q = fma(q, z, 1.11111111111111111111e-01);      // 1/9
-  q = fma(q, z, 1.42857142857142857143e-01);      // 1/7
-  q = fma(q, z, 2.00000000000000000000e-01);      // 1/5
-  q = fma(q, z, 3.33333333333333333333e-01);      // 1/3
+  double q = CBL_KL(0);                           // 1/21
+  q = fma(q, z, CBL_KL(1));                       // 1/19
+  q = fma(q, z, CBL_KL(2));                       // 1/17
+  q = fma(q, z, CBL_KL(3));                       // 1/15
+  q = fma(q, z, CBL_KL(4));                       // 1/13
+  q = fma(q, z, CBL_KL(5));                       // 1/11
+  q = fma(q, z, CBL_KL(6));                       // 1/9
+  q = fma(q, z, CBL_KL(7));                       // 1/7
+  q = fma(q, z, CBL_KL(8));                       // 1/5
+  q = fma(q, z, CBL_KL(9));                       // 1/3
   // log(m) = 2 atanh(s) = 2s + 2s z q ;  log(x) = e ln2 + log(m)
   const double ed = (double)e, s2 = s + s;
-  const double tail = fma(ed, 1.90821492927058770002e-10, s2 * z * q);
-  return (float)fma(ed, 6.93147180369123816490e-01, s2 + tail);
+  const double tail = fma(ed, CBL_KE(13), s2 * z * q);
+  return (float)fma(ed, CBL_KE(12), s2 + tail);
+}
+
+// x**y on REAL(r_2) for finite x > 0 and |y*ln x| < 690 (the soil-hydraulics powers of smoisturev:
+// (wh/ssat)**(i2bp3-1), wbh**(ibp2-1) with 0 < x <= ~1 and exponents of 2..30): exp(y * log x) with both halves
+// evaluated like the fp32-argument routines above.  Relative error <= ~(2 + |y ln x|) ulp(fp64), i.e. < 3e-14 here,
+// eight orders below the 1e-6 tolerance of the fp64 fields; ~75 instructions instead of the ~200 of the general pow.
+// Returns false when the arguments are outside that domain (the caller falls back to the general routine).
+CBL_HD bool pow_pos(double x, double y, double &out) {
+  if (!(x > 0.0) || !(x < 1.0e300) || !(fabs(y) < 1.0e3)) return false;
+  int hi = d_hi(x);
+  if (hi < 0x00100000) return false;              // fp64 subnormal
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;
+  double m = d_make(hi, d_lo(x));
+  if (hi > 0x3ff6a09e) { m = m * 0.5; e = e + 1; }
+  const double f = m - 1.0, den = m + 1.0;
+  double rc = rcp_seed(den);
+  rc = fma(rc, fma(-den, rc, 1.0), rc);
+  rc = fma(rc, fma(-den, rc, 1.0), rc);
+  double s = f * rc;
+  s = fma(fma(-s, den, f), rc, s);
+  const double z = s * s;
+  double q = CBL_KL(0);
+  q = fma(q, z, CBL_KL(1)); q = fma(q, z, CBL_KL(2)); q = fma(q, z, CBL_KL(3)); q = fma(q, z, CBL_KL(4));
+  q = fma(q, z, CBL_KL(5)); q = fma(q, z, CBL_KL(6)); q = fma(q, z, CBL_KL(7)); q = fma(q, z, CBL_KL(8));
+  q = fma(q, z, CBL_KL(9));
+  const double ed = (double)e, s2 = s + s;
+  // ln x = hi + lo (the low part keeps the product y*ln x accurate when |ln x| is large)
+  const double lh = fma(ed, CBL_KE(12), s2);
+  const double ll = fma(ed, CBL_KE(13), s2 * z * q) + (fma(ed, CBL_KE(12), -lh) + s2);
+  const double v = y * lh, vl = fma(y, lh, -v) + y * ll;        // y * ln x = v + vl
+  if (!(fabs(v) < 690.0)) return false;
+  const double magic = CBL_KE(10);
+  const double t = fma(v, CBL_KE(11), magic);
+  const int k = d_lo(t);
+  const double kd = t - magic;
+  double r = fma(-kd, CBL_KE(12), v);
+  r = fma(-kd, CBL_KE(13), r) + vl;
+  out = exp_reduced(r, k);
+  return true;
 }
 
 }  // namespace lean

@@ -425,7 +425,7 @@ CBL_DEV void smoisturev(Tile &t, const DevCfg &c, float dels) {
     const double delt = wbl_kp - wbl_k;
     double wh = mn(wbl_k, wbl_kp);
     if (t.ssnow_wbice[k - 1] > (double)0.05f || t.ssnow_wbice[k] > (double)0.01f) wh = (double)0.9f * wbl_k + (double)0.1f * wbl_kp;
-    double speed_k = hyds * d_pow(wh / ssat, e_k);
+    double speed_k = hyds * d_pow_soil(wh / ssat, e_k);
     const double rat = delt_prev / (delt + copysign((double)1.0e-20f, delt));
     const double phi = mx(mx(0.0, mn(1.0, 2.0 * rat)), mn(2.0, rat));
     speed_k = mn(speed_k, (double)(0.5f * c.zse[k - 1] / dels));
@@ -439,7 +439,7 @@ CBL_DEV void smoisturev(Tile &t, const DevCfg &c, float dels) {
     const double wbl_kp = mx(0.001, ssat - wbice);
     double wh = mn(wbl_k, wbl_kp);
     if (wbice > (double)0.05f) wh = (double)0.9f * wbl_k + (double)0.1f * wbl_kp;
-    double speed_k = hyds * d_pow(wh / ssat, e_k);
+    double speed_k = hyds * d_pow_soil(wh / ssat, e_k);
     if (!c.l_new_runoff_speed) {
       speed_k = (double)0.5f * speed_k / ((double)1.f - mn(0.5, (double)10.f * wbice));
       speed_k = mn((double)0.5f * speed_k, 0.5 * (double)c.zse[K::ms - 1] / (double)dels);
@@ -469,7 +469,7 @@ CBL_DEV void smoisturev(Tile &t, const DevCfg &c, float dels) {
   for (int k = 2; k <= K::ms; k++) {
     const double zk = (double)c.zse[k - 1], zkm = (double)c.zse[k - 2];
     const double wbh_k = (zk * t.ssnow_wblf[k - 2] + zkm * t.ssnow_wblf[k - 1]) / (double)(c.zse[k - 1] + c.zse[k - 2]);
-    const double fact = d_pow(wbh_k, e_d);
+    const double fact = d_pow_soil(wbh_k, e_d);
     const double icefrac = mx(t.ssnow_wbice[k - 2] / mx(0.01, t.ssnow_wb[k - 2]), t.ssnow_wbice[k - 1] / mx(0.01, t.ssnow_wb[k - 1]));
     const double pwb_wbh = ((double)t.soil_hsbh * ((double)1.f - mn((double)2.f * mn(0.1, icefrac), 0.1)))
                            * mx(t.soil_pwb_min, wbh_k * fact);

@@ -62,6 +62,28 @@ int main(int argc, char **argv) {
   const float inf = INFINITY;
   if (exp_cr(inf) != inf || exp_cr(-inf) != 0.f || !(exp_cr(NAN) != exp_cr(NAN)) || exp_cr(0.f) != 1.f) { printf("exp specials FAILED\n"); rc = 1; }
   if (exp2_cr(inf) != inf || exp2_cr(-inf) != 0.f || exp2_cr(0.f) != 1.f || exp2_cr(10.f) != 1024.f) { printf("exp2 specials FAILED\n"); rc = 1; }
+  // pow_pos: relative error against libm pow over the soil-hydraulics domain and a wider one
+  {
+    uint64_t st = 88172645463325252ull;
+    auto rnd = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+    double worst = 0.0; long n = 0, refused = 0;
+    for (long i = 0; i < 4000000; i++) {
+      const bool wide = (i & 1);
+      const double x = wide ? std::exp((rnd() - 0.5) * 40.0) : 1e-4 + rnd() * 1.2;
+      const double y = wide ? (rnd() - 0.5) * 30.0 : 0.5 + rnd() * 30.0;
+      double got;
+      if (!pow_pos(x, y, got)) { refused++; continue; }
+      const double ref = std::pow(x, y);
+      const double rel = std::fabs(got - ref) / ref;
+      if (rel > worst) worst = rel;
+      n++;
+    }
+    printf("pow_pos                      n=%ld refused=%ld worst relative error %.3g\n", n, refused, worst);
+    if (!(worst < 3e-14) || refused > n / 10) rc = 1;
+    double o;
+    if (pow_pos(0.0, 2.0, o) || pow_pos(-1.0, 2.0, o) || pow_pos(INFINITY, 2.0, o) || pow_pos(2.0, NAN, o) || pow_pos(NAN, 2.0, o) ||
+        pow_pos(10.0, 400.0, o) || !pow_pos(1.0, 5.0, o) || o != 1.0) { printf("pow_pos domain checks FAILED\n"); rc = 1; }
+  }
   printf(rc ? "FAILED\n" : "ok\n");
   return rc;
 }
