@@ -123,7 +123,7 @@ struct cable_handle {
   double *leaf_scr_d = nullptr; float *leaf_scr_f = nullptr;   // dryLeaf pass-pool scratch (kernel A)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
-  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148, max_l1 = 1;
+  int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148, max_l1 = 1, step_chains = 2;
   // driver stages (cbm_driver.cuh); allocated by cable_b200_driver_init
   struct Driver {
     bool on = false;
@@ -335,6 +335,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   // tuning knobs (DESIGN.md 'Kernel'): split step into kernels A/B, min resident blocks per SM of each
   if (const char *e = getenv("CABLE_B200_SPLIT")) h->split = atoi(e);
   if (const char *e = getenv("CABLE_B200_MAXL1")) h->max_l1 = atoi(e);
+  if (const char *e = getenv("CABLE_B200_STEP_CHAINS")) h->step_chains = atoi(e);
   // device-side config + host-evaluated constants
   DevCfg &d = h->dcfg;
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
@@ -388,10 +389,14 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaMemset(h->leaf_scr_f, 0, (size_t)mp * SF_ROWS * sizeof(float));
   cudaMalloc(&h->d_warn, sizeof(unsigned long long));
   cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
-  cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking);
+  {
+    int lo = 0, hi = 0;                                   // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&h->s_compute, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&h->s_compute2, cudaStreamNonBlocking, lo);
+  }
   cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&h->s_compute2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_join_c2, cudaEventDisableTiming);
   // drop-in call pipelining: tiles are cut into chunks so that forcing H2D, the kernels and the D2H of results of
   // different chunks overlap (PCIe is full duplex); tiny shards are not worth cutting
@@ -544,7 +549,22 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
     e0 = h->prof_ev[h->prof_n++]; e1 = h->prof_ev[h->prof_n++];
     CUDA_TRY(cudaEventRecord(e0, h->s_compute));
   }
-  { int rc = launch_range(h, d, dels, first, 0, h->mp, h->s_compute); if (rc) return rc; }
+  // Kernel A runs one block per SM, so a shard is walked in whole "rounds" of sms*BLOCK_A tiles and the last round
+  // leaves SMs idle (310 000 tiles = 2.73 rounds).  The tiles of the full rounds and the remainder therefore go out
+  // as two chains A->B on two streams (the first at higher priority): kernel B of the full rounds starts while the
+  // remainder's kernel A still occupies only part of the chip, and fills the idle SMs.
+  const int round_tiles = h->sms * CBL_BLOCK_A;
+  const int head = h->step_chains > 1 ? (h->mp / round_tiles) * round_tiles : 0;
+  if (h->split && head > 0 && head < h->mp) {
+    CUDA_TRY(cudaEventRecord(h->ev_fork, h->s_compute));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_compute2, h->ev_fork, 0));
+    { int rc = launch_range(h, d, dels, first, 0, head, h->s_compute); if (rc) return rc; }
+    { int rc = launch_range(h, d, dels, first, head, h->mp, h->s_compute2); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(h->ev_join_c2, h->s_compute2));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_join_c2, 0));
+  } else {
+    int rc = launch_range(h, d, dels, first, 0, h->mp, h->s_compute); if (rc) return rc;
+  }
   if (h->profile) CUDA_TRY(cudaEventRecord(e1, h->s_compute));
   CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], h->s_compute));
   h->soil_snow_calls++;
