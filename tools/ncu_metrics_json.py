@@ -30,6 +30,6 @@ for r in data:
         "registers_per_thread": col(r, "launch__registers_per_thread"),
         "block_size": col(r, "launch__block_size"), "grid_size": col(r, "launch__grid_size"),
     })
-json.dump({"source": rep.split("/")[-1], "command": "ncu --set full --clock-control none -k regex:cbm_kernel -s 20 -c 2 python tools/quick_perf.py 62000 12",
+json.dump({"source": rep.split("/")[-1], "command": "CABLE_B200_STEP_CHAINS=1 ncu --set full --clock-control none -k regex:cbm_kernel -s 20 -c 2 python tools/quick_perf.py 62000 12 (single-chain step so that one launch of each kernel covers all tiles)",
            "tiles": 310000, "kernels": kernels}, open(out, "w"), indent=1)
 print(open(out).read()[:1500])
