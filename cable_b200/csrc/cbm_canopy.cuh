@@ -698,7 +698,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
   float zet_cur = K::zeta0;
 #pragma unroll 1
   for (int iter = 1; iter <= CABLE_NITER; iter++) {
-    CBL_PHASE_BARRIER(CBL_SYNC_A, 1);  // the block's warps walk the loop body together (cbm_consts.cuh)
+    CBL_PHASE_BARRIER(CBL_SYNC_A, 2 * (iter - 1));      // the block's warps walk the loop body together (cbm_consts.cuh)
     const float zet = zet_cur;
     // friction velocity (cbl_friction_vel.F90:19-108)
     {
@@ -730,7 +730,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
     }
     w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
     dryLeaf(t, c, w, dels, iter, d, tile, smp);
-    CBL_PHASE_BARRIER(CBL_SYNC_A, 2);  // re-align after the data-dependent number of dryLeaf passes
+    CBL_PHASE_BARRIER(CBL_SYNC_A, 2 * (iter - 1) + 1);  // re-align after the data-dependent number of dryLeaf passes
     wetLeaf(t, w, dels);
     // vegetation fluxes and temperature (:418-456)
     t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
