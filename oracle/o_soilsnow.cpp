@@ -624,6 +624,11 @@ static void surfbv(Oracle &o, float dels) {
 }
 
 // ---- soil_snow: cbl_soilsnow_main.F90:28-207 --------------------------------
+// test hooks: run ONE routine on the handle's arrays (tests/test_oracle_numpy_xcheck.py checks them against an
+// independent NumPy restatement of the same Fortran)
+extern "C" void oracle_run_smoisturev(void *h, float dels) { smoisturev(*(Oracle *)h, dels); }
+extern "C" void oracle_run_stempv(void *h, float dels) { stempv(*(Oracle *)h, dels); }
+
 void soil_snow(Oracle &o, float dels) {
   const int mp = o.mp; Fields &f = o.f; const float *zse = o.cfg.zse;
   std::vector<float> snowmlt(mp);

@@ -155,3 +155,47 @@ def test_output_every_step_without_accumulate_is_the_sample():
     for r, (name, comp, _) in enumerate(rows):
         want = pyoracle.grid_reduce(T_gpu[name][comp].astype(np.float32), grid.patchfrac, grid.cstart, grid.cend)
         assert np.array_equal(out[r], want), name
+
+
+def test_driver_api_rejects_bad_arguments():
+    """Status codes instead of the reference's STOPs: driver stages before driver_init, land points that do not partition
+    the tiles, unknown fields / methods / non-resident sources in the output plan, icycle > 1 in post_step."""
+    from cable_b200.lib import CableError
+    cfg, grid, T, F = make_case(50)
+    cfg.n_forcing_slots = 2
+    Tg = {k: v.copy() for k, v in T.items()}
+    lat = grid.lat[grid.tile2land]
+    with CableB200(grid.mp, cfg) as h:
+        h.bind(Tg); h.upload_params(); h.upload_state()
+        conv = lib.MetConvert(**CONVERT)
+        h.nland = grid.nland
+        with pytest.raises(CableError):
+            h.set_met_async(0, F.land_slice(0), conv)                       # before driver_init
+        with pytest.raises(CableError):
+            h.post_step(1, 1, DELS)
+        bad_end = grid.cend.copy(); bad_end[-1] -= 1
+        with pytest.raises(CableError):
+            h.driver_init(grid.cstart, bad_end, grid.patchfrac, lat)        # tiles not covered
+        with pytest.raises(CableError):
+            h.driver_init(grid.cstart[::-1].copy(), grid.cend[::-1].copy(), grid.patchfrac, lat)    # not in order
+        h.driver_init(grid.cstart, grid.cend, grid.patchfrac, lat)
+        with pytest.raises(CableError):
+            h.post_step(1, 1, DELS)                                          # no step has run yet
+        with pytest.raises(CableError):
+            h.output_plan([("canopy_fe", 3, "mean")])                        # component out of range
+        with pytest.raises(CableError):
+            h.output_plan([("canopy_fe", 0, 9)])                             # unknown method
+        with pytest.raises(CableError):
+            h.output_plan([("met_tk", 0, "mean")])                           # forcing lives in ring slots, not resident
+        with pytest.raises(CableError):
+            h.output_plan([("rough_z0m", 0, "mean")])                        # non-STAR diagnostic at output_level 1
+        with pytest.raises(KeyError):
+            h.output_plan([("no_such_field", 0, "mean")])
+        h.nrows = 1
+        with pytest.raises(CableError):
+            h.output_fetch_async(np.zeros((1, grid.nland), np.float32))      # no plan yet
+        h.output_plan([("canopy_fe", 0, "mean"), ("bal_wbal", 0, "point")])
+        out = np.zeros((2, grid.nland), np.float32)
+        F.fill(Tg, 0); h.set_forcing_async(0); h.step(1, DELS, 0); h.post_step(1, 1, DELS)
+        h.output_fetch_async(out); h.output_wait()
+        assert np.isfinite(out).all()
