@@ -156,6 +156,38 @@ CBL_HD float log_cr_pos(float x) {
   return (float)fma(ed, CBL_KE(12), s2 + tail);
 }
 
+// x**0.25 on default REAL: the value (float)sqrt(sqrt((double)x)) -- two correctly rounded fp64 square roots, i.e.
+// (float)pow((double)x, 0.25) outside ~1e-9 of the arguments -- at under half the instructions.  z0 ~ x^(-1/4) from two
+// MUFU.RSQ seeds (relative error <= ~2^-21), one cubically convergent correction in fp64
+//   z = z0 (1 - e)^(-1/4) = z0 (1 + e/4 + 5 e^2/32 + O(e^3)),  e = 1 - x z0^4,  |e| < 2^-19  =>  truncation < 2^-60,
+// then x^(1/4) = x z^3; five roundings put the fp64 result within ~4 ulp(fp64) of the exact root.  Rounding THAT to fp32
+// can only differ from rounding the exact root when it lies within those few ulps of an fp32 rounding boundary, so the
+// 29 bits below the fp32 mantissa are inspected and anything within 64 ulp(fp64) of a tie takes the two square roots:
+// bit-identical to the sqrt(sqrt()) form on every argument (tests/cpp/test_lean_math.cpp, seed perturbed by +-2^-20).
+CBL_HD float rsqrt_seed(float x, float perturb) {
+#if defined(__CUDA_ARCH__)
+  (void)perturb; float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return (1.0f / sqrtf(x)) * (1.0f + perturb);    // host model of the MUFU seed, error injected by the test
+#endif
+}
+CBL_HD float pow025_cr(float x, float perturb = 0.0f) {
+  if (x >= 1.0e-30f && x <= 1.0e30f) {
+    const float s = rsqrt_seed(x, perturb);
+    const float z0 = rsqrt_seed(x * s, -perturb);
+    const double xd = (double)x, z = (double)z0;
+    const double z2 = z * z;
+    const double e = fma(-xd, z2 * z2, 1.0);
+    const double c = e * fma(e, 0.15625, 0.25);
+    const double z1 = fma(z, c, z);
+    const double y = (xd * z1) * (z1 * z1);
+    int lo = (d_lo(y) & 0x1fffffff) - 0x10000000;
+    lo = lo < 0 ? -lo : lo;
+    if (lo > 64) return (float)y;
+  }
+  return (float)sqrt(sqrt((double)x));
+}
+
 // x**y on REAL(r_2) for finite x > 0 and |y*ln x| < 690 (the soil-hydraulics powers of smoisturev:
 // (wh/ssat)**(i2bp3-1), wbh**(ibp2-1) with 0 < x <= ~1 and exponents of 2..30): exp(y * log x) with both halves
 // evaluated like the fp32-argument routines above.  Relative error <= ~(2 + |y ln x|) ulp(fp64), i.e. < 3e-14 here,

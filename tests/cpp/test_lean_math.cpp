@@ -58,6 +58,18 @@ int main(int argc, char **argv) {
   report("exp2_cr y in [-300, -0]", sweep(0x80000000u, b_of(-300.f), stride, exp2_cr, e2_ref));
   // log: every positive finite fp32 incl. subnormals
   report("log_cr_pos x in (0, FLT_MAX]", sweep(0x00000001u, 0x7f7fffffu, stride, log_cr_pos, l_ref));
+  // x**0.25: bit-identical to two correctly rounded fp64 square roots, whatever the MUFU seed error (model: +-2^-20)
+  {
+    auto q_ref = [](float x) { return (float)std::sqrt(std::sqrt((double)x)); };
+    const float perturbs[4] = {0.0f, 9.5367431640625e-07f, -9.5367431640625e-07f, 4.76837158203125e-07f};
+    for (float pt : perturbs) {
+      auto q_lean = [pt](float x) { return pow025_cr(x, pt); };
+      Result r = sweep(0x00000001u, 0x7f800000u, stride, q_lean, q_ref);     // every positive fp32, Inf included
+      printf("pow025_cr seed error %+.1e   n=%llu mismatches=%llu (last arg %.9g)\n", (double)pt, r.n, r.bad, r.worst_arg);
+      if (r.bad) rc = 1;
+    }
+    if (pow025_cr(0.0f) != 0.0f || pow025_cr(16.0f) != 2.0f || !(pow025_cr(-1.0f) != pow025_cr(-1.0f))) { printf("pow025 specials FAILED\n"); rc = 1; }
+  }
   // special values of exp
   const float inf = INFINITY;
   if (exp_cr(inf) != inf || exp_cr(-inf) != 0.f || !(exp_cr(NAN) != exp_cr(NAN)) || exp_cr(0.f) != 1.f) { printf("exp specials FAILED\n"); rc = 1; }
