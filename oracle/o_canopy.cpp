@@ -650,7 +650,12 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       w.hcy[i] = 0.0;
       w.ecy[i] = w.rny[i] - w.hcy[i];
     }
+    const void *const hook_args[14] = {w.dsx.data(), w.fwsoil.data(), w.tlfx.data(), w.tlfy.data(), w.ecy.data(), w.hcy.data(),
+                                       w.rny.data(), w.gbhu.data(), w.gbhf.data(), w.csx.data(), w.cansat.data(), w.ghwet.data(),
+                                       w.sum_rad_rniso.data(), w.sum_rad_gradis.data()};
+    if (o.dryleaf_hook) o.dryleaf_hook(0, iter, hook_args);
     dryLeaf(o, dels, w, iter);                                                            // :404
+    if (o.dryleaf_hook) o.dryleaf_hook(1, iter, hook_args);
     wetLeaf(o, dels, w);                                                                  // :409
     for (int j = 0; j < mp; j++) {
       f.canopy_fev[j] = (float)(f.canopy_fevc[j] + f.canopy_fevw[j]);                     // :418

