@@ -73,12 +73,29 @@ def profiled_metrics() -> dict | None:
             m = json.load(fh)
         ks = m["kernels"]
         return {"file": os.path.relpath(files[-1], ROOT), "tiles": m.get("tiles"),
+                "flops_per_tile_step": m.get("flops_per_tile_step"),
                 "traffic_bytes_per_step": sum(k["dram_bytes"] for k in ks),
                 "kernels": [{k2: k[k2] for k2 in ("kernel", "duration_ms", "dram_bytes", "issue_active_pct", "pipe_fp64_pct",
                                                     "pipe_fma_fp32_pct", "pipe_alu_pct", "pipe_xu_pct", "dram_pct_of_peak",
                                                     "active_threads_per_warp_inst", "icache_hit_pct")} for k in ks]}
     except Exception:
         return None
+
+
+def pipe_roof(prof: dict | None, tile_steps_per_s_per_gpu: float, clocks: dict | None) -> dict | None:
+    """Second candidate bound: executed fp64 / fp32 flops per tile-step, COUNTED by ncu in the committed
+    capture, x this run's measured throughput, against the non-tensor pipe peaks of one B200 (148 SMs x 64 DFMA or
+    128 FFMA lanes per cycle -- ncu's sm__sass_thread_inst_executed_op_{dfma,ffma}_pred_on.peak_sustained -- x 2 flops
+    x the SM clock sampled during the timed region)."""
+    f = (prof or {}).get("flops_per_tile_step")
+    if not f:
+        return None
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak64, peak32 = 148 * 64 * 2 * mhz * 1e6 / 1e12, 148 * 128 * 2 * mhz * 1e6 / 1e12
+    a64, a32 = f["fp64"] * tile_steps_per_s_per_gpu / 1e12, f["fp32"] * tile_steps_per_s_per_gpu / 1e12
+    return {"flops_per_tile_step_fp64": f["fp64"], "flops_per_tile_step_fp32": f["fp32"], "counted": f.get("how"),
+            "fp64": {"achieved": a64, "peak": peak64, "unit": "TFLOP/s", "frac": a64 / peak64},
+            "fp32": {"achieved": a32, "peak": peak32, "unit": "TFLOP/s", "frac": a32 / peak32}}
 
 
 class ClockSampler(threading.Thread):
@@ -413,6 +430,7 @@ def run_b200(args) -> None:
                          "launch": "one step = kernel A (surface+canopy) + kernel B (soil/snow/carbon) over all tiles; kernel_ms is "
                                    "the pair, timed with CUDA events on the library's compute stream",
                          "ncu": prof,
+                         "pipe": pipe_roof(prof, value / world, clocks),
                          "note": "instruction-issue / latency-bound step (fp64 islands, ~300 correctly rounded transcendentals "
                                  "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 46 %, FP64 pipe 18-26 %, "
                                  "DRAM 5-22 % in the ncu capture; the HBM fraction is reported because it is the official "

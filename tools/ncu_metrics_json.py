@@ -9,6 +9,15 @@ def col(r, name):
     try: return float(r[hdr.index(name)].replace(",", ""))
     except Exception: return None
 U = hdr.index
+def flop_counts(r):
+    cyc = col(r, "smsp__cycles_elapsed.avg")
+    n = {}
+    for op in ("dfma", "dadd", "dmul", "ffma", "fadd", "fmul"):
+        rate = col(r, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed")
+        n[op] = (rate or 0.0) * (cyc or 0.0)
+    return {"thread_inst": {k: round(v) for k, v in n.items()},
+            "flops_fp64": 2 * n["dfma"] + n["dadd"] + n["dmul"], "flops_fp32": 2 * n["ffma"] + n["fadd"] + n["fmul"],
+            "sm_cycles_elapsed": cyc}
 kernels = []
 for r in data:
     unit = {n: rows[1][U(n)] for n in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum")}
@@ -27,9 +36,20 @@ for r in data:
         "warp_inst_executed": col(r, "smsp__inst_executed.sum"),
         "active_threads_per_warp_inst": col(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
         "icache_hit_pct": col(r, "sm__icc_request_hit_rate.pct"),
+        # executed floating-point operations, counted by the hardware: predicated-on thread instructions by opcode
+        # (rate summed over the SM sub-partitions x elapsed cycles); FMA = 2 flops
+        **flop_counts(r),
         "registers_per_thread": col(r, "launch__registers_per_thread"),
         "block_size": col(r, "launch__block_size"), "grid_size": col(r, "launch__grid_size"),
     })
+TILES = 310000
+for k in kernels:
+    k["flops_fp64_per_tile_step"] = k["flops_fp64"] / TILES
+    k["flops_fp32_per_tile_step"] = k["flops_fp32"] / TILES
 json.dump({"source": rep.split("/")[-1], "command": "CABLE_B200_STEP_CHAINS=1 ncu --set full --clock-control none -k regex:cbm_kernel -s 20 -c 2 python tools/quick_perf.py 62000 12 (single-chain step so that one launch of each kernel covers all tiles)",
-           "tiles": 310000, "kernels": kernels}, open(out, "w"), indent=1)
+           "tiles": TILES,
+           "flops_per_tile_step": {"fp64": sum(k["flops_fp64_per_tile_step"] for k in kernels), "fp32": sum(k["flops_fp32_per_tile_step"] for k in kernels),
+                                   "how": "executed, counted by ncu (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul,ffma,fadd,fmul}_pred_on; FMA = 2), "
+                                          "kernel A + kernel B; includes the fp64 evaluation of the correctly rounded fp32 intrinsics and the IEEE divide / square-root sequences"},
+           "kernels": kernels}, open(out, "w"), indent=1)
 print(open(out).read()[:1500])
