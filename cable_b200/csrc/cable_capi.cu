@@ -126,6 +126,7 @@ struct cable_handle {
   double *leaf_scr_d = nullptr; float *leaf_scr_f = nullptr;   // dryLeaf pass-pool scratch (kernel A)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
+  int xsw = 0;                         // any of litter / l_rev_corr / l_new_roughness_soil / soil_thermal_fix set
   int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148, max_l1 = 1, step_chains = 2;
   // driver stages (cbm_driver.cuh); allocated by cable_b200_driver_init
   struct Driver {
@@ -207,22 +208,32 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
   d.tile_order = (h->d_order && whole_windows) ? h->d_order : nullptr;
   // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
   // CBL_MINB_x = resident blocks per SM the compiler must allow (register cap 65536 / (BLOCK*MINB)).
-#define CBL_LAUNCH(PH, BL, MB, LV) {                                                                                        \
+#define CBL_LAUNCH_X(PH, BL, MB, LV, XS) {                                                                                     \
     const size_t sm_ = ((PH) & 1) ? pool_smem_bytes(BL) : 0;                                                                 \
     {                                                                                                                          \
       static bool once_ = false;   /* per instantiation */                                                                    \
       if (!once_) {                                                                                                            \
-        if (sm_ > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+        if (sm_ > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
         /* no shared memory in the default build: give the whole unified array to L1, which holds the spill slots */          \
-        if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); \
+        if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); \
         cudaGetLastError();                                                                                                    \
         once_ = true;                                                                                                          \
       }                                                                                                                        \
     }                                                                                                                          \
-    cbm_kernel<PH, BL, MB, LV><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn); }
+    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn); }
+#define CBL_LAUNCH(PH, BL, MB, LV) CBL_LAUNCH_X(PH, BL, MB, LV, 0)
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
   switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
-  if (h->split) {
+  // the instantiations that carry litter / l_rev_corr / l_new_roughness_soil / soil_thermal_fix (output levels 1 and 2
+  // only: level 0 runs as level 1; kernel A always as 256-thread blocks)
+#define CBL_DISPATCH_X(PH, BL, MB)                                                   \
+  switch (h->cfg.output_level) { case 2: CBL_LAUNCH_X(PH, BL, MB, 2, 1); break; default: CBL_LAUNCH_X(PH, BL, MB, 1, 1); break; }
+  if (h->xsw) {
+    CBL_DISPATCH_X(1, 256, 3);
+    CUDA_TRY(cudaGetLastError());
+    CBL_DISPATCH_X(2, CBL_BLOCK_B, CBL_MINB_B);
+    h->ctr.kernel_launches++;
+  } else if (h->split) {
     // kernel A: one 768-thread block per SM when the range fills the chip that way; small ranges (a shard of an
     // 8-GPU run, a pipeline chunk) take 256-thread blocks, three per SM, so that every SM still gets work
     if (i1 - i0 >= h->sms * CBL_BLOCK_A) { CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A); }
@@ -233,6 +244,8 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
   } else {
     CBL_DISPATCH(3, 128, CBL_MINB_FUSED);
   }
+#undef CBL_DISPATCH_X
+#undef CBL_LAUNCH_X
 #undef CBL_DISPATCH
 #undef CBL_LAUNCH
   CUDA_TRY(cudaGetLastError());
@@ -246,6 +259,13 @@ bool wanted_output(const cable_handle *h, int id) {
   const int lvl = h->cfg.output_level;
   if (lvl < 1) return false;
   return (f.role == STATE) || (f.role == DIAG && (lvl >= 2 || (f.flags & CABLE_FLAG_STAR)));
+}
+
+// PARAM fields flagged OPTIN are inputs of one non-default switch: they must be bound only when it is set
+bool optin_param_needed(const cable_handle *h, int id) {
+  if (id == FID_veg_clitt) return h->cfg.litter != 0;
+  if (id == FID_soil_cnsd_vec || id == FID_soil_sand_vec || id == FID_soil_watr) return h->cfg.soil_thermal_fix != 0;
+  return true;
 }
 
 // soil%*_vec must be the spreads the default configuration builds (cable_parameters.F90:1685-1691);
@@ -320,10 +340,9 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   if (mp <= 0 || !cfg) return fail(CABLE_E_ARG, "mp must be > 0 and cfg non-null");
   if (cfg->struct_bytes != (int)sizeof(cable_cfg)) return fail(CABLE_E_ARG, "cable_cfg size mismatch (ABI)");
   // switch combinations the device path does not implement
-  if (cfg->litter || cfg->or_evap || cfg->gw_model || cfg->l_rev_corr || cfg->soil_thermal_fix ||
-      cfg->l_new_roughness_soil || cfg->call_climate || cfg->redistrb || cfg->soil_struc_sli || cfg->runtime_um)
-    return fail(CABLE_E_UNSUPPORTED, "unsupported switch: litter/or_evap/gw_model/l_rev_corr/soil_thermal_fix/"
-                                     "l_new_roughness_soil/call_climate/redistrb/soil_struc=sli/cable_runtime%um must be off");
+  if (cfg->or_evap || cfg->gw_model || cfg->call_climate || cfg->redistrb || cfg->soil_struc_sli || cfg->runtime_um)
+    return fail(CABLE_E_UNSUPPORTED, "unsupported switch: or_evap/gw_model/call_climate/redistrb/soil_struc=sli/"
+                                     "cable_runtime%um must be off");
   if (cfg->gs_switch != CABLE_GS_LEUNING && cfg->gs_switch != CABLE_GS_MEDLYN)
     return fail(CABLE_E_UNSUPPORTED, "gs_model_switch failed.");                 // cbl_dryLeaf.F90:436
   if (cfg->fwsoil_switch < 0 || cfg->fwsoil_switch > CABLE_FWSOIL_LAI_KTAUL)
@@ -350,6 +369,9 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
   d.diag_soil_resp_on = cfg->diag_soil_resp_on; d.l_new_runoff_speed = cfg->l_new_runoff_speed;
   d.l_new_reduce_soilevp = cfg->l_new_reduce_soilevp; d.icycle = cfg->icycle; d.mvtype = cfg->mvtype;
+  d.litter = cfg->litter != 0; d.l_rev_corr = cfg->l_rev_corr != 0; d.soil_thermal_fix = cfg->soil_thermal_fix != 0;
+  d.l_new_roughness_soil = cfg->l_new_roughness_soil != 0;
+  h->xsw = d.litter || d.l_rev_corr || d.soil_thermal_fix || d.l_new_roughness_soil;
   d.met_tv_is_tk = cfg->met_tv_is_tk; d.caller_duties = cfg->caller_duties; d.output_level = cfg->output_level;
   d.snmin = cfg->snmin; d.max_glacier_snowd = cfg->max_glacier_snowd; d.snow_ccnsw = cfg->snow_ccnsw;
   d.max_ssdn = cfg->max_ssdn; d.max_sconds = cfg->max_sconds; d.frozen_limit = cfg->frozen_limit;
@@ -529,9 +551,17 @@ int cable_b200_upload(cable_handle *h, unsigned role_mask) {
     const cable_field_info &f = g_fields[id];
     if (!(f.role & role_mask) || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
     if (f.role == FORCING) continue;                       // forcing goes through set_forcing_async
+    if (f.role == PARAM && (f.flags & CABLE_FLAG_OPTIN) && !optin_param_needed(h, id)) {
+      if (h->host[id]) { int rc = copy_field(h, id, 0, true, h->s_compute); if (rc) return rc; }
+      continue;
+    }
     if ((f.role & (PARAM | STATE)) && !h->host[id])
       return fail(CABLE_E_UNBOUND, std::string("field not bound: ") + f.name);
     int rc = copy_field(h, id, 0, true, h->s_compute); if (rc) return rc;
+  }
+  if ((role_mask & STATE) && h->cfg.l_new_roughness_soil) {     // canopy%us feeds the next ruff_resist (cable_roughness.F90:197)
+    if (!h->host[FID_canopy_us]) return fail(CABLE_E_UNBOUND, "field not bound: canopy_us (l_new_roughness_soil)");
+    int rc = copy_field(h, FID_canopy_us, 0, true, h->s_compute); if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
   if (role_mask & PARAM) { int rc = build_tile_order(h); if (rc) return rc; }

@@ -94,16 +94,25 @@ CBL_DEV void surf_wetness_fact(Tile &t, float cansat, float dels) {
 }
 
 // soil potential evaporation: Humidity_deficit_method / Penman_Monteith (cbl_pot_evap_snow.F90)
+// canopy%kthLitt, canopy%DvLitt: REAL(r_2) constants set at cable_canopy.F90:203-204
+#define CBL_KTHLITT 0.3
+#define CBL_DVLITT 3.1415841138194147e-05
+// XSW: the rarely used cable_user switches (litter, l_rev_corr, l_new_roughness_soil, soil_thermal_fix) are compiled
+// into a second instantiation of the kernels; the default instantiation (XSW = false) carries none of their code.
+template <bool XSW>
 CBL_DEV float soil_potev(const Tile &t, const DevCfg &c, float q_air) {
+  // litter: the resistance the caller passes as REAL(veg%clitt), REAL(canopy%DvLitt) (cbl_pot_evap_snow.F90:64-68,158-161)
+  float rsoil = t.ssnow_rtsoil;
+  if (XSW && c.litter) rsoil = rsoil + dv((float)(1 - t.ssnow_isflag) * (float)t.veg_clitt * 0.003f, (float)CBL_DVLITT);
   if (c.ssnow_potev == CABLE_POTEV_PM) {
     float sss = t.air_dsatdk;
     float cc1 = sss / (sss + t.air_psyc), cc2 = t.air_psyc / (sss + t.air_psyc);
     float qs = qsatf(t.met_tvair - K::tfrz, t.met_pmb);
-    return cc1 * (t.canopy_fns - t.canopy_ga) + dv(cc2 * t.air_rho * t.air_rlam * (qs - t.met_qvair), t.ssnow_rtsoil);
+    return cc1 * (t.canopy_fns - t.canopy_ga) + dv(cc2 * t.air_rho * t.air_rlam * (qs - t.met_qvair), rsoil);
   }
   float dq = t.ssnow_qstss - q_air;
   if (t.ssnow_snowd > 1.0f || t.ssnow_tgg[0] == K::tfrz) dq = mx(-0.1e-3f, dq);
-  return dv(t.air_rho * t.air_rlam * dq, t.ssnow_rtsoil);
+  return dv(t.air_rho * t.air_rlam * dq, rsoil);
 }
 
 // Latent_heat_flux: cbl_latent_heat.F90:15-285
@@ -623,14 +632,14 @@ CBL_DEV void wetLeaf(Tile &t, const CanopyWork &w, float dels) {
   }
 }
 
-// within_canopy: cbl_within_canopy.F90:10-159 (no litter, no or_evap)
-CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0) {
+// within_canopy: cbl_within_canopy.F90:10-159 (no or_evap); rhlitt = relitt = 0 unless cable_user%litter
+CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0, const float rhlitt, const float relitt) {
   if (!(t.veg_meth > 0 && t.canopy_vlaiw > K::lai_thresh && t.rough_hruff > t.rough_z0soilsn)) return;
   const float rrbw = (float)dv((w.gbhu[0] + w.gbhf[0]) + (w.gbhu[1] + w.gbhf[1]), (double)t.air_cmolar);
   const float rrsw = dv(t.canopy_gswx[0] + t.canopy_gswx[1], t.air_cmolar);
-  float fix_eqn = dv(t.ssnow_cls * rt0, rt0 + 0.f);
+  float fix_eqn = dv(t.ssnow_cls * rt0, rt0 + relitt);
   if (t.ssnow_potev > 0.f) fix_eqn = fix_eqn * t.ssnow_wetfac;
-  const float fix_eqn2 = dv(rt0, rt0 + 0.f);
+  const float fix_eqn2 = dv(rt0, rt0 + rhlitt);
   const float epsi = t.air_epsi, rt1 = t.rough_rt1;
   const float cond = (1.f + epsi) * rrsw + rrbw, r01 = rt0 * rt1, bs = rrbw * rrsw;
   const float dmah = (rt0 + fix_eqn2 * rt1) * cond + epsi * r01 * bs;
@@ -655,13 +664,16 @@ CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0) {
 }
 
 // define_canopy: cable_canopy.F90:10-1048.  Returns number of dryLeaf soft warnings.
+template <bool XSW>
 CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg, const DevPtrs &d, const int tile,
-                          const size_t smp, const bool valid) {
+                          const size_t smp, const bool valid, bool &veg_branch) {
   CanopyWork w;
   w.warn = 0; w.valid = valid;
   const float cr = K::capp * K::rmair;
   const float lai = t.canopy_vlaiw;
   const bool veg = lai > K::lai_thresh;
+  const bool litter = XSW && c.litter, rev_corr = XSW && c.l_rev_corr;
+  float rhlitt = 0.f, relitt = 0.f;                                               // :239-240
   t.canopy_cansto = t.canopy_oldcansto;
   w.cansat = t.veg_canst1 * lai;
   surf_wetness_fact(t, w.cansat, dels);
@@ -690,10 +702,10 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
   w.sum_gradis = t.rad_gradis[0] + t.rad_gradis[1];
 
   float rt1usc = 0.f, rt0 = 0.f;
-  const float zr = mx(t.rough_zruffs - t.rough_disp, t.rough_z0soilsn);
-  const bool above = !signbit(t.rough_zref_tq + t.rough_disp - t.rough_zruffs);   // xx = 0.5 + SIGN(0.5, .)
+  float zr = mx(t.rough_zruffs - t.rough_disp, t.rough_z0soilsn);
+  bool above = !signbit(t.rough_zref_tq + t.rough_disp - t.rough_zruffs);         // xx = 0.5 + SIGN(0.5, .)
   const float tvrad4 = p4(t.met_tvrad);
-  const bool dense = veg && t.rough_hruff > t.rough_z0soilsn;
+  bool dense = veg && t.rough_hruff > t.rough_z0soilsn;
 
   float zet_cur = K::zeta0;
 #pragma unroll 1
@@ -709,6 +721,12 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
       t.canopy_us = mn(mx(1.e-6f, dv(rescale, m_log(z_eff) - psim_1 + psim_2)), 10.0f);
     }
     const float us = t.canopy_us;
+    if (XSW && c.l_new_roughness_soil) {                                          // E.Kowalczyk 2014 (:268-269)
+      if (ruff_resist<true>(t, c)) veg_branch = true;
+      zr = mx(t.rough_zruffs - t.rough_disp, t.rough_z0soilsn);
+      above = !signbit(t.rough_zref_tq + t.rough_disp - t.rough_zruffs);
+      dense = veg && t.rough_hruff > t.rough_z0soilsn;
+    }
     // aerodynamic resistances (:276-363)
     float r1c = dv(m_log(dv(t.rough_zref_tq, zr)) - psis(zet) + psis(dv(zet * zr, t.rough_zref_tq)), K::vonk);
     rt1usc = above ? 1.0f * r1c : 0.0f * r1c;
@@ -747,13 +765,20 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
                    - K::emsoil * K::sboltz * tss4;
     // soil evaporation and sensible heat, before and after the in-canopy air update (:461-610)
     t.ssnow_qstss = qsatf(t.ssnow_tss - K::tfrz, t.met_pmb);
-    t.ssnow_potev = soil_potev(t, c, t.met_qv);
+    if (litter) {                                                                 // :471-476 (r_2 expressions stored to REAL)
+      const double cl = (double)(float)(1 - t.ssnow_isflag) * t.veg_clitt * (double)0.003f;
+      rhlitt = (float)dv(dv(cl, CBL_KTHLITT), (double)(t.air_rho * K::capp));
+      relitt = (float)dv(cl, CBL_DVLITT);
+    }
+    t.ssnow_potev = soil_potev<XSW>(t, c, t.met_qv);
     latent_heat_flux(t, c, dels);
-    t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil);
-    within_canopy(t, w, rt0);
-    t.ssnow_potev = soil_potev(t, c, t.met_qvair);
+    if (litter) t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tk), t.ssnow_rtsoil + rhlitt);   // :525-530 (met%tk)
+    else t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil);
+    within_canopy(t, w, rt0, rhlitt, relitt);
+    t.ssnow_potev = soil_potev<XSW>(t, c, t.met_qvair);
     latent_heat_flux(t, c, dels);
-    t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil);
+    if (litter) t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil + rhlitt);   // :596-601
+    else t.canopy_fhs = dv(t.air_rho * K::capp * (t.ssnow_tss - t.met_tvair), t.ssnow_rtsoil);
     t.canopy_ga = (float)((double)(t.canopy_fns - t.canopy_fhs) - t.canopy_fes);
     t.canopy_fe = (float)((double)t.canopy_fev + t.canopy_fes);
     t.canopy_fh = t.canopy_fhv + t.canopy_fhs;
@@ -829,7 +854,8 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
              + dv(m_log(dv(zscl - disp, mx(t.rough_zruffs - disp, t.rough_z0soilsn)))
                   - psis(dv((zscl - disp) * zN, t.rough_zref_tq)) + psis(dv((t.rough_zruffs - disp) * zN, t.rough_zref_tq)), K::vonk);
     }
-    tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, dv(r_sc, mx(1.f, rsum))) - K::tfrz;
+    if (litter) tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, dv(r_sc + rhlitt * us, mx(1.f, rsum + rhlitt * us))) - K::tfrz;   // :808-812
+    else tscrn = t.ssnow_tss + (t.met_tk - t.ssnow_tss) * mn(1.f, dv(r_sc, mx(1.f, rsum))) - K::tfrz;
   }
   t.canopy_tscrn = tscrn;
   {
@@ -838,7 +864,10 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
     const float qsurf = (qtgnet > 0.f) ? rsts * t.ssnow_wetfac : 0.1f * rsts * t.ssnow_wetfac + 0.9f * t.met_qv;
     t.canopy_qmom = t.air_rho * (us * us);
     float qscrn = t.met_qv - qstar * ftemp;
-    if (canopy_scrn) qscrn = qsurf + (t.met_qv - qsurf) * mn(1.f, dv(r_sc, mx(1.f, rsum)));
+    if (canopy_scrn) {
+      if (litter) qscrn = qsurf + (t.met_qv - qsurf) * mn(1.f, dv(r_sc + relitt * us, mx(1.f, rsum + relitt * us)));   // :851-854
+      else qscrn = qsurf + (t.met_qv - qsurf) * mn(1.f, dv(r_sc, mx(1.f, rsum)));
+    }
     t.canopy_qscrn = qscrn;
   }
   // canopy water store (:881-906)
@@ -852,8 +881,17 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
   t.canopy_delwc = t.canopy_cansto - t.canopy_oldcansto;
   // sensitivities for the implicit soil-temperature solve (:913-1027), default branch
   t.ssnow_dfn_dtg = dv((-1.f) * 4.f * K::emsoil * K::sboltz * tss4, t.ssnow_tss);
-  t.ssnow_dfh_dtg = dv(t.air_rho * K::capp, t.ssnow_rtsoil);
-  t.ssnow_dfe_ddq = dv(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, t.ssnow_rtsoil);
+  if (!XSW) {
+    t.ssnow_dfh_dtg = dv(t.air_rho * K::capp, t.ssnow_rtsoil);
+    t.ssnow_dfe_ddq = dv(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, t.ssnow_rtsoil);
+  } else {
+    float rttsoil = t.ssnow_rtsoil;
+    if (rev_corr && veg) rttsoil = rttsoil + t.rough_rt1;                           // :917-922
+    // rhlitt / relitt as recomputed at :987-988 are the values of the last stability iteration (same operands)
+    t.ssnow_dfh_dtg = dv(t.air_rho * K::capp, rttsoil + rhlitt);                     // :991 / :1006 (rhlitt = 0)
+    t.ssnow_dfe_ddq = dv(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, rttsoil + relitt);
+    if (rev_corr && t.ssnow_potev < 0.f) t.ssnow_dfe_ddq = dv(t.air_rho * t.air_rlam * t.ssnow_cls, rttsoil + relitt);   // :995-999, :1010-1014
+  }
   {
     const float tc = t.ssnow_tss - K::tfrz;
     t.ssnow_ddq_dtg = dv(dv(K::rmh2o / K::rmair, t.met_pmb) * K::tetena * K::tetenb * K::tetenc, p2(K::tetenc + t.ssnow_tss - K::tfrz))

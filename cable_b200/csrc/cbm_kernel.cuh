@@ -63,7 +63,10 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
 #define CBL_ST(p, v) (*(p) = (v))
 #endif
 
-template <int PHASE, int BLOCK, int MINB, int LVL>
+// XSW = 1: the instantiation that also carries the rarely used cable_user switches (litter, l_rev_corr,
+// l_new_roughness_soil, soil_thermal_fix); chosen at launch when any of them is set.  XSW = 0 is the default program,
+// unchanged by their existence.
+template <int PHASE, int BLOCK, int MINB, int LVL, int XSW>
 __global__ void __launch_bounds__(BLOCK, MINB)
 cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const float dels, const int first_call,
            unsigned long long *warn_counter) {
@@ -100,9 +103,11 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
     else { t.met_tvair = d.met_tvair[i]; t.met_tvrad = d.met_tvrad[i]; }
     if (c.ssnow_potev == CABLE_POTEV_PM) t.canopy_ga = d.canopy_ga[i];           // cable_canopy.F90:487
     if (c.caller_duties) t.canopy_oldcansto = t.canopy_cansto;                   // cable_serial.F90:573
+    if (XSW && c.litter) t.veg_clitt = d.veg_clitt[i];                           // cable_canopy.F90:472
+    if (XSW && c.l_new_roughness_soil) t.canopy_us = d.canopy_us[i];             // cable_roughness.F90:197: last step's us
 
     lake_refill(t, c);
-    veg_branch = ruff_resist(t, c);
+    veg_branch = ruff_resist<XSW != 0>(t, c);
     define_air(t);
     veg_mask = t.canopy_vlaiw > K::lai_thresh;                                    // masks_cbl.F90:45
     const bool sunlit_mask = (t.met_fsd[0] + t.met_fsd[1]) > K::rad_thresh;       // cbm:131 (D9)
@@ -112,12 +117,19 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
     t.rad_albedo_T = (t.rad_albedo[0] + t.rad_albedo[1]) * 0.5f;
     t.ssnow_otss_0 = t.ssnow_otss;
     t.ssnow_otss = t.ssnow_tss;
-    const int warn = define_canopy(t, c, dels, sunlit_veg, d, i, smp, valid);
+    const int warn = define_canopy<XSW != 0>(t, c, dels, sunlit_veg, d, i, smp, valid, veg_branch);
     t.ssnow_owetfac = t.ssnow_wetfac;
     if (warn && valid) atomicAdd(warn_counter, (unsigned long long)warn);
   }
   if (PHASE & 2) {
-    soil_snow(t, c, dels, first_call != 0);
+    if (XSW && c.soil_thermal_fix) {                                             // cbl_conductivity.F90:30-58
+#pragma unroll
+      for (int k = 0; k < K::ms; k++) {
+        t.soil_cnsd_vec[k] = d.soil_cnsd_vec[i + smp * k]; t.soil_sand_vec[k] = d.soil_sand_vec[i + smp * k];
+        t.soil_watr[k] = d.soil_watr[i + smp * k];
+      }
+    }
+    soil_snow<XSW != 0>(t, c, dels, first_call != 0);
     snow_aging(t, dels);
     t.ssnow_deltss = t.ssnow_tss - t.ssnow_otss;
     t.canopy_fev = (float)(t.canopy_fevc + (double)t.canopy_fevw);
@@ -142,6 +154,8 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
 #include "../../include/cable_b200_fields.def"
 #undef CBL_WANT
 
+  // canopy%us is an input of the next step's ruff_resist under l_new_roughness_soil: keep it whatever the output level
+  if ((PHASE & 1) && XSW && c.l_new_roughness_soil && lvl < 2) d.canopy_us[i] = t.canopy_us;
   // fields the reference writes only on some tiles: keep the device copy stale elsewhere (all belong to kernel A)
   if ((PHASE & 1) && lvl >= 2) {
     if (veg_branch) {                                                           // cable_roughness.F90:290-295

@@ -283,13 +283,34 @@ CBL_DEV double soil_heat_cap(const Tile &t, int k, float hcll) {
   return mx((double)hcll, (double)((1.0f - t.soil_ssat) * t.soil_css * t.soil_rhosoil) + wet);
 }
 
+// total_soil_conductivity: cbl_conductivity.F90:11-89 (cable_user%soil_thermal_fix), layer k of this tile.
+// soil%ssat_vec is the verified spread of soil%ssat (cable_capi.cu check_spreads).
+CBL_DEV double total_soil_conductivity(const Tile &t, const DevCfg &c, int k) {
+  const double cnsd_vec = t.soil_cnsd_vec[k], ssat_vec = (double)t.soil_ssat, watr = t.soil_watr[k];
+  if (t.soil_isoilm == 9) return (double)c.snow_ccnsw;
+  const double quartz = mx((double)0.0f, mn((double)0.8f, t.soil_sand_vec[k] * (double)0.92f));
+  const double Ko = (quartz > (double)0.2f) ? 2.0 : 3.0;
+  const double Ktmp = d_pow(d_pow((double)7.7f, quartz) * d_pow(Ko, (double)1.0f - quartz), (double)1.0f - ssat_vec);
+  double liq_frac = 0.0;
+  if (t.ssnow_wb[k] >= (double)1.0e-15f) liq_frac = mn(1.0, mx(0.0, dv(t.ssnow_wbliq[k], t.ssnow_wb[k])));
+  const double Ksat = Ktmp * d_pow((double)2.2f, ssat_vec * ((double)1.0f - liq_frac)) * d_pow((double)0.57f, liq_frac);
+  const double Sr = mn((double)0.9999f, dv(mx((double)0.f, t.ssnow_wb[k] - watr), ssat_vec - watr));
+  double Ke = (Sr >= (double)0.05f) ? (double)0.7f * log10(Sr) + (double)1.0f : 0.0;
+  if (t.ssnow_wbice[k] > 0.0 || t.ssnow_tgg[k] < K::tfrz || t.ssnow_isflag != 0 || t.ssnow_snowd >= 0.1f) Ke = Sr;
+  const double tot = Ke * Ksat + ((double)1.0f - Ke) * cnsd_vec;
+  return mn(Ksat, mx(cnsd_vec, tot));
+}
+
 // stempv: cbl_stempv.F90:13-221 with old_soil_conductivity (cbl_Oldconductivity.F90:7-59)
+template <bool XSW>
 CBL_DEV void stempv(Tile &t, const DevCfg &c, float dels) {
   const float ssat = t.soil_ssat;
   double ccnsw[K::ms];
 #pragma unroll
   for (int k = 0; k < K::ms; k++) {
-    if (t.soil_isoilm == 9) {
+    if (XSW && c.soil_thermal_fix) {                                        // cbl_stempv.F90:57-61
+      ccnsw[k] = total_soil_conductivity(t, c, k);
+    } else if (t.soil_isoilm == 9) {
       ccnsw[k] = (double)c.snow_ccnsw;
     } else {
       const float ew = (float)(t.ssnow_wblf[k] * (double)ssat);
@@ -560,6 +581,7 @@ CBL_DEV void surfbv(Tile &t, const DevCfg &c, float dels) {
 }
 
 // soil_snow: cbl_soilsnow_main.F90:28-207.  first_call <=> the reference's SAVE ktau <= 1 (D3)
+template <bool XSW>
 CBL_DEV void soil_snow(Tile &t, const DevCfg &c, float dels, bool first_call) {
   float tggav = 0.f;
   const float hcll = mx(0.01f, t.soil_css * t.soil_rhosoil);
@@ -590,7 +612,7 @@ CBL_DEV void soil_snow(Tile &t, const DevCfg &c, float dels, bool first_call) {
   snow_accum(t, c, dels);
   float smelt = snow_melting(t, c, dels);
   snowl_adjust(t, c);
-  stempv(t, c, dels);
+  stempv<XSW>(t, c, dels);
   t.ssnow_tss = (float)(1 - t.ssnow_isflag) * t.ssnow_tgg[0] + (float)t.ssnow_isflag * t.ssnow_tggsn[0];
   smelt = smelt + snow_melting(t, c, dels);
   // remove_trans (cbl_remove_trans.F90:9-40): take transpiration out of the root zone

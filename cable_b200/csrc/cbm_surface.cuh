@@ -19,6 +19,7 @@ CBL_DEV void lake_refill(Tile &t, const DevCfg &c) {
 // ruff_resist: cable_roughness.F90:64-332 with HgtAboveSnow / LAI_eff
 // (roughnessHGT_effLAI_cbl.F90:42-149); default soil_struc, offline branch.
 // Returns true when the tile takes the vegetated branch (term2..term6a written).
+template <bool XSW>
 CBL_DEV bool ruff_resist(Tile &t, const DevCfg &c) {
   const float z0soilsn_min = 1.e-7f, z0soilsn_min_PF = 1.e-4f;
   // canopy height above the snow pack and the LAI that is still exposed
@@ -31,6 +32,10 @@ CBL_DEV bool ruff_resist(Tile &t, const DevCfg &c) {
   // soil / snow-covered soil roughness length (:193-205)
   float z0soil = 0.0009f * mn(1.0f, lai) + 1.e-4f;
   float z0sn = z0soil;
+  if (XSW && c.l_new_roughness_soil) {                    // E.Kowalczyk 2014 (:197-198); canopy%us of the previous call
+    z0soil = 0.01f * mn(1.0f, lai) + 0.02f * mn(t.canopy_us * t.canopy_us / K::grav, 1.0f);
+    z0sn = mx(1.e-7f, z0soil);
+  }
   if (t.ssnow_snowd > 0.01f) {
     z0sn = mx(z0soilsn_min, z0soil - z0soil * mn(t.ssnow_snowd, 10.f) / 10.f);
     if (t.veg_iveg == K::ice_cable) z0sn = mx(z0sn, z0soilsn_min_PF);

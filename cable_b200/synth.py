@@ -43,6 +43,7 @@ PFT = {
     "a1gs": _rep([(6, 9.0), 4.0, 9.0, 9.0, 4.0, (7, 9.0)]),
     "alpha": _rep([(6, 0.2), 0.05, 0.2, 0.2, 0.05, (7, 0.2)]),
     "canst1": _rep([(17, 0.1)]),
+    "clitt": _rep([20., 6., 10., 13., 2., 2., 0.3, 0.3, 0., 0., 2., 2., (5, 0.)]),
     "cfrd": _rep([(6, 0.015), 0.025, 0.015, 0.015, 0.025, (7, 0.015)]),
     "conkc0": _rep([(17, 0.000302)]),
     "conko0": _rep([(17, 0.256)]),
@@ -231,6 +232,12 @@ def make_tiles(grid: Grid, cfg=None, single_pft: int | None = None) -> dict[str,
         T["soil_sfc_vec"][k] = T["soil_sfc"][0].astype(np.float64)
         T["soil_ssat_vec"][k] = T["soil_ssat"][0].astype(np.float64)
         T["soil_zse_vec"][k] = np.float64(zse[k])
+        # soil-type-table path of the reference (cable_parameters.F90:1526-1529); cnsd_vec as the spread of cnsd
+        T["soil_sand_vec"][k] = SOIL["sand"][st].astype(np.float64)
+        T["soil_cnsd_vec"][k] = T["soil_cnsd"][0]
+        T["soil_watr"][k] = np.float64(np.float32(0.01))
+    T["veg_clitt"][0] = PFT["clitt"][iv].astype(np.float64)                  # pft_params.nml vegin%clitt
+    T["canopy_us"][0] = 0.1                                                  # cable_parameters.F90 write_default_params
     T["rough_za_uv"][0] = 40.0
     T["rough_za_tq"][0] = 40.0
     # ---- initial state (write_default_params) ----

@@ -69,6 +69,9 @@ static void surf_wetness_fact(Oracle &o, const std::vector<float> &cansat, float
   }
 }
 
+// canopy%kthLitt, canopy%DvLitt: REAL(r_2) constants set at cable_canopy.F90:203-204
+static const double KTHLITT = 0.3, DVLITT = 3.1415841138194147e-05;
+
 // ---- Humidity_deficit_method / Penman_Monteith: cbl_pot_evap_snow.F90 -------
 static void potev_calc(Oracle &o, bool second_pass) {
   const int mp = o.mp; Fields &f = o.f;
@@ -78,6 +81,11 @@ static void potev_calc(Oracle &o, bool second_pass) {
       float cc1 = sss / (sss + f.air_psyc[j]);
       float cc2 = f.air_psyc[j] / (sss + f.air_psyc[j]);
       float qsatfvar = qsatf(f.met_tvair[j] - CTFRZ, f.met_pmb[j]);
+      if (o.cfg.litter)                                                                   // :64-68 (REAL(veg%clitt), REAL(DvLitt))
+        f.ssnow_potev[j] = cc1 * (f.canopy_fns[j] - f.canopy_ga[j])
+                           + cc2 * f.air_rho[j] * f.air_rlam[j] * (qsatfvar - f.met_qvair[j])
+                             / (f.ssnow_rtsoil[j] + (float)(1 - f.ssnow_isflag[j]) * (float)f.veg_clitt[j] * 0.003f / (float)DVLITT);
+      else
       f.ssnow_potev[j] = cc1 * (f.canopy_fns[j] - f.canopy_ga[j])
                          + cc2 * f.air_rho[j] * f.air_rlam[j] * (qsatfvar - f.met_qvair[j]) / f.ssnow_rtsoil[j];
     } else {                                                                              // :79-167
@@ -91,6 +99,10 @@ static void potev_calc(Oracle &o, bool second_pass) {
       }
       if (dq <= 0.0f && dqu < dq) dqu = dq;
       if (dq >= 0.0f && dqu < 0.0f) dqu = 0.0f;
+      if (o.cfg.litter)                                                                   // :158-161
+        f.ssnow_potev[j] = f.air_rho[j] * f.air_rlam[j] * dq
+                           / (f.ssnow_rtsoil[j] + (float)(1 - f.ssnow_isflag[j]) * (float)f.veg_clitt[j] * 0.003f / (float)DVLITT);
+      else
       f.ssnow_potev[j] = f.air_rho[j] * f.air_rlam[j] * dq / f.ssnow_rtsoil[j];           // :163
     }
   }
@@ -523,12 +535,13 @@ static void wetLeaf(Oracle &o, float dels, CanopyWork &w) {
 }
 
 // ---- within_canopy: cbl_within_canopy.F90:10-159 ----------------------------
-static void within_canopy(Oracle &o, CanopyWork &w, const std::vector<float> &rt0, std::vector<float> &qstvair) {
+static void within_canopy(Oracle &o, CanopyWork &w, const std::vector<float> &rt0, std::vector<float> &qstvair,
+                          const std::vector<float> &rhlitt_v, const std::vector<float> &relitt_v) {
   const int mp = o.mp; Fields &f = o.f;
   for (int j = 0; j < mp; j++) {
     float rrbw = (float)(((w.gbhu[j].v[0] + w.gbhf[j].v[0]) + (w.gbhu[j].v[1] + w.gbhf[j].v[1])) / f.air_cmolar[j]);   // :67 (f64 / f32)
     float rrsw = (f.canopy_gswx[IX(j, 0)] + f.canopy_gswx[IX(j, 1)]) / f.air_cmolar[j];   // :70
-    const float relitt = 0.f, rhlitt = 0.f;
+    const float relitt = relitt_v[j], rhlitt = rhlitt_v[j];                                // 0 unless cable_user%litter
     float fix_eqn = f.ssnow_cls[j] * rt0[j] / (rt0[j] + relitt);                          // :82
     if (f.ssnow_potev[j] > 0.f) fix_eqn = fix_eqn * f.ssnow_wetfac[j];
     float fix_eqn2 = rt0[j] / (rt0[j] + rhlitt);
@@ -567,6 +580,15 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
   w.gbhu.resize(mp); w.gbhf.resize(mp); w.csx.resize(mp);
   w.sum_rad_rniso.resize(mp); w.sum_rad_gradis.resize(mp);
   std::vector<float> rt0(mp), ortsoil(mp), rt1usc(mp), tss4(mp), qstvair(mp), pwet(mp, 0.f);
+  std::vector<float> rhlitt(mp, 0.f), relitt(mp, 0.f);                                    // :239-240
+  const bool litter = o.cfg.litter != 0, rev_corr = o.cfg.l_rev_corr != 0;
+  // REAL((1-isflag))*veg%clitt*0.003/kthLitt/(rho*CCAPP), .../DvLitt: r_2 expressions stored to REAL (:472-475, :987-988)
+  auto litter_resistances = [&]() {
+    for (int j = 0; j < mp; j++) {
+      rhlitt[j] = (float)((double)(float)(1 - f.ssnow_isflag[j]) * f.veg_clitt[j] * (double)0.003f / KTHLITT / (double)(f.air_rho[j] * CCAPP));
+      relitt[j] = (float)((double)(float)(1 - f.ssnow_isflag[j]) * f.veg_clitt[j] * (double)0.003f / DVLITT);
+    }
+  };
   const float rt_min = 5.f;
   int iterplus = 0;
 
@@ -625,6 +647,10 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       float psim_2 = psim(psim_arg);
       float lower_limit = rescale / (o_logf(z_eff) - psim_1 + psim_2);
       f.canopy_us[i] = fminf_(fmaxf_(1.e-6f, lower_limit), 10.0f);
+    }
+    if (o.cfg.l_new_roughness_soil) ruff_resist(o);                                       // :268-269 (E.Kowalczyk 2014)
+    for (int i = 0; i < mp; i++) {
+      float zet = f.canopy_zetar[IX(i, iter - 1)];
       // :276-284
       float xx = 0.5f + sign_(0.5f, f.rough_zref_tq[i] + f.rough_disp[i] - f.rough_zruffs[i]);
       float zr = fmaxf_(f.rough_zruffs[i] - f.rough_disp[i], f.rough_z0soilsn[i]);
@@ -675,15 +701,23 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
                         + (1.0f - f.rad_transd[j]) * CEMLEAF * CSBOLTZ * pow4(f.canopy_tv[j]) - CEMSOIL * CSBOLTZ * tss4[j];  // :455
       f.ssnow_qstss[j] = qsatf(f.ssnow_tss[j] - CTFRZ, f.met_pmb[j]);                      // :461
     }
+    if (litter) litter_resistances();                                                     // :471-476
     potev_calc(o, false);                                                                 // :480-506
     latent_heat_flux(o, dels, pwet);                                                      // :510
-    for (int j = 0; j < mp; j++)
-      f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tvair[j]) / f.ssnow_rtsoil[j];      // :532
-    within_canopy(o, w, rt0, qstvair);                                                    // :545
+    for (int j = 0; j < mp; j++) {
+      if (litter)                                                                         // :525-530: met%tk here, met%tvair at :600
+        f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tk[j]) / (f.ssnow_rtsoil[j] + rhlitt[j]);
+      else
+        f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tvair[j]) / f.ssnow_rtsoil[j];    // :532
+    }
+    within_canopy(o, w, rt0, qstvair, rhlitt, relitt);                                    // :545
     for (int j = 0; j < mp; j++) f.ssnow_qstss[j] = qsatf(f.ssnow_tss[j] - CTFRZ, f.met_pmb[j]);           // :549
     potev_calc(o, true);                                                                  // :553-579
     latent_heat_flux(o, dels, pwet);                                                      // :582
     for (int j = 0; j < mp; j++) {
+      if (litter)                                                                         // :596-601
+        f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tvair[j]) / (f.ssnow_rtsoil[j] + rhlitt[j]);
+      else
       f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tvair[j]) / f.ssnow_rtsoil[j];      // :603
       f.canopy_ga[j] = (float)(f.canopy_fns[j] - f.canopy_fhs[j] - f.canopy_fes[j]);      // :610
       f.canopy_fe[j] = (float)(f.canopy_fev[j] + f.canopy_fes[j]);                        // :621
@@ -764,6 +798,12 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
                   - psis((zscl - disp) * zP / f.rough_zref_tq[j])
                   + psis((f.rough_zruffs[j] - disp) * zP / f.rough_zref_tq[j])) / CVONK;
       }
+      if (litter)                                                                         // :808-812
+        f.canopy_tscrn[j] = f.ssnow_tss[j] + (f.met_tk[j] - f.ssnow_tss[j])
+                            * fminf_(1.f, ((r_sc + rhlitt[j] * f.canopy_us[j])
+                                           / fmaxf_(1.f, f.rough_rt0us[j] + f.rough_rt1usa[j] + f.rough_rt1usb[j] + rt1usc[j]
+                                                         + rhlitt[j] * f.canopy_us[j]))) - CTFRZ;
+      else
       f.canopy_tscrn[j] = f.ssnow_tss[j] + (f.met_tk[j] - f.ssnow_tss[j])
                           * fminf_(1.f, (r_sc / fmaxf_(1.f, f.rough_rt0us[j] + f.rough_rt1usa[j] + f.rough_rt1usb[j] + rt1usc[j])))
                           - CTFRZ;                                                        // :819
@@ -775,9 +815,16 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
     else qsurf = 0.1f * rsts * f.ssnow_wetfac[j] + 0.9f * f.met_qv[j];
     f.canopy_qmom[j] = f.air_rho[j] * (f.canopy_us[j] * f.canopy_us[j]);                  // :843 (us**2.0)
     f.canopy_qscrn[j] = f.met_qv[j] - qstar * ftemp;
-    if (f.canopy_vlaiw[j] > CLAI_THRESH && hr > 0.01f)
+    if (f.canopy_vlaiw[j] > CLAI_THRESH && hr > 0.01f) {
+      if (litter)                                                                         // :851-854
+        f.canopy_qscrn[j] = qsurf + (f.met_qv[j] - qsurf)
+                            * fminf_(1.f, ((r_sc + relitt[j] * f.canopy_us[j])
+                                           / fmaxf_(1.f, f.rough_rt0us[j] + f.rough_rt1usa[j] + f.rough_rt1usb[j] + rt1usc[j]
+                                                         + relitt[j] * f.canopy_us[j])));
+      else
       f.canopy_qscrn[j] = qsurf + (f.met_qv[j] - qsurf)
                           * fminf_(1.f, (r_sc / fmaxf_(1.f, f.rough_rt0us[j] + f.rough_rt1usa[j] + f.rough_rt1usb[j] + rt1usc[j])));  // :870
+    }
     f.canopy_dewmm[j] = (float)(-(fminf_(0.0f, f.canopy_fevw[j]) + dmin_(0.0, f.canopy_fevc[j])) * dels / f.air_rlam[j]);   // :881
     f.canopy_cansto[j] = f.canopy_cansto[j] + f.canopy_dewmm[j];
     f.canopy_cansto[j] = fmaxf_(f.canopy_cansto[j] - fmaxf_(0.0f, f.canopy_fevw[j]) * dels / f.air_rlam[j], 0.0f);
@@ -788,8 +835,18 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
     f.canopy_delwc[j] = f.canopy_cansto[j] - f.canopy_oldcansto[j];                       // :906
     f.ssnow_dfn_dtg[j] = (-1.f) * 4.f * CEMSOIL * CSBOLTZ * tss4[j] / f.ssnow_tss[j];     // :913
     float rttsoil = f.ssnow_rtsoil[j];
+    if (rev_corr && f.canopy_vlaiw[j] > CLAI_THRESH) rttsoil = rttsoil + f.rough_rt1[j];  // :917-922
+    if (litter) {                                                                         // :979-999
+      rhlitt[j] = (float)((double)(float)(1 - f.ssnow_isflag[j]) * f.veg_clitt[j] * (double)0.003f / KTHLITT / (double)(f.air_rho[j] * CCAPP));
+      relitt[j] = (float)((double)(float)(1 - f.ssnow_isflag[j]) * f.veg_clitt[j] * (double)0.003f / DVLITT);
+      f.ssnow_dfh_dtg[j] = f.air_rho[j] * CCAPP / (rttsoil + rhlitt[j]);
+      f.ssnow_dfe_ddq[j] = f.ssnow_wetfac[j] * f.air_rho[j] * f.air_rlam[j] * f.ssnow_cls[j] / (rttsoil + relitt[j]);
+    } else {
     f.ssnow_dfh_dtg[j] = f.air_rho[j] * CCAPP / rttsoil;                                  // :1006
     f.ssnow_dfe_ddq[j] = f.ssnow_wetfac[j] * f.air_rho[j] * f.air_rlam[j] * f.ssnow_cls[j] / rttsoil;
+    }
+    if (rev_corr && f.ssnow_potev[j] < 0.f)                                               // :995-999, :1010-1014 (relitt = 0 without litter)
+      f.ssnow_dfe_ddq[j] = f.air_rho[j] * f.air_rlam[j] * f.ssnow_cls[j] / (rttsoil + relitt[j]);
     f.ssnow_ddq_dtg[j] = (CRMH2O / CRMAIR) / f.met_pmb[j] * CTETENA * CTETENB * CTETENC
                          / (sq(CTETENC + f.ssnow_tss[j] - CTFRZ))
                          * o_expf(CTETENB * (f.ssnow_tss[j] - CTFRZ) / (CTETENC + f.ssnow_tss[j] - CTFRZ));   // :1018

@@ -21,9 +21,14 @@ void ruff_resist(Oracle &o) {
     float FracOfCanopyAboveSnow = HeightAboveSnow / fmaxf_(0.01f, f.veg_hc[i]);
     f.canopy_vlaiw[i] = f.veg_vlai[i] * FracOfCanopyAboveSnow;
     f.canopy_rghlai[i] = f.canopy_vlaiw[i];                          // :186
-    // soil roughness, default soil_struc, not l_new_roughness_soil (:193-205)
-    f.rough_z0soil[i] = 0.0009f * fminf_(1.0f, f.canopy_vlaiw[i]) + 1.e-4f;
-    f.rough_z0soilsn[i] = f.rough_z0soil[i];
+    // soil roughness, default soil_struc (:193-205)
+    if (!o.cfg.l_new_roughness_soil) {                                // (.NOT. or_evap: or_evap is rejected at create)
+      f.rough_z0soil[i] = 0.0009f * fminf_(1.0f, f.canopy_vlaiw[i]) + 1.e-4f;
+      f.rough_z0soilsn[i] = f.rough_z0soil[i];
+    } else {                                                         // E.Kowalczyk 2014 (:197-198)
+      f.rough_z0soil[i] = 0.01f * fminf_(1.0f, f.canopy_vlaiw[i]) + 0.02f * fminf_(f.canopy_us[i] * f.canopy_us[i] / CGRAV, 1.0f);
+      f.rough_z0soilsn[i] = fmaxf_(1.e-7f, f.rough_z0soil[i]);
+    }
     if (f.ssnow_snowd[i] > 0.01f)
       f.rough_z0soilsn[i] = fmaxf_(z0soilsn_min,
           f.rough_z0soil[i] - f.rough_z0soil[i] * fminf_(f.ssnow_snowd[i], 10.f) / 10.f);

@@ -323,6 +323,32 @@ static void old_soil_conductivity(Oracle &o, std::vector<double> &ccnsw) {
     }
 }
 
+// ---- total_soil_conductivity: cbl_conductivity.F90:11-89 (cable_user%soil_thermal_fix) ----
+static void total_soil_conductivity(Oracle &o, std::vector<double> &cond) {
+  const int mp = o.mp; Fields &f = o.f;
+  for (int k = 0; k < ms; k++)
+    for (int j = 0; j < mp; j++) {
+      const double cnsd_vec = f.soil_cnsd_vec[IX(j, k)], ssat_vec = f.soil_ssat_vec[IX(j, k)], watr = f.soil_watr[IX(j, k)];
+      cond[IX(j, k)] = cnsd_vec;                                                          // :30
+      if (f.soil_isoilm[j] == 9) {
+        cond[IX(j, k)] = o.cfg.snow_ccnsw;
+      } else {
+        double quartz = dmax_(0.0f, dmin_(0.8f, f.soil_sand_vec[IX(j, k)] * 0.92f));      // :37
+        double Ko = (quartz > 0.2f) ? 2.0 : 3.0;
+        double Ktmp = std::pow(std::pow((double)7.7f, quartz) * std::pow(Ko, 1.0f - quartz), 1.0f - ssat_vec);   // :44-45
+        double liq_frac = 0.0;
+        if (f.ssnow_wb[IX(j, k)] >= 1.0e-15f) liq_frac = dmin_(1.0, dmax_(0.0, f.ssnow_wbliq[IX(j, k)] / f.ssnow_wb[IX(j, k)]));
+        double Ksat = Ktmp * std::pow((double)2.2f, ssat_vec * (1.0f - liq_frac)) * std::pow((double)0.57f, liq_frac);   // :53-55
+        double Sr = dmin_(0.9999f, dmax_(0.f, f.ssnow_wb[IX(j, k)] - watr) / (ssat_vec - watr));                          // :57-58
+        double Ke = (Sr >= 0.05f) ? 0.7f * std::log10(Sr) + 1.0f : 0.0;
+        if (f.ssnow_wbice[IX(j, k)] > 0.0f || f.ssnow_tgg[IX(j, k)] < CTFRZ || f.ssnow_isflag[j] != 0 || f.ssnow_snowd[j] >= 0.1f)
+          Ke = Sr;                                                                        // :66-73
+        double t = Ke * Ksat + (1.0f - Ke) * cnsd_vec;
+        cond[IX(j, k)] = dmin_(Ksat, dmax_(cnsd_vec, t));                                 // :78-79
+      }
+    }
+}
+
 // ---- stempv: cbl_stempv.F90:13-221 ------------------------------------------
 static void stempv(Oracle &o, float dels) {
   const int mp = o.mp; Fields &f = o.f; const float *zse = o.cfg.zse; const float max_sconds = o.cfg.max_sconds;
@@ -335,7 +361,8 @@ static void stempv(Oracle &o, float dels) {
 #define BT(i, k) bt[IX(i, (k) + 2)]
 #define CT(i, k) ct[IX(i, (k) + 2)]
 #define CO(i, k) coeff[IX(i, (k) + 2)]
-  old_soil_conductivity(o, ccnsw);                                                        // :60
+  if (o.cfg.soil_thermal_fix) total_soil_conductivity(o, ccnsw);                          // :57-61
+  else old_soil_conductivity(o, ccnsw);
   for (int i = 0; i < mp; i++) {
     const float ssat = f.soil_ssat[i], css = f.soil_css[i], rhosoil = f.soil_rhosoil[i];
     double xx = 0.;

@@ -64,9 +64,11 @@ def test_create_error_behaviour_without_compute():
     h = C.c_void_p()
     cfg = lib.default_cfg()
     # unsupported switches are rejected before any device work (reference: STOP 'fwsoil_switch failed.')
-    cfg.litter = 1
-    assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -2
-    assert b"unsupported" in L.cable_b200_last_error()
+    for sw in ("or_evap", "gw_model", "call_climate", "redistrb", "soil_struc_sli", "runtime_um"):
+        cfg = lib.default_cfg()
+        setattr(cfg, sw, 1)
+        assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -2, sw
+        assert b"unsupported" in L.cable_b200_last_error()
     cfg = lib.default_cfg()
     cfg.fwsoil_switch = 3                      # Haverd2013
     assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -2

@@ -80,7 +80,11 @@ def test_libm_oracle_fraction_within_tolerance():
 
 @pytest.mark.parametrize("switches", [dict(fwsoil_switch=1), dict(fwsoil_switch=2), dict(ssnow_potev=1),
                                       dict(diag_soil_resp_on=0), dict(l_new_runoff_speed=1, l_new_reduce_soilevp=1),
-                                      dict(gs_switch=1, fwsoil_switch=1)])
+                                      dict(gs_switch=1, fwsoil_switch=1),
+                                      # the XSW instantiation of the kernels (cbm_kernel.cuh)
+                                      dict(litter=1), dict(l_rev_corr=1), dict(litter=1, l_rev_corr=1, ssnow_potev=1),
+                                      dict(soil_thermal_fix=1), dict(l_new_roughness_soil=1),
+                                      dict(gs_switch=1, litter=1, l_rev_corr=1, soil_thermal_fix=1, l_new_roughness_soil=1)])
 def test_switch_matrix(switches):
     """cable_user switches on the supported path."""
     cfg = lib.default_cfg()
@@ -89,6 +93,28 @@ def test_switch_matrix(switches):
     cfg, grid, T, F = make_case(300, cfg=cfg, start_doy=200)
     T_gpu, o, _ = run_pair(cfg, grid, T, F, 6)
     assert_logic_parity(T, T_gpu)
+
+
+def test_new_roughness_soil_carries_us_at_output_level_1():
+    """l_new_roughness_soil makes canopy%us an input of the next step (cable_roughness.F90:197): the device must keep it
+    at every output level, and the initial value must come from the host array (0.1, cable_parameters.F90:1213)."""
+    cfg = lib.default_cfg(); cfg.l_new_roughness_soil = 1
+    cfg, grid, T, F = make_case(300, cfg=cfg, start_doy=200)
+    dev_cfg = lib.default_cfg(); dev_cfg.l_new_roughness_soil = 1; dev_cfg.output_level = 1
+    T_gpu = {k: v.copy() for k, v in T.items()}
+    o = Oracle(T, cfg, cr_math=True)
+    with CableB200(grid.mp, dev_cfg) as h:
+        h.bind(T_gpu); h.upload_params(); h.upload_state()
+        for k in range(6):
+            F.fill(T, k)
+            for n in synth.FORCING_FIELDS:
+                T_gpu[n][...] = T[n]
+            o.cbm(k + 1, DELS)
+            h.cbm(k + 1, DELS)
+    fields = [f for f in output_fields() if f.role == ROLE["STATE"] or f.star()]
+    res = compare_tiles(T, T_gpu, fields)
+    bad = {n: r for n, r in res.items() if r[0] > r[1]}
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("mp_case", [(1, 1), (1, 3), (7, 5), (26, 5)])      # 1, 3, 35, 130 tiles: ragged vs the 128-thread block

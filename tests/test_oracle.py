@@ -85,6 +85,45 @@ def test_reference_closure_invariants(gs):
     assert o.warnings() == 0
 
 
+@pytest.mark.parametrize("switches", [dict(litter=1), dict(l_rev_corr=1), dict(litter=1, l_rev_corr=1, ssnow_potev=1),
+                                      dict(soil_thermal_fix=1), dict(l_new_roughness_soil=1)])
+def test_optional_switch_closure_and_effect(switches):
+    """cable_user%litter / l_rev_corr / soil_thermal_fix / l_new_roughness_soil (cable_canopy.F90:471-476,917-1015,
+    cbl_conductivity.F90:11, cable_roughness.F90:193-199): the reference's closure checks still hold on the oracle
+    output and the switch changes the fields it is documented to change."""
+    def run(sw):
+        cfg = lib.default_cfg()
+        for k, v in sw.items():
+            setattr(cfg, k, v)
+        cfg, grid, T, F = make_case(300, cfg=cfg)
+        o = Oracle(T, cfg)
+        for k in range(10):
+            F.fill(T, k)
+            wb_prev = T["ssnow_wbtot"][0].copy()
+            o.cbm(k + 1, DELS)
+            if k == 0:
+                continue
+            radbal, ebalsoil, ebalveg, ebal = energy_balances(T)
+            assert np.abs(radbal).max() < 5e-3 and np.abs(ebalsoil).max() < 1e-3
+            assert np.abs(ebalveg).max() < 5e-3 and np.abs(ebal).max() < 5e-3
+            wbal = water_balance(T, DELS, wb_prev)
+            assert np.abs(wbal[T["veg_iveg"][0] < 16]).max() < 2e-2
+        return T
+    base = run({k: v for k, v in switches.items() if k == "ssnow_potev"})
+    T = run(switches)
+    for name in ("canopy_fe", "ssnow_tgg", "canopy_tscrn", "ssnow_wb"):
+        assert np.all(np.isfinite(T[name]))
+    changed = {"litter": "canopy_fhs", "l_rev_corr": "canopy_dgdtg", "soil_thermal_fix": "ssnow_tgg",
+               "l_new_roughness_soil": "rough_z0soil"}
+    for sw, name in changed.items():
+        if switches.get(sw):
+            assert np.abs(T[name].astype(np.float64) - base[name]).max() > 0, (sw, name)
+    if switches.get("l_new_roughness_soil"):        # z0soil = 0.01 min(1,LAI) + 0.02 min(us^2/g, 1)  (:197)
+        us, lai = T["canopy_us"][0], T["canopy_vlaiw"][0]
+        assert np.all(T["rough_z0soil"][0] <= np.float32(0.01) * np.minimum(1, lai) + np.float32(0.02) + 1e-7)
+        assert np.all(T["rough_z0soilsn"][0] >= 1e-7)
+
+
 @pytest.mark.parametrize("tag,gs", [("leuning", 0), ("medlyn", 1)])
 def test_oracle_reproduces_golden_vectors(tag, gs):
     gold = np.load(GOLD)

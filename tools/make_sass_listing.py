@@ -4,7 +4,7 @@ import collections, os, re, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(root, "cable_b200", "libcable_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-want = {"kernelA_cbm_kernel_1_768_1_1": "cbm_kernelILi1ELi768ELi1ELi1E", "kernelB_cbm_kernel_2_128_6_1": "cbm_kernelILi2ELi128ELi6ELi1E",
+want = {"kernelA_cbm_kernel_1_768_1_1": "cbm_kernelILi1ELi768ELi1ELi1ELi0E", "kernelB_cbm_kernel_2_128_6_1": "cbm_kernelILi2ELi128ELi6ELi1ELi0E",
         "driver_kernels": None}
 cur, out = None, collections.defaultdict(list)
 for line in sass.splitlines():
