@@ -23,7 +23,7 @@ from .registry import FIELDS, BY_NAME, ROLE, FLAG, alloc_tiles
 TYPE_NAMES = {
     "met": "met_type", "air": "air_type", "veg": "veg_parameter_type", "soil": "soil_parameter_type",
     "ssnow": "soil_snow_type", "canopy": "canopy_type", "rad": "radiation_type", "rough": "roughness_type",
-    "bal": "balances_type", "bgc": "bgc_pool_type", "scr": "(xk, c1, rhoch scratch)",
+    "bal": "balances_type", "bgc": "bgc_pool_type", "scr": "(xk, c1, rhoch scratch)", "climate": "climate_type",
 }
 
 

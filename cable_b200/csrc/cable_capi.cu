@@ -264,6 +264,7 @@ bool wanted_output(const cable_handle *h, int id) {
 // PARAM fields flagged OPTIN are inputs of one non-default switch: they must be bound only when it is set
 bool optin_param_needed(const cable_handle *h, int id) {
   if (id == FID_veg_clitt) return h->cfg.litter != 0;
+  if (id == FID_climate_qtemp_max_last_year) return h->cfg.call_climate != 0;
   if (id == FID_soil_cnsd_vec || id == FID_soil_sand_vec || id == FID_soil_watr) return h->cfg.soil_thermal_fix != 0;
   return true;
 }
@@ -323,6 +324,7 @@ void cable_b200_default_cfg(cable_cfg *c) {
   c->snmin = 1.0f;                            // cable_runtime_opts_mod.F90:9
   c->max_glacier_snowd = 1100.0f; c->snow_ccnsw = 2.0f; c->max_ssdn = 750.0f;   // cable_common.F90:217-222
   c->max_sconds = 2.51f; c->frozen_limit = 0.85f;
+  c->wiltParam = 0.5f; c->satuParam = 0.8f;   // cable.nml:55-56 (only read when redistrb is set)
   const float zse[CABLE_MS] = {.022f, .058f, .154f, .409f, 1.085f, 2.872f};      // cable_parameters.F90:1241
   for (int k = 0; k < CABLE_MS; k++) c->zse[k] = zse[k];
   c->zshh[0] = 0.5f * zse[0];                                                    // cable_parameters.F90:1828-1831
@@ -340,9 +342,8 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   if (mp <= 0 || !cfg) return fail(CABLE_E_ARG, "mp must be > 0 and cfg non-null");
   if (cfg->struct_bytes != (int)sizeof(cable_cfg)) return fail(CABLE_E_ARG, "cable_cfg size mismatch (ABI)");
   // switch combinations the device path does not implement
-  if (cfg->or_evap || cfg->gw_model || cfg->call_climate || cfg->redistrb || cfg->soil_struc_sli || cfg->runtime_um)
-    return fail(CABLE_E_UNSUPPORTED, "unsupported switch: or_evap/gw_model/call_climate/redistrb/soil_struc=sli/"
-                                     "cable_runtime%um must be off");
+  if (cfg->or_evap || cfg->gw_model || cfg->soil_struc_sli || cfg->runtime_um)
+    return fail(CABLE_E_UNSUPPORTED, "unsupported switch: or_evap/gw_model/soil_struc=sli/cable_runtime%um must be off");
   if (cfg->gs_switch != CABLE_GS_LEUNING && cfg->gs_switch != CABLE_GS_MEDLYN)
     return fail(CABLE_E_UNSUPPORTED, "gs_model_switch failed.");                 // cbl_dryLeaf.F90:436
   if (cfg->fwsoil_switch < 0 || cfg->fwsoil_switch > CABLE_FWSOIL_LAI_KTAUL)
@@ -371,7 +372,9 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   d.l_new_reduce_soilevp = cfg->l_new_reduce_soilevp; d.icycle = cfg->icycle; d.mvtype = cfg->mvtype;
   d.litter = cfg->litter != 0; d.l_rev_corr = cfg->l_rev_corr != 0; d.soil_thermal_fix = cfg->soil_thermal_fix != 0;
   d.l_new_roughness_soil = cfg->l_new_roughness_soil != 0;
-  h->xsw = d.litter || d.l_rev_corr || d.soil_thermal_fix || d.l_new_roughness_soil;
+  d.redistrb = cfg->redistrb != 0; d.call_climate = cfg->call_climate != 0;
+  d.wiltParam = cfg->wiltParam; d.satuParam = cfg->satuParam;
+  h->xsw = d.litter || d.l_rev_corr || d.soil_thermal_fix || d.l_new_roughness_soil || d.redistrb || d.call_climate;
   d.met_tv_is_tk = cfg->met_tv_is_tk; d.caller_duties = cfg->caller_duties; d.output_level = cfg->output_level;
   d.snmin = cfg->snmin; d.max_glacier_snowd = cfg->max_glacier_snowd; d.snow_ccnsw = cfg->snow_ccnsw;
   d.max_ssdn = cfg->max_ssdn; d.max_sconds = cfg->max_sconds; d.frozen_limit = cfg->frozen_limit;

@@ -263,11 +263,15 @@ struct LeafPass {
   float tlfy;
   double rny, hcy, ecy;
   float rdy[2], an_y[2], oldevapfbl[K::ms];
+  // call_climate only (:328-393): Rd at 25 C per unit scalex, light-inhibition factor of each leaf and whether it applies
+  float rd25, rdfac[2];
+  bool rdinh[2];
 };
 
 // One ACTIVE pass k (the reference's loop body for a tile with vlaiw > thresh and |deltlf| > 0.1, :243-560), then the
 // bookkeeping every pass ends with (keep the best iterate, damp after k > 5, :565-606).
 // Returns true while the tile needs another pass; `captured` tells whether the best iterate was replaced.
+template <bool XSW>
 CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int k, bool &captured) {
   const float jtomol = 4.6e-6f;
   const float cr = K::capp * K::rmair;
@@ -291,6 +295,10 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
   const float cx1 = conkct * (1.0f + dv(0.21f, conkot));
   const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
   float vsum0 = p.fvlai[0] + p.fvlai[1];
+  // call_climate: variable-Q10 temperature response of dark respiration, xrdt (:843-853)
+  float xrdt = 0.f;
+  if (XSW && c.call_climate)
+    xrdt = m_pow(3.09f - dv(0.043f * ((tlfx - 273.15f) + 25.f), 2.0f), dv(tlfx - 273.15f - 25.0f, 10.0f));
   // stomatal-slope factors that do not depend on the leaf
   float gs_shared;
   if (c.gs_switch == CABLE_GS_LEUNING) {
@@ -322,7 +330,11 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
     const float par4 = qcan_l * jtomol * p.frac4;
     const float vx3 = mx(0.0f, 0.25f * ejx_root(par3, p.alpha, p.convex, ejmxt3));
     const float vx4 = mx(0.0f, ejx_root(par4, p.alpha, p.convex, vcmxt4));
-    const float rdx_l = (p.cfrd * vcmxt3 + p.cfrd * vcmxt4);
+    float rdx_l = (p.cfrd * vcmxt3 + p.cfrd * vcmxt4);
+    if (XSW && c.call_climate) {                                                   // :328-393
+      rdx_l = p.rd25 * xrdt * scalex_l;
+      if (l ? p.rdinh[1] : p.rdinh[0]) rdx_l = rdx_l * (l ? p.rdfac[1] : p.rdfac[0]);
+    }
     // stomatal slope coefficient
     float gs_coeff;
     if (c.gs_switch == CABLE_GS_LEUNING) {
@@ -441,6 +453,7 @@ __host__ __device__ constexpr size_t leaf_pool_smem_bytes(int block) {
 #endif
 
 // dryLeaf for the calling thread's tile.  `d`, `tile`, `smp`: global arrays / this thread's tile / mp (pool mode only).
+template <bool XSW>
 CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int iter, const DevPtrs &d, const int tile,
                      const size_t smp) {
   if (iter == 1) { w.fwsoil = fwsoil_calc(t, c); t.canopy_fwsoil = (double)w.fwsoil; }
@@ -460,6 +473,21 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
     p.rdy[l] = 0.f; p.an_y[l] = 0.f;
   }
   if (c.gs_switch == CABLE_GS_MEDLYN && veg) { p.gswmin[0] = t.veg_g0; p.gswmin[1] = t.veg_g0; }   // per-tile form of D4
+  p.rd25 = 0.f; p.rdfac[0] = 1.f; p.rdfac[1] = 1.f; p.rdinh[0] = false; p.rdinh[1] = false;
+  if (XSW && c.call_climate) {                                                     // Atkin et al. 2015 (:328-393)
+    const int iv = t.veg_iveg;
+    const float tail = 0.0116f * t.veg_vcmax, twq = 0.0334f * t.climate_qtemp_max_last_year * 1.0e-6f;
+    if (iv == 2 || iv == 4 || iv == 12 || iv == 13) p.rd25 = 0.60f * (1.2818e-6f + tail - twq);      // broadleaf, aust_mesic/xeric
+    else if (iv == 1 || iv == 3) p.rd25 = 1.0f * (1.2877e-6f + tail - twq);                         // needleleaf
+    else if (iv == 6 || iv == 8 || iv == 9) p.rd25 = 0.60f * (1.6737e-6f + tail - twq);             // C3 grass, tundra, C3 crop
+    else p.rd25 = 0.60f * (1.5758e-6f + tail - twq);
+    // light inhibition; the shaded leaf reads qcan(i,1,2) = sunlit NIR
+    const float jt = 4.6e-6f * 1.0e6f;
+    const float i0 = jt * t.rad_qcan[0], i1 = jt * t.rad_qcan[0 + 2 * 1];
+    p.rdinh[0] = i0 > 10.0f; p.rdinh[1] = i1 > 10.0f;
+    if (p.rdinh[0]) p.rdfac[0] = 0.5f - 0.05f * m_log(i0);
+    if (p.rdinh[1]) p.rdfac[1] = 0.5f - 0.05f * m_log(i1);
+  }
 #pragma unroll
   for (int k = 0; k < K::ms; k++) { p.froot[k] = t.veg_froot[k]; p.wbliq[k] = t.ssnow_wbliq[k]; p.evapfbl[k] = 0.0; p.oldevapfbl[k] = 0.f; }
   p.tlfx = w.tlfx; p.dsx = w.dsx;
@@ -478,7 +506,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
   if (veg) {
     for (int k = 1; k <= K::maxiter; k++) {
       bool captured;
-      if (!leaf_pass(p, c, dels, k, captured)) break;
+      if (!leaf_pass<XSW>(p, c, dels, k, captured)) break;
     }
   }
 #else
@@ -555,7 +583,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
         q.evapfbl[kk] = d.ssnow_evapfbl[ti + smp * kk];
       }
       bool captured;
-      leaf_pass(q, c, dels, k, captured);
+      leaf_pass<XSW>(q, c, dels, k, captured);
       rf[LR_TLFX * nslot + s] = q.tlfx; rf[LR_DSX * nslot + s] = q.dsx; rf[LR_ABSD * nslot + s] = q.abs_deltlf;
       rf[LR_DELTLFY * nslot + s] = q.deltlfy;
       rf[LR_GW0 * nslot + s] = q.gw[0]; rf[LR_GW1 * nslot + s] = q.gw[1];
@@ -747,7 +775,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
       w.gbhu[1] = (double)dv(2.0f, t.rough_coexp) * gbvtop * (double)(1.0f - m_exp(-mn(hc * lai, 20.0f))) - w.gbhu[0];
     }
     w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
-    dryLeaf(t, c, w, dels, iter, d, tile, smp);
+    dryLeaf<XSW>(t, c, w, dels, iter, d, tile, smp);
     CBL_PHASE_BARRIER(CBL_SYNC_A, 2 * (iter - 1) + 1);  // re-align after the data-dependent number of dryLeaf passes
     wetLeaf(t, w, dels);
     // vegetation fluxes and temperature (:418-456)

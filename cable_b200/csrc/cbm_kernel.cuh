@@ -104,6 +104,7 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
     if (c.ssnow_potev == CABLE_POTEV_PM) t.canopy_ga = d.canopy_ga[i];           // cable_canopy.F90:487
     if (c.caller_duties) t.canopy_oldcansto = t.canopy_cansto;                   // cable_serial.F90:573
     if (XSW && c.litter) t.veg_clitt = d.veg_clitt[i];                           // cable_canopy.F90:472
+    if (XSW && c.call_climate) t.climate_qtemp_max_last_year = d.climate_qtemp_max_last_year[i];   // cbl_dryLeaf.F90:349
     if (XSW && c.l_new_roughness_soil) t.canopy_us = d.canopy_us[i];             // cable_roughness.F90:197: last step's us
 
     lake_refill(t, c);

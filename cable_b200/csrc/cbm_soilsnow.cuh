@@ -581,6 +581,70 @@ CBL_DEV void surfbv(Tile &t, const DevCfg &c, float dels) {
 }
 
 // soil_snow: cbl_soilsnow_main.F90:28-207.  first_call <=> the reference's SAVE ktau <= 1 (D3)
+// hydraulic_redistribution: cbl_hyd_redistrib.F90:13-221 (redistrb).  Default-REAL working variables, ssnow%wb r_2.
+// One exchange between layers k and j (zero based); UPPER selects the second sweep's forms (:166-167, :183, :197).
+template <bool UPPER>
+CBL_DEV void hr_exchange(Tile &t, const DevCfg &c, const float (&wpsy)[K::ms], const float (&C_hr)[K::ms], const int k, const int j,
+                         const float Dtran, const bool hr_pft, const float dels) {
+  const float CRT = 125.0f;
+  const float fk = t.veg_froot[k], fj = t.veg_froot[j], zk = c.zse[k], zj = c.zse[j];
+  const float frootX = mx(0.01f, mx(fk, fj));
+  const float prod = UPPER ? (mx(0.01f, fk) * mx(0.01f, fj)) : (fk * fj);
+  const float hr_term = dv(CRT * (wpsy[j] - wpsy[k]) * mx(C_hr[k], C_hr[j]) * prod, 1 - frootX) * Dtran;
+  float hkj = dv(hr_term * 1.0E-2f, 3600.0f) * dels;
+  float hjk = -1.0f * hkj;
+  hkj = dv(hkj, zk);
+  hjk = dv(hjk, zj);
+  if (!hr_pft) { hkj = 0.0f; hjk = 0.0f; }
+  const double wbk = t.ssnow_wb[k], wbj = t.ssnow_wb[j];
+  const float field_third = t.soil_swilt + dv(t.soil_sfc - t.soil_swilt, 3.f);
+  if (hkj < 0.0f) {
+    const float available = (float)mx(0.0, UPPER ? wbk - (double)t.soil_sfc : wbk - (double)field_third);
+    const float accommodate = (float)mx(0.0, (double)t.soil_ssat - wbj);
+    const float temp = mx(mx(hkj, -1.0f * c.wiltParam * available), dv(-1.0f * c.satuParam * accommodate * zj, zk));
+    hkj = temp;
+    hjk = dv(-1.0f * temp * zk, zj);
+  } else if (hjk < 0.0f) {
+    const float available = (float)mx(0.0, UPPER ? wbj - (double)t.soil_sfc : wbj - (double)field_third);
+    const float accommodate = (float)mx(0.0, (double)t.soil_ssat - wbk);
+    const float temp = mx(mx(hjk, -1.0f * c.wiltParam * available), dv(-1.0f * c.satuParam * accommodate * zk, zj));
+    hjk = temp;
+    hkj = dv(-1.0f * temp * zj, zk);
+  }
+  t.ssnow_wb[k] = t.ssnow_wb[k] + (double)hkj;
+  t.ssnow_wb[j] = t.ssnow_wb[j] + (double)hjk;
+}
+CBL_DEV void hr_potentials(const Tile &t, float (&wpsy)[K::ms], float (&C_hr)[K::ms]) {           // :78-85, :144-151
+  const float n_hr = 3.22f, wpsy50 = -1.0f, n_VG = 2.06f, m_VG = 1.0f - 1.0f / n_VG, alpha_VG = 0.00423f;
+#pragma unroll
+  for (int k = 0; k < K::ms; k++) {
+    const float S_VG = mn(1.0f, dv(mx(1.0E-4f, (float)t.ssnow_wb[k] - t.soil_swilt), t.soil_ssat - t.soil_swilt));
+    wpsy[k] = (-1.0f / alpha_VG) * m_pow(m_pow(S_VG, -1.0f / m_VG) - 1.0f, 1 / n_VG) * 100 * 1.0E-6f;
+    C_hr[k] = dv(1.f, 1 + m_pow(dv(wpsy[k], wpsy50), n_hr));
+  }
+}
+CBL_DEV void hydraulic_redistribution(Tile &t, const DevCfg &c, const float dels) {
+  float totalice = 0.0f;                                                                           // :70-73
+#pragma unroll
+  for (int k = 0; k < K::ms; k++) totalice = (float)((double)totalice + dv(t.ssnow_wbice[k] * (double)c.zse[k], (double)c.zsetot));
+  float Dtran = (t.canopy_fevc < (double)10.0f && totalice < 1.e-2f) ? 1.0f : 0.0f;                // :76
+  const bool hr_pft = t.veg_iveg == 2 || t.veg_iveg == 7;         // evergreen_broadleaf, c4_grassland (cable_surface_types.F90:17,22)
+  float wpsy[K::ms], C_hr[K::ms];
+  hr_potentials(t, wpsy, C_hr);
+#pragma unroll
+  for (int k = K::ms; k >= 3; k--) {                                                               // :91-140
+#pragma unroll
+    for (int j = k - 1; j >= 2; j--) hr_exchange<false>(t, c, wpsy, C_hr, k - 1, j - 1, Dtran, hr_pft, dels);
+  }
+  if (t.met_tk < K::tfrz + 5.f) Dtran = 0.0f;                                                      // :142
+  hr_potentials(t, wpsy, C_hr);
+#pragma unroll
+  for (int k = 1; k <= K::ms - 2; k++) {                                                           // :155-208
+#pragma unroll
+    for (int j = k + 1; j <= K::ms - 1; j++) hr_exchange<true>(t, c, wpsy, C_hr, k - 1, j - 1, Dtran, hr_pft, dels);
+  }
+}
+
 template <bool XSW>
 CBL_DEV void soil_snow(Tile &t, const DevCfg &c, float dels, bool first_call) {
   float tggav = 0.f;
@@ -596,6 +660,12 @@ CBL_DEV void soil_snow(Tile &t, const DevCfg &c, float dels, bool first_call) {
   t.ssnow_runoff = 0.0f; t.ssnow_rnof1 = 0.0f; t.ssnow_rnof2 = 0.0f; t.ssnow_smelt = 0.0f;
   t.ssnow_dtmlt[0] = 0.0f; t.ssnow_dtmlt[1] = 0.0f; t.ssnow_dtmlt[2] = 0.0f;
   t.ssnow_osnowd = t.ssnow_snowd;
+  // ssnow%wbliq = ssnow%wb - ssnow%wbice (cbl_soilsnow_main.F90:87): only total_soil_conductivity reads it before the
+  // end-of-step refresh, and it differs from the carried value only where cbm refilled a lake's top layer
+  if (XSW) {
+#pragma unroll
+    for (int k = 0; k < K::ms; k++) t.ssnow_wbliq[k] = t.ssnow_wb[k] - t.ssnow_wbice[k];
+  }
   const float xx = t.soil_css * t.soil_rhosoil;
   if (first_call)
     t.ssnow_gammzz[0] = mx((double)((1.0f - t.soil_ssat) * t.soil_css * t.soil_rhosoil)
@@ -639,6 +709,7 @@ CBL_DEV void soil_snow(Tile &t, const DevCfg &c, float dels, bool first_call) {
     t.ssnow_pudsto = pud - t.ssnow_rnof1;
   }
   surfbv(t, c, dels);
+  if (XSW && c.redistrb) hydraulic_redistribution(t, c, dels);                                     // cbl_soilsnow_main.F90:186-187
   t.ssnow_smelt = smelt / dels;
   t.ssnow_tss = (float)(1 - t.ssnow_isflag) * t.ssnow_tgg[0] + (float)t.ssnow_isflag * t.ssnow_tggsn[0];
   t.ssnow_totsdepth = (t.ssnow_sdepth[0] + t.ssnow_sdepth[1]) + t.ssnow_sdepth[2];

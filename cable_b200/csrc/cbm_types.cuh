@@ -48,7 +48,8 @@ struct Tile {
 struct DevCfg {
   int   gs_switch, fwsoil_switch, ssnow_potev, diag_soil_resp_on;
   int   l_new_runoff_speed, l_new_reduce_soilevp;
-  int   litter, l_rev_corr, soil_thermal_fix, l_new_roughness_soil;   // only read by the XSW instantiations (cbm_kernel.cuh)
+  int   litter, l_rev_corr, soil_thermal_fix, l_new_roughness_soil, redistrb, call_climate;   // only read by the XSW instantiations (cbm_kernel.cuh)
+  float wiltParam, satuParam;                                         // hydraulic_redistribution (redistrb)
   int   icycle, mvtype;
   int   met_tv_is_tk, caller_duties, output_level;
   float snmin, max_glacier_snowd, snow_ccnsw, max_ssdn, max_sconds, frozen_limit;

@@ -16,7 +16,6 @@ namespace cable_cbm_module {
 #include "host_mirror_types.inc"
 
 struct sum_flux_type {};   // untouched by cbm (cable_define_types.F90:688-702)
-struct climate_type {};    // only read with call_climate, which the device path rejects
 
 class cbm_device {
  public:
@@ -30,7 +29,7 @@ class cbm_device {
   // same argument list as the reference cbm()
   void cbm(int ktau, float dels, air_type &air, bgc_pool_type &bgc, canopy_type &canopy, met_type &met, balances_type &bal,
            radiation_type &rad, roughness_type &rough, soil_parameter_type &soil, soil_snow_type &ssnow, sum_flux_type &,
-           veg_parameter_type &veg, const climate_type &, float *xk, float *c1, float *rhoch) {
+           veg_parameter_type &veg, const climate_type &climate, float *xk, float *c1, float *rhoch) {
     if (!h_) {
       check(cable_b200_create(mp_, &cfg_, -1, &h_));
       cbm_scratch_type scr; scr.xk = xk; scr.c1 = c1; scr.rhoch = rhoch;

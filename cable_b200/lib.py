@@ -29,6 +29,7 @@ class CableCfg(C.Structure):
         ("runtime_um", C.c_int), ("icycle", C.c_int), ("mvtype", C.c_int),
         ("snmin", C.c_float), ("max_glacier_snowd", C.c_float), ("snow_ccnsw", C.c_float),
         ("max_ssdn", C.c_float), ("max_sconds", C.c_float), ("frozen_limit", C.c_float),
+        ("wiltParam", C.c_float), ("satuParam", C.c_float),
         ("zse", C.c_float * MS), ("zshh", C.c_float * (MS + 1)),
         ("ratecp", C.c_float * NCP), ("ratecs", C.c_float * NCS),
         ("met_tv_is_tk", C.c_int), ("caller_duties", C.c_int), ("output_level", C.c_int),

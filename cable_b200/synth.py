@@ -238,6 +238,8 @@ def make_tiles(grid: Grid, cfg=None, single_pft: int | None = None) -> dict[str,
         T["soil_watr"][k] = np.float64(np.float32(0.01))
     T["veg_clitt"][0] = PFT["clitt"][iv].astype(np.float64)                  # pft_params.nml vegin%clitt
     T["canopy_us"][0] = 0.1                                                  # cable_parameters.F90 write_default_params
+    # climate%qtemp_max_last_year (deg C, mean of the warmest quarter): only read under call_climate
+    T["climate_qtemp_max_last_year"][0] = (grid.tmean + np.float32(0.7) * grid.tamp - np.float32(273.15))[grid.tile2land]
     T["rough_za_uv"][0] = 40.0
     T["rough_za_tq"][0] = 40.0
     # ---- initial state (write_default_params) ----

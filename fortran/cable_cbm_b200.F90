@@ -31,6 +31,7 @@ MODULE cable_cbm_module
      INTEGER(C_INT) :: l_new_roughness_soil, call_climate, redistrb, soil_struc_sli
      INTEGER(C_INT) :: runtime_um, icycle, mvtype
      REAL(C_FLOAT)  :: snmin, max_glacier_snowd, snow_ccnsw, max_ssdn, max_sconds, frozen_limit
+     REAL(C_FLOAT)  :: wiltParam, satuParam
      REAL(C_FLOAT)  :: zse(6), zshh(7), ratecp(3), ratecs(2)
      INTEGER(C_INT) :: met_tv_is_tk, caller_duties, output_level, n_forcing_slots, threads_per_block
   END TYPE cable_cfg

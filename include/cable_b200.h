@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CABLE_B200_ABI_VERSION 1
+#define CABLE_B200_ABI_VERSION 2
 
 /* dims fixed by the reference (cable_define_types.F90:62-71) */
 #define CABLE_MS    6   /* soil layers            */
@@ -93,7 +93,9 @@ typedef struct cable_cfg {
   int   l_new_reduce_soilevp;  /* cbl_latent_heat.F90:205                    */
   int   litter, or_evap, gw_model, l_rev_corr, soil_thermal_fix,
         l_new_roughness_soil, call_climate, redistrb, soil_struc_sli;
-                               /* must all be 0: CABLE_E_UNSUPPORTED otherwise */
+                               /* litter, l_rev_corr, soil_thermal_fix, l_new_roughness_soil, call_climate, redistrb:
+                                  supported (second kernel instantiation); or_evap, gw_model, soil_struc_sli must be
+                                  0: CABLE_E_UNSUPPORTED otherwise (dead or SLI-only in this reference snapshot) */
   /* cable_runtime, casadimension */
   int   runtime_um;            /* must be 0 (offline path)                   */
   int   icycle;                /* 0: simple carbon inside cbm (cbm:214)      */
@@ -105,6 +107,7 @@ typedef struct cable_cfg {
   float max_ssdn;
   float max_sconds;
   float frozen_limit;
+  float wiltParam, satuParam;  /* hydraulic_redistribution limits (cable_runtime_opts_mod.F90:6-7; cable.nml:55-56) */
   /* non-per-tile members of the derived types */
   float zse[CABLE_MS];         /* soil%zse                                   */
   float zshh[CABLE_MS + 1];    /* soil%zshh                                  */

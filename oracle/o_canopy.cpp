@@ -409,6 +409,28 @@ static void dryLeaf(Oracle &o, float dels, CanopyWork &w, int iter) {
         vx4[i].v[1] = ej4x(temp2[i].v[1], f.veg_alpha[i], f.veg_convex[i], vcmxt4[i].v[1]);
         rdx[i].v[0] = (f.veg_cfrd[i] * vcmxt3[i].v[0] + f.veg_cfrd[i] * vcmxt4[i].v[0]);  // :320,398
         rdx[i].v[1] = (f.veg_cfrd[i] * vcmxt3[i].v[1] + f.veg_cfrd[i] * vcmxt4[i].v[1]);
+        if (o.cfg.call_climate) {                                                         // :328-393 (Atkin et al. 2015)
+          const int iv = f.veg_iveg[i];
+          const float q = f.climate_qtemp_max_last_year[i], vc = f.veg_vcmax[i];
+          float r;
+          if (iv == EVERGREEN_BROADLEAF || iv == DECIDUOUS_BROADLEAF || iv == AUST_MESIC || iv == AUST_XERIC)
+            r = 0.60f * (1.2818e-6f + 0.0116f * vc - 0.0334f * q * 1.0e-6f);
+          else if (iv == EVERGREEN_NEEDLELEAF || iv == DECIDUOUS_NEEDLELEAF)
+            r = 1.0f * (1.2877e-6f + 0.0116f * vc - 0.0334f * q * 1.0e-6f);
+          else if (iv == C3_GRASSLAND || iv == TUNDRA || iv == C3_CROPLAND)
+            r = 0.60f * (1.6737e-6f + 0.0116f * vc - 0.0334f * q * 1e-6f);
+          else
+            r = 0.60f * (1.5758e-6f + 0.0116f * vc - 0.0334f * q * 1.0e-6f);
+          // xrdt (:843-853): variable-Q10 temperature response of dark respiration
+          const float x = w.tlfx[i];
+          const float xrdt = o_powf(3.09f - 0.043f * ((x - 273.15f) + 25.f) / 2.0f, (x - 273.15f - 25.0f) / 10.0f);
+          rdx[i].v[0] = r * xrdt * f.rad_scalex[IX(i, 0)];
+          rdx[i].v[1] = r * xrdt * f.rad_scalex[IX(i, 1)];
+          // light inhibition (:387-393); the shaded leaf reads qcan(i,1,2) = sunlit NIR (D6)
+          const float q11 = f.rad_qcan[(size_t)i + (size_t)mp * (0 + 2 * 0)], q12 = f.rad_qcan[(size_t)i + (size_t)mp * (0 + 2 * 1)];
+          if (jtomol * 1.0e6f * q11 > 10.0f) rdx[i].v[0] = rdx[i].v[0] * (0.5f - 0.05f * o_logf(jtomol * 1.0e6f * q11));
+          if (jtomol * 1.0e6f * q12 > 10.0f) rdx[i].v[1] = rdx[i].v[1] * (0.5f - 0.05f * o_logf(jtomol * 1.0e6f * q12));
+        }
         if (o.cfg.gs_switch == CABLE_GS_LEUNING) {                                        // :404-409
           gs_coeff[i].v[0] = (float)((w.fwsoil[i] / (w.csx[i].v[0] - co2cp3)) * (f.veg_a1gs[i] / (1.0f + w.dsx[i] / f.veg_d0gs[i])));
           gs_coeff[i].v[1] = (float)((w.fwsoil[i] / (w.csx[i].v[1] - co2cp3)) * (f.veg_a1gs[i] / (1.0f + w.dsx[i] / f.veg_d0gs[i])));

@@ -656,6 +656,67 @@ static void surfbv(Oracle &o, float dels) {
 extern "C" void oracle_run_smoisturev(void *h, float dels) { smoisturev(*(Oracle *)h, dels); }
 extern "C" void oracle_run_stempv(void *h, float dels) { stempv(*(Oracle *)h, dels); }
 
+// ---- hydraulic_redistribution: cbl_hyd_redistrib.F90:13-221 (redistrb) -------
+// All working variables are default REAL; ssnow%wb is r_2.  wiltParam / satuParam: cable_runtime_opts_mod.F90:6-7.
+static void hydraulic_redistribution(Oracle &o, float dels) {
+  const int mp = o.mp; Fields &f = o.f; const float *zse = o.cfg.zse;
+  const float n_hr = 3.22f, wpsy50 = -1.0f, n_VG = 2.06f, m_VG = 1.0f - 1.0f / n_VG, alpha_VG = 0.00423f, CRT = 125.0f;   // :33-41
+  const float wiltParam = o.cfg.wiltParam, satuParam = o.cfg.satuParam;
+  float zsetot = 0.f;
+  for (int k = 0; k < ms; k++) zsetot = zsetot + zse[k];                                  // SUM(soil%zse)
+  for (int i = 0; i < mp; i++) {
+    float totalice = 0.0f;                                                                // :70-73 (totalmoist is unused)
+    for (int k = 0; k < ms; k++) totalice = (float)(totalice + f.ssnow_wbice[IX(i, k)] * zse[k] / zsetot);
+    float Dtran = 0.0f;
+    if (f.canopy_fevc[i] < 10.0f && totalice < 1.e-2f) Dtran = 1.0f;                      // :76
+    const bool hr_pft = f.veg_iveg[i] == EVERGREEN_BROADLEAF || f.veg_iveg[i] == 7;       // c4_grassland = 7
+    const float swilt = f.soil_swilt[i], sfc = f.soil_sfc[i], ssat = f.soil_ssat[i];
+    float wpsy[ms], C_hr[ms];
+    auto potentials = [&]() {                                                             // :78-85, :144-151
+      for (int k = 0; k < ms; k++) {
+        float S_VG = fminf_(1.0f, fmaxf_(1.0E-4f, (float)f.ssnow_wb[IX(i, k)] - swilt) / (ssat - swilt));
+        wpsy[k] = -1.0f / alpha_VG * o_powf(o_powf(S_VG, -1.0f / m_VG) - 1.0f, 1 / n_VG) * 100 * 1.0E-6f;
+        C_hr[k] = 1.f / (1 + o_powf(wpsy[k] / wpsy50, n_hr));
+      }
+    };
+    // one pair (k, j), zero based; `upper` selects the second sweep's froot / `available` forms (:166-167,:183,:197)
+    auto exchange = [&](int k, int j, bool upper) {
+      const float fk = f.veg_froot[IX(i, k)], fj = f.veg_froot[IX(i, j)];
+      float frootX = fmaxf_(0.01f, fmaxf_(fk, fj));
+      float prod = upper ? (fmaxf_(0.01f, fk) * fmaxf_(0.01f, fj)) : (fk * fj);
+      float hr_term = CRT * (wpsy[j] - wpsy[k]) * fmaxf_(C_hr[k], C_hr[j]) * prod / (1 - frootX) * Dtran;
+      float hkj = hr_term * 1.0E-2f / 3600.0f * dels;                                     // m per timestep
+      float hjk = -1.0f * hkj;
+      hkj = hkj / zse[k];
+      hjk = hjk / zse[j];
+      if (!hr_pft) { hkj = 0.0f; hjk = 0.0f; }
+      const double wbk = f.ssnow_wb[IX(i, k)], wbj = f.ssnow_wb[IX(i, j)];
+      if (hkj < 0.0f) {
+        float available = (float)dmax_(0.0, upper ? wbk - sfc : wbk - (swilt + (sfc - swilt) / 3.f));
+        float accommodate = (float)dmax_(0.0, ssat - wbj);
+        float temp = fmaxf_(fmaxf_(hkj, -1.0f * wiltParam * available), -1.0f * satuParam * accommodate * zse[j] / zse[k]);
+        hkj = temp;
+        hjk = -1.0f * temp * zse[k] / zse[j];
+      } else if (hjk < 0.0f) {
+        float available = (float)dmax_(0.0, upper ? wbj - sfc : wbj - (swilt + (sfc - swilt) / 3.f));
+        float accommodate = (float)dmax_(0.0, ssat - wbk);
+        float temp = fmaxf_(fmaxf_(hjk, -1.0f * wiltParam * available), -1.0f * satuParam * accommodate * zse[k] / zse[j]);
+        hjk = temp;
+        hkj = -1.0f * temp * zse[j] / zse[k];
+      }
+      f.ssnow_wb[IX(i, k)] = f.ssnow_wb[IX(i, k)] + hkj;
+      f.ssnow_wb[IX(i, j)] = f.ssnow_wb[IX(i, j)] + hjk;
+    };
+    potentials();
+    for (int k = ms; k >= 3; k--)                                                         // :91-140 (1-based k = ms..3, j = k-1..2)
+      for (int j = k - 1; j >= 2; j--) exchange(k - 1, j - 1, false);
+    if (f.met_tk[i] < CTFRZ + 5.f) Dtran = 0.0f;                                          // :142
+    potentials();
+    for (int k = 1; k <= ms - 2; k++)                                                     // :155-208
+      for (int j = k + 1; j <= ms - 1; j++) exchange(k - 1, j - 1, true);
+  }
+}
+
 void soil_snow(Oracle &o, float dels) {
   const int mp = o.mp; Fields &f = o.f; const float *zse = o.cfg.zse;
   std::vector<float> snowmlt(mp);
@@ -716,6 +777,7 @@ void soil_snow(Oracle &o, float dels) {
     f.ssnow_pudsto[i] = f.ssnow_pudsto[i] - f.ssnow_rnof1[i];
   }
   surfbv(o, dels);                                                                        // :161
+  if (o.cfg.redistrb) hydraulic_redistribution(o, dels);                                  // :186-187
   for (int i = 0; i < mp; i++) {
     f.ssnow_smelt[i] = f.ssnow_smelt[i] / dels;                                           // :189
     f.ssnow_tss[i] = (1 - f.ssnow_isflag[i]) * f.ssnow_tgg[IX(i, 0)] + f.ssnow_isflag[i] * f.ssnow_tggsn[IX(i, 0)];

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/cable_b200.h but not exported"
     assert sorted(lib.EXPORTS) == declared
-    assert L.cable_b200_abi_version() == 1
+    assert L.cable_b200_abi_version() == 2
 
 
 def test_registry_matches_def_file():
@@ -64,7 +64,7 @@ def test_create_error_behaviour_without_compute():
     h = C.c_void_p()
     cfg = lib.default_cfg()
     # unsupported switches are rejected before any device work (reference: STOP 'fwsoil_switch failed.')
-    for sw in ("or_evap", "gw_model", "call_climate", "redistrb", "soil_struc_sli", "runtime_um"):
+    for sw in ("or_evap", "gw_model", "soil_struc_sli", "runtime_um"):
         cfg = lib.default_cfg()
         setattr(cfg, sw, 1)
         assert L.cable_b200_create(10, C.byref(cfg), 0, C.byref(h)) == -2, sw

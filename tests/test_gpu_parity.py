@@ -83,8 +83,10 @@ def test_libm_oracle_fraction_within_tolerance():
                                       dict(gs_switch=1, fwsoil_switch=1),
                                       # the XSW instantiation of the kernels (cbm_kernel.cuh)
                                       dict(litter=1), dict(l_rev_corr=1), dict(litter=1, l_rev_corr=1, ssnow_potev=1),
-                                      dict(soil_thermal_fix=1), dict(l_new_roughness_soil=1),
-                                      dict(gs_switch=1, litter=1, l_rev_corr=1, soil_thermal_fix=1, l_new_roughness_soil=1)])
+                                      dict(soil_thermal_fix=1), dict(l_new_roughness_soil=1), dict(redistrb=1),
+                                      dict(call_climate=1), dict(call_climate=1, gs_switch=1),
+                                      dict(gs_switch=1, litter=1, l_rev_corr=1, soil_thermal_fix=1, l_new_roughness_soil=1,
+                                           redistrb=1, call_climate=1)])
 def test_switch_matrix(switches):
     """cable_user switches on the supported path."""
     cfg = lib.default_cfg()

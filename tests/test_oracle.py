@@ -86,7 +86,8 @@ def test_reference_closure_invariants(gs):
 
 
 @pytest.mark.parametrize("switches", [dict(litter=1), dict(l_rev_corr=1), dict(litter=1, l_rev_corr=1, ssnow_potev=1),
-                                      dict(soil_thermal_fix=1), dict(l_new_roughness_soil=1)])
+                                      dict(soil_thermal_fix=1), dict(l_new_roughness_soil=1), dict(redistrb=1),
+                                      dict(call_climate=1)])
 def test_optional_switch_closure_and_effect(switches):
     """cable_user%litter / l_rev_corr / soil_thermal_fix / l_new_roughness_soil (cable_canopy.F90:471-476,917-1015,
     cbl_conductivity.F90:11, cable_roughness.F90:193-199): the reference's closure checks still hold on the oracle
@@ -114,10 +115,13 @@ def test_optional_switch_closure_and_effect(switches):
     for name in ("canopy_fe", "ssnow_tgg", "canopy_tscrn", "ssnow_wb"):
         assert np.all(np.isfinite(T[name]))
     changed = {"litter": "canopy_fhs", "l_rev_corr": "canopy_dgdtg", "soil_thermal_fix": "ssnow_tgg",
-               "l_new_roughness_soil": "rough_z0soil"}
+               "l_new_roughness_soil": "rough_z0soil", "redistrb": "ssnow_wb", "call_climate": "canopy_frday"}
     for sw, name in changed.items():
         if switches.get(sw):
             assert np.abs(T[name].astype(np.float64) - base[name]).max() > 0, (sw, name)
+    if switches.get("redistrb"):                    # only evergreen broadleaf and C4 grass redistribute (cbl_hyd_redistrib.F90:109-115)
+        other = ~np.isin(T["veg_iveg"][0], (2, 7))
+        assert np.array_equal(T["ssnow_wb"][:, other], base["ssnow_wb"][:, other])
     if switches.get("l_new_roughness_soil"):        # z0soil = 0.01 min(1,LAI) + 0.02 min(us^2/g, 1)  (:197)
         us, lai = T["canopy_us"][0], T["canopy_vlaiw"][0]
         assert np.all(T["rough_z0soil"][0] <= np.float32(0.01) * np.minimum(1, lai) + np.float32(0.02) + 1e-7)
