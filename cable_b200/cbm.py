@@ -192,14 +192,15 @@ def cbm(ktau, dels, air, bgc, canopy, met, bal, rad, rough, soil, ssnow, sum_flu
 
     The derived-type arguments are namespaces of (ncomp, mp) NumPy arrays (see `derived_types`).
     On first call for a given `ssnow` object a handle is created and every member is bound; parameters
-    and state are uploaded once; afterwards each call is cable_b200_cbm().  `sum_flux` and `climate`
-    are accepted and ignored exactly as the reference ignores them on the default path.
+    and state are uploaded once; afterwards each call is cable_b200_cbm().  `sum_flux` is accepted and ignored
+    exactly as the reference ignores it; `climate` (may be None) is read only under cable_user%call_climate.
     """
     key = id(ssnow)
     h = _HANDLES.get(key)
     if h is None:
         groups = {"air": air, "bgc": bgc, "canopy": canopy, "met": met, "bal": bal, "rad": rad, "rough": rough,
-                  "soil": soil, "ssnow": ssnow, "veg": veg, "scr": SimpleNamespace(xk=xk, c1=c1, rhoch=rhoch)}
+                  "soil": soil, "ssnow": ssnow, "veg": veg, "scr": SimpleNamespace(xk=xk, c1=c1, rhoch=rhoch),
+                  "climate": climate if climate is not None else SimpleNamespace()}
         mp = np.asarray(met.tk).shape[-1]
         tiles = {}
         for f in FIELDS:

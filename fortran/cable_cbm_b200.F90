@@ -81,7 +81,7 @@ CONTAINS
                   ssnow, sum_flux, veg, climate, xk, c1, rhoch )
     USE cable_def_types_mod
     USE cable_common_module, ONLY : cable_user, cable_runtime, redistrb, snow_ccnsw, max_ssdn,   &
-                                    max_sconds, frozen_limit, max_glacier_snowd, snmin
+                                    max_sconds, frozen_limit, max_glacier_snowd, snmin, wiltParam, satuParam
     USE casadimension,       ONLY : icycle
     TYPE (air_type),            INTENT(INOUT), TARGET :: air
     TYPE (bgc_pool_type),       INTENT(INOUT), TARGET :: bgc
@@ -123,6 +123,7 @@ CONTAINS
        cfg%icycle = icycle;  cfg%mvtype = mvtype
        cfg%snmin = snmin;  cfg%max_glacier_snowd = max_glacier_snowd;  cfg%snow_ccnsw = snow_ccnsw
        cfg%max_ssdn = max_ssdn;  cfg%max_sconds = max_sconds;  cfg%frozen_limit = frozen_limit
+       cfg%wiltParam = wiltParam;  cfg%satuParam = satuParam       ! cable_runtime_opts_mod.F90:6-7
        cfg%zse = soil%zse;  cfg%zshh = soil%zshh;  cfg%ratecp = bgc%ratecp;  cfg%ratecs = bgc%ratecs
        cfg%caller_duties = 0        ! the Fortran driver keeps doing canopy%oldcansto = canopy%cansto itself
        rc = cable_b200_create(INT(mp, C_INT), cfg, -1_C_INT, handle);  CALL check(rc)
@@ -135,6 +136,10 @@ CONTAINS
        CALL bind('met_doy',   C_LOC(met%doy));     CALL bind('veg_vlai',   C_LOC(veg%vlai))
        CALL bind('ssnow_tgg', C_LOC(ssnow%tgg));   CALL bind('ssnow_wb',   C_LOC(ssnow%wb))
        CALL bind('canopy_fe', C_LOC(canopy%fe));   CALL bind('scr_xk',     C_LOC(xk))
+       ! inputs of non-default switches (registry flag OPTIN): bound always, uploaded when the switch is set
+       CALL bind('veg_clitt', C_LOC(veg%clitt));   CALL bind('soil_watr',  C_LOC(soil%watr))
+       CALL bind('soil_cnsd_vec', C_LOC(soil%cnsd_vec)); CALL bind('soil_sand_vec', C_LOC(soil%sand_vec))
+       CALL bind('climate_qtemp_max_last_year', C_LOC(climate%qtemp_max_last_year))
        ! ... (every remaining row of the registry, same pattern) ...
        rc = cable_b200_upload(handle, 2_C_INT);  CALL check(rc)     ! CABLE_ROLE_PARAM
        rc = cable_b200_upload(handle, 4_C_INT);  CALL check(rc)     ! CABLE_ROLE_STATE
