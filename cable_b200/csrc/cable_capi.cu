@@ -19,6 +19,12 @@
 
 using namespace cbl;
 
+// cable_fast.cu: kernel A compiled with CBL_FASTDIV=1 in its own namespace (own copy of the constant-memory config)
+int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, int mp, int i0, int i1, float dels, int first, unsigned long long *warn,
+                  int *redo, int big, int lvl, int max_l1, cudaStream_t st);
+int cblf_set_cfg(const void *cfg, size_t bytes, cudaStream_t st);
+void cblf_debug_dump();
+
 // scratch rows / shared memory of kernel A's dryLeaf pass pool (0 when the pool is compiled out)
 #if CBL_COMPACT
 constexpr int SD_ROWS = SD_ND, SF_ROWS = SF_NF;
@@ -126,6 +132,8 @@ struct cable_handle {
   double *leaf_scr_d = nullptr; float *leaf_scr_f = nullptr;   // dryLeaf pass-pool scratch (kernel A)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
+  int fastdiv = 1;                     // kernel A's CBL_FASTDIV build first (CABLE_B200_FASTDIV=0: ordinary build only)
+  int *d_redo = nullptr;               // per-block redo flags written by the fast build
   int xsw = 0;                         // any of litter / l_rev_corr / l_new_roughness_soil / soil_thermal_fix set
   int block = 128, split = 1, minb_a = CBL_MINB_A, minb_b = CBL_MINB_B, sms = 148, max_l1 = 1, step_chains = 2;
   // driver stages (cbm_driver.cuh); allocated by cable_b200_driver_init
@@ -220,7 +228,7 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
         once_ = true;                                                                                                          \
       }                                                                                                                        \
     }                                                                                                                          \
-    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn); }
+    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn, redo_); }
 #define CBL_LAUNCH(PH, BL, MB, LV) CBL_LAUNCH_X(PH, BL, MB, LV, 0)
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
   switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
@@ -228,6 +236,7 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
   // only: level 0 runs as level 1; kernel A always as 256-thread blocks)
 #define CBL_DISPATCH_X(PH, BL, MB)                                                   \
   switch (h->cfg.output_level) { case 2: CBL_LAUNCH_X(PH, BL, MB, 2, 1); break; default: CBL_LAUNCH_X(PH, BL, MB, 1, 1); break; }
+  int *redo_ = nullptr;
   if (h->xsw) {
     CBL_DISPATCH_X(1, 256, 3);
     CUDA_TRY(cudaGetLastError());
@@ -236,8 +245,27 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
   } else if (h->split) {
     // kernel A: one 768-thread block per SM when the range fills the chip that way; small ranges (a shard of an
     // 8-GPU run, a pipeline chunk) take 256-thread blocks, three per SM, so that every SM still gets work
-    if (i1 - i0 >= h->sms * CBL_BLOCK_A) { CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A); }
+    // kernel A runs first as its CBL_FASTDIV build (cable_fast.cu: IEEE divisions / square roots without the slow-path
+    // scaffolding); the ordinary build that follows only computes the blocks that build flagged (normally none)
+    const bool big = i1 - i0 >= h->sms * CBL_BLOCK_A;
+    if (h->fastdiv) {
+      const int bl = big ? CBL_BLOCK_A : 256, nblk = (i1 - i0 + bl - 1) / bl;
+      redo_ = h->d_redo + (size_t)(i0 / 256);              // disjoint slices for ranges launched concurrently
+      const int rc = cblf_launch_A(&d, sizeof(d), h->mp, i0, i1, dels, first, h->d_warn, redo_, big ? 1 : 0, h->cfg.output_level, h->max_l1, st);
+      if (rc) return fail(CABLE_E_CUDA, std::string("fast kernel A launch: ") + cudaGetErrorString((cudaError_t)rc));
+      if (getenv("CABLE_B200_FASTDIV_DEBUG")) {             // debugging aid: how many blocks the fast build handed back
+        std::vector<int> fl(nblk);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(fl.data(), redo_, nblk * sizeof(int), cudaMemcpyDeviceToHost);
+        int n = 0; for (int v : fl) n += v != 0;
+        fprintf(stderr, "[cable_b200] fastdiv: %d of %d blocks flagged (tiles %d..%d)\n", n, nblk, i0, i1);
+        cblf_debug_dump();
+      }
+      h->ctr.kernel_launches++;
+    }
+    if (big) { CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A); }
     else { CBL_DISPATCH(1, 256, 3); }
+    redo_ = nullptr;
     CUDA_TRY(cudaGetLastError());
     CBL_DISPATCH(2, CBL_BLOCK_B, CBL_MINB_B);
     h->ctr.kernel_launches++;
@@ -365,6 +393,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   if (const char *e = getenv("CABLE_B200_MAXL1")) h->max_l1 = atoi(e);
   if (const char *e = getenv("CABLE_B200_STEP_CHAINS")) h->step_chains = atoi(e);
   if (const char *e = getenv("CABLE_B200_TILE_ORDER")) h->tile_order = atoi(e);
+  if (const char *e = getenv("CABLE_B200_FASTDIV")) h->fastdiv = atoi(e);
   // device-side config + host-evaluated constants
   DevCfg &d = h->dcfg;
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
@@ -421,8 +450,10 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaMalloc(&h->leaf_scr_f, (size_t)mp * SF_ROWS * sizeof(float));
   cudaMemset(h->leaf_scr_d, 0, (size_t)mp * SD_ROWS * sizeof(double));
   cudaMemset(h->leaf_scr_f, 0, (size_t)mp * SF_ROWS * sizeof(float));
-  cudaMalloc(&h->d_warn, sizeof(unsigned long long));
-  cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
+  cudaMalloc(&h->d_redo, ((size_t)mp / 256 + 2) * sizeof(int));
+  cudaMemset(h->d_redo, 0, ((size_t)mp / 256 + 2) * sizeof(int));
+  cudaMalloc(&h->d_warn, 2 * sizeof(unsigned long long));       // [0] dryLeaf soft warnings, [1] blocks recomputed after a fast-path miss
+  cudaMemset(h->d_warn, 0, 2 * sizeof(unsigned long long));
   {
     int lo = 0, hi = 0;                                   // numerically lower = higher priority
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -465,6 +496,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
     cudaEventCreateWithFlags(&h->ev_slot_free[s], cudaEventDisableTiming);
   }
   e = cudaMemcpyToSymbol(c_cfg, &h->dcfg, sizeof(DevCfg));
+  if (e == cudaSuccess) e = (cudaError_t)cblf_set_cfg(&h->dcfg, sizeof(DevCfg), nullptr);
   if (e != cudaSuccess) { cable_b200_destroy(h); return fail(CABLE_E_CUDA, std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(e)); }
   CUDA_TRY(cudaDeviceSynchronize());
   g_cfg_owner = h;
@@ -492,6 +524,7 @@ int cable_b200_destroy(cable_handle *h) {
   for (auto ev : h->ev_chunk_done) cudaEventDestroy(ev);
   if (h->drv.on) driver_free(h);
   if (h->d_warn) cudaFree(h->d_warn);
+  if (h->d_redo) cudaFree(h->d_redo);
   if (h->d_order) cudaFree(h->d_order);
   cudaFree(h->leaf_scr_d); cudaFree(h->leaf_scr_f);
   if (h->arena) cudaFree(h->arena);
@@ -607,6 +640,7 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
   if (h->slot_has_data[slot]) CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_forcing_ready[slot], 0));
   if (g_cfg_owner != h) {      // several handles (e.g. differing switches) may share the device
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->s_compute));
+    CUDA_TRY((cudaError_t)cblf_set_cfg(&h->dcfg, sizeof(DevCfg), h->s_compute));
     g_cfg_owner = h;
   }
   const DevPtrs d = make_ptrs(h, slot);
@@ -714,6 +748,7 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
     if (is_forcing_input(h, id) && !h->host[id]) return fail(CABLE_E_UNBOUND, std::string("forcing field not bound: ") + g_fields[id].name);
   if (g_cfg_owner != h) {
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->s_compute));
+    CUDA_TRY((cudaError_t)cblf_set_cfg(&h->dcfg, sizeof(DevCfg), h->s_compute));
     g_cfg_owner = h;
   }
   const DevPtrs d = make_ptrs(h, slot);
@@ -806,6 +841,8 @@ int cable_b200_get_counters(cable_handle *h, cable_counters *out) {
   unsigned long long w = 0;
   CUDA_TRY(cudaMemcpy(&w, h->d_warn, sizeof(w), cudaMemcpyDeviceToHost));
   h->ctr.n_dryleaf_warn = (long long)w;
+  CUDA_TRY(cudaMemcpy(&w, h->d_warn + 1, sizeof(w), cudaMemcpyDeviceToHost));
+  h->ctr.n_fastdiv_redo_blocks = (long long)w;
   *out = h->ctr;
   return CABLE_OK;
 }
@@ -817,7 +854,7 @@ int cable_b200_reset_counters(cable_handle *h) {
   const long long steps = h->ctr.steps;       // steps also drives the forcing-slot rotation: keep it
   h->ctr = cable_counters{}; h->ctr.steps = steps;
   h->prof_n = 0;
-  cudaMemset(h->d_warn, 0, sizeof(unsigned long long));
+  cudaMemset(h->d_warn, 0, 2 * sizeof(unsigned long long));
   return CABLE_OK;
 }
 

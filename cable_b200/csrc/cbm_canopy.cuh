@@ -192,8 +192,11 @@ CBL_NOINLINE float ejx_root(float parx, float alpha, float convex, float x) {
 CBL_DEV float xvcmxt4(float x) {
   return dv(m_exp2(0.1f * x - 2.5f), (1.0f + m_exp(0.3f * (13.0f - x))) * (1.0f + m_exp(0.3f * (x - 36.0f))));
 }
-CBL_NOINLINE float arrhenius_peaked(float x, float coef, float eha, float ehd, float entrop) {
-  float num = coef * m_exp((eha / (K::rgas * K::trefk)) * (1.f - dv(K::trefk, x)));
+// xvcmxt3 / xejmxt3 (:821-877).  `arr` = 1 - trefk/x is what the caller already needs for conkct/conkot, and
+// `eha_rt` = eha/(rgas*trefk) is a ratio of literals that the compiler folds (correctly rounded): the same values the
+// reference's expressions produce, without repeating three divisions per call.
+CBL_NOINLINE float arrhenius_peaked(float x, float arr, float coef, float eha_rt, float ehd, float entrop) {
+  float num = coef * m_exp(eha_rt * arr);
   float den = 1.0f + m_exp(dv(entrop * x - ehd, K::rgas * x));
   return mx(0.0f, dv(num, den));
 }
@@ -263,10 +266,26 @@ struct LeafPass {
   float tlfy;
   double rny, hcy, ecy;
   float rdy[2], an_y[2], oldevapfbl[K::ms];
+  // loop invariants of the pass, evaluated once per dryLeaf call by leaf_pass_prepare (same operands, same roundings)
+  float ekc_rt, eko_rt, g0t[2];
+  double avail[K::ms];
   // call_climate only (:328-393): Rd at 25 C per unit scalex, light-inhibition factor of each leaf and whether it applies
   float rd25, rdfac[2];
   bool rdinh[2];
 };
+
+// Quantities a pass would otherwise re-evaluate from operands that do not change during one dryLeaf call:
+// ekc/(rgas*trefk), eko/(rgas*trefk) (:293-297), gswmin*fwsoil/rgswc (cbl_photosynthesis.F90:66) and the water each layer
+// can supply to transpiration (cbl_remove_trans.F90:73-77).
+CBL_DEV void leaf_pass_prepare(LeafPass &p, const DevCfg &c) {
+  p.ekc_rt = p.ekc / (K::rgas * K::trefk);
+  p.eko_rt = p.eko / (K::rgas * K::trefk);
+  p.g0t[0] = dvc(p.gswmin[0] * p.fwsoil, K::rgswc);
+  p.g0t[1] = dvc(p.gswmin[1] * p.fwsoil, K::rgswc);
+#pragma unroll
+  for (int kk = 0; kk < K::ms; kk++)
+    p.avail[kk] = mx(0.0, p.wbliq[kk] - (double)1.1f * (double)p.swilt) * (double)c.zse[kk] * (double)K::density_liq;
+}
 
 // One ACTIVE pass k (the reference's loop body for a tile with vlaiw > thresh and |deltlf| > 0.1, :243-560), then the
 // bookkeeping every pass ends with (keep the best iterate, damp after k > 5, :565-606).
@@ -284,13 +303,13 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
   float gras = mx(1.0e-6f, 1.595E8f * fabsf(tlfx - p.tvair) * p.dleaf3);
   float gras4 = m_pow025(gras);
   // temperature responses of Vcmax (C3, C4) and Jmax
-  float temp3 = arrhenius_peaked(tlfx, 1.17461f, 73637.0f, 149252.0f, 486.0f) * p.vcmax * (1.0f - p.frac4);
-  float temp4 = xvcmxt4(tlfx - K::tfrz) * p.vcmax * p.frac4;
-  float tempj = arrhenius_peaked(tlfx, 1.16715f, 50300.0f, 152044.0f, 495.0f) * p.ejmax * (1.0f - p.frac4);
-  const float tdiff = tlfx - K::trefk;
   const float arr = 1.0f - dv(K::trefk, tlfx);
-  float conkct = p.conkc0 * m_exp((p.ekc / (K::rgas * K::trefk)) * arr);
-  float conkot = p.conko0 * m_exp((p.eko / (K::rgas * K::trefk)) * arr);
+  float temp3 = arrhenius_peaked(tlfx, arr, 1.17461f, 73637.0f / (K::rgas * K::trefk), 149252.0f, 486.0f) * p.vcmax * (1.0f - p.frac4);
+  float temp4 = xvcmxt4(tlfx - K::tfrz) * p.vcmax * p.frac4;
+  float tempj = arrhenius_peaked(tlfx, arr, 1.16715f, 50300.0f / (K::rgas * K::trefk), 152044.0f, 495.0f) * p.ejmax * (1.0f - p.frac4);
+  const float tdiff = tlfx - K::trefk;
+  float conkct = p.conkc0 * m_exp(p.ekc_rt * arr);
+  float conkot = p.conko0 * m_exp(p.eko_rt * arr);
   const float tlfxx = tlfx;
   const float cx1 = conkct * (1.0f + dv(0.21f, conkot));
   const float cx2 = 2.0f * K::gam0 * (1.0f + K::gam1 * tdiff + K::gam2 * tdiff * tdiff);
@@ -347,7 +366,7 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
     float an = 0.f;
     if (vsum0 > K::lai_thresh && fvlai_l > K::lai_thresh) {
       const double csx = csx_l;
-      const float g0t = dv(gswmin_l * fwsoil, K::rgswc);
+      const float g0t = l ? p.g0t[1] : p.g0t[0];
       const double one_m = (double)1.0f - csx * (double)gs_coeff;
       double coef2 = (double)(g0t + gs_coeff * (vcmxt3 - (rdx_l - vcmxt4)));
       double coef1 = one_m * (double)(vcmxt3 + vcmxt4 - rdx_l) + (double)g0t * ((double)cx1 - csx)
@@ -363,7 +382,7 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
       coef2 = (double)gs_coeff;
       coef1 = (double)(g0t + gs_coeff * (rdx_l - 0.5f * vcmxt3) + effc4 * vcmxt4)
               - (double)gs_coeff * csx * (double)effc4 * (double)vcmxt4;
-      coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)dv((rdx_l - 0.5f * vcmxt3) * gswmin_l * fwsoil, K::rgswc);
+      coef0 = -(double)g0t * csx * (double)effc4 * (double)vcmxt4 + (double)dvc((rdx_l - 0.5f * vcmxt3) * gswmin_l * fwsoil, K::rgswc);
       double ansink = an_limited(2, coef2, coef1, coef0, 0.f, 0.f, 0.f, 0.f, 0.f);
       an = (float)mn(mn(anrubisco, anrubp), ansink);
     }
@@ -395,7 +414,7 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
 #pragma unroll
     for (int kk = 0; kk < K::ms; kk++) {
       double xx = demand * (double)p.froot[kk] + diff;
-      double avail = mx(0.0, p.wbliq[kk] - (double)1.1f * (double)p.swilt) * (double)c.zse[kk] * (double)K::density_liq;
+      const double avail = p.avail[kk];
       double xxd = xx - avail;
       double e;
       if (xxd > 0.0) { e = avail; diff = xxd; } else { e = xx; diff = 0.0; }
@@ -500,6 +519,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
     p.tlfy = w.tlfx; p.rny = 0.0; p.hcy = 0.0; p.ecy = 0.0;
   }
   p.deltlfy = p.abs_deltlf;
+  leaf_pass_prepare(p, c);
 
 #if !CBL_COMPACT
   (void)d; (void)tile; (void)smp;
@@ -583,6 +603,7 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
         q.evapfbl[kk] = d.ssnow_evapfbl[ti + smp * kk];
       }
       bool captured;
+      leaf_pass_prepare(q, c);
       leaf_pass<XSW>(q, c, dels, k, captured);
       rf[LR_TLFX * nslot + s] = q.tlfx; rf[LR_DSX * nslot + s] = q.dsx; rf[LR_ABSD * nslot + s] = q.abs_deltlf;
       rf[LR_DELTLFY * nslot + s] = q.deltlfy;

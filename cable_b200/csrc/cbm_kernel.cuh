@@ -69,7 +69,20 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
 template <int PHASE, int BLOCK, int MINB, int LVL, int XSW>
 __global__ void __launch_bounds__(BLOCK, MINB)
 cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const float dels, const int first_call,
-           unsigned long long *warn_counter) {
+           unsigned long long *warn_counter, int *redo) {
+  // `redo` (one int per block of this launch geometry, or null): the CBL_FASTDIV build of kernel A (cable_fast.cu) writes 1
+  // for a block in which some division / square root met an operand outside the fast path's window and stores nothing for
+  // that block; the ordinary build, launched right after with the same geometry and the same array, computes exactly
+  // those blocks (cbm_consts.cuh, CBL_FASTDIV).
+#if CBL_FASTDIV
+  if (threadIdx.x == 0) *fastdiv_flag() = 0;
+  __syncthreads();
+#else
+  if (redo) {
+    if (!redo[blockIdx.x]) return;
+    if (threadIdx.x == 0) atomicAdd(warn_counter + 1, 1ull);                   // cable_counters.n_fastdiv_redo_blocks
+  }
+#endif
   // Tiles [i0, i1) of this launch (a whole shard, or one chunk of the pipelined drop-in call), BLOCK per block.
   // Blocks are handed out by the hardware scheduler on purpose: the cost of a tile varies with time of day and
   // vegetation (1-20 dryLeaf passes), and a static even split of the range over the SMs measured 35 % slower.
@@ -120,6 +133,12 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
     t.ssnow_otss = t.ssnow_tss;
     const int warn = define_canopy<XSW != 0>(t, c, dels, sunlit_veg, d, i, smp, valid, veg_branch);
     t.ssnow_owetfac = t.ssnow_wetfac;
+#if CBL_FASTDIV
+    __syncthreads();
+    const bool missed = *fastdiv_flag() != 0;
+    if (threadIdx.x == 0) redo[blockIdx.x] = missed ? 1 : 0;
+    if (missed) return;                                                          // the ordinary kernel redoes this block
+#endif
     if (warn && valid) atomicAdd(warn_counter, (unsigned long long)warn);
   }
   if (PHASE & 2) {

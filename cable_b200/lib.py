@@ -45,7 +45,7 @@ class FieldInfo(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("kernel_launches", C.c_longlong), ("h2d_bytes", C.c_longlong),
                 ("d2h_bytes", C.c_longlong), ("kernel_ms", C.c_double), ("kernel_ms_count", C.c_longlong),
-                ("n_dryleaf_warn", C.c_longlong)]
+                ("n_dryleaf_warn", C.c_longlong), ("n_fastdiv_redo_blocks", C.c_longlong)]
 
 
 EXPORTS = [

@@ -142,6 +142,9 @@ typedef struct cable_counters {
   long long kernel_ms_count;   /* launches in kernel_ms                      */
   long long n_dryleaf_warn;    /* tiles that hit the 'oldevapfbl not right'
                                   soft failure (cbl_dryLeaf.F90:630)         */
+  long long n_fastdiv_redo_blocks; /* kernel-A blocks recomputed by the ordinary
+                                  build after the fast IEEE divide / sqrt paths
+                                  met an operand outside their window        */
 } cable_counters;
 
 typedef struct cable_handle cable_handle;

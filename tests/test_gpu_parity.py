@@ -56,7 +56,8 @@ def test_every_field_matches_cr_oracle(gs):
     T_gpu, o, ctr = run_pair(cfg, grid, T, F, 16)
     worst = assert_logic_parity(T, T_gpu)
     assert worst < 1e-5
-    assert ctr.kernel_launches == 32 and ctr.n_dryleaf_warn == o.warnings()
+    # per step: kernel A's CBL_FASTDIV build, the ordinary kernel A over the blocks it handed back (normally none), kernel B
+    assert ctr.kernel_launches == 48 and ctr.n_dryleaf_warn == o.warnings()
     # the synthetic case must actually exercise the branches we claim to cover
     assert (T["ssnow_isflag"] == 1).any() and (T["ssnow_snowd"] > 0).any() and (T["ssnow_wbice"] > 0).any()
     assert (T["veg_iveg"] == 16).any() and (T["soil_isoilm"] == 9).any() and (T["canopy_vlaiw"] > 0.001).any()
@@ -119,6 +120,31 @@ def test_new_roughness_soil_carries_us_at_output_level_1():
     assert not bad, bad
 
 
+def test_fastdiv_build_is_bit_identical_and_falls_back(monkeypatch):
+    """Kernel A's CBL_FASTDIV build (IEEE divisions / square roots without the slow-path scaffolding, cable_fast.cu) must
+    give the same bits as the ordinary build; and a tile whose operands leave the fast path's window (here: a
+    subnormal-scale CO2 concentration, so csx and the quantities derived from it are ~1e-38) must come out identical
+    too, through the flag -> recompute path."""
+    def run(fast, tiny_ca):
+        monkeypatch.setenv("CABLE_B200_FASTDIV", str(fast))
+        cfg, grid, T, F = make_case(300)
+        cfg.output_level = 2
+        with CableB200(grid.mp, cfg) as h:
+            h.bind(T); h.upload_params(); h.upload_state()
+            for k in range(4):
+                F.fill(T, k)
+                if tiny_ca:
+                    T["met_ca"][0][::7] = np.float32(3e-38)
+                h.cbm(k + 1, DELS)
+            redo = h.counters().n_fastdiv_redo_blocks
+        return T, redo
+    for tiny in (False, True):
+        (a, ra), (b, rb) = run(1, tiny), run(0, tiny)
+        assert rb == 0 and (ra > 0) == tiny, (tiny, ra, rb)       # the fallback runs exactly when operands leave the window
+        for f in output_fields():
+            assert np.array_equal(a[f.name], b[f.name], equal_nan=True), (tiny, f.name)
+
+
 @pytest.mark.parametrize("mp_case", [(1, 1), (1, 3), (7, 5), (26, 5)])      # 1, 3, 35, 130 tiles: ragged vs the 128-thread block
 def test_ragged_and_tiny_sizes(mp_case):
     nland, nap = mp_case
@@ -144,7 +170,7 @@ def test_fused_and_split_kernels_agree(monkeypatch):
     Ta_gpu, _, ca = run_pair(cfg, grid, T, F, 5)
     monkeypatch.setenv("CABLE_B200_SPLIT", "1")
     Tb_gpu, _, cb = run_pair(cfg, grid, Tb, F, 5)
-    assert ca.kernel_launches == 5 and cb.kernel_launches == 10
+    assert ca.kernel_launches == 5 and cb.kernel_launches == 15
     for f in output_fields():
         np.testing.assert_array_equal(Ta_gpu[f.name], Tb_gpu[f.name], err_msg=f.name)
 
