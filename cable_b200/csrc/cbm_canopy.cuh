@@ -74,7 +74,7 @@ CBL_DEV void surf_wetness_fact(Tile &t, float cansat, float dels) {
   t.canopy_wcint = (ftemp > 0.0f && t.met_tk > K::tfrz) ? mn(room, ftemp) : 0.0f;
   t.canopy_through = t.met_precip_sn + mn(rain, mx(0.0f, rain - t.canopy_wcint));
   t.canopy_cansto = t.canopy_cansto + t.canopy_wcint;
-  t.canopy_fwet = mx(0.0f, mn(0.9f, dv(0.8f * t.canopy_cansto, mx(cansat, 0.01f))));
+  t.canopy_fwet = mx(0.0f, mn(0.9f, dvw(0.8f * t.canopy_cansto, mx(cansat, 0.01f))));
   t.ssnow_satfrac = (double)1.0e-8f;
   t.ssnow_rh_srf = 1.0;
   const float wilting_pt = t.soil_swilt / K::wilt_limitfactor;
@@ -82,7 +82,7 @@ CBL_DEV void surf_wetness_fact(Tile &t, float cansat, float dels) {
   float den = mx(0.0830f, t.soil_sfc - wilting_pt);
   float wetfac = mx(0.0f, mn(1.0f, dv(num, den)));
   if (t.ssnow_wbice[0] > 0.0) {
-    double r = dv(t.ssnow_wbice[0], t.ssnow_wb[0]);
+    double r = dvx(t.ssnow_wbice[0], t.ssnow_wb[0]);
     float ice_ratio = (float)(r * r);
     float ice_factor = (float)(1.0 - mn(0.2, (double)ice_ratio));
     ice_factor = (float)mx(0.5, (double)ice_factor);
@@ -127,7 +127,7 @@ CBL_DEV void latent_heat_flux(Tile &t, const DevCfg &c, float dels) {
     float lower = (float)t.ssnow_wb[0] - (c.l_new_reduce_soilevp ? t.soil_swilt : t.soil_swilt / 2.0f);
     float upper = (float)mx(0., (double)(lower * frescale) - dv(t.ssnow_evapfbl[0] * (double)rlam, (double)dels));
     fess = mn(fess, (double)upper);
-    upper = (float)(t.ssnow_wb[0] - dv(t.ssnow_wbice[0], (double)c.frozen_limit)) * frescale;
+    upper = (float)(t.ssnow_wb[0] - dvx(t.ssnow_wbice[0], (double)c.frozen_limit)) * frescale;
     upper = mx(upper, 0.f);
     fess = mn(fess, (double)upper);
   }
@@ -672,10 +672,10 @@ CBL_DEV void wetLeaf(Tile &t, const CanopyWork &w, float dels) {
     const double ghwet = (double)(2.0f * sum_gbh);
     const float gwwet = 1.075f * sum_gbh;
     const float ghrwet = (float)((double)w.sum_gradis + ghwet);
-    const float ccfevw = mn(dv(t.canopy_cansto * t.air_rlam, dels), dv(2.0f, dv(1440.0f, dv(dels, 60.0f))) * t.air_rlam);
+    const float ccfevw = mn(dvw(t.canopy_cansto * t.air_rlam, dels), dv(2.0f, dv(1440.0f, dv(dels, 60.0f))) * t.air_rlam);
     const float num = t.air_dsatdk * (w.sum_rniso - cr * (t.met_tvair - t.met_tk) * w.sum_gradis) + cr * t.met_dva * ghrwet;
     const float den = t.air_dsatdk + dv(t.air_psyc * ghrwet, gwwet);
-    t.canopy_fevw = mn(dv(t.canopy_fwet * num, den), ccfevw);
+    t.canopy_fevw = mn(dvw(t.canopy_fwet * num, den), ccfevw);
     t.canopy_fevw_pot = dv(num, den);
     t.canopy_fhvw = t.canopy_fwet * (w.sum_rniso - cr * (w.tlfy - t.met_tk) * w.sum_gradis) - t.canopy_fevw;
   }
@@ -852,8 +852,8 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
   {
     float rlow = dv(t.canopy_epot * t.air_rlam, dels);
     if (rlow == 0.f) rlow = 1.e-7f;
-    float wcs = mx(0.f, mn(1.0f, dv(t.canopy_fe, rlow)));
-    if (wcs <= 0.f) wcs = mx(0.f, mn(1.f, mx(dv(t.canopy_fev, t.canopy_fevw_pot), dv((float)t.canopy_fes, t.ssnow_potev))));
+    float wcs = mx(0.f, mn(1.0f, dvw(t.canopy_fe, rlow)));
+    if (wcs <= 0.f) wcs = mx(0.f, mn(1.f, mx(dvw(t.canopy_fev, t.canopy_fevw_pot), dvw((float)t.canopy_fes, t.ssnow_potev))));
     t.canopy_wetfac_cs = wcs;
   }
 
@@ -873,7 +873,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
                      m_log(dv(t.rough_zref_tq, 0.1f * t.rough_z0m)) - psis(zN) + psis(dv(zN * 0.1f * t.rough_z0m, t.rough_zref_tq)));
   // screen-level temperature and humidity (:731-878)
   const float tstar = dv(-t.canopy_fh, t.air_rho * K::capp * us);
-  const float qstar = dv(-t.canopy_fe, t.air_rho * t.air_rlam * us * t.ssnow_cls);
+  const float qstar = dvw(-t.canopy_fe, t.air_rho * t.air_rlam * us * t.ssnow_cls);
   const float zscrn = mx(t.rough_z0m, 2.0f - t.rough_disp);
   const float ftemp = dv(m_log(dv(t.rough_zref_tq, zscrn)) - psis(zN) + psis(dv(zN * zscrn, t.rough_zref_tq)), K::vonk);
   float tscrn = t.met_tk - K::tfrz - tstar * ftemp;
@@ -922,7 +922,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
   // canopy water store (:881-906)
   t.canopy_dewmm = (float)dv(-((double)mn(0.0f, t.canopy_fevw) + mn(0.0, t.canopy_fevc)) * (double)dels, (double)t.air_rlam);
   t.canopy_cansto = t.canopy_cansto + t.canopy_dewmm;
-  t.canopy_cansto = mx(t.canopy_cansto - dv(mx(0.0f, t.canopy_fevw) * dels, t.air_rlam), 0.0f);
+  t.canopy_cansto = mx(t.canopy_cansto - dvw(mx(0.0f, t.canopy_fevw) * dels, t.air_rlam), 0.0f);
   t.canopy_spill = mx(0.0f, t.canopy_cansto - w.cansat);
   t.canopy_through = t.canopy_through + t.canopy_spill;
   t.canopy_precis = mx(0.f, t.canopy_through);
@@ -932,13 +932,13 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
   t.ssnow_dfn_dtg = dv((-1.f) * 4.f * K::emsoil * K::sboltz * tss4, t.ssnow_tss);
   if (!XSW) {
     t.ssnow_dfh_dtg = dv(t.air_rho * K::capp, t.ssnow_rtsoil);
-    t.ssnow_dfe_ddq = dv(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, t.ssnow_rtsoil);
+    t.ssnow_dfe_ddq = dvw(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, t.ssnow_rtsoil);
   } else {
     float rttsoil = t.ssnow_rtsoil;
     if (rev_corr && veg) rttsoil = rttsoil + t.rough_rt1;                           // :917-922
     // rhlitt / relitt as recomputed at :987-988 are the values of the last stability iteration (same operands)
     t.ssnow_dfh_dtg = dv(t.air_rho * K::capp, rttsoil + rhlitt);                     // :991 / :1006 (rhlitt = 0)
-    t.ssnow_dfe_ddq = dv(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, rttsoil + relitt);
+    t.ssnow_dfe_ddq = dvw(t.ssnow_wetfac * t.air_rho * t.air_rlam * t.ssnow_cls, rttsoil + relitt);
     if (rev_corr && t.ssnow_potev < 0.f) t.ssnow_dfe_ddq = dv(t.air_rho * t.air_rlam * t.ssnow_cls, rttsoil + relitt);   // :995-999, :1010-1014
   }
   {

@@ -57,7 +57,11 @@ __global__ void property(unsigned long long seed, int per_thread, int wide, unsi
     const double ad = (double)a, bd = (double)b;
     { const double r = fx::div64(ad, bd); const bool f = took_flag(); flg += f; if (!f && __double_as_longlong(r) != __double_as_longlong(ad / bd)) { bad++; record_fail(5, ad, bd); } }
     { const double r = fx::sqrt64((double)x); const bool f = took_flag(); flg += f; if (!f && __double_as_longlong(r) != __double_as_longlong(sqrt((double)x))) { bad++; record_fail(6, x, 0); } }
-    n += 7;
+    // fp32 division through the fp64 chain (dvw): numerators down to the smallest subnormal in both modes
+    const float as = rnd32(h3, 0u, wide ? 255u : 127u);
+    { const float r = fx::div32w(as, b); const bool f = took_flag(); flg += f; if (!f && __float_as_uint(r) != __float_as_uint(as / b)) { bad++; record_fail(7, as, b); } }
+    { const float r = fx::div32w(a, b); const bool f = took_flag(); flg += f; if (!f && __float_as_uint(r) != __float_as_uint(a / b)) { bad++; record_fail(8, a, b); } }
+    n += 9;
   }
   atomicAdd(&cnt[0], bad); atomicAdd(&cnt[1], flg); atomicAdd(&cnt[2], n);
 }

@@ -19,4 +19,4 @@ for k in range(8, 8 + steps): h.step(k + 1, 10800.0, k % 8)
 h.sync(); dt = time.perf_counter() - t0
 c = h.counters()
 print(f"mp={g.mp} steps={steps} block={block or 128}: kernel {c.kernel_ms / c.kernel_ms_count:.3f} ms/step, wall {dt / steps * 1e3:.3f} ms/step, "
-      f"{g.mp * steps / dt / 1e6:.1f} M tile-steps/s, warns={c.n_dryleaf_warn}")
+      f"{g.mp * steps / dt / 1e6:.1f} M tile-steps/s, warns={c.n_dryleaf_warn}, fastdiv redo blocks={c.n_fastdiv_redo_blocks}")

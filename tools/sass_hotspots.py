@@ -5,8 +5,8 @@ rep, so = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cubin = glob.glob(tmp + "/*.cubin")[0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+# the library holds one cubin per translation unit (ordinary kernels; kernel A's CBL_FASTDIV build): disassemble all
+dis = "\n".join(subprocess.run(["nvdisasm", "-g", "-c", c], capture_output=True, text=True).stdout for c in sorted(glob.glob(tmp + "/*.cubin")))
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 allrows = list(csv.reader(io.StringIO(sass)))
 # the page concatenates kernels: "Kernel Name" row, header row, instruction rows ...
