@@ -427,13 +427,15 @@ def run_b200(args) -> None:
                          "traffic": traffic, "peak_source": which, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_tile_step": ALGO_BYTES_PER_TILE_STEP,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_TILE_STEP * mp,
-                         "launch": "one step = kernel A (surface+canopy) + kernel B (soil/snow/carbon) over all tiles; kernel_ms is "
-                                   "the pair, timed with CUDA events on the library's compute stream",
+                         "launch": "one step over all tiles = two A->B chains (full rounds of 148 x 768 tiles, remainder): kernel A "
+                                   "(surface+canopy, CBL_FASTDIV build, then the ordinary build over the blocks it handed "
+                                   "back -- normally none) + kernel B (soil/snow/carbon); kernel_ms is the whole step, "
+                                   "timed with CUDA events on the library's streams",
                          "ncu": prof,
                          "pipe": pipe_roof(prof, value / world, clocks),
                          "note": "instruction-issue / latency-bound step (fp64 islands, ~300 correctly rounded transcendentals "
-                                 "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 46 %, FP64 pipe 18-26 %, "
-                                 "DRAM 5-22 % in the ncu capture; the HBM fraction is reported because it is the official "
+                                 "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 48 %, FP64 pipe 21-25 %, "
+                                 "DRAM 5-23 % in the ncu capture; the HBM fraction is reported because it is the official "
                                  "denominator.  traffic > algorithmic bytes: per-tile parameter arrays of the reference "
                                  "interface (230 B/tile), driver-visible diagnostics (336 B/tile at output_level=1), the A->B "
                                  "exchange (132 B/tile) and register-spill write-backs"},

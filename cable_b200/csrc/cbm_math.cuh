@@ -228,5 +228,21 @@ CBL_HD bool pow_pos(double x, double y, double &out) {
   return true;
 }
 
+// x**y on default REAL, rounded once from fp64 like the other fp32 intrinsics: pow_pos is within (2 + |y ln x|) < 100 fp64
+// ulp of x**y for results inside the fp32 normal range, so it rounds to the same fp32 number as the exact power -- and as
+// any <= 2 ulp fp64 pow -- unless it lies within 2048 fp64 ulp of an fp32 rounding boundary (the 29 fraction bits below
+// fp32 precision within 2^11 of 0x10000000; 8e-6 of all arguments).  Those, and everything outside pow_pos's domain, are
+// left to the general routine (returns false).
+CBL_HD bool pow32_cr(float x, float y, float &out) {
+  double o;
+  if (!pow_pos((double)x, (double)y, o)) return false;
+  if (!(o >= 0x1p-126 && o < 0x1p127)) return false;
+  int lo = (d_lo(o) & 0x1fffffff) - 0x10000000;
+  lo = lo < 0 ? -lo : lo;
+  if (lo <= 2048) return false;
+  out = (float)o;
+  return true;
+}
+
 }  // namespace lean
 }  // namespace cbl

@@ -96,6 +96,32 @@ int main(int argc, char **argv) {
     if (pow_pos(0.0, 2.0, o) || pow_pos(-1.0, 2.0, o) || pow_pos(INFINITY, 2.0, o) || pow_pos(2.0, NAN, o) || pow_pos(NAN, 2.0, o) ||
         pow_pos(10.0, 400.0, o) || !pow_pos(1.0, 5.0, o) || o != 1.0) { printf("pow_pos domain checks FAILED\n"); rc = 1; }
   }
+  // pow32_cr: whenever it accepts, the result must be the fp32 rounding of the exact power (long double pow as the
+  // reference: 64-bit significand, so its own error cannot move an fp32 rounding that pow32_cr accepted)
+  {
+    uint64_t st = 0x9e3779b97f4a7c15ull;
+    auto rnd = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) / 9007199254740992.0; };
+    unsigned long long n = 0, bad = 0, refused = 0;
+    for (long i = 0; i < 6000000; i++) {
+      float x, y;
+      switch (i % 4) {
+        case 0: x = (float)(1e-6 + rnd() * 5.0); y = (float)((rnd() - 0.5) * 12.0); break;          // plantcarb tmp1**tmp2
+        case 1: x = (float)(rnd() * 45.0); y = 1.3053f; break;                                       // soilcarb avgtrs**1.3053
+        case 2: x = (float)(0.01 + rnd()); y = (float)(2.0 - (2.0 + rnd() * 24.0)); break;          // carbon_pl wbav**(2-ibp2)
+        default: x = (float)std::exp((rnd() - 0.5) * 60.0); y = (float)((rnd() - 0.5) * 8.0); break; // wide
+      }
+      float got;
+      if (!pow32_cr(x, y, got)) { refused++; continue; }
+      const float ref = (float)powl((long double)x, (long double)y);
+      n++;
+      if (b_of(got) != b_of(ref)) { bad++; printf("   pow32_cr(%.9g, %.9g) = %.9g, expected %.9g\n", x, y, got, ref); if (bad > 8) break; }
+    }
+    printf("pow32_cr                     n=%llu mismatches=%llu refused=%llu\n", n, bad, refused);
+    if (bad || refused > n / 4) rc = 1;
+    float o;
+    if (pow32_cr(0.0f, 2.0f, o) || pow32_cr(-1.0f, 2.0f, o) || pow32_cr(1e-30f, 2.0f, o) || pow32_cr(1e30f, 2.0f, o) ||
+        !pow32_cr(3.0f, 2.0f, o) || o != 9.0f || !pow32_cr(2.0f, 0.5f, o) || o != 1.41421354f) { printf("pow32_cr specials FAILED\n"); rc = 1; }
+  }
   printf(rc ? "FAILED\n" : "ok\n");
   return rc;
 }
