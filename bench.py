@@ -467,10 +467,18 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its
+    # version banner there at NCCL_DEBUG=VERSION and above) are sent to stderr for the whole run, and print() gets the
+    # saved descriptor back
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
