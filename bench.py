@@ -192,8 +192,13 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": "tile-timesteps/sec for cbm()", "value": rate, "unit": "tile-timesteps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": "global 0.5deg GSWP3-shape synthetic forcing, 5 tiles/land point, dels=10800s "
-                               "(bounded sample of the 62000-point grid)", "sample_tiles_per_step": nland_w * NAP * cores},
+        # the b200 arm's workload (same text, same sizes); each CPU step is a bounded sample of it
+        "config": {"workload": f"global 0.5deg GSWP3-shape synthetic forcing: {args.nland} land points x {NAP} tiles "
+                               f"= {args.nland * NAP} tiles per GPU, dels={int(DELS)}s, leuning/standard/HDM/icycle=0 (cable.nml)",
+                   "tiles_per_gpu": args.nland * NAP, "global_tiles": args.nland * NAP * args.gpus,
+                   "parallelism": f"land-point blocks x{cores} host processes (master_decomp rule)",
+                   "sample": f"each step = {nland_w * NAP * cores} tiles of that grid ({cores} blocks of {nland_w} land points)",
+                   "sample_tiles_per_step": nland_w * NAP * cores},
         "cpu_baseline": {"value": rate, "unit": "tile-timesteps/s", "cores": cores, "kind": "port",
                          "sample": f"{cores} workers x {nland_w} land points x {NAP} tiles x {args.steps} steps, "
                                    "C++ restatement of the reference (not the Fortran binary), forcing in memory"},
