@@ -130,3 +130,36 @@ def test_dryleaf_numpy_vs_oracle(gs_switch):
             np.testing.assert_allclose(g, want, rtol=tol, atol=1e-30, err_msg=f"{name} iter {c['iter']}")
     veg = captured[0]["inp"]["canopy_vlaiw"][0] > 1e-3
     assert veg.sum() > 500 and total_passes > 4 * veg.sum()      # the leaf loop iterated: > 1 pass per vegetated tile and call
+
+
+# ---- init_radiation + Albedo (two-stream set-up, snow albedo, Spitters beam fraction) -------------------------------
+def test_radiation_albedo_numpy_vs_oracle():
+    """tests/np_radiation.py (written from the Fortran alone) against the oracle's rad%* / ssnow%albsoilsn outputs of
+    whole cbm() steps: day and night, vegetated / bare / lake / ice tiles, with and without snow."""
+    import np_radiation as R
+    cfg, grid, T, F = make_case(600, start_doy=20)
+    o = Oracle(T, cfg, cr_math=True)
+    seen_snow = seen_day = seen_night = 0
+    nbits = {}
+    for k in range(24):
+        F.fill(T, k)
+        pre = {n: T[n].copy() for n in ("ssnow_snowd", "ssnow_ssdnn", "ssnow_tgg", "ssnow_snage", "rad_cexpkbm")}
+        o.cbm(k + 1, DELS)
+        vlaiw, coszen = T["canopy_vlaiw"][0], T["met_coszen"][0]
+        r = R.init_radiation(T["veg_xfang"][0], T["veg_taul"], T["veg_refl"], coszen, T["met_doy"][0].astype(np.int32),
+                             T["met_fsd"], vlaiw)
+        a = R.albedo(r, T["soil_albsoil"], T["veg_iveg"][0], T["soil_isoilm"][0], pre["ssnow_snowd"][0], pre["ssnow_ssdnn"][0],
+                     pre["ssnow_tgg"][0], pre["ssnow_snage"][0], coszen, vlaiw, pre["rad_cexpkbm"])
+        seen_snow += int((pre["ssnow_snowd"][0] > 1.0).sum()); seen_day += int((coszen > 0.1).sum()); seen_night += int((coszen < 1e-6).sum())
+        want = {"rad_extkb": r["extkb"][None], "rad_extkd": r["extkd"][None], "rad_extkbm": r["extkbm"], "rad_extkdm": r["extkdm"],
+                "rad_fbeam": r["fbeam"], "ssnow_albsoilsn": a["albsoilsn"], "rad_rhocbm": a["rhocbm"], "rad_rhocdf": a["rhocdf"],
+                "rad_cexpkbm": a["cexpkbm"], "rad_cexpkdm": a["cexpkdm"], "rad_reffbm": a["reffbm"], "rad_reffdf": a["reffdf"],
+                "rad_albedo": a["albedo"], "rad_albedo_T": a["albedo_T"][None]}
+        for name, w in want.items():
+            got = T[name][: w.shape[0]]
+            np.testing.assert_allclose(got, w, rtol=3e-7, atol=1e-30, err_msg=f"{name} step {k + 1}")
+            nbits[name] = nbits.get(name, 0) + int((got.view(np.int32) != w.view(np.int32)).sum())
+    assert seen_snow > 100 and seen_day > 1000 and seen_night > 1000, (seen_snow, seen_day, seen_night)
+    assert (T["veg_iveg"][0] == 16).any() and (T["soil_isoilm"][0] == 9).any()
+    # same kinds, same order, correctly rounded intrinsics on both sides: expected bit-identical
+    assert sum(nbits.values()) == 0, nbits
