@@ -112,3 +112,100 @@ def smoisturev(dels, wb, wbice, tgg, gammzz, fwtop, ssat, sfc, hyds, hsbh, ibp2,
         wb[k] = np.where(over, wb[k] - F64(dfactor * sicemelt), wb[k])
         tgg[k] = np.where(over, tgg[k] - sicemelt * zse[k] * DENSITY_ICE * CHLF / gammzz[k].astype(F32), tgg[k])
     return dict(wb=wb, wbice=wbice, tgg=tgg, wblf=wblf, rnof2=rnof2.astype(F32))
+
+
+# ---- stempv + old_soil_conductivity --------------------------------------------------------------------------------
+CSWAT, CSICE, CGSNOW = F32(4.218e3), F32(2.100e3), F32(2090.0)      # src/params/cable_phys_constants_mod.F90:38-42
+
+
+def _cr32(fn, x):
+    """default-REAL intrinsic: evaluated in float64, rounded once (the convention of the correctly rounded oracle build)"""
+    return fn(np.asarray(x, F64)).astype(F32)
+
+
+def old_soil_conductivity(wblf, wbfice, ssat, cnsd, isoilm, snow_ccnsw):
+    """cbl_Oldconductivity.F90:7-53.  wblf, wbfice (6, mp) f64; ssat (mp) f32; cnsd (mp) f64 -> ccnsw (6, mp) f64."""
+    ms, mp = wblf.shape
+    out = np.zeros((ms, mp), F64)
+    log60, log250 = _cr32(np.log, F32(60.0)), _cr32(np.log, F32(250.0))
+    for k in range(ms):
+        ew = (wblf[k] * F64(ssat)).astype(F32)                                            # REAL ew = r_2 * REAL
+        exp_arg = (F64(ew * log60) + (wbfice[k] * F64(ssat)) * F64(log250)).astype(F32)   # REAL exp_arg = REAL + r_2
+        with np.errstate(all="ignore"):
+            shape = np.maximum(1.0, np.sqrt(np.minimum(2.0, F64(F32(0.5) * ssat) / np.minimum(F64(ew), 0.5 * F64(ssat)))))
+            lean = np.minimum(cnsd * F64(_cr32(np.exp, exp_arg)), 1.5) * shape
+        out[k] = np.where(isoilm == 9, F64(F32(snow_ccnsw)), np.where(exp_arg > F32(30.0), f32lit(1.5) * shape, lean))
+    return out
+
+
+def stempv(dels, tgg, tggsn, gammzz, wblf, wbfice, isflag, snowd, ssdnn, ssdn, sdepth, sconds, ga, dgdtg, ssat, css, rhosoil,
+           cnsd, isoilm, hcll, zse, snow_ccnsw, max_sconds):
+    """cbl_stempv.F90:13-221 (soil_thermal_fix = .FALSE.).  (k, mp) arrays: tgg f32 (6), tggsn/ssdn/sdepth/sconds f32 (3),
+    gammzz/wblf/wbfice f64 (6), hcll f32 (6); (mp): isflag i32, snowd/ssdnn/ga/ssat/css/rhosoil f32, dgdtg/cnsd f64; zse (6) f32.
+    Returns dict(tgg, tggsn, gammzz, sconds, ghflux, sghflux)."""
+    dels = F32(dels)
+    ms, mp = tgg.shape
+    tgg, tggsn, gammzz, sconds = tgg.copy(), tggsn.copy(), gammzz.copy(), sconds.copy()
+    nos, sn = isflag == 0, isflag != 0
+    ccnsw = old_soil_conductivity(wblf, wbfice, ssat, cnsd, isoilm, snow_ccnsw)
+    # rows -2..ms of at/bt/ct/coeff live at index row + 2 (coeff has one more row, ms+1)
+    at = np.zeros((ms + 3, mp), F64); bt = np.ones((ms + 3, mp), F64); ct = np.zeros((ms + 3, mp), F64)
+    coeff = np.zeros((ms + 4, mp), F64)
+    R = lambda row: row + 2
+    with np.errstate(all="ignore"):
+        xx = np.where(nos, F64(np.maximum(F32(0.0), snowd / ssdnn)), 0.0)
+        ccnsw[0] = np.where(nos, (ccnsw[0] - f32lit(0.2)) * (F64(zse[0]) / (F64(zse[0]) + xx)) + f32lit(0.2), ccnsw[0])
+        for k in range(3, ms + 1):
+            coeff[R(k)] = np.where(nos, 2.0 / (F64(zse[k - 2]) / ccnsw[k - 2] + F64(zse[k - 1]) / ccnsw[k - 1]), coeff[R(k)])
+        coeff[R(2)] = np.where(nos, 2.0 / ((F64(zse[0]) + xx) / ccnsw[0] + F64(zse[1]) / ccnsw[1]), coeff[R(2)])
+        coefa = np.zeros(mp, F32)
+        coefb = np.where(nos, coeff[R(2)].astype(F32), F32(0.0)).astype(F32)
+        dry = ((F32(1.0) - ssat) * css) * rhosoil                                          # REAL
+
+        def heat_cap(k):          # k = 1..ms; the two argument orders of MAX are the same value
+            wet = F64(ssat) * ((wblf[k - 1] * F64(CSWAT)) * F64(DENSITY_LIQ) + (wbfice[k - 1] * F64(CSICE)) * F64(DENSITY_ICE))
+            return np.maximum(F64(hcll[k - 1]), F64(dry) + wet) * F64(zse[k - 1])
+
+        # no snow layers (isflag == 0)
+        g1 = heat_cap(1) + F64(CGSNOW * snowd)
+        gammzz[0] = np.where(nos, g1, gammzz[0])
+        for k in range(1, ms + 1):
+            if k > 1:
+                gammzz[k - 1] = np.where(nos, heat_cap(k), gammzz[k - 1])
+            dtg = F64(dels) / gammzz[k - 1]
+            a_, c_ = -dtg * coeff[R(k)], -dtg * coeff[R(k + 1)]
+            at[R(k)] = np.where(nos, a_, at[R(k)]); ct[R(k)] = np.where(nos, c_, ct[R(k)])
+            bt[R(k)] = np.where(nos, 1.0 - a_ - c_, bt[R(k)])
+        bt[R(1)] = np.where(nos, bt[R(1)] - dgdtg * F64(dels) / gammzz[0], bt[R(1)])
+        tgg[0] = np.where(nos, tgg[0] + (ga - tgg[0] * dgdtg.astype(F32)) * dels / gammzz[0].astype(F32), tgg[0])
+        coeff[R(-2)] = 0.0
+        # three snow layers (isflag /= 0)
+        for l in range(3):
+            sc = np.maximum(F32(0.2), np.minimum(F32(2.876e-6) * (ssdn[l] * ssdn[l]) + F32(0.074), F32(max_sconds)))
+            sconds[l] = np.where(sn, sc, sconds[l])
+        coeff[R(-1)] = np.where(sn, F64(F32(2.0) / (sdepth[0] / sconds[0] + sdepth[1] / sconds[1])), coeff[R(-1)])
+        coeff[R(0)] = np.where(sn, F64(F32(2.0) / (sdepth[1] / sconds[1] + sdepth[2] / sconds[2])), coeff[R(0)])
+        coeff[R(1)] = np.where(sn, 2.0 / (F64(sdepth[2] / sconds[2]) + F64(zse[0]) / ccnsw[0]), coeff[R(1)])
+        for k in range(2, ms + 1):
+            coeff[R(k)] = np.where(sn, 2.0 / (F64(zse[k - 2]) / ccnsw[k - 2] + F64(zse[k - 1]) / ccnsw[k - 1]), coeff[R(k)])
+        coefa = np.where(sn, coeff[R(-1)].astype(F32), coefa).astype(F32)
+        coefb = np.where(sn, coeff[R(1)].astype(F32), coefb).astype(F32)
+        for k in range(1, 4):
+            sgamm = (ssdn[k - 1] * CGSNOW) * sdepth[k - 1]                                 # REAL
+            dtg = F64(dels / sgamm)                                                        # REAL quotient stored in r_2
+            a_, c_ = -dtg * coeff[R(k - 3)], -dtg * coeff[R(k - 2)]
+            at[R(k - 3)] = np.where(sn, a_, at[R(k - 3)]); ct[R(k - 3)] = np.where(sn, c_, ct[R(k - 3)])
+            bt[R(k - 3)] = np.where(sn, 1.0 - a_ - c_, bt[R(k - 3)])
+        for k in range(1, ms + 1):
+            gammzz[k - 1] = np.where(sn, heat_cap(k), gammzz[k - 1])
+            dtg = F64(dels) / gammzz[k - 1]
+            a_, c_ = -dtg * coeff[R(k)], -dtg * coeff[R(k + 1)]
+            at[R(k)] = np.where(sn, a_, at[R(k)]); ct[R(k)] = np.where(sn, c_, ct[R(k)])
+            bt[R(k)] = np.where(sn, 1.0 - a_ - c_, bt[R(k)])
+        sgamm = (ssdn[0] * CGSNOW) * sdepth[0]
+        bt[R(-2)] = np.where(sn, bt[R(-2)] - dgdtg * F64(dels) / F64(sgamm), bt[R(-2)])
+        tggsn[0] = np.where(sn, tggsn[0] + (ga - tggsn[0] * dgdtg.astype(F32)) * dels / sgamm, tggsn[0])
+        sol = trimb(at, bt, ct, np.concatenate([tggsn.astype(F64), tgg.astype(F64)]))
+    tggsn, tgg = sol[:3].astype(F32), sol[3:].astype(F32)
+    return dict(tgg=tgg, tggsn=tggsn, gammzz=gammzz, sconds=sconds, sghflux=coefa * (tggsn[0] - tggsn[1]),
+                ghflux=coefb * (tgg[0] - tgg[1]))

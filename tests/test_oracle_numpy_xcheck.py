@@ -163,3 +163,45 @@ def test_radiation_albedo_numpy_vs_oracle():
     assert (T["veg_iveg"][0] == 16).any() and (T["soil_isoilm"][0] == 9).any()
     # same kinds, same order, correctly rounded intrinsics on both sides: expected bit-identical
     assert sum(nbits.values()) == 0, nbits
+
+
+# ---- stempv (soil + snow heat conduction, Thomas(9)) ----------------------------------------------------------------
+def test_stempv_numpy_vs_oracle():
+    """tests/np_restatement.py::stempv against the oracle's stempv on states taken from a running winter simulation:
+    tiles without snow layers (isflag = 0, with and without a thin pack), with three snow layers, permanent ice."""
+    from np_restatement import stempv as stempv_np
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    o._lib.oracle_run_stempv.argtypes = [C.c_void_p, C.c_float]
+    o._lib.oracle_run_stempv.restype = None
+    checked = 0
+    for k in range(48):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        if k not in (3, 20, 47):
+            continue
+        isflag = T["ssnow_isflag"][0]
+        assert (isflag != 0).sum() > 20 and (isflag == 0).sum() > 1000 and (T["soil_isoilm"][0] == 9).any()
+        assert ((isflag == 0) & (T["ssnow_snowd"][0] > 0)).any()
+        # what soil_snow hands stempv: liquid / ice fractions rebuilt from wb, wbice (cbl_soilsnow_main.F90:102-108)
+        T["ssnow_wblf"][...] = np.maximum(0.01, T["ssnow_wb"] - T["ssnow_wbice"]) / T["soil_ssat"][0].astype(np.float64)
+        T["ssnow_wbfice"][...] = (T["ssnow_wbice"].astype(np.float32) / T["soil_ssat"][0]).astype(np.float64)
+        want = stempv_np(DELS, T["ssnow_tgg"], T["ssnow_tggsn"], T["ssnow_gammzz"], T["ssnow_wblf"], T["ssnow_wbfice"], isflag,
+                         T["ssnow_snowd"][0], T["ssnow_ssdnn"][0], T["ssnow_ssdn"], T["ssnow_sdepth"], T["ssnow_sconds"],
+                         T["canopy_ga"][0], T["canopy_dgdtg"][0], T["soil_ssat"][0], T["soil_css"][0], T["soil_rhosoil"][0],
+                         T["soil_cnsd"][0], T["soil_isoilm"][0], T["soil_heat_cap_lower_limit"],
+                         np.array(list(cfg.zse), np.float32), cfg.snow_ccnsw, cfg.max_sconds)
+        before = T["ssnow_tgg"].copy()
+        o._lib.oracle_run_stempv(o._h, DELS)
+        np.testing.assert_allclose(T["ssnow_gammzz"], want["gammzz"], rtol=1e-14, err_msg="gammzz")
+        np.testing.assert_allclose(T["ssnow_sconds"], want["sconds"], rtol=0, atol=0, err_msg="sconds")
+        # fp32 results of an fp64 solve: identical up to the last bit of the cast
+        np.testing.assert_allclose(T["ssnow_tgg"], want["tgg"], rtol=1.2e-7, err_msg="tgg")
+        np.testing.assert_allclose(T["ssnow_tggsn"], want["tggsn"], rtol=1.2e-7, err_msg="tggsn")
+        scale = max(float(np.abs(want["ghflux"]).max()), 1.0)
+        np.testing.assert_allclose(T["canopy_ghflux"][0], want["ghflux"], rtol=1e-4, atol=1e-5 * scale, err_msg="ghflux")
+        np.testing.assert_allclose(T["canopy_sghflux"][0], want["sghflux"], rtol=1e-4, atol=1e-5 * scale, err_msg="sghflux")
+        assert np.isfinite(T["ssnow_tgg"]).all() and np.isfinite(T["ssnow_tggsn"]).all()
+        assert np.abs(T["ssnow_tgg"] - before).max() > 1e-3                                  # the routine did something
+        checked += 1
+    assert checked == 3
