@@ -209,3 +209,21 @@ def stempv(dels, tgg, tggsn, gammzz, wblf, wbfice, isflag, snowd, ssdnn, ssdn, s
     tggsn, tgg = sol[:3].astype(F32), sol[3:].astype(F32)
     return dict(tgg=tgg, tggsn=tggsn, gammzz=gammzz, sconds=sconds, sghflux=coefa * (tggsn[0] - tggsn[1]),
                 ghflux=coefb * (tgg[0] - tgg[1]))
+
+
+# ---- snow_aging ----------------------------------------------------------------------------------------------------
+def snow_aging(snage, dels, snowd, osnowd, tggsn1, tgg1, isflag, isoilm):
+    """cbl_snow_aging.F90:11-81 (called after soil_snow, cbl_model_driver_offline.F90:197-198); all default REAL."""
+    tfrz, dels = F32(273.16), F32(dels)
+    with np.errstate(all="ignore"):
+        dnsnow = np.minimum(F32(1.0), F32(0.1) * np.maximum(F32(0.0), snowd - osnowd))
+        fl = isflag.astype(F32)
+        tmp = np.minimum(fl * tggsn1 + (F32(1.0) - fl) * tgg1, tfrz)       # INTEGER * REAL, (1 - INTEGER) * REAL
+        ar1 = F32(5000.0) * (F32(1.0) / (tfrz - F32(0.01)) - F32(1.0) / tmp)
+        ar2 = F32(10.0) * ar1
+        ice = isoilm == 9
+        ar3 = np.where(ice, F32(0.0000001), F32(0.1)).astype(F32)
+        dnsnow = np.where(ice, F32(1.0), dnsnow).astype(F32)
+        dtau = F32(1.0e-6) * ((_cr32(np.exp, ar1) + _cr32(np.exp, ar2)) + ar3) * dels
+        new = np.maximum(F32(0.0), (snage + dtau) * (F32(1.0) - dnsnow))
+    return np.where(snowd > F32(1.0), new, snage).astype(F32)

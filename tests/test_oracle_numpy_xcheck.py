@@ -205,3 +205,21 @@ def test_stempv_numpy_vs_oracle():
         assert np.abs(T["ssnow_tgg"] - before).max() > 1e-3                                  # the routine did something
         checked += 1
     assert checked == 3
+
+
+def test_snow_aging_numpy_vs_oracle():
+    """snage after whole cbm() steps against tests/np_restatement.py::snow_aging fed with the step's own outputs
+    (snow_aging is the only writer of ssnow%snage and runs after soil_snow)."""
+    from np_restatement import snow_aging as snow_aging_np
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    aged = 0
+    for k in range(40):
+        F.fill(T, k)
+        before = T["ssnow_snage"][0].copy()
+        o.cbm(k + 1, DELS)
+        want = snow_aging_np(before, DELS, T["ssnow_snowd"][0], T["ssnow_osnowd"][0], T["ssnow_tggsn"][0], T["ssnow_tgg"][0],
+                             T["ssnow_isflag"][0], T["soil_isoilm"][0])
+        assert np.array_equal(T["ssnow_snage"][0].view(np.int32), want.view(np.int32)), f"step {k + 1}"
+        aged += int((want != before).sum())
+    assert aged > 1000 and (T["ssnow_snage"][0] > 0).any() and (T["soil_isoilm"][0] == 9).any()
