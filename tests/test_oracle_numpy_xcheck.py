@@ -223,3 +223,27 @@ def test_snow_aging_numpy_vs_oracle():
         assert np.array_equal(T["ssnow_snage"][0].view(np.int32), want.view(np.int32)), f"step {k + 1}"
         aged += int((want != before).sum())
     assert aged > 1000 and (T["ssnow_snage"][0] > 0).any() and (T["soil_isoilm"][0] == 9).any()
+
+
+def test_ruff_resist_numpy_vs_oracle():
+    """tests/np_roughness.py (written from the Fortran alone) against the rough%* / canopy%vlaiw outputs of whole cbm()
+    steps: bare, vegetated, snow-covered and buried canopies, ice."""
+    import np_roughness as RR
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    nveg = nbare = nsnow = 0
+    for k in range(30):
+        F.fill(T, k)
+        snowd, ssdnn = T["ssnow_snowd"][0].copy(), T["ssnow_ssdnn"][0].copy()
+        o.cbm(k + 1, DELS)
+        r = RR.ruff_resist(T["veg_hc"][0], T["veg_vlai"][0], T["veg_iveg"][0], snowd, ssdnn, T["rough_za_uv"][0], T["rough_za_tq"][0])
+        veg = r["veg"]
+        nveg += int(veg.sum()); nbare += int((~veg).sum()); nsnow += int(((snowd > 0.01) & veg).sum())
+        for name in ("hruff", "z0soil", "z0soilsn", "z0m", "disp", "zref_uv", "zref_tq", "usuh", "coexp", "rt0us", "zruffs",
+                     "rt1usa", "rt1usb"):
+            assert np.array_equal(T["rough_" + name][0].view(np.int32), r[name].view(np.int32)), f"rough%{name} step {k + 1}"
+        for name in ("vlaiw", "rghlai"):
+            assert np.array_equal(T["canopy_" + name][0].view(np.int32), r[name].view(np.int32)), f"canopy%{name} step {k + 1}"
+        for name in ("term2", "term3", "term5", "term6", "term6a"):      # written on the vegetated branch only
+            assert np.array_equal(T["rough_" + name][0][veg].view(np.int32), r[name][veg].view(np.int32)), f"rough%{name} step {k + 1}"
+    assert nveg > 10000 and nbare > 10000 and nsnow > 1000 and (T["veg_iveg"][0] == 17).any()
