@@ -56,3 +56,23 @@ def ruff_resist(hc, vlai, iveg, snowd, ssdnn, za_uv, za_tq):
              zref_tq=zref_tq, usuh=usuh, coexp=coexp, rt0us=z(rt0us), zruffs=z(zruffs), rt1usa=z(rt1usa), rt1usb=z(rt1usb),
              term2=term2, term3=term3, term5=term5, term6=term6, term6a=term6a, veg=veg)
     return o
+
+
+def define_air(tvair, pmb):
+    """src/science/misc/cable_air.F90:51-97 at met%tvair = met%tk (cable_canopy.F90:191, 206)."""
+    tfrz, capp, hl, rgas, rmair, rmh2o = F(273.16), F(1004.64), F(2.5014e6), F(8.3143), F(0.02897), F(0.018016)
+    a, b, c = F(6.106), F(17.27), F(237.3)
+    tc = tvair - tfrz
+    es = a * _cr(np.exp, b * tc / (c + tc))
+    cmolar = pmb * F(100.0) / (rgas * tvair)
+    rho = np.minimum(F(1.3), rmair * cmolar)
+    volm = rgas * tvair / (F(100.0) * pmb)
+    rlam = np.full_like(tvair, hl)
+    qsat = (rmh2o / rmair) * es / pmb
+    d = c + tc
+    epsi = (rlam / capp) * (rmh2o / rmair) * es * b * c / (d * d) / pmb
+    visc = F(1e-5) * np.maximum(F(1.0), F(1.35) + F(0.0092) * tc)
+    psyc = pmb * F(100.0) * capp * rmair / rlam / rmh2o
+    d2 = tc + c
+    dsatdk = F(100.0) * (a * b * c) / (d2 * d2) * _cr(np.exp, b * tc / (tc + c))
+    return dict(cmolar=cmolar, rho=rho, volm=volm, rlam=rlam, qsat=qsat, epsi=epsi, visc=visc, psyc=psyc, dsatdk=dsatdk)

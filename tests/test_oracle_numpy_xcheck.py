@@ -247,3 +247,17 @@ def test_ruff_resist_numpy_vs_oracle():
         for name in ("term2", "term3", "term5", "term6", "term6a"):      # written on the vegetated branch only
             assert np.array_equal(T["rough_" + name][0][veg].view(np.int32), r[name][veg].view(np.int32)), f"rough%{name} step {k + 1}"
     assert nveg > 10000 and nbare > 10000 and nsnow > 1000 and (T["veg_iveg"][0] == 17).any()
+
+
+def test_define_air_numpy_vs_oracle():
+    import np_roughness as RR
+    cfg, grid, T, F = make_case(800, start_doy=200)
+    o = Oracle(T, cfg, cr_math=True)
+    for k in range(8):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        a = RR.define_air(T["met_tk"][0], T["met_pmb"][0])
+        for name, w in a.items():
+            if "air_" + name in T:
+                assert np.array_equal(T["air_" + name][0].view(np.int32), w.view(np.int32)), f"air%{name} step {k + 1}"
+    assert sum(("air_" + n) in T for n in a) >= 8
