@@ -127,3 +127,56 @@ def albedo(r, albsoil, iveg, isoilm, snowd, ssdnn, tgg1, snage, coszen, vlaiw, c
             alb[b] = np.where(veg, (F(1.0) - fb) * reffdf[b] + fb * reffbm[b], alb[b])
     return dict(albsoilsn=asn, rhocbm=rhocbm, rhocdf=rhocdf, cexpkbm=cexpkbm, cexpkdm=cexpkdm, reffbm=reffbm, reffdf=reffdf,
                 albedo=alb.astype(np.float32), albedo_T=((alb[0] + alb[1]) * F(0.5)).astype(np.float32))
+
+
+def radiation(r, a, taul, refl, extkn, fsd, fld, tvrad, tss, vlaiw, rho, cmolar):
+    """cbl_radiation.F90:30-218.  r, a = the dicts of init_radiation / albedo of the same step; tss = ssnow%tss at entry.
+    -> dict(transd, transb, flws, gradis(2), qcan(6: leaf + 2 * band), qssabs, scalex(2), fvlai(2), rniso(2))."""
+    sboltz, emsoil, emleaf, capp = F(5.67e-8), F(1.0), F(1.0), F(1004.64)
+    mp = vlaiw.shape[0]
+    veg = vlaiw > LAI_THRESH
+    sunlit_veg = veg & ((fsd[0] + fsd[1]) > F(0.001))               # masks_cbl.F90:69-115 with rad_thresh (SURVEY D9)
+    extkb, extkd = r["extkb"], r["extkd"]
+    p4 = lambda x: (x * x) * (x * x)
+    with np.errstate(all="ignore"):
+        cf2n = _cr(np.exp, -extkn * vlaiw)
+        transd = np.where(veg, _cr(np.exp, -extkd * vlaiw), F(1.0)).astype(F)
+        transb = _cr(np.exp, -np.minimum(extkb * vlaiw, F(30.)))
+        flpwb = sboltz * p4(tvrad)
+        flwv = emleaf * flpwb
+        flws = sboltz * emsoil * p4(tss)
+        emair = fld / flpwb
+        g1 = (F(4.0) * emleaf / (capp * rho)) * flpwb / tvrad * extkd * (
+            (F(1.0) - transb * transd) / (extkb + extkd) + (transd - transb) / (extkb - extkd))
+        g2 = (F(8.0) * emleaf / (capp * rho)) * flpwb / tvrad * extkd * (F(1.0) - transd) / extkd - g1
+        q13 = (flws - flwv) * extkd * (transd - transb) / (extkb - extkd) \
+            + (emair - emleaf) * extkd * flpwb * (F(1.0) - transd * transb) / (extkb + extkd)
+        q23 = (F(1.0) - transd) * (flws + fld - F(2.0) * flwv) - q13
+        gradis = np.stack([np.where(veg, g1, F(0.0)), np.where(veg, g2, F(0.0))]).astype(F)
+        gradis = np.maximum(np.float64(1.0e-3), (cmolar * gradis).astype(np.float64)).astype(F)
+        qcan = np.zeros((6, mp), F)                                   # component = leaf + 2 * band
+        qcan[0 + 2 * 2] = np.where(veg, q13, F(0.0)); qcan[1 + 2 * 2] = np.where(veg, q23, F(0.0))
+        for b in range(2):
+            fb, reffdf, reffbm = r["fbeam"][b], a["reffdf"][b], a["reffbm"][b]
+            extkdm, extkbm, cexpkdm, cexpkbm = r["extkdm"][b], r["extkbm"][b], a["cexpkdm"][b], a["cexpkbm"][b]
+            cf1 = (F(1.0) - transb * cexpkdm) / (extkb + extkdm)
+            cf3 = (F(1.0) - transb * cexpkbm) / (extkb + extkbm)
+            beam = fb * (F(1.0) - taul[b] - refl[b]) * extkb * ((F(1) - transb) / extkb - (F(1) - transb * transb) / (extkb + extkb))
+            dif = (F(1.0) - fb) * (F(1.0) - reffdf) * extkdm
+            bm = fb * (F(1.0) - reffbm) * extkbm
+            q1 = fsd[b] * (dif * cf1 + bm * cf3 + beam)
+            q2 = fsd[b] * (dif * ((F(1.0) - cexpkdm) / extkdm - cf1) + bm * ((F(1.0) - cexpkbm) / extkbm - cf3) - beam)
+            qcan[0 + 2 * b] = np.where(sunlit_veg, q1, F(0.0)); qcan[1 + 2 * b] = np.where(sunlit_veg, q2, F(0.0))
+        fb1, fb2 = r["fbeam"][0], r["fbeam"][1]
+        qs_veg = fsd[0] * (fb1 * (F(1.) - a["reffbm"][0]) * _cr(np.exp, -np.minimum(r["extkbm"][0] * vlaiw, F(20.)))
+                           + (F(1.) - fb1) * (F(1.) - a["reffdf"][0]) * _cr(np.exp, -np.minimum(r["extkdm"][0] * vlaiw, F(20.)))) \
+            + fsd[1] * (fb2 * (F(1.) - a["reffbm"][1]) * a["cexpkbm"][1] + (F(1.) - fb2) * (F(1.) - a["reffdf"][1]) * a["cexpkdm"][1])
+        qs_bare = (F(1.0) - a["albsoilsn"][0]) * fsd[0] + (F(1.0) - a["albsoilsn"][1]) * fsd[1]
+        qssabs = np.where(sunlit_veg, qs_veg, qs_bare).astype(F)
+        sx1 = np.where(sunlit_veg, (F(1.0) - transb * cf2n) / (extkb + extkn), F(0.0)).astype(F)
+        fv1 = np.where(sunlit_veg, (F(1.0) - transb) / extkb, F(0.0)).astype(F)
+        fv2 = vlaiw - fv1
+        sx2 = (F(1.0) - cf2n) / extkn - sx1
+        rniso = np.stack([(qcan[l] + qcan[l + 2]) + qcan[l + 4] for l in range(2)])
+    return dict(transd=transd, transb=transb, flws=flws, gradis=gradis, qcan=qcan, qssabs=qssabs, scalex=np.stack([sx1, sx2]),
+                fvlai=np.stack([fv1, fv2]), rniso=rniso)

@@ -134,8 +134,8 @@ def test_dryleaf_numpy_vs_oracle(gs_switch):
 
 # ---- init_radiation + Albedo (two-stream set-up, snow albedo, Spitters beam fraction) -------------------------------
 def test_radiation_albedo_numpy_vs_oracle():
-    """tests/np_radiation.py (written from the Fortran alone) against the oracle's rad%* / ssnow%albsoilsn outputs of
-    whole cbm() steps: day and night, vegetated / bare / lake / ice tiles, with and without snow."""
+    """tests/np_radiation.py (written from the Fortran alone: init_radiation, Albedo, radiation) against the oracle's rad%* /
+    ssnow%albsoilsn outputs of whole cbm() steps: day and night, vegetated / bare / lake / ice tiles, with and without snow."""
     import np_radiation as R
     cfg, grid, T, F = make_case(600, start_doy=20)
     o = Oracle(T, cfg, cr_math=True)
@@ -143,7 +143,7 @@ def test_radiation_albedo_numpy_vs_oracle():
     nbits = {}
     for k in range(24):
         F.fill(T, k)
-        pre = {n: T[n].copy() for n in ("ssnow_snowd", "ssnow_ssdnn", "ssnow_tgg", "ssnow_snage", "rad_cexpkbm")}
+        pre = {n: T[n].copy() for n in ("ssnow_snowd", "ssnow_ssdnn", "ssnow_tgg", "ssnow_snage", "rad_cexpkbm", "ssnow_tss")}
         o.cbm(k + 1, DELS)
         vlaiw, coszen = T["canopy_vlaiw"][0], T["met_coszen"][0]
         r = R.init_radiation(T["veg_xfang"][0], T["veg_taul"], T["veg_refl"], coszen, T["met_doy"][0].astype(np.int32),
@@ -155,6 +155,12 @@ def test_radiation_albedo_numpy_vs_oracle():
                 "rad_fbeam": r["fbeam"], "ssnow_albsoilsn": a["albsoilsn"], "rad_rhocbm": a["rhocbm"], "rad_rhocdf": a["rhocdf"],
                 "rad_cexpkbm": a["cexpkbm"], "rad_cexpkdm": a["cexpkdm"], "rad_reffbm": a["reffbm"], "rad_reffdf": a["reffdf"],
                 "rad_albedo": a["albedo"], "rad_albedo_T": a["albedo_T"][None]}
+        # the in-canopy radiation of the same step (cbl_radiation.F90), from the restated set-up above
+        q = R.radiation(r, a, T["veg_taul"], T["veg_refl"], T["veg_extkn"][0], T["met_fsd"], T["met_fld"][0], T["met_tk"][0],
+                        pre["ssnow_tss"][0], vlaiw, T["air_rho"][0], T["air_cmolar"][0])
+        want.update({"rad_transd": q["transd"][None], "rad_transb": q["transb"][None], "rad_flws": q["flws"][None],
+                     "rad_gradis": q["gradis"], "rad_qcan": q["qcan"], "rad_qssabs": q["qssabs"][None], "rad_scalex": q["scalex"],
+                     "rad_fvlai": q["fvlai"], "rad_rniso": q["rniso"]})
         for name, w in want.items():
             got = T[name][: w.shape[0]]
             np.testing.assert_allclose(got, w, rtol=3e-7, atol=1e-30, err_msg=f"{name} step {k + 1}")
