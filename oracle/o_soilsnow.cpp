@@ -655,6 +655,8 @@ static void surfbv(Oracle &o, float dels) {
 // independent NumPy restatement of the same Fortran)
 extern "C" void oracle_run_smoisturev(void *h, float dels) { smoisturev(*(Oracle *)h, dels); }
 extern "C" void oracle_run_stempv(void *h, float dels) { stempv(*(Oracle *)h, dels); }
+extern "C" void oracle_run_remove_trans(void *h) { remove_trans(*(Oracle *)h); }
+extern "C" void oracle_run_soilfreeze(void *h) { soilfreeze(*(Oracle *)h); }
 
 // ---- hydraulic_redistribution: cbl_hyd_redistrib.F90:13-221 (redistrb) -------
 // All working variables are default REAL; ssnow%wb is r_2.  wiltParam / satuParam: cable_runtime_opts_mod.F90:6-7.

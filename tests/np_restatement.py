@@ -227,3 +227,46 @@ def snow_aging(snage, dels, snowd, osnowd, tggsn1, tgg1, isflag, isoilm):
         dtau = F32(1.0e-6) * ((_cr32(np.exp, ar1) + _cr32(np.exp, ar2)) + ar3) * dels
         new = np.maximum(F32(0.0), (snage + dtau) * (F32(1.0) - dnsnow))
     return np.where(snowd > F32(1.0), new, snage).astype(F32)
+
+
+# ---- remove_trans, soilfreeze -------------------------------------------------------------------------------------
+def remove_trans(fevc, fevw, wbliq, wbice, evapfbl, zse):
+    """cbl_remove_trans.F90:9-40 (no gw_model).  fevc (mp) f64, fevw (mp) f32, wbliq/wbice/evapfbl (6, mp) f64; zse (6) f32
+    (soil%zse_vec is the spread of soil%zse, an r_2 array).  -> dict(fevc, fevw, wbliq, wb)."""
+    neg = fevc < 0.0
+    fevw = np.where(neg, (F64(fevw) + fevc).astype(F32), fevw).astype(F32)
+    fevc = np.where(neg, 0.0, fevc)
+    wbliq = wbliq.copy(); wb = np.zeros_like(wbliq)
+    for k in range(wbliq.shape[0]):
+        wbliq[k] = wbliq[k] - evapfbl[k] / (F64(zse[k]) * F64(DENSITY_LIQ))
+        wb[k] = wbliq[k] + wbice[k]
+    return dict(fevc=fevc, fevw=fevw, wbliq=wbliq, wb=wb)
+
+
+def soilfreeze(tgg, wb, wbice, gammzz, isflag, snowd, ssat, css, rhosoil, hcll, zse, frozen_limit):
+    """cbl_soilfreeze.F90:9-81.  tgg (6, mp) f32; wb, wbice, gammzz (6, mp) f64; hcll (6, mp) f32; (mp) f32 parameters."""
+    tfrz, fl = F32(273.16), F64(F32(frozen_limit))
+    tgg, wb, wbice, gammzz = tgg.copy(), wb.copy(), wbice.copy(), gammzz.copy()
+    dry = F64(((F32(1.0) - ssat) * css) * rhosoil)
+    cw, ci = F64(CSWAT * DENSITY_LIQ), F64(CSICE * DENSITY_ICE)
+    den = F64(np.maximum(F32(1.0) - DENSITY_ICE / DENSITY_LIQ, F32(1.0E-3)))
+    with np.errstate(all="ignore"):
+        for k in range(tgg.shape[0]):
+            zi, zl = F64(zse[k] * DENSITY_ICE), F64(zse[k] * DENSITY_LIQ)
+            frz = (tgg[k] < tfrz) & (fl * wb[k] - wbice[k] > f32lit(.001))
+            mlt = ~frz & (tgg[k] > tfrz) & (wbice[k] > 0.)
+            s = np.minimum(fl * wb[k] - wbice[k], (F64(ssat) - wb[k]) / den)
+            s = np.minimum(np.maximum(0.0, s) * F64(zse[k]) * F64(DENSITY_ICE), F64(tfrz - tgg[k]) * gammzz[k] / F64(CHLF))
+            m = np.minimum(wbice[k] * F64(zse[k]) * F64(DENSITY_ICE), F64(tgg[k] - tfrz) * gammzz[k] / F64(CHLF))
+            ice_f = np.minimum(wbice[k] + s / zi, fl * wb[k]); wb_f = wb[k] + s / zi - s / zl
+            ice_m = np.maximum(0.0, wbice[k] - m / zi); wb_m = wb[k] - m / zi + m / zl
+            wbice[k] = np.where(frz, ice_f, np.where(mlt, ice_m, wbice[k]))
+            wb[k] = np.where(frz, wb_f, np.where(mlt, wb_m, wb[k]))
+            arg2 = (dry + (wb[k] - wbice[k]) * cw + wbice[k] * ci).astype(F32)              # REAL :: max_arg2
+            g = F64(np.maximum(hcll[k], arg2)) * F64(zse[k])
+            if k == 0:
+                g = np.where(isflag == 0, g + F64(CGSNOW * snowd), g)
+            gammzz[k] = np.where(frz | mlt, g, gammzz[k])
+            tgg[k] = np.where(frz, tgg[k] + s.astype(F32) * CHLF / gammzz[k].astype(F32),
+                              np.where(mlt, tgg[k] - m.astype(F32) * CHLF / gammzz[k].astype(F32), tgg[k])).astype(F32)
+    return dict(tgg=tgg, wb=wb, wbice=wbice, gammzz=gammzz, n_freeze_melt=None)

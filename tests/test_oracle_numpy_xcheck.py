@@ -267,3 +267,41 @@ def test_define_air_numpy_vs_oracle():
             if "air_" + name in T:
                 assert np.array_equal(T["air_" + name][0].view(np.int32), w.view(np.int32)), f"air%{name} step {k + 1}"
     assert sum(("air_" + n) in T for n in a) >= 8
+
+
+def test_remove_trans_and_soilfreeze_numpy_vs_oracle():
+    """remove_trans and soilfreeze (tests/np_restatement.py) against the oracle's routines, each run on states of a winter
+    simulation that contain transpiring, dew-forming, freezing and thawing layers."""
+    from np_restatement import remove_trans as remove_trans_np, soilfreeze as soilfreeze_np
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    for fn in ("oracle_run_remove_trans", "oracle_run_soilfreeze"):
+        getattr(o._lib, fn).argtypes = [C.c_void_p]; getattr(o._lib, fn).restype = None
+    zse = np.array(list(cfg.zse), np.float32)
+    n_frz = n_mlt = n_neg = 0
+    for k in range(30):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        if k % 5 != 4:
+            continue
+        # remove_trans on the step's transpiration extraction (a second application: any state is a valid input)
+        if k == 9:
+            T["canopy_fevc"][0][::7] = -np.abs(T["canopy_fevc"][0][::7]) - 1.0          # dew on the dry canopy fraction
+        n_neg += int((T["canopy_fevc"][0] < 0).sum())
+        want = remove_trans_np(T["canopy_fevc"][0].copy(), T["canopy_fevw"][0].copy(), T["ssnow_wbliq"], T["ssnow_wbice"],
+                               T["ssnow_evapfbl"], zse)
+        o._lib.oracle_run_remove_trans(o._h)
+        assert np.array_equal(T["canopy_fevc"][0], want["fevc"]) and np.array_equal(T["canopy_fevw"][0], want["fevw"])
+        assert np.array_equal(T["ssnow_wbliq"], want["wbliq"]) and np.array_equal(T["ssnow_wb"], want["wb"])
+        # soilfreeze after nudging the profile across the freezing point both ways
+        T["ssnow_tgg"][:, ::3] -= np.float32(1.5); T["ssnow_tgg"][:, 1::3] += np.float32(1.5)
+        tgg, wb, wbice = T["ssnow_tgg"].copy(), T["ssnow_wb"].copy(), T["ssnow_wbice"].copy()
+        n_frz += int(((tgg < 273.16) & (cfg.frozen_limit * wb - wbice > 1e-3)).sum()); n_mlt += int(((tgg > 273.16) & (wbice > 0)).sum())
+        want = soilfreeze_np(tgg, wb, wbice, T["ssnow_gammzz"].copy(), T["ssnow_isflag"][0], T["ssnow_snowd"][0], T["soil_ssat"][0],
+                             T["soil_css"][0], T["soil_rhosoil"][0], T["soil_heat_cap_lower_limit"], zse, cfg.frozen_limit)
+        o._lib.oracle_run_soilfreeze(o._h)
+        for name in ("wb", "wbice", "gammzz"):
+            np.testing.assert_allclose(T["ssnow_" + name], want[name], rtol=1e-15, atol=0, err_msg=name)
+        assert np.array_equal(T["ssnow_tgg"].view(np.int32), want["tgg"].view(np.int32)), "tgg"
+        assert np.abs(T["ssnow_wbice"] - wbice).max() > 1e-4
+    assert n_frz > 1000 and n_mlt > 1000 and n_neg > 100, (n_frz, n_mlt, n_neg)
