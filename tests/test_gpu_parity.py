@@ -145,6 +145,32 @@ def test_fastdiv_build_is_bit_identical_and_falls_back(monkeypatch):
             assert np.array_equal(a[f.name], b[f.name], equal_nan=True), (tiny, f.name)
 
 
+def test_fastdiv_decaying_numerators_stay_on_the_fast_path(monkeypatch):
+    """Quantities that decay through the subnormal range over a long run (canopy storage, wet fraction, the halving
+    soil wetness factor, soil ice) reach divisions of kernel A as numerators below the fast path's 2^-100 window.  Those
+    sites divide through the fp64 chain (dvw) or the operator (dvx), cbm_consts.cuh: same bits as the ordinary build and
+    no block handed back."""
+    def run(fast):
+        monkeypatch.setenv("CABLE_B200_FASTDIV", str(fast))
+        cfg, grid, T, F = make_case(300)
+        cfg.output_level = 2
+        T["canopy_cansto"][0][::5] = np.float32(1e-42); T["canopy_cansto"][0][1::5] = np.float32(3e-33)
+        T["canopy_oldcansto"][...] = T["canopy_cansto"]                     # D10: cbm restores cansto from oldcansto
+        T["ssnow_owetfac"][0][::4] = np.float32(2e-36); T["ssnow_wetfac"][0][::4] = np.float32(2e-36)
+        T["ssnow_wbice"][0][::3] = 1e-310; T["ssnow_wbice"][0][1::3] = 4e-300
+        with CableB200(grid.mp, cfg) as h:
+            h.bind(T); h.upload_params(); h.upload_state()
+            for k in range(6):
+                F.fill(T, k)
+                h.cbm(k + 1, DELS)
+            redo = h.counters().n_fastdiv_redo_blocks
+        return T, redo
+    (a, ra), (b, rb) = run(1), run(0)
+    assert ra == 0 and rb == 0, (ra, rb)
+    for f in output_fields():
+        assert np.array_equal(a[f.name], b[f.name], equal_nan=True), f.name
+
+
 @pytest.mark.parametrize("mp_case", [(1, 1), (1, 3), (7, 5), (26, 5)])      # 1, 3, 35, 130 tiles: ragged vs the 128-thread block
 def test_ragged_and_tiny_sizes(mp_case):
     nland, nap = mp_case
