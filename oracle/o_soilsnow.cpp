@@ -656,6 +656,8 @@ static void surfbv(Oracle &o, float dels) {
 extern "C" void oracle_run_smoisturev(void *h, float dels) { smoisturev(*(Oracle *)h, dels); }
 extern "C" void oracle_run_stempv(void *h, float dels) { stempv(*(Oracle *)h, dels); }
 extern "C" void oracle_run_remove_trans(void *h) { remove_trans(*(Oracle *)h); }
+extern "C" void oracle_run_snowdensity(void *h, float dels) { snowdensity(*(Oracle *)h, dels); }
+extern "C" void oracle_run_snow_accum(void *h, float dels) { snow_accum(*(Oracle *)h, dels); }
 extern "C" void oracle_run_soilfreeze(void *h) { soilfreeze(*(Oracle *)h); }
 
 // ---- hydraulic_redistribution: cbl_hyd_redistrib.F90:13-221 (redistrb) -------

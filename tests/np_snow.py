@@ -1,0 +1,113 @@
+"""Independent NumPy / scalar restatements of the snow-pack routines at the head of soil_snow, written from the Fortran
+alone as cross-checks of the C++ oracle:
+  snowdensity   src/science/soilsnow/cbl_snowDensity.F90:9-102
+  snow_accum    src/science/soilsnow/cbl_snowAccum.F90:10-188
+  snow_melting  src/science/soilsnow/cbl_snowMelt.F90:9-120
+Default REAL = np.float32, REAL(r_2) = np.float64, Fortran operation order; EXP evaluated in float64 and rounded once (the
+correctly rounded oracle build's convention).  State is a dict of registry-layout arrays ((k, mp), layer index first),
+modified in place.  TEST INFRASTRUCTURE ONLY."""
+import numpy as np
+
+F, D = np.float32, np.float64
+TFRZ, CHLF, CHL, CSWAT, CGSNOW, DENSITY_LIQ = F(273.16), F(0.334e6), F(2.5014e6), F(4.218e3), F(2090.0), F(1000.0)
+
+
+def _exp(x):
+    with np.errstate(all="ignore"):
+        return np.exp(np.asarray(x, D)).astype(F)
+
+
+def snowdensity(S, dels, max_ssdn, max_sconds):
+    dels, max_ssdn, max_sconds = F(dels), F(max_ssdn), F(max_sconds)
+    ssdn, tgg1, tggsn, snowd, isflag = S["ssnow_ssdn"], S["ssnow_tgg"][0], S["ssnow_tggsn"], S["ssnow_snowd"][0], S["ssnow_isflag"][0]
+    smass, sdepth, sconds, t_snwlr = S["ssnow_smass"], S["ssnow_sdepth"], S["ssnow_sconds"], S["ssnow_t_snwlr"][0]
+    sc = lambda d: np.maximum(F(0.2), np.minimum(F(2.876e-6) * (d * d) + F(0.074), max_sconds))
+    merge = lambda d: np.where(d >= F(150.0), F(0.046), F(0.0)).astype(F)
+    with np.errstate(all="ignore"):
+        m0 = (snowd > F(0.1)) & (isflag == 0)
+        tmin1 = np.minimum(TFRZ, tgg1)
+        d = ssdn[0]
+        d1 = np.minimum(max_ssdn, np.maximum(F(120.0), d + dels * d * F(3.1e-6) * _exp(F(-0.03) * (F(273.15) - tmin1) - merge(d) * (d - F(150.0)))))
+        d1 = np.minimum(max_ssdn, d1 + dels * F(9.806) * d1 * F(0.75) * snowd
+                        / (F(3.0e7) * _exp(F(0.021) * d1 + F(0.081) * (F(273.15) - np.minimum(TFRZ, tgg1)))))
+        d1 = np.where(S["soil_isoilm"][0] != 9, np.minimum(F(450.0), d1), d1).astype(F)
+        m1 = isflag == 1
+        e = [None] * 3
+        for l in range(3):
+            dl = ssdn[l]
+            e[l] = dl + dels * dl * F(3.1e-6) * _exp(F(-0.03) * (F(273.15) - np.minimum(TFRZ, tggsn[l])) - merge(dl) * (dl - F(150.0)))
+        den = lambda l: F(3.0e7) * _exp(F(.021) * e[l] + F(0.081) * (F(273.15) - np.minimum(TFRZ, tggsn[l])))
+        e[0] = e[0] + dels * F(9.806) * e[0] * t_snwlr * e[0] / den(0)
+        e[1] = e[1] + dels * F(9.806) * e[1] * (t_snwlr * e[0] + F(0.5) * smass[1]) / den(1)
+        e[2] = e[2] + dels * F(9.806) * e[2] * (t_snwlr * e[0] + smass[1] + F(0.5) * smass[2]) / den(2)
+        ssdnn1 = (e[0] * smass[0] + e[1] * smass[1] + e[2] * smass[2]) / snowd
+        for l in range(3):
+            sdepth[l] = np.where(m1, smass[l] / e[l], sdepth[l])
+            sconds[l] = np.where(m1, sc(e[l]), np.where(m0, sc(d1), sconds[l]))
+            ssdn[l] = np.where(m1, e[l], np.where(m0, d1, ssdn[l]))
+        S["ssnow_ssdnn"][0] = np.where(m1, ssdnn1, np.where(m0, d1, S["ssnow_ssdnn"][0]))
+
+
+def snow_accum(S, dels, max_ssdn):
+    dels, max_ssdn = F(dels), F(max_ssdn)
+    precis, precip_sn = S["canopy_precis"][0], S["met_precip_sn"][0]
+    snowd, osnowd, isflag, isoilm = S["ssnow_snowd"][0], S["ssnow_osnowd"][0], S["ssnow_isflag"][0], S["soil_isoilm"][0]
+    ssdn, ssdnn, tgg, tggsn, dtmlt = S["ssnow_ssdn"], S["ssnow_ssdnn"][0], S["ssnow_tgg"], S["ssnow_tggsn"], S["ssnow_dtmlt"]
+    smass, sdepth, gammzz = S["ssnow_smass"], S["ssnow_sdepth"], S["ssnow_gammzz"]
+    fess, fes_cor, cls = S["canopy_fess"][0], S["canopy_fes_cor"][0], S["ssnow_cls"][0]
+    segg, evapsn = S["canopy_segg"][0], S["ssnow_evapsn"][0]
+    mx, mn = max, min
+    for i in range(snowd.shape[0]):
+        if precis[i] > 0 and isflag[i] == 0:
+            snowd[i] = mx(snowd[i] + precip_sn[i], F(0.0))
+            precis[i] = precis[i] - precip_sn[i]
+            ssdn[0, i] = mx(F(120.0), ssdn[0, i] * osnowd[i] / mx(F(0.01), snowd[i]) + F(120.0) * precip_sn[i] / mx(F(0.01), snowd[i]))
+            ssdnn[i] = ssdn[0, i]
+            if precis[i] > 0 and tgg[0, i] < TFRZ:
+                snowd[i] = mx(snowd[i] + precis[i], F(0.0))
+                dt = precis[i] * CHLF / (F(gammzz[0, i]) + CSWAT * precis[i])
+                tgg[0, i] = tgg[0, i] + dt
+                dtmlt[0, i] = dtmlt[0, i] + dt
+                ssdn[0, i] = mn(max_ssdn, mx(F(120.0), ssdn[0, i] * osnowd[i] / mx(F(0.01), snowd[i])
+                                             + DENSITY_LIQ * precis[i] / mx(F(0.01), snowd[i])))
+                if isoilm[i] != 9:
+                    ssdn[0, i] = mn(F(450.0), ssdn[0, i])
+                precis[i] = F(0.0)
+                ssdnn[i] = ssdn[0, i]
+        if precis[i] > 0 and isflag[i] > 0:
+            snowd[i] = mx(snowd[i] + precip_sn[i], F(0.0))
+            precis[i] = precis[i] - precip_sn[i]
+            osm = smass[0, i]
+            smass[0, i] = smass[0, i] + precip_sn[i]
+            ssdn[0, i] = mx(F(120.0), ssdn[0, i] * osm / smass[0, i] + F(120.0) * precip_sn[i] / smass[0, i])
+            sdepth[0, i] = mx(F(0.02), smass[0, i] / ssdn[0, i])
+            if precis[i] > 0:
+                snowd[i] = mx(snowd[i] + precis[i], F(0.0))
+                for l in range(3):
+                    sgamm = ssdn[l, i] * CGSNOW * sdepth[l, i]
+                    osm = smass[l, i]
+                    dt = precis[i] * CHLF * osm / (sgamm * osnowd[i])
+                    tggsn[l, i] = tggsn[l, i] + dt
+                    if l == 0:
+                        dtmlt[0, i] = dtmlt[0, i] + dt
+                    smass[l, i] = smass[l, i] + precis[i] * osm / osnowd[i]
+                    ssdn[l, i] = mx(F(120.0), mn(ssdn[l, i] * osm / smass[l, i] + DENSITY_LIQ * (F(1.0) - osm / smass[l, i]), max_ssdn))
+                    if isoilm[i] != 9:
+                        ssdn[l, i] = mn(F(450.0), ssdn[l, i])
+                    sdepth[l, i] = smass[l, i] / ssdn[l, i]
+                precis[i] = F(0.0)
+    segg[:] = ((fess + fes_cor) / D(CHL)).astype(F)
+    evapsn[:] = F(0.0)
+    for i in np.flatnonzero(cls == F(1.1335)):
+        ftot = fess[i] + fes_cor[i]                                     # r_2
+        evapsn[i] = F(D(dels) * ftot / D(CHL + CHLF))
+        xxx = evapsn[i]
+        if isflag[i] == 0 and ftot > 0.0:
+            evapsn[i] = mn(snowd[i], xxx)
+        if isflag[i] > 0 and ftot > 0.0:
+            evapsn[i] = mn(F(0.9) * smass[0, i], xxx)
+        snowd[i] = snowd[i] - evapsn[i]
+        if isflag[i] > 0:
+            smass[0, i] = smass[0, i] - evapsn[i]
+            sdepth[0, i] = mx(F(0.02), smass[0, i] / ssdn[0, i])
+        segg[i] = (CHL + CHLF) * (xxx - evapsn[i]) / CHL / dels

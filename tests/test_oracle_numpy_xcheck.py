@@ -305,3 +305,47 @@ def test_remove_trans_and_soilfreeze_numpy_vs_oracle():
         assert np.array_equal(T["ssnow_tgg"].view(np.int32), want["tgg"].view(np.int32)), "tgg"
         assert np.abs(T["ssnow_wbice"] - wbice).max() > 1e-4
     assert n_frz > 1000 and n_mlt > 1000 and n_neg > 100, (n_frz, n_mlt, n_neg)
+
+
+SNOW_FIELDS = ("ssnow_ssdn", "ssnow_ssdnn", "ssnow_sconds", "ssnow_sdepth", "ssnow_smass", "ssnow_snowd", "ssnow_tgg", "ssnow_tggsn",
+               "ssnow_dtmlt", "ssnow_evapsn", "canopy_precis", "canopy_segg")
+
+
+def test_snowdensity_and_snow_accum_numpy_vs_oracle():
+    """tests/np_snow.py against the oracle's snowdensity and snow_accum, each run on states of a winter simulation:
+    thin packs (isflag = 0), three-layer packs, snowfall, rain on snow and on frozen ground, sublimation."""
+    import np_snow as NS
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    for fn in ("oracle_run_snowdensity", "oracle_run_snow_accum"):
+        getattr(o._lib, fn).argtypes = [C.c_void_p, C.c_float]; getattr(o._lib, fn).restype = None
+    seen = dict(thin=0, deep=0, snowfall=0, rain_cold=0, rain_deep=0, subl=0)
+    rng = np.random.default_rng(5)
+    for k in range(40):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        if k % 8 != 7:
+            continue
+        isflag, snowd = T["ssnow_isflag"][0], T["ssnow_snowd"][0]
+        seen["thin"] += int(((snowd > 0.1) & (isflag == 0)).sum()); seen["deep"] += int((isflag == 1).sum())
+        S = {n: T[n].copy() for n in T}
+        NS.snowdensity(S, DELS, cfg.max_ssdn, cfg.max_sconds)
+        o._lib.oracle_run_snowdensity(o._h, DELS)
+        for n in ("ssnow_ssdn", "ssnow_ssdnn", "ssnow_sconds", "ssnow_sdepth"):
+            assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snowdensity {n} step {k + 1}"
+        # snow_accum: what soil_snow hands it -- osnowd = snowd, this step's throughfall; some rain added on cold tiles
+        T["ssnow_osnowd"][...] = T["ssnow_snowd"]
+        T["canopy_precis"][...] = T["met_precip"]
+        wet = rng.random(snowd.shape[0]) < 0.3
+        T["canopy_precis"][0][wet] += np.float32(1.7)
+        T["ssnow_dtmlt"][...] = 0.0
+        pr, sn = T["canopy_precis"][0], T["met_precip_sn"][0]
+        seen["snowfall"] += int((sn > 0).sum()); seen["rain_cold"] += int(((pr - sn > 0) & (isflag == 0) & (T["ssnow_tgg"][0] < 273.16)).sum())
+        seen["rain_deep"] += int(((pr - sn > 0) & (isflag > 0)).sum())
+        seen["subl"] += int((T["ssnow_cls"][0] == np.float32(1.1335)).sum())
+        S = {n: T[n].copy() for n in T}
+        NS.snow_accum(S, DELS, cfg.max_ssdn)
+        o._lib.oracle_run_snow_accum(o._h, DELS)
+        for n in SNOW_FIELDS:
+            assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snow_accum {n} step {k + 1}"
+    assert all(v > 20 for v in seen.values()), seen
