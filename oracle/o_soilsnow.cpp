@@ -658,6 +658,12 @@ extern "C" void oracle_run_stempv(void *h, float dels) { stempv(*(Oracle *)h, de
 extern "C" void oracle_run_remove_trans(void *h) { remove_trans(*(Oracle *)h); }
 extern "C" void oracle_run_snowdensity(void *h, float dels) { snowdensity(*(Oracle *)h, dels); }
 extern "C" void oracle_run_snow_accum(void *h, float dels) { snow_accum(*(Oracle *)h, dels); }
+extern "C" void oracle_run_snow_melting(void *h, float dels, float *snowmlt_out) {
+  Oracle &o = *(Oracle *)h;
+  std::vector<float> snowmlt(o.mp, 0.f);
+  snow_melting(o, dels, snowmlt);
+  for (int i = 0; i < o.mp; i++) snowmlt_out[i] = snowmlt[i];
+}
 extern "C" void oracle_run_soilfreeze(void *h) { soilfreeze(*(Oracle *)h); }
 
 // ---- hydraulic_redistribution: cbl_hyd_redistrib.F90:13-221 (redistrb) -------

@@ -111,3 +111,45 @@ def snow_accum(S, dels, max_ssdn):
             smass[0, i] = smass[0, i] - evapsn[i]
             sdepth[0, i] = mx(F(0.02), smass[0, i] / ssdn[0, i])
         segg[i] = (CHL + CHLF) * (xxx - evapsn[i]) / CHL / dels
+
+
+def snow_melting(S, dels, max_ssdn):
+    """-> snowmlt (mp) f32.  Per tile, in the Fortran's statement order (the WHERE masks are evaluated where they stand)."""
+    dels, max_ssdn = F(dels), F(max_ssdn)
+    snowd, isflag, isoilm = S["ssnow_snowd"][0], S["ssnow_isflag"][0], S["soil_isoilm"][0]
+    tgg, tggsn, gammzz, dtmlt = S["ssnow_tgg"], S["ssnow_tggsn"], S["ssnow_gammzz"], S["ssnow_dtmlt"]
+    ssdn, sdepth, smass = S["ssnow_ssdn"], S["ssnow_sdepth"], S["ssnow_smass"]
+    mp = snowd.shape[0]
+    snowmlt = np.zeros(mp, F)
+    for j in range(mp):
+        if snowd[j] > 0 and isflag[j] == 0 and tgg[0, j] >= TFRZ:
+            snowflx = F(D(tgg[0, j] - TFRZ) * gammzz[0, j])
+            snowmlt[j] = min(snowflx / CHLF, snowd[j])
+            dtmlt[0, j] = F(D(dtmlt[0, j]) + D(snowmlt[j] * CHLF) / gammzz[0, j])
+            snowd[j] = snowd[j] - snowmlt[j]
+            tgg[0, j] = F(D(tgg[0, j]) - D(snowmlt[j] * CHLF) / gammzz[0, j])
+        if snowd[j] > 0 and isflag[j] > 0:
+            sm = [F(0.0)] * 4                                            # smelt1(j, 0:3)
+            for k in (1, 2, 3):
+                l = k - 1
+                sgamm = ssdn[l, j] * CGSNOW * sdepth[l, j]
+                snowflx = sm[k - 1] * CHLF / dels
+                tggsn[l, j] = tggsn[l, j] + (snowflx * dels + sm[k - 1] * CSWAT * (TFRZ - tggsn[l, j])) / (sgamm + CSWAT * sm[k - 1])
+                osm = smass[l, j]
+                smass[l, j] = smass[l, j] + sm[k - 1]
+                ssdn[l, j] = max(F(120.0), min(ssdn[l, j] * osm / smass[l, j] + DENSITY_LIQ * (F(1.0) - osm / smass[l, j]), max_ssdn))
+                if isoilm[j] != 9:
+                    ssdn[l, j] = min(F(450.0), ssdn[l, j])
+                sdepth[l, j] = smass[l, j] / ssdn[l, j]
+                sgamm = smass[l, j] * CGSNOW
+                sm[k - 1] = F(0.0); sm[k] = F(0.0)
+                if tggsn[l, j] > TFRZ:
+                    snowflx = (tggsn[l, j] - TFRZ) * sgamm
+                    sm[k] = min(snowflx / CHLF, F(0.6) * smass[l, j])
+                    dtmlt[l, j] = dtmlt[l, j] + sm[k] * CHLF / sgamm
+                    smass[l, j] = smass[l, j] - sm[k]
+                    tggsn[l, j] = tggsn[l, j] - sm[k] * CHLF / sgamm
+                    sdepth[l, j] = smass[l, j] / ssdn[l, j]
+            snowmlt[j] = sm[1] + sm[2] + sm[3]
+            snowd[j] = snowd[j] - snowmlt[j]
+    return snowmlt

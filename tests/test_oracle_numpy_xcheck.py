@@ -349,3 +349,34 @@ def test_snowdensity_and_snow_accum_numpy_vs_oracle():
         for n in SNOW_FIELDS:
             assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snow_accum {n} step {k + 1}"
     assert all(v > 20 for v in seen.values()), seen
+
+
+def test_snow_melting_numpy_vs_oracle():
+    """tests/np_snow.py::snow_melting against the oracle's, on winter states warmed across the melting point (thin packs on
+    thawed ground, three-layer packs with melt water percolating and refreezing downwards)."""
+    import np_snow as NS
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    o._lib.oracle_run_snow_melting.argtypes = [C.c_void_p, C.c_float, C.c_void_p]; o._lib.oracle_run_snow_melting.restype = None
+    n_thin = n_deep = n_melt = 0
+    for k in range(40):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        if k % 8 != 7:
+            continue
+        T["ssnow_tgg"][0][::2] += np.float32(2.5)
+        deep = np.flatnonzero(T["ssnow_isflag"][0] > 0)[::2]             # half of the three-layer packs brought to the melting point
+        T["ssnow_tggsn"][:, deep] = (np.float32(272.6) + np.float32(1.5) * np.random.default_rng(k).random((3, deep.size))).astype(np.float32)
+        T["ssnow_dtmlt"][...] = 0.0
+        isflag, snowd = T["ssnow_isflag"][0], T["ssnow_snowd"][0]
+        n_thin += int(((snowd > 0) & (isflag == 0) & (T["ssnow_tgg"][0] >= 273.16)).sum())
+        n_deep += int(((snowd > 0) & (isflag > 0) & (T["ssnow_tggsn"] > 273.16).any(axis=0)).sum())
+        S = {n: T[n].copy() for n in T}
+        want = NS.snow_melting(S, DELS, cfg.max_ssdn)
+        got = np.zeros(snowd.shape[0], np.float32)
+        o._lib.oracle_run_snow_melting(o._h, DELS, got.ctypes.data)
+        assert np.array_equal(got.view(np.int32), want.view(np.int32)), f"snowmlt step {k + 1}"
+        for n in ("ssnow_snowd", "ssnow_tgg", "ssnow_tggsn", "ssnow_dtmlt", "ssnow_smass", "ssnow_ssdn", "ssnow_sdepth"):
+            assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snow_melting {n} step {k + 1}"
+        n_melt += int((want > 0).sum())
+    assert n_thin > 50 and n_deep > 20 and n_melt > 50, (n_thin, n_deep, n_melt)
