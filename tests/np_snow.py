@@ -153,3 +153,91 @@ def snow_melting(S, dels, max_ssdn):
             snowmlt[j] = sm[1] + sm[2] + sm[3]
             snowd[j] = snowd[j] - snowmlt[j]
     return snowmlt
+
+
+def snowcheck(S, snmin):
+    """cbl_snowCheck.F90:9-100: the one-layer <-> three-layer regime of the pack."""
+    snmin = F(snmin)
+    snowd, isflag, ssdnn, t_snwlr = S["ssnow_snowd"][0], S["ssnow_isflag"][0], S["ssnow_ssdnn"][0], S["ssnow_t_snwlr"][0]
+    ssdn, tggsn, tgg, sdepth, smass = S["ssnow_ssdn"], S["ssnow_tggsn"], S["ssnow_tgg"], S["ssnow_sdepth"], S["ssnow_smass"]
+    for j in range(snowd.shape[0]):
+        if snowd[j] <= 0:
+            isflag[j] = 0
+            ssdn[:, j] = F(120.0); ssdnn[j] = F(120.0); tggsn[:, j] = TFRZ
+            sdepth[0, j] = snowd[j] / ssdn[0, j]; sdepth[1, j] = F(0.0); sdepth[2, j] = F(0.0)
+            smass[0, j] = snowd[j]; smass[1, j] = F(0.0); smass[2, j] = F(0.0)
+        elif snowd[j] < snmin * ssdnn[j]:
+            if isflag[j] == 1:
+                ssdn[0, j] = ssdnn[j]
+                tgg[0, j] = tggsn[0, j]
+            isflag[j] = 0
+            ssdnn[j] = min(F(400.0), max(F(120.0), ssdn[0, j]))
+            tggsn[:, j] = min(TFRZ, tgg[0, j])
+            sdepth[0, j] = snowd[j] / ssdn[0, j]; sdepth[1, j] = F(0.0); sdepth[2, j] = F(0.0)
+            smass[0, j] = snowd[j]; smass[1, j] = F(0.0); smass[2, j] = F(0.0)
+            ssdn[:, j] = ssdnn[j]
+        else:
+            if isflag[j] == 0:
+                tggsn[:, j] = min(TFRZ, tgg[0, j])
+                ssdn[1, j] = ssdn[0, j]; ssdn[2, j] = ssdn[0, j]
+                sdepth[0, j] = t_snwlr[j]
+                smass[0, j] = t_snwlr[j] * ssdn[0, j]
+                smass[1, j] = (snowd[j] - smass[0, j]) * F(0.4)
+                smass[2, j] = (snowd[j] - smass[0, j]) * F(0.6)
+                sdepth[1, j] = smass[1, j] / ssdn[1, j]
+                sdepth[2, j] = smass[2, j] / ssdn[2, j]
+                ssdnn[j] = (ssdn[0, j] * smass[0, j] + ssdn[1, j] * smass[1, j] + ssdn[2, j] * smass[2, j]) / snowd[j]
+            isflag[j] = 1
+
+
+def snowl_adjust(S, max_ssdn):
+    """cbl_snowl_adjust.F90:9-156: re-partition of mass between the three layers (excd, excm, frac, xfrac are r_2)."""
+    max_ssdn = F(max_ssdn)
+    snowd, isflag, ssdnn, t_snwlr = S["ssnow_snowd"][0], S["ssnow_isflag"][0], S["ssnow_ssdnn"][0], S["ssnow_t_snwlr"][0]
+    ssdn, tggsn, sdepth, smass = S["ssnow_ssdn"], S["ssnow_tggsn"], S["ssnow_sdepth"], S["ssnow_smass"]
+    for j in np.flatnonzero(isflag > 0):
+        if sdepth[0, j] > t_snwlr[j]:
+            excd = D(sdepth[0, j] - t_snwlr[j])
+            excm = excd * D(ssdn[0, j])
+            sdepth[0, j] = sdepth[0, j] - F(excd)
+            smass[0, j] = smass[0, j] - F(excm)
+            osm = smass[1, j]
+            smass[1, j] = max(F(0.01), smass[1, j] + F(excm))
+            ssdn[1, j] = F(max(120.0, min(D(max_ssdn), D(ssdn[1, j] * osm / smass[1, j]) + D(ssdn[0, j]) * excm / D(smass[1, j]))))
+            sdepth[1, j] = smass[1, j] / ssdn[1, j]
+            tggsn[1, j] = F(D(tggsn[1, j] * osm / smass[1, j]) + D(tggsn[0, j]) * excm / D(smass[1, j]))
+            smass[2, j] = max(F(0.01), snowd[j] - smass[0, j] - smass[1, j])
+        else:
+            excd = D(t_snwlr[j] - sdepth[0, j])
+            excm = excd * D(ssdn[1, j])
+            osm = smass[0, j]
+            smass[0, j] = smass[0, j] + F(excm)
+            sdepth[0, j] = t_snwlr[j]
+            ssdn[0, j] = F(max(120.0, min(D(max_ssdn), D(ssdn[0, j] * osm / smass[0, j]) + D(ssdn[1, j]) * excm / D(smass[0, j]))))
+            tggsn[0, j] = F(D(tggsn[0, j] * osm / smass[0, j]) + D(tggsn[1, j]) * excm / D(smass[0, j]))
+            smass[1, j] = max(F(0.01), smass[1, j] - F(excm))
+            sdepth[1, j] = smass[1, j] / ssdn[1, j]
+            smass[2, j] = max(F(0.01), snowd[j] - smass[0, j] - smass[1, j])
+    for j in np.flatnonzero(isflag > 0):
+        frac = D(smass[1, j] / max(F(0.02), smass[2, j]))
+        xfrac = D(F(2.0) / F(3.0)) / frac
+        if xfrac > 1.0:
+            excm = (xfrac - 1.0) * D(smass[1, j])
+            osm = smass[1, j]
+            smass[1, j] = max(F(0.01), smass[1, j] + F(excm))
+            tggsn[1, j] = tggsn[1, j] * osm / smass[1, j] + tggsn[2, j] * F(excm) / smass[1, j]
+            ssdn[1, j] = max(F(120.0), min(max_ssdn, ssdn[1, j] * osm / smass[1, j] + ssdn[2, j] * F(excm) / smass[1, j]))
+            smass[2, j] = max(F(0.01), snowd[j] - smass[0, j] - smass[1, j])
+            sdepth[2, j] = max(F(0.02), smass[2, j] / ssdn[2, j])
+        else:
+            excm = (1.0 - xfrac) * D(smass[1, j])
+            smass[1, j] = max(F(0.01), smass[1, j] - F(excm))
+            sdepth[1, j] = max(F(0.02), smass[1, j] / ssdn[1, j])
+            osm = smass[2, j]
+            smass[2, j] = max(F(0.01), snowd[j] - smass[0, j] - smass[1, j])
+            tggsn[2, j] = tggsn[2, j] * osm / smass[2, j] + tggsn[1, j] * F(excm) / smass[2, j]
+            ssdn[2, j] = max(F(120.0), min(max_ssdn, ssdn[2, j] * osm / smass[2, j] + ssdn[1, j] * F(excm) / smass[2, j]))
+            sdepth[2, j] = smass[2, j] / ssdn[2, j]
+        isflag[j] = 1
+        ssdnn[j] = (ssdn[0, j] * sdepth[0, j] + ssdn[1, j] * sdepth[1, j] + ssdn[2, j] * sdepth[2, j]) \
+            / (sdepth[0, j] + sdepth[1, j] + sdepth[2, j])

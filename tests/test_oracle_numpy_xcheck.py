@@ -380,3 +380,45 @@ def test_snow_melting_numpy_vs_oracle():
             assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snow_melting {n} step {k + 1}"
         n_melt += int((want > 0).sum())
     assert n_thin > 50 and n_deep > 20 and n_melt > 50, (n_thin, n_deep, n_melt)
+
+
+def test_snowcheck_and_snowl_adjust_numpy_vs_oracle():
+    """tests/np_snow.py::snowcheck / snowl_adjust against the oracle's: packs appearing, vanishing, crossing the
+    snmin * ssdnn threshold both ways, and three-layer packs whose top layer is thicker / thinner than t_snwlr."""
+    import np_snow as NS
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    for fn in ("oracle_run_snowcheck", "oracle_run_snowl_adjust"):
+        getattr(o._lib, fn).argtypes = [C.c_void_p]; getattr(o._lib, fn).restype = None
+    fields = ("ssnow_isflag", "ssnow_ssdn", "ssnow_ssdnn", "ssnow_tggsn", "ssnow_tgg", "ssnow_sdepth", "ssnow_smass")
+    seen = dict(none=0, thin_from_deep=0, deep_from_thin=0, deep=0, top_thick=0, top_thin=0)
+    for k in range(40):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        if k % 8 != 7:
+            continue
+        rng = np.random.default_rng(100 + k)
+        snowd, isflag = T["ssnow_snowd"][0], T["ssnow_isflag"][0]
+        # move packs across the regime thresholds both ways
+        thr = cfg.snmin * T["ssnow_ssdnn"][0]
+        up = np.flatnonzero((isflag == 0) & (snowd > 0))[::3]; snowd[up] = (thr[up] * np.float32(1.3)).astype(np.float32)
+        down = np.flatnonzero(isflag == 1)[::3]; snowd[down] = (thr[down] * np.float32(0.6)).astype(np.float32)
+        gone = np.flatnonzero(snowd > 0)[::11]; snowd[gone] = np.float32(0.0)
+        seen["none"] += int((snowd <= 0).sum()); seen["thin_from_deep"] += down.size; seen["deep_from_thin"] += up.size
+        seen["deep"] += int(((isflag == 1) & (snowd >= thr)).sum())
+        S = {n: T[n].copy() for n in T}
+        NS.snowcheck(S, cfg.snmin)
+        o._lib.oracle_run_snowcheck(o._h)
+        for n in fields:
+            assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snowcheck {n} step {k + 1}"
+        # snowl_adjust on the three-layer packs, with the top layer perturbed both ways
+        deep = np.flatnonzero(T["ssnow_isflag"][0] > 0)
+        T["ssnow_sdepth"][0][deep] *= rng.uniform(0.5, 1.8, deep.size).astype(np.float32)
+        seen["top_thick"] += int((T["ssnow_sdepth"][0][deep] > T["ssnow_t_snwlr"][0][deep]).sum())
+        seen["top_thin"] += int((T["ssnow_sdepth"][0][deep] <= T["ssnow_t_snwlr"][0][deep]).sum())
+        S = {n: T[n].copy() for n in T}
+        NS.snowl_adjust(S, cfg.max_ssdn)
+        o._lib.oracle_run_snowl_adjust(o._h)
+        for n in fields:
+            assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snowl_adjust {n} step {k + 1}"
+    assert all(v > 20 for v in seen.values()), seen
