@@ -659,6 +659,7 @@ extern "C" void oracle_run_remove_trans(void *h) { remove_trans(*(Oracle *)h); }
 extern "C" void oracle_run_snowdensity(void *h, float dels) { snowdensity(*(Oracle *)h, dels); }
 extern "C" void oracle_run_snow_accum(void *h, float dels) { snow_accum(*(Oracle *)h, dels); }
 extern "C" void oracle_run_snowcheck(void *h) { snowcheck(*(Oracle *)h); }
+extern "C" void oracle_run_surfbv(void *h, float dels) { surfbv(*(Oracle *)h, dels); }
 extern "C" void oracle_run_snowl_adjust(void *h) { snowl_adjust(*(Oracle *)h); }
 extern "C" void oracle_run_snow_melting(void *h, float dels, float *snowmlt_out) {
   Oracle &o = *(Oracle *)h;

@@ -270,3 +270,54 @@ def soilfreeze(tgg, wb, wbice, gammzz, isflag, snowd, ssat, css, rhosoil, hcll, 
             tgg[k] = np.where(frz, tgg[k] + s.astype(F32) * CHLF / gammzz[k].astype(F32),
                               np.where(mlt, tgg[k] - m.astype(F32) * CHLF / gammzz[k].astype(F32), tgg[k])).astype(F32)
     return dict(tgg=tgg, wb=wb, wbice=wbice, gammzz=gammzz, n_freeze_melt=None)
+
+
+# ---- surfbv (after its call of smoisturev) -------------------------------------------------------------------------
+def surfbv_tail(dels, S, zse, max_glacier_snowd):
+    """cbl_surfbv.F90:55-140, the statements after CALL smoisturev (offline: nglacier = 2).  S: dict of registry-layout
+    arrays, modified in place (wb (6, mp) f64; rnof1, rnof2, runoff, snowd, wb_lake, sinfil (1, mp) f32; tgg (6, mp) f32;
+    smass/ssdn/sdepth (3, mp) f32; gammzz f64; isflag, veg_iveg i32; soil_ssat/swilt/sfc f32)."""
+    dels, mg = F32(dels), F32(max_glacier_snowd)
+    wb, rnof1, rnof2 = S["ssnow_wb"], S["ssnow_rnof1"][0], S["ssnow_rnof2"][0]
+    ssat, swilt, sfc = S["soil_ssat"][0], S["soil_swilt"][0], S["soil_sfc"][0]
+    snowd, isflag, tgg, gammzz, smass = S["ssnow_snowd"][0], S["ssnow_isflag"][0], S["ssnow_tgg"], S["ssnow_gammzz"], S["ssnow_smass"]
+    wb_lake, sinfil = S["ssnow_wb_lake"][0], S["ssnow_sinfil"][0]
+    ms, mp = wb.shape
+    xs = F64(ssat)
+    for k in range(ms):
+        rnof1[:] = rnof1 + (np.maximum(wb[k] - xs, 0.0) * F64(DENSITY_LIQ)).astype(F32) * zse[k]
+        wb[k] = np.maximum(F64(swilt / (F32(2.) * F32(2.0))), np.minimum(wb[k], xs))
+    rnof5 = np.zeros(mp, F32)
+    smelt1 = np.zeros((4, mp), F32)
+    smasstot = np.zeros(mp, F32)
+    gl = snowd > mg
+    with np.errstate(all="ignore"):
+        rnof5 = np.where(gl, np.minimum(F32(0.1), snowd - mg), rnof5).astype(F32)
+        thin = gl & (isflag == 0)
+        tgg[0] = np.where(thin, tgg[0] - rnof5 * CHLF / gammzz[0].astype(F32), tgg[0])
+        snowd[:] = np.where(thin, snowd - rnof5, snowd)
+        smasstot = np.where(gl & (isflag != 0), smass[0] + smass[1] + smass[2], F32(0.0)).astype(F32)
+        for k in (1, 2, 3):
+            m = (snowd > mg) & (isflag > 0)
+            sm = np.minimum(rnof5 * smass[k - 1] / smasstot, F32(0.2) * smass[k - 1])
+            smelt1[k] = np.where(m, sm, smelt1[k])
+            smass[k - 1] = np.where(m, smass[k - 1] - smelt1[k], smass[k - 1])
+            snowd[:] = np.where(m, snowd - smelt1[k], snowd)
+        rnof5 = np.where(isflag > 0, smelt1[1] + smelt1[2] + smelt1[3], rnof5).astype(F32)
+    sinfil[:] = F32(0.0)
+    lake = S["veg_iveg"][0] == 16
+    zl = zse[ms - 1] * DENSITY_LIQ
+    for j in np.flatnonzero(lake):
+        sinfil[j] = min(rnof1[j], wb_lake[j]); rnof1[j] = max(F32(0.0), rnof1[j] - sinfil[j]); wb_lake[j] = max(F32(0.0), wb_lake[j] - sinfil[j])
+        sinfil[j] = min(rnof2[j], wb_lake[j]); rnof2[j] = max(F32(0.0), rnof2[j] - sinfil[j]); wb_lake[j] = max(F32(0.0), wb_lake[j] - sinfil[j])
+        xxx = max(0.0, (wb[ms - 1, j] - F64(sfc[j])) * F64(zse[ms - 1]) * F64(DENSITY_LIQ))
+        sinfil[j] = min(F32(xxx), wb_lake[j])
+        wb[ms - 1, j] = wb[ms - 1, j] - F64(sinfil[j] / zl)
+        wb_lake[j] = max(F32(0.0), wb_lake[j] - sinfil[j])
+        xxx = max(0.0, (wb[ms - 1, j] - F64(F32(0.5) * (sfc[j] + swilt[j]))) * F64(zse[ms - 1]) * F64(DENSITY_LIQ))
+        sinfil[j] = min(F32(xxx), wb_lake[j])
+        wb[ms - 1, j] = wb[ms - 1, j] - F64(sinfil[j] / zl)
+        wb_lake[j] = max(F32(0.0), wb_lake[j] - sinfil[j])
+    rnof1[:] = rnof1 / dels + rnof5 / dels
+    rnof2[:] = rnof2 / dels
+    S["ssnow_runoff"][0][:] = rnof1 + rnof2

@@ -422,3 +422,48 @@ def test_snowcheck_and_snowl_adjust_numpy_vs_oracle():
         for n in fields:
             assert np.array_equal(T[n].view(np.int32), S[n].view(np.int32)), f"snowl_adjust {n} step {k + 1}"
     assert all(v > 20 for v in seen.values()), seen
+
+
+def test_surfbv_numpy_vs_oracle():
+    """surfbv = smoisturev + saturation-excess runoff, the wb floor, the glacier cap and the lake bookkeeping
+    (tests/np_restatement.py::smoisturev, surfbv_tail) against the oracle's surfbv."""
+    from np_restatement import surfbv_tail
+    cfg, grid, T, F = make_case(1500, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    o._lib.oracle_run_surfbv.argtypes = [C.c_void_p, C.c_float]; o._lib.oracle_run_surfbv.restype = None
+    zse = np.array(list(cfg.zse), np.float32)
+    seen = dict(lakes=0, glacier_thin=0, glacier_deep=0, satex=0)
+    for k in range(24):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        if k % 8 != 7:
+            continue
+        # entry state of surfbv: runoff accumulators as soil_snow leaves them, some packs above the glacier cap,
+        # some layers above saturation, lakes with and without stored deficit
+        n = T["ssnow_snowd"].shape[1]
+        rng = np.random.default_rng(k)
+        T["ssnow_rnof1"][0][:] = (rng.random(n) < 0.3) * rng.random(n).astype(np.float32) * np.float32(2.0)
+        T["ssnow_rnof2"][...] = 0.0
+        big = np.flatnonzero(T["ssnow_snowd"][0] > 0)[::4]
+        T["ssnow_snowd"][0][big] = np.float32(cfg.max_glacier_snowd) + rng.uniform(0.01, 0.3, big.size).astype(np.float32)
+        over = rng.random((6, n)) < 0.05
+        T["ssnow_wb"][over] = T["ssnow_wb"][over] + 0.2
+        lake = T["veg_iveg"][0] == 16
+        T["ssnow_wb_lake"][0][lake] = rng.uniform(0.0, 3.0, int(lake.sum())).astype(np.float32)
+        isflag = T["ssnow_isflag"][0]
+        seen["lakes"] += int(lake.sum()); seen["satex"] += int(over.sum())
+        seen["glacier_thin"] += int((isflag[big] == 0).sum()); seen["glacier_deep"] += int((isflag[big] > 0).sum())
+        S = {nm: T[nm].copy() for nm in T}
+        sm = smoisturev_np(dels=DELS, wb=S["ssnow_wb"], wbice=S["ssnow_wbice"], tgg=S["ssnow_tgg"], gammzz=S["ssnow_gammzz"],
+                           fwtop=[S["ssnow_fwtop1"][0], S["ssnow_fwtop2"][0], S["ssnow_fwtop3"][0]], ssat=S["soil_ssat"][0],
+                           sfc=S["soil_sfc"][0], hyds=S["soil_hyds"][0], hsbh=S["soil_hsbh"][0], ibp2=S["soil_ibp2"][0],
+                           i2bp3=S["soil_i2bp3"][0], pwb_min=S["soil_pwb_min"][0], zse=zse, zshh=np.array(list(cfg.zshh), np.float32),
+                           frozen_limit=cfg.frozen_limit, l_new_runoff_speed=bool(cfg.l_new_runoff_speed))
+        S["ssnow_wb"][...] = sm["wb"]; S["ssnow_wbice"][...] = sm["wbice"]; S["ssnow_tgg"][...] = sm["tgg"]
+        S["ssnow_rnof2"][0][:] = sm["rnof2"]
+        surfbv_tail(DELS, S, zse, cfg.max_glacier_snowd)
+        o._lib.oracle_run_surfbv(o._h, DELS)
+        np.testing.assert_allclose(T["ssnow_wb"], S["ssnow_wb"], rtol=2e-12, atol=1e-300, err_msg="wb")   # the fp64 powers of smoisturev: libm vs NumPy
+        for nm in ("ssnow_rnof1", "ssnow_rnof2", "ssnow_runoff", "ssnow_snowd", "ssnow_smass", "ssnow_tgg", "ssnow_wb_lake", "ssnow_sinfil"):
+            np.testing.assert_allclose(T[nm], S[nm], rtol=3e-7, atol=1e-12, err_msg=f"{nm} step {k + 1}")
+    assert all(v > 20 for v in seen.values()), seen
