@@ -467,3 +467,38 @@ def test_surfbv_numpy_vs_oracle():
         for nm in ("ssnow_rnof1", "ssnow_rnof2", "ssnow_runoff", "ssnow_snowd", "ssnow_smass", "ssnow_tgg", "ssnow_wb_lake", "ssnow_sinfil"):
             np.testing.assert_allclose(T[nm], S[nm], rtol=3e-7, atol=1e-12, err_msg=f"{nm} step {k + 1}")
     assert all(v > 20 for v in seen.values()), seen
+
+
+@pytest.mark.parametrize("diag_soil_resp_on", [1, 0])
+def test_carbon_numpy_vs_oracle(diag_soil_resp_on):
+    """plantcarb, soilcarb (both DIAG_SOIL_RESP branches) and carbon_pl (tests/np_carbon.py, written from
+    cable_carbon.F90 alone) against the carbon fluxes and pools of whole cbm() steps: they run last in cbm
+    (cbl_model_driver_offline.F90:214-229), so their inputs are the step's own final state plus the pools before it."""
+    import np_carbon as NC
+    cfg = lib.default_cfg()
+    cfg.diag_soil_resp_on = diag_soil_resp_on
+    cfg, grid, T, F = make_case(1200, cfg=cfg, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    bits = lambda a: np.ascontiguousarray(a).view(np.int32)
+    moved = 0
+    for k in range(24):
+        F.fill(T, k)
+        cplant, csoil = T["bgc_cplant"].copy(), T["bgc_csoil"].copy()
+        o.cbm(k + 1, DELS)
+        frp, frpw, frpr = NC.plantcarb(T["veg_rp20"][0], T["met_tk"][0], cplant, list(cfg.ratecp))
+        frs = NC.soilcarb(diag_soil_resp_on, T["veg_froot"], T["ssnow_wb"], T["ssnow_tgg"], T["veg_rs20"][0], T["veg_vegcf"][0],
+                          T["soil_sfc"][0], T["soil_swilt"][0], csoil, list(cfg.ratecs), T["ssnow_snowd"][0])
+        for name, w in (("frp", frp), ("frpw", frpw), ("frpr", frpr), ("frs", frs)):
+            assert np.array_equal(bits(T["canopy_" + name][0]), bits(w)), f"canopy%{name} step {k + 1}"
+        cp, cs = NC.carbon_pl(DELS, cfg.mvtype, T["veg_iveg"][0], T["canopy_tv"][0], T["veg_froot"], T["ssnow_wb"],
+                              T["soil_ibp2"][0], T["soil_swilt"][0], T["veg_vlai"][0], T["canopy_fpn"][0], frpw, frpr, frs,
+                              cplant, csoil)
+        assert np.array_equal(bits(T["bgc_cplant"]), bits(cp)), f"bgc%cplant step {k + 1}"
+        assert np.array_equal(bits(T["bgc_csoil"]), bits(cs)), f"bgc%csoil step {k + 1}"
+        moved += int((cp != cplant).sum()) + int((cs != csoil).sum())
+        fpn, frday = T["canopy_fpn"][0], T["canopy_frday"][0]                              # :224-227
+        assert np.array_equal(bits(T["canopy_fnpp"][0]), bits(np.float32(-1.0) * fpn - frp))
+        assert np.array_equal(bits(T["canopy_fgpp"][0]), bits(np.float32(-1.0) * fpn + frday))
+        assert np.array_equal(bits(T["canopy_fnee"][0]), bits(fpn + frs + frp))
+        assert np.array_equal(bits(T["canopy_fra"][0]), bits(frp + frday))
+    assert moved > 10000 and (T["canopy_frs"][0] > 0).any() and (T["ssnow_snowd"][0] > 1.).any()
