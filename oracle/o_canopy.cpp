@@ -698,13 +698,16 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       w.hcy[i] = 0.0;
       w.ecy[i] = w.rny[i] - w.hcy[i];
     }
-    const void *const hook_args[14] = {w.dsx.data(), w.fwsoil.data(), w.tlfx.data(), w.tlfy.data(), w.ecy.data(), w.hcy.data(),
+    const void *const hook_args[18] = {w.dsx.data(), w.fwsoil.data(), w.tlfx.data(), w.tlfy.data(), w.ecy.data(), w.hcy.data(),
                                        w.rny.data(), w.gbhu.data(), w.gbhf.data(), w.csx.data(), w.cansat.data(), w.ghwet.data(),
-                                       w.sum_rad_rniso.data(), w.sum_rad_gradis.data()};
+                                       w.sum_rad_rniso.data(), w.sum_rad_gradis.data(), rt0.data(), pwet.data(), rt1usc.data(),
+                                       tss4.data()};
+    auto stage = [&](int when) { if (o.dryleaf_hook) o.dryleaf_hook(when, iter, hook_args); };
     if (o.dryleaf_hook) o.dryleaf_hook(0, iter, hook_args);
     dryLeaf(o, dels, w, iter);                                                            // :404
     if (o.dryleaf_hook) o.dryleaf_hook(1, iter, hook_args);
     wetLeaf(o, dels, w);                                                                  // :409
+    stage(2);
     for (int j = 0; j < mp; j++) {
       f.canopy_fev[j] = (float)(f.canopy_fevc[j] + f.canopy_fevw[j]);                     // :418
       float ftemp = (1.0f - f.canopy_fwet[j]) * (float)(w.hcy[j]) + f.canopy_fhvw[j];
@@ -724,15 +727,19 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       f.ssnow_qstss[j] = qsatf(f.ssnow_tss[j] - CTFRZ, f.met_pmb[j]);                      // :461
     }
     if (litter) litter_resistances();                                                     // :471-476
+    stage(3);
     potev_calc(o, false);                                                                 // :480-506
     latent_heat_flux(o, dels, pwet);                                                      // :510
+    stage(4);
     for (int j = 0; j < mp; j++) {
       if (litter)                                                                         // :525-530: met%tk here, met%tvair at :600
         f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tk[j]) / (f.ssnow_rtsoil[j] + rhlitt[j]);
       else
         f.canopy_fhs[j] = f.air_rho[j] * CCAPP * (f.ssnow_tss[j] - f.met_tvair[j]) / f.ssnow_rtsoil[j];    // :532
     }
+    stage(5);
     within_canopy(o, w, rt0, qstvair, rhlitt, relitt);                                    // :545
+    stage(6);
     for (int j = 0; j < mp; j++) f.ssnow_qstss[j] = qsatf(f.ssnow_tss[j] - CTFRZ, f.met_pmb[j]);           // :549
     potev_calc(o, true);                                                                  // :553-579
     latent_heat_flux(o, dels, pwet);                                                      // :582
@@ -760,6 +767,7 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
         f.canopy_wetfac_cs[j] = fmaxf_(0.f, fminf_(1.f, fmaxf_(f.canopy_fev[j] / f.canopy_fevw_pot[j],
                                                                 (float)(f.canopy_fes[j]) / f.ssnow_potev[j])));  // :664
     }
+    stage(7);
     // update_zetar (cbl_zetar.F90:13-159)
     if (iter < niter) {
       iterplus = std::max(iter + 1, 2);

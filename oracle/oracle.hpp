@@ -50,7 +50,9 @@ struct Oracle {
   long long n_dryleaf_warn;
   std::vector<int> dbg_kiter;   // [NITER][mp]: dryLeaf passes executed in the last step (profiling aid for the device design)
   // test hook: called immediately before (when = 0) and after (when = 1) every dryLeaf call with the routine's work-array
-  // arguments, in the order of DRYLEAF_WORK in oracle/pyoracle.py (tests/test_oracle_numpy_xcheck.py)
+  // arguments, in the order of DRYLEAF_WORK / CANOPY_WORK in tests/test_oracle_numpy_xcheck.py; further stages of one
+  // stability iteration of define_canopy: 2 after wetLeaf, 3 before / 4 after the first potev + Latent_heat_flux, 5 before /
+  // 6 after within_canopy, 7 at the end of the iteration before update_zetar (work gains rt0, pwet, rt1usc, tss4)
   void (*dryleaf_hook)(int when, int iter, const void *const *work) = nullptr;
 };
 

@@ -92,7 +92,7 @@ def _run_with_dryleaf_capture(gs_switch, ntiles_land=400, steps=7):
             for j, (n, dt, nc) in enumerate(DRYLEAF_WORK):
                 snap["w_" + n] = view(work[j], dt, nc)
             captured.append(dict(iter=it, inp=snap))
-        else:
+        elif when == 1:
             out = {n: T[n].copy() for n in DRYLEAF_FIELDS_OUT}
             for j, (n, dt, nc) in enumerate(DRYLEAF_WORK):
                 if n in DRYLEAF_WORK_OUT:
@@ -502,3 +502,128 @@ def test_carbon_numpy_vs_oracle(diag_soil_resp_on):
         assert np.array_equal(bits(T["canopy_fnee"][0]), bits(fpn + frs + frp))
         assert np.array_equal(bits(T["canopy_fra"][0]), bits(frp + frday))
     assert moved > 10000 and (T["canopy_frs"][0] > 0).any() and (T["ssnow_snowd"][0] > 1.).any()
+
+
+# ---- one stability iteration of define_canopy around dryLeaf ---------------------------------------------------------
+CANOPY_WORK = DRYLEAF_WORK + (("rt0", np.float32, 1), ("pwet", np.float32, 1), ("rt1usc", np.float32, 1), ("tss4", np.float32, 1))
+
+
+def _run_with_canopy_stages(ntiles_land, steps, start_doy):
+    """cbm on the oracle; on the last step every stage of the four stability iterations is captured through the oracle's
+    stage hook (oracle.hpp): all bound fields plus define_canopy's work arrays."""
+    cfg, grid, T, F = make_case(ntiles_land, start_doy=start_doy)
+    o = Oracle(T, cfg, cr_math=True)
+    mp = grid.mp
+    snaps = {}
+
+    def view(ptr, dtype, ncol):
+        n = mp * ncol
+        buf = (C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        a = np.frombuffer(buf, dtype=dtype, count=n)
+        return a.reshape(mp, ncol).T.copy() if ncol > 1 else a.copy()                       # (k, mp) like the bound fields
+
+    HOOK = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_void_p))
+
+    def hook(when, it, work):
+        S = {n: (a[0].copy() if a.ndim == 2 and a.shape[0] == 1 else a.copy()) for n, a in T.items()}
+        for j, (n, dt, nc) in enumerate(CANOPY_WORK):
+            S["w_" + n] = view(work[j], dt, nc)
+        snaps[(it, when)] = S
+
+    cb = HOOK(hook)
+    o._lib.oracle_set_dryleaf_hook.argtypes = [C.c_void_p, HOOK]
+    o._lib.oracle_set_dryleaf_hook.restype = None
+    for k in range(steps):
+        F.fill(T, k)
+        if k == steps - 1:
+            ortsoil = T["ssnow_rtsoil"][0].copy()
+            o._lib.oracle_set_dryleaf_hook(o._h, cb)
+        o.cbm(k + 1, DELS)
+    o._lib.oracle_set_dryleaf_hook(o._h, HOOK(0))
+    return cfg, T, snaps, ortsoil
+
+
+@pytest.mark.parametrize("start_doy", [15, 196], ids=["january", "july"])
+def test_canopy_iteration_numpy_vs_oracle(start_doy):
+    """tests/np_canopy.py (written from the Fortran alone) against every stage of the four stability iterations of one
+    timestep: friction velocity, resistances and boundary-layer conductances, wetLeaf, canopy flux sums and radiative
+    temperature, HDM potential evaporation + Latent_heat_flux (both calls), within_canopy, the end-of-iteration block and
+    update_zetar.  fp32 fields to the bit, fp64 fields to 1e-14 relative."""
+    import np_canopy as NC
+    cfg, T, snaps, ortsoil = _run_with_canopy_stages(900, 9, start_doy)
+    zse1 = cfg.zse[0]
+    bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.int32)
+
+    def same(got, want, what, mask=None):
+        got, want = np.asarray(got), np.asarray(want)
+        if mask is not None:
+            got, want = got[..., mask], want[..., mask]
+        if want.dtype == np.float32:
+            assert got.dtype == np.float32, what
+            bad = bits(got) != bits(want)
+            assert not bad.any(), (what, int(bad.sum()), got[bad][:3], want[bad][:3])
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-300, err_msg=what)
+
+    n_on = n_frost = n_snow = 0
+    for it in (1, 2, 3, 4):
+        tag = f"iter {it}: "
+        S0, S1, S2, S3, S4, S5, S6, S7 = (snaps[(it, w)] for w in range(8))
+        zet = S0["canopy_zetar"][it - 1]
+        us = NC.comp_friction_vel(zet, S0["rough_zref_uv"], S0["rough_zref_tq"], S0["rough_z0m"], S0["met_ua"])
+        same(us, S0["canopy_us"], tag + "canopy%us")
+        gb_prev = snaps[(it - 1, 7)]["w_gbhu"] if it > 1 else np.full_like(S0["w_gbhu"], np.float64(np.float32(1e-3)))
+        rt1usc, rt0, rt1, rtsoil, gbhu = NC.resistances(S0, us, zet, ortsoil, gb_prev)
+        same(rt1usc, S0["w_rt1usc"], tag + "rt1usc"); same(rt0, S0["w_rt0"], tag + "rt0")
+        same(rt1, S0["rough_rt1"], tag + "rough%rt1"); same(rtsoil, S0["ssnow_rtsoil"], tag + "ssnow%rtsoil")
+        same(gbhu, S0["w_gbhu"], tag + "gbhu")
+        # wetLeaf
+        ghwet, fevw, fevw_pot, fhvw = NC.wetleaf(DELS, S1, S1["w_tlfy"], S1["w_gbhu"], S1["w_gbhf"], S1["w_sum_rad_rniso"],
+                                                 S1["w_sum_rad_gradis"])
+        same(ghwet, S2["w_ghwet"], tag + "ghwet")
+        for n, g in (("fevw", fevw), ("fevw_pot", fevw_pot), ("fhvw", fhvw)):
+            same(g, S2["canopy_" + n], tag + "canopy%" + n)
+        # flux sums, tv, fns, qstss
+        fev, fhv, fnv, lwabv, dense, tv, fns, qstss = NC.canopy_fluxes(S2, S2["canopy_fevw"], S2["canopy_fhvw"], S2["w_hcy"],
+                                                                        S2["w_rny"], S2["w_tlfy"], S2["w_sum_rad_gradis"], S2["w_tss4"])
+        for n, g in (("fev", fev), ("fhv", fhv), ("fnv", fnv), ("tv", tv), ("fns", fns)):
+            same(g, S3["canopy_" + n], tag + "canopy%" + n)
+        same(lwabv, S3["rad_lwabv"], tag + "rad%lwabv", dense); same(qstss, S3["ssnow_qstss"], tag + "ssnow%qstss")
+        # potential evaporation + latent heat flux, first and second call, and the ground sensible heat flux after each
+        for (Sa, Sb, call) in ((S3, S4, "1st"), (S6, S7, "2nd")):
+            potev = NC.potev_hdm(Sa, Sa["ssnow_qstss"], Sa["ssnow_rtsoil"], Sa["met_qv" if call == "1st" else "met_qvair"])
+            wetfac, pwet, cls, fess, fesp, fes = NC.latent_heat_flux(DELS, Sa, zse1, potev, Sa["ssnow_wetfac"],
+                                                                     bool(cfg.l_new_reduce_soilevp))
+            if call == "1st":
+                same(potev, Sb["ssnow_potev"], tag + "ssnow%potev 1st")
+            same(wetfac, Sb["ssnow_wetfac"], tag + "ssnow%wetfac " + call); same(cls, Sb["ssnow_cls"], tag + "ssnow%cls " + call)
+            same(pwet, Sb["w_pwet"], tag + "pwet " + call)
+            for n, g in (("fess", fess), ("fesp", fesp), ("fes", fes)):
+                same(g, Sb["canopy_" + n], tag + f"canopy%{n} " + call)
+            n_frost += int(((cls > 1) & (Sa["ssnow_snowd"] < 0.1)).sum()); n_snow += int((Sa["ssnow_snowd"] >= 0.1).sum())
+        fhs = S4["air_rho"] * NC.CAPP * (S4["ssnow_tss"] - S4["met_tvair"]) / S4["ssnow_rtsoil"]
+        same(fhs, S5["canopy_fhs"], tag + "canopy%fhs 1st")
+        # within_canopy
+        on, tvair, qvair, dva = NC.within_canopy(S5, S5["w_gbhu"], S5["w_gbhf"], S5["w_rt0"], S5["rough_rt1"], S5["ssnow_potev"],
+                                                 S5["ssnow_wetfac"], S5["ssnow_cls"], S5["ssnow_qstss"], S5["canopy_fhv"],
+                                                 S5["canopy_fhs"], S5["canopy_fev"], S5["canopy_fes"])
+        n_on += int(on.sum())
+        for n, g in (("tvair", tvair), ("qvair", qvair), ("dva", dva)):
+            same(g, S6["met_" + n], tag + "met%" + n, on)
+            same(S5["met_" + n], S6["met_" + n], tag + f"met%{n} untouched", ~on)
+        # end of the iteration
+        potev2 = NC.potev_hdm(S6, S6["ssnow_qstss"], S6["ssnow_rtsoil"], S6["met_qvair"])
+        fhs = S6["air_rho"] * NC.CAPP * (S6["ssnow_tss"] - S6["met_tvair"]) / S6["ssnow_rtsoil"]
+        same(fhs, S7["canopy_fhs"], tag + "canopy%fhs 2nd")
+        ga, fe, fh, potev, fevw_pot, rnet, rniso, epot, wetfac_cs = NC.end_of_iteration(
+            DELS, S6, S6["w_sum_rad_rniso"], S6["canopy_fns"], fhs, S7["canopy_fes"], S6["canopy_fev"], S6["canopy_fhv"],
+            S6["canopy_fnv"], potev2, S6["canopy_fevw_pot"], S7["ssnow_cls"])
+        for n, g in (("ga", ga), ("fe", fe), ("fh", fh), ("fevw_pot", fevw_pot), ("rnet", rnet), ("rniso", rniso), ("epot", epot),
+                     ("wetfac_cs", wetfac_cs)):
+            same(g, S7["canopy_" + n], tag + "canopy%" + n)
+        same(potev, S7["ssnow_potev"], tag + "ssnow%potev 2nd")
+        if it < 4:
+            z = NC.update_zetar(S7, S7["canopy_fh"], S7["canopy_fe"], S7["canopy_us"])
+            same(z, T["canopy_zetar"][it], tag + "canopy%zetar")
+            assert (z < 0).any() and (z > 0).any()
+    assert n_on > 2000 and n_snow > 500
