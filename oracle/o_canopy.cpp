@@ -618,7 +618,15 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
     f.canopy_cansto[i] = f.canopy_oldcansto[i];                                           // :169
     w.cansat[i] = f.veg_canst1[i] * f.canopy_vlaiw[i];                                    // :178
   }
+  const void *const hook_args[18] = {w.dsx.data(), w.fwsoil.data(), w.tlfx.data(), w.tlfy.data(), w.ecy.data(), w.hcy.data(),
+                                     w.rny.data(), w.gbhu.data(), w.gbhf.data(), w.csx.data(), w.cansat.data(), w.ghwet.data(),
+                                     w.sum_rad_rniso.data(), w.sum_rad_gradis.data(), rt0.data(), pwet.data(), rt1usc.data(),
+                                     tss4.data()};
+  int hook_iter = 0;
+  auto stage = [&](int when) { if (o.dryleaf_hook) o.dryleaf_hook(when, hook_iter, hook_args); };
+  stage(-1);                                                                              // before Surf_wetness_fact (work arrays not set yet)
   surf_wetness_fact(o, w.cansat, dels);                                                   // :181
+  stage(-2);
   for (int i = 0; i < mp; i++) {
     f.canopy_fevw_pot[i] = 0.0f;
     for (int l = 0; l < mf; l++) {
@@ -659,6 +667,7 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
   }
 
   for (int iter = 1; iter <= niter; iter++) {                                             // :258
+    hook_iter = iter;
     for (int i = 0; i < mp; i++) {
       float zet = f.canopy_zetar[IX(i, iter - 1)];
       // comp_friction_vel (cbl_friction_vel.F90:19-108)
@@ -698,11 +707,6 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
       w.hcy[i] = 0.0;
       w.ecy[i] = w.rny[i] - w.hcy[i];
     }
-    const void *const hook_args[18] = {w.dsx.data(), w.fwsoil.data(), w.tlfx.data(), w.tlfy.data(), w.ecy.data(), w.hcy.data(),
-                                       w.rny.data(), w.gbhu.data(), w.gbhf.data(), w.csx.data(), w.cansat.data(), w.ghwet.data(),
-                                       w.sum_rad_rniso.data(), w.sum_rad_gradis.data(), rt0.data(), pwet.data(), rt1usc.data(),
-                                       tss4.data()};
-    auto stage = [&](int when) { if (o.dryleaf_hook) o.dryleaf_hook(when, iter, hook_args); };
     if (o.dryleaf_hook) o.dryleaf_hook(0, iter, hook_args);
     dryLeaf(o, dels, w, iter);                                                            // :404
     if (o.dryleaf_hook) o.dryleaf_hook(1, iter, hook_args);
@@ -894,6 +898,7 @@ void define_canopy(Oracle &o, float dels, const std::vector<char> &sunlit_veg_ma
                      - f.rad_flws[j] * f.rad_transd[j];
     f.rad_rnet[j] = f.rad_swnet[j] + f.rad_lwnet[j];
   }
+  stage(8);                                                                               // end of define_canopy (hook_iter == niter)
 }
 
 }  // namespace orc

@@ -52,7 +52,8 @@ struct Oracle {
   // test hook: called immediately before (when = 0) and after (when = 1) every dryLeaf call with the routine's work-array
   // arguments, in the order of DRYLEAF_WORK / CANOPY_WORK in tests/test_oracle_numpy_xcheck.py; further stages of one
   // stability iteration of define_canopy: 2 after wetLeaf, 3 before / 4 after the first potev + Latent_heat_flux, 5 before /
-  // 6 after within_canopy, 7 at the end of the iteration before update_zetar (work gains rt0, pwet, rt1usc, tss4)
+  // 6 after within_canopy, 7 at the end of the iteration before update_zetar (work gains rt0, pwet, rt1usc, tss4); -1 before /
+  // -2 after Surf_wetness_fact (iter 0), 8 at the end of define_canopy (iter NITER)
   void (*dryleaf_hook)(int when, int iter, const void *const *work) = nullptr;
 };
 

@@ -236,3 +236,120 @@ def update_zetar(S, fh, fe, us):
     """cbl_zetar.F90:60-64,130-140 (NITER > 2, soil_struc /= 'sli')"""
     z = -(VONK * GRAV * S["rough_zref_tq"] * (fh + F(0.07) * fe)) / (S["air_rho"] * CAPP * S["met_tk"] * _p3(us))
     return np.maximum(ZETNEG, np.minimum(ZETPOS, z))
+
+
+CSW, A33, CTL = F(0.50), F(1.25), F(0.40)                      # cable_phys_constants_mod.F90:58-65
+ICE_SOILTYPE, LAKES = 9, 16                                    # cable_surface_types.F90:31; permanent-ice soil (SURVEY D11)
+WILT_LIMITFACTOR = F(2.0)                                      # cable_other_constants_mod.F90:47
+
+
+def surf_wetness_fact(dels, S, cansat):
+    """cbl_SurfaceWetness.F90:10-79 + initialize_wetfac (cbl_init_wetfac_mod.F90:9-116) -> wcint, through, cansto, fwet,
+    wetfac.  S is the state before the call (cansto already restored from oldcansto)."""
+    dels = F(dels)
+    precip, precip_sn, tk = S["met_precip"], S["met_precip_sn"], S["met_tk"]
+    upper = F(4.0) * np.minimum(dels, F(1800.0)) / (F(60.0) * F(1440.0))
+    ftemp = np.minimum(precip - precip_sn, upper)
+    upper_limit = np.maximum(cansat - S["canopy_cansto"], F(0.0))
+    wcint = np.where((ftemp > F(0.0)) & (tk > TFRZ), np.minimum(upper_limit, ftemp), F(0.0)).astype(F)
+    through = precip_sn + np.minimum(precip - precip_sn, np.maximum(F(0.0), precip - precip_sn - wcint))
+    cansto = S["canopy_cansto"] + wcint
+    fwet = np.maximum(F(0.0), np.minimum(F(0.9), F(0.8) * cansto / np.maximum(cansat, F(0.01))))
+    wb1, wbice1 = S["ssnow_wb"][0], S["ssnow_wbice"][0]
+    wilting_pt = S["soil_swilt"] / WILT_LIMITFACTOR
+    num = wb1.astype(F) - wilting_pt
+    den = np.maximum(F(0.0830), S["soil_sfc"] - wilting_pt)
+    wetfac = np.maximum(F(0.0), np.minimum(F(1.0), num / den))
+    with np.errstate(all="ignore"):
+        q = wbice1 / wb1
+        ice_ratio = (q * q).astype(F)
+    ice_factor = (D(1.) - np.minimum(D(0.2), ice_ratio.astype(D))).astype(F)
+    ice_factor = np.maximum(D(0.5), ice_factor.astype(D)).astype(F)
+    wetfac = np.where(wbice1 > 0.0, wetfac * ice_factor, wetfac).astype(F)
+    wetfac = np.where(S["ssnow_snowd"] > F(0.1), F(0.9), wetfac).astype(F)
+    lake = S["veg_iveg"] == LAKES
+    wetfac = np.where(lake, np.where(tk >= TFRZ + F(5.), F(1.0), F(0.7)), wetfac).astype(F)
+    wetfac = F(0.5) * (wetfac + S["ssnow_owetfac"])
+    return wcint, through, cansto, fwet, wetfac
+
+
+def after_stability_loop(dels, S, W, zetar_niter, zetar_iterplus):
+    """cable_canopy.F90:684-1040 (no litter / or_evap / L_REV_CORR) from the state at the end of the last iteration; W holds
+    define_canopy's work arrays cansat, rt1usc, tss4, ecy, hcy, tlfy, sum_rad_rniso, sum_rad_gradis."""
+    dels = F(dels)
+    o = {}
+    us, ua, rho, rlam = S["canopy_us"], S["met_ua"], S["air_rho"], S["air_rlam"]
+    zref_uv, zref_tq, z0m, disp, hruff = S["rough_zref_uv"], S["rough_zref_tq"], S["rough_z0m"], S["rough_disp"], S["rough_hruff"]
+    z0soilsn, zruffs, rt0us, rt1usa, rt1usb = S["rough_z0soilsn"], S["rough_zruffs"], S["rough_rt0us"], S["rough_rt1usa"], S["rough_rt1usb"]
+    vlaiw, rghlai, transd, tk, qv, tss = S["canopy_vlaiw"], S["canopy_rghlai"], S["rad_transd"], S["met_tk"], S["met_qv"], S["ssnow_tss"]
+    m = np.maximum(ua, UMIN)
+    o["canopy_cduv"] = us * us / (m * m)
+    lai_min = np.maximum(LAI_THRESH, vlaiw)
+    cond = (S["rad_fvlai"][0] / lai_min) * S["canopy_gswx"][0] + (S["rad_fvlai"][1] / lai_min) * S["canopy_gswx"][1]
+    cond = (F(1.) - transd) * np.maximum(F(1.e-06), cond)
+    rel_moisture = (S["ssnow_wb"][0] / S["soil_sfc"].astype(D)).astype(F)
+    t = F(0.01) * rel_moisture
+    surf = cond + transd * (t * t)
+    o["canopy_gswx_T"] = np.where(S["soil_isoilm"] == ICE_SOILTYPE, F(1.e6), surf).astype(F)
+    zN, zP = zetar_niter, zetar_iterplus
+    with np.errstate(all="ignore"):
+        o["canopy_cdtq"] = (o["canopy_cduv"] * (_log(zref_uv / z0m) - psim(zN * zref_uv / zref_tq) + psim(zN * z0m / zref_tq))
+                            / (_log(zref_tq / (F(0.1) * z0m)) - psis(zN) + psis(zN * F(0.1) * z0m / zref_tq)))
+        tstar = -S["canopy_fh"] / (rho * CAPP * us)
+        qstar = -S["canopy_fe"] / (rho * rlam * us * S["ssnow_cls"])
+        zscrn = np.maximum(z0m, F(2.0) - disp)
+        ftemp = (_log(zref_tq / zscrn) - psis(zP) + psis(zP * zscrn / zref_tq)) / VONK
+        tscrn = tk - TFRZ - tstar * ftemp
+        zscl = np.maximum(z0soilsn, F(2.0))
+        dense = (vlaiw > LAI_THRESH) & (hruff > F(0.01))
+        hasd = disp > F(0.0)
+        k2 = F(2) * CSW * rghlai
+        term1 = np.where(hasd, _exp(k2 * (F(1) - zscl / hruff)), F(0.)).astype(F)
+        term2 = np.where(hasd, _exp(k2 * (F(1) - disp / hruff)), F(0.)).astype(F)
+        term5 = np.where(hasd, np.maximum(F(2.) / F(3.) * hruff / disp, F(1.)), F(0.)).astype(F)
+        term3 = (A33 * A33) * CTL * F(2) * CSW * rghlai
+        e2 = _exp(k2)
+        ra = term5 * _log(zscl / z0soilsn) * (e2 - term2) / term3
+        ra = ra + term5 * _log(disp / zscl) * (e2 - term1) / term3
+        rb = rt0us + term5 * (term2 - term1) / term3
+        rc = rt0us + rt1usa + term5 * (zscl - hruff) / ((A33 * A33) * CTL * hruff)
+        rd = (rt0us + rt1usa + rt1usb
+              + (_log((zscl - disp) / np.maximum(zruffs - disp, z0soilsn)) - psis((zscl - disp) * zP / zref_tq)
+                 + psis((zruffs - disp) * zP / zref_tq)) / VONK)
+        r_sc = np.select([zscl < disp, (disp <= zscl) & (zscl < hruff), (hruff <= zscl) & (zscl < zruffs), zscl >= zruffs],
+                         [ra, rb, rc, rd], F(0.)).astype(F)
+        frac = np.minimum(F(1.), r_sc / np.maximum(F(1.), rt0us + rt1usa + rt1usb + W["rt1usc"]))
+        tscrn = np.where(dense, tss + (tk - tss) * frac - TFRZ, tscrn).astype(F)
+        o["canopy_tscrn"] = tscrn
+        rsts = qsatf(tscrn, S["met_pmb"])
+        wetfac = S["ssnow_wetfac"]
+        qtgnet = rsts * wetfac - qv
+        qsurf = np.where(qtgnet > F(0.), rsts * wetfac, F(0.1) * rsts * wetfac + F(0.9) * qv).astype(F)
+        o["canopy_qmom"] = rho * (us * us)
+        o["canopy_qscrn"] = np.where(dense, qsurf + (qv - qsurf) * frac, qv - qstar * ftemp).astype(F)
+    fevw, fevc = S["canopy_fevw"], S["canopy_fevc"]
+    dewmm = (-(np.minimum(F(0.0), fevw).astype(D) + np.minimum(D(0.0), fevc)) * D(dels) / rlam.astype(D)).astype(F)
+    cansto = S["canopy_cansto"] + dewmm
+    cansto = np.maximum(cansto - np.maximum(F(0.0), fevw) * dels / rlam, F(0.0))
+    spill = np.maximum(F(0.0), cansto - W["cansat"])
+    through = S["canopy_through"] + spill
+    cansto = cansto - spill
+    o.update(canopy_dewmm=dewmm, canopy_spill=spill, canopy_through=through, canopy_precis=np.maximum(F(0.), through),
+             canopy_cansto=cansto, canopy_delwc=cansto - S["canopy_oldcansto"])
+    dfn = F(-1.) * F(4.) * EMSOIL * SBOLTZ * W["tss4"] / tss
+    rttsoil = S["ssnow_rtsoil"]
+    dfh = rho * CAPP / rttsoil
+    dfe_ddq = wetfac * rho * rlam * S["ssnow_cls"] / rttsoil
+    d = TETENC + tss - TFRZ
+    ddq = (RMH2O / RMAIR) / S["met_pmb"] * TETENA * TETENB * TETENC / (d * d) * _exp(TETENB * (tss - TFRZ) / d)
+    dfe_dtg = dfe_ddq * ddq
+    o.update(ssnow_dfn_dtg=dfn, ssnow_dfh_dtg=dfh, ssnow_dfe_ddq=dfe_ddq, ssnow_ddq_dtg=ddq, ssnow_dfe_dtg=dfe_dtg,
+             canopy_dgdtg=dfn - dfh - dfe_dtg)
+    lw = CAPP * RMAIR * (W["tlfy"] - tk) * W["sum_rad_gradis"]
+    o["bal_drybal"] = (W["ecy"] + W["hcy"]).astype(F) - W["sum_rad_rniso"] + lw
+    o["bal_wetbal"] = fevw + S["canopy_fhvw"] - W["sum_rad_rniso"] * S["canopy_fwet"] + lw * S["canopy_fwet"]
+    q = S["rad_qcan"].reshape(-1, tk.shape[0])
+    o["rad_swnet"] = (q[0] + q[1]) + (q[2] + q[3]) + S["rad_qssabs"]
+    o["rad_lwnet"] = S["met_fld"] - SBOLTZ * EMLEAF * _p4(S["canopy_tv"]) * (F(1) - transd) - S["rad_flws"] * transd
+    o["rad_rnet"] = o["rad_swnet"] + o["rad_lwnet"]
+    return o

@@ -627,3 +627,18 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy):
             same(z, T["canopy_zetar"][it], tag + "canopy%zetar")
             assert (z < 0).any() and (z > 0).any()
     assert n_on > 2000 and n_snow > 500
+    # Surf_wetness_fact + initialize_wetfac, before the loop
+    Sa, Sb = snaps[(0, -1)], snaps[(0, -2)]
+    wcint, through, cansto, fwet, wetfac = NC.surf_wetness_fact(DELS, Sa, Sa["w_cansat"])
+    for n, g in (("wcint", wcint), ("through", through), ("cansto", cansto), ("fwet", fwet)):
+        same(g, Sb["canopy_" + n], "Surf_wetness_fact canopy%" + n)
+    same(wetfac, Sb["ssnow_wetfac"], "Surf_wetness_fact ssnow%wetfac")
+    assert (wcint > 0).any() and (Sa["ssnow_wbice"][0] > 0).any() and (Sa["veg_iveg"] == 16).any()
+    # screen-level diagnostics, canopy water store, d(ground flux)/dT, balances and net radiation after the loop
+    Sa, Sb = snaps[(4, 7)], snaps[(4, 8)]
+    W = {n[2:]: a for n, a in Sa.items() if n.startswith("w_")}
+    got = NC.after_stability_loop(DELS, Sa, W, Sa["canopy_zetar"][3], Sa["canopy_zetar"][3])
+    assert len(got) == 23
+    for n, g in got.items():
+        same(g, Sb[n], "after the loop: " + n)
+    assert (got["canopy_spill"] > 0).any() or (got["canopy_dewmm"] > 0).any()
