@@ -642,3 +642,82 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy):
     for n, g in got.items():
         same(g, Sb[n], "after the loop: " + n)
     assert (got["canopy_spill"] > 0).any() or (got["canopy_dewmm"] > 0).any()
+
+
+def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
+    """The statements BETWEEN the calls in cbm and soil_snow (tests/np_orchestration.py, written from the Fortran alone):
+    lake refill, the otss shuffle, albedo_T, owetfac, soil_snow's set-up, infiltration / puddle arithmetic and closing
+    bookkeeping, and cbm's final flux sums and radiative temperature.  soil_snow is re-run on a copy of the state captured at
+    the end of define_canopy, with the oracle's single-routine hooks (each cross-checked above) called in the Fortran's
+    order from Python; every bound field must then equal the oracle's own step to the bit."""
+    import np_orchestration as NO
+    cfg, grid, T, F = make_case(1200, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    zse = np.array(list(cfg.zse), np.float32)
+    HOOK = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_void_p))
+    snaps = {}
+
+    def hook(when, it, work):
+        if when in (-1, 8):
+            snaps[when] = {n: a.copy() for n, a in T.items()}
+
+    cb = HOOK(hook)
+    o._lib.oracle_set_dryleaf_hook.argtypes = [C.c_void_p, HOOK]; o._lib.oracle_set_dryleaf_hook.restype = None
+    o._lib.oracle_set_dryleaf_hook(o._h, cb)
+    after = ("ssnow_snage", "ssnow_deltss", "canopy_fev", "canopy_fe", "canopy_rnet", "rad_trad", "canopy_frp", "canopy_frpw",
+             "canopy_frpr", "canopy_frs", "canopy_fnpp", "canopy_fgpp", "canopy_fnee", "canopy_fra", "bgc_cplant", "bgc_csoil")
+    refilled = snowy = puddles = overflow = 0
+    for k in range(20):
+        F.fill(T, k)
+        if k == 5:                                              # dry out some lakes so that the refill has work to do
+            lake = T["veg_iveg"][0] == 16
+            T["ssnow_wb"][0][lake] = T["soil_sfc"][0][lake] * 0.5
+            T["ssnow_pudsmx"][0][::3] = 3.0                     # and let a third of the tiles hold puddles
+            T["ssnow_pudsto"][0][::6] = 1.0
+        B = {n: a.copy() for n, a in T.items()}                 # state at entry of cbm
+        o.cbm(k + 1, DELS)
+        if k == 0:
+            continue                                            # first call ever initialises gammzz(:,1) (D3); restated elsewhere
+        # --- head of cbm, against the snapshot at entry of define_canopy
+        S = snaps[-1]
+        refilled += NO.cbm_head(B, zse)
+        for n in ("ssnow_wbtot1", "ssnow_wbtot2", "ssnow_wb_lake", "ssnow_wb"):
+            assert np.array_equal(B[n], S[n]), (n, k)
+        assert np.array_equal(S["ssnow_otss_0"], B["ssnow_otss"]) and np.array_equal(S["ssnow_otss"], B["ssnow_tss"])
+        assert np.array_equal(S["rad_albedo_T"][0], (S["rad_albedo"][0] + S["rad_albedo"][1]) * np.float32(0.5))
+        # --- soil_snow re-run from the end of define_canopy
+        P = snaps[8]
+        P["ssnow_owetfac"][...] = P["ssnow_wetfac"]             # cbm:192
+        ob = Oracle(P, cfg, cr_math=True)
+        L, h = ob._lib, ob._h
+        for nm in ("snowcheck", "snowl_adjust", "remove_trans", "soilfreeze"):
+            fn = getattr(L, "oracle_run_" + nm); fn.argtypes = [C.c_void_p]; fn.restype = None
+        for nm in ("snowdensity", "snow_accum", "stempv", "surfbv"):
+            fn = getattr(L, "oracle_run_" + nm); fn.argtypes = [C.c_void_p, C.c_float]; fn.restype = None
+        L.oracle_run_snow_melting.argtypes = [C.c_void_p, C.c_float, C.c_void_p]; L.oracle_run_snow_melting.restype = None
+        calls = []
+
+        def melt(dels):
+            out = np.zeros(grid.mp, np.float32)
+            calls.append("snow_melting"); L.oracle_run_snow_melting(h, dels, out.ctypes.data)
+            return out
+
+        def run0(nm): return lambda: (calls.append(nm), getattr(L, "oracle_run_" + nm)(h))[0]
+        def run1(nm): return lambda dels: (calls.append(nm), getattr(L, "oracle_run_" + nm)(h, dels))[0]
+        R = {nm: run0(nm) for nm in ("snowcheck", "snowl_adjust", "remove_trans", "soilfreeze")}
+        R.update({nm: run1(nm) for nm in ("snowdensity", "snow_accum", "stempv", "surfbv")})
+        R["snow_melting"] = melt
+        NO.soil_snow(DELS, P, zse, R)
+        assert calls == ["snowcheck", "snowdensity", "snow_accum", "snow_melting", "snowl_adjust", "stempv", "snow_melting",
+                         "remove_trans", "soilfreeze", "surfbv"]
+        ob.close()
+        for n in T:
+            if n not in after:
+                assert np.array_equal(P[n], T[n], equal_nan=True), (n, k, float(np.abs(P[n].astype(np.float64) - T[n]).max()))
+        # --- tail of cbm from soil_snow's output
+        for n, g in NO.cbm_tail(P).items():
+            assert g.dtype == T[n].dtype and np.array_equal(g, T[n][0]), (n, k)
+        snowy += int((T["ssnow_isflag"][0] > 0).sum()); puddles += int((T["ssnow_pudsto"][0] > 0).sum())
+        overflow += int((T["ssnow_rnof1"][0] > 0).sum())
+    assert refilled > 10 and snowy > 300 and (T["ssnow_snowd"][0] > 0).sum() > 300 and puddles > 100 and overflow > 100, \
+        (refilled, snowy, puddles, overflow)
