@@ -8,6 +8,7 @@ import numpy as np
 
 F, D = np.float32, np.float64
 DENSITY_LIQ, DENSITY_ICE, HL = F(1000.0), F(921.0), F(2.5014e6)          # cable_phys_constants_mod.F90:29,43,44
+CGSNOW, CSICE, CSWAT = F(2090.0), F(2.100e3), F(4.218e3)                 # :38,41,42
 LAKES = 16                                                               # cable_surface_types.F90:31
 
 
@@ -38,9 +39,8 @@ def cbm_tail(T):
 
 def soil_snow(dels, T, zse, R, first_call=False):
     """cbl_soilsnow_main.F90:62-203 for cable_runtime%offline, redistrb = .FALSE.; R = the called routines, each working in
-    place on T: snowcheck(), snowdensity(dels), snow_accum(dels), snow_melting(dels) -> snowmlt, snowl_adjust(),
+    place on T (first_call = the process's first call ever): snowcheck(), snowdensity(dels), snow_accum(dels), snow_melting(dels) -> snowmlt, snowl_adjust(),
     stempv(dels), remove_trans(), soilfreeze(), surfbv(dels)."""
-    assert not first_call, "gammzz(:,1) initialisation of the process's first call (:92-96) is not restated here"
     dels = F(dels)
     zse = np.asarray(zse, F)
     ms = zse.shape[0]
@@ -60,6 +60,13 @@ def soil_snow(dels, T, zse, R, first_call=False):
     s("ssnow_osnowd")[:] = s("ssnow_snowd")
     T["ssnow_wbliq"][...] = T["ssnow_wb"] - T["ssnow_wbice"]
     ssat = s("soil_ssat")
+    if first_call:                                                                   # IF (ktau <= 1), SAVE ktau (:60-62, :92-96)
+        css, rhosoil, wb1, wbice1 = s("soil_css"), s("soil_rhosoil"), T["ssnow_wb"][0], T["ssnow_wbice"][0]
+        xx = css * rhosoil
+        heat = (((F(1.0) - ssat) * css * rhosoil).astype(D) + (wb1 - wbice1) * D(CSWAT) * D(DENSITY_LIQ)
+                + wbice1 * D(CSICE) * D(DENSITY_ICE))
+        T["ssnow_gammzz"][0][:] = (np.maximum(heat, xx.astype(D)) * D(zse[0])
+                                   + ((F(1.) - s("ssnow_isflag").astype(F)) * CGSNOW * s("ssnow_snowd")).astype(D))
     for k in range(ms):
         T["ssnow_wblf"][k][:] = np.maximum(D(0.01), T["ssnow_wb"][k] - T["ssnow_wbice"][k]) / ssat.astype(D)
         T["ssnow_wbfice"][k][:] = T["ssnow_wbice"][k].astype(F) / ssat

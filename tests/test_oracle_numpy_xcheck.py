@@ -676,8 +676,6 @@ def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
             T["ssnow_pudsto"][0][::6] = 1.0
         B = {n: a.copy() for n, a in T.items()}                 # state at entry of cbm
         o.cbm(k + 1, DELS)
-        if k == 0:
-            continue                                            # first call ever initialises gammzz(:,1) (D3); restated elsewhere
         # --- head of cbm, against the snapshot at entry of define_canopy
         S = snaps[-1]
         refilled += NO.cbm_head(B, zse)
@@ -707,7 +705,7 @@ def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
         R = {nm: run0(nm) for nm in ("snowcheck", "snowl_adjust", "remove_trans", "soilfreeze")}
         R.update({nm: run1(nm) for nm in ("snowdensity", "snow_accum", "stempv", "surfbv")})
         R["snow_melting"] = melt
-        NO.soil_snow(DELS, P, zse, R)
+        NO.soil_snow(DELS, P, zse, R, first_call=(k == 0))       # the first call ever initialises gammzz(:,1) (D3)
         assert calls == ["snowcheck", "snowdensity", "snow_accum", "snow_melting", "snowl_adjust", "stempv", "snow_melting",
                          "remove_trans", "soilfreeze", "surfbv"]
         ob.close()
