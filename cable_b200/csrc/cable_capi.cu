@@ -1060,6 +1060,9 @@ int cable_b200_output_plan(cable_handle *h, int nrows, const int *field_id, cons
   CUDA_TRY(cudaMalloc(&v.d_agg, (size_t)nrows * h->mp * sizeof(double)));
   for (int b = 0; b < 2; b++) CUDA_TRY(cudaMalloc(&v.d_out[b], (size_t)nrows * v.nland * sizeof(float)));
   v.rows = rows; v.agg_counter = 0; v.out_buf = 0;
+  // 'point' rows have no reset value (aggregator.F90 never resets them) and the accumulate pass reads every row before
+  // it overwrites: give them a defined first value (compute-sanitizer initcheck, tools/gpu_sanitize.sh)
+  CUDA_TRY(cudaMemsetAsync(v.d_agg, 0, (size_t)nrows * h->mp * sizeof(double), h->s_compute));
   aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, h->mp);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
