@@ -21,6 +21,15 @@ LAI_THRESH = F(0.001)
 FROZEN_LIMIT = F(0.85)
 
 
+KTHLITT, DVLITT = D(0.3), D(3.1415841138194147e-05)          # canopy%kthLitt, canopy%DvLitt (cable_canopy.F90:203-204)
+
+
+def litter_resistances(S):
+    """cable_canopy.F90:472-475 and :987-988 (cable_user%litter): r_2 expressions stored to REAL -> rhlitt, relitt."""
+    a = (1 - S["ssnow_isflag"]).astype(F).astype(D) * S["veg_clitt"] * D(F(0.003))
+    return (a / KTHLITT / (S["air_rho"] * CAPP).astype(D)).astype(F), (a / DVLITT).astype(F)
+
+
 def _cr(fn, *x):
     with np.errstate(all="ignore"):
         return fn(*[np.asarray(v, D) for v in x]).astype(F)
@@ -140,12 +149,15 @@ def canopy_fluxes(S, fevw, fhvw, hcy, rny, tlfy, sum_gradis, tss4):
     return fev, fhv, fnv, lwabv, dense, tv, fns, qstss
 
 
-def potev_hdm(S, qstss, rtsoil, q_air):
+def potev_hdm(S, qstss, rtsoil, q_air, litter=False):
     """dq at cable_canopy.F90:494 (q_air = met%qv) / :566 (q_air = met%qvair, after within_canopy) +
     Humidity_deficit_method (cbl_pot_evap_snow.F90:79-160, default branch); the clamps on dq_unsat do not reach the result."""
     dq = qstss - q_air
     cold = (S["ssnow_snowd"] > F(1.0)) | (S["ssnow_tgg"][0] == TFRZ)
     dq = np.where(cold, np.maximum(F(-0.1e-3), dq), dq).astype(F)
+    if litter:                                                     # :158-161 with REAL(veg%clitt), REAL(canopy%DvLitt)
+        return S["air_rho"] * S["air_rlam"] * dq / (rtsoil + (1 - S["ssnow_isflag"]).astype(F) * S["veg_clitt"].astype(F)
+                                                    * F(0.003) / F(DVLITT))
     return S["air_rho"] * S["air_rlam"] * dq / rtsoil
 
 
@@ -181,15 +193,16 @@ def latent_heat_flux(dels, S, zse1, potev, wetfac, l_new_reduce_soilevp=False):
     return wetfac, pwet, cls, fess, fesp, fess + fesp
 
 
-def within_canopy(S, gbhu, gbhf, rt0, rt1, potev, wetfac, cls, qstss, fhv, fhs, fev, fes):
-    """cbl_within_canopy.F90:10-159 (relitt = rhlitt = 0) -> met%tvair, met%qvair, met%dva and the mask they are written on."""
+def within_canopy(S, gbhu, gbhf, rt0, rt1, potev, wetfac, cls, qstss, fhv, fhs, fev, fes, rhlitt=None, relitt=None):
+    """cbl_within_canopy.F90:10-159 (relitt = rhlitt = 0 unless cable_user%litter) -> met%tvair, met%qvair, met%dva and the
+    mask they are written on."""
     cmolar, epsi, rlam, rho = S["air_cmolar"], S["air_epsi"], S["air_rlam"], S["air_rho"]
     rrbw = (((gbhu[0] + gbhf[0]) + (gbhu[1] + gbhf[1])) / cmolar.astype(D)).astype(F)
     rrsw = (S["canopy_gswx"][0] + S["canopy_gswx"][1]) / cmolar
     zero = np.zeros_like(rt0)
-    fix_eqn = cls * rt0 / (rt0 + zero)
+    fix_eqn = cls * rt0 / (rt0 + (zero if relitt is None else relitt))
     fix_eqn = np.where(potev > F(0.), fix_eqn * wetfac, fix_eqn).astype(F)
-    fix_eqn2 = rt0 / (rt0 + zero)
+    fix_eqn2 = rt0 / (rt0 + (zero if rhlitt is None else rhlitt))
     on = (S["veg_meth"] > 0) & (S["canopy_vlaiw"] > LAI_THRESH) & (S["rough_hruff"] > S["rough_z0soilsn"])
     tk, qv, tss = S["met_tk"], S["met_qv"], S["ssnow_tss"]
     with np.errstate(all="ignore"):
@@ -273,8 +286,8 @@ def surf_wetness_fact(dels, S, cansat):
     return wcint, through, cansto, fwet, wetfac
 
 
-def after_stability_loop(dels, S, W, zetar_niter, zetar_iterplus):
-    """cable_canopy.F90:684-1040 (no litter / or_evap / L_REV_CORR) from the state at the end of the last iteration; W holds
+def after_stability_loop(dels, S, W, zetar_niter, zetar_iterplus, litter=False, rev_corr=False):
+    """cable_canopy.F90:684-1040 (no or_evap / gw; cable_user%litter and L_REV_CORR as given) from the state at the end of the last iteration; W holds
     define_canopy's work arrays cansat, rt1usc, tss4, ecy, hcy, tlfy, sum_rad_rniso, sum_rad_gradis."""
     dels = F(dels)
     o = {}
@@ -318,7 +331,13 @@ def after_stability_loop(dels, S, W, zetar_niter, zetar_iterplus):
                  + psis((zruffs - disp) * zP / zref_tq)) / VONK)
         r_sc = np.select([zscl < disp, (disp <= zscl) & (zscl < hruff), (hruff <= zscl) & (zscl < zruffs), zscl >= zruffs],
                          [ra, rb, rc, rd], F(0.)).astype(F)
-        frac = np.minimum(F(1.), r_sc / np.maximum(F(1.), rt0us + rt1usa + rt1usb + W["rt1usc"]))
+        rsum = rt0us + rt1usa + rt1usb + W["rt1usc"]
+        if litter:                                                 # :808-812, :851-854
+            rhlitt, relitt = litter_resistances(S)
+            frac = np.minimum(F(1.), (r_sc + rhlitt * us) / np.maximum(F(1.), rsum + rhlitt * us))
+            frac_q = np.minimum(F(1.), (r_sc + relitt * us) / np.maximum(F(1.), rsum + relitt * us))
+        else:
+            frac = frac_q = np.minimum(F(1.), r_sc / np.maximum(F(1.), rsum))
         tscrn = np.where(dense, tss + (tk - tss) * frac - TFRZ, tscrn).astype(F)
         o["canopy_tscrn"] = tscrn
         rsts = qsatf(tscrn, S["met_pmb"])
@@ -326,7 +345,7 @@ def after_stability_loop(dels, S, W, zetar_niter, zetar_iterplus):
         qtgnet = rsts * wetfac - qv
         qsurf = np.where(qtgnet > F(0.), rsts * wetfac, F(0.1) * rsts * wetfac + F(0.9) * qv).astype(F)
         o["canopy_qmom"] = rho * (us * us)
-        o["canopy_qscrn"] = np.where(dense, qsurf + (qv - qsurf) * frac, qv - qstar * ftemp).astype(F)
+        o["canopy_qscrn"] = np.where(dense, qsurf + (qv - qsurf) * frac_q, qv - qstar * ftemp).astype(F)
     fevw, fevc = S["canopy_fevw"], S["canopy_fevc"]
     dewmm = (-(np.minimum(F(0.0), fevw).astype(D) + np.minimum(D(0.0), fevc)) * D(dels) / rlam.astype(D)).astype(F)
     cansto = S["canopy_cansto"] + dewmm
@@ -338,8 +357,14 @@ def after_stability_loop(dels, S, W, zetar_niter, zetar_iterplus):
              canopy_cansto=cansto, canopy_delwc=cansto - S["canopy_oldcansto"])
     dfn = F(-1.) * F(4.) * EMSOIL * SBOLTZ * W["tss4"] / tss
     rttsoil = S["ssnow_rtsoil"]
-    dfh = rho * CAPP / rttsoil
-    dfe_ddq = wetfac * rho * rlam * S["ssnow_cls"] / rttsoil
+    if rev_corr:                                                   # :917-922
+        rttsoil = np.where(vlaiw > LAI_THRESH, rttsoil + S["rough_rt1"], rttsoil).astype(F)
+    zero = np.zeros_like(rttsoil)
+    rhl, rel = litter_resistances(S) if litter else (zero, zero)  # :987-988
+    dfh = rho * CAPP / (rttsoil + rhl) if litter else rho * CAPP / rttsoil
+    dfe_ddq = wetfac * rho * rlam * S["ssnow_cls"] / ((rttsoil + rel) if litter else rttsoil)
+    if rev_corr:                                                   # :995-999, :1010-1014
+        dfe_ddq = np.where(S["ssnow_potev"] < F(0.), rho * rlam * S["ssnow_cls"] / (rttsoil + rel), dfe_ddq).astype(F)
     d = TETENC + tss - TFRZ
     ddq = (RMH2O / RMAIR) / S["met_pmb"] * TETENA * TETENB * TETENC / (d * d) * _exp(TETENB * (tss - TFRZ) / d)
     dfe_dtg = dfe_ddq * ddq
