@@ -508,10 +508,13 @@ def test_carbon_numpy_vs_oracle(diag_soil_resp_on):
 CANOPY_WORK = DRYLEAF_WORK + (("rt0", np.float32, 1), ("pwet", np.float32, 1), ("rt1usc", np.float32, 1), ("tss4", np.float32, 1))
 
 
-def _run_with_canopy_stages(ntiles_land, steps, start_doy):
+def _run_with_canopy_stages(ntiles_land, steps, start_doy, switches=None):
     """cbm on the oracle; on the last step every stage of the four stability iterations is captured through the oracle's
     stage hook (oracle.hpp): all bound fields plus define_canopy's work arrays."""
-    cfg, grid, T, F = make_case(ntiles_land, start_doy=start_doy)
+    cfg = lib.default_cfg()
+    for k, v in (switches or {}).items():
+        setattr(cfg, k, v)
+    cfg, grid, T, F = make_case(ntiles_land, cfg=cfg, start_doy=start_doy)
     o = Oracle(T, cfg, cr_math=True)
     mp = grid.mp
     snaps = {}
@@ -543,14 +546,17 @@ def _run_with_canopy_stages(ntiles_land, steps, start_doy):
     return cfg, T, snaps, ortsoil
 
 
-@pytest.mark.parametrize("start_doy", [15, 196], ids=["january", "july"])
-def test_canopy_iteration_numpy_vs_oracle(start_doy):
+@pytest.mark.parametrize("start_doy,switches", [(15, {}), (196, {}), (15, dict(litter=1, l_rev_corr=1)), (196, dict(litter=1)),
+                                                (15, dict(l_rev_corr=1))],
+                         ids=["january", "july", "january-litter-revcorr", "july-litter", "january-revcorr"])
+def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
     """tests/np_canopy.py (written from the Fortran alone) against every stage of the four stability iterations of one
     timestep: friction velocity, resistances and boundary-layer conductances, wetLeaf, canopy flux sums and radiative
     temperature, HDM potential evaporation + Latent_heat_flux (both calls), within_canopy, the end-of-iteration block and
     update_zetar.  fp32 fields to the bit, fp64 fields to 1e-14 relative."""
     import np_canopy as NC
-    cfg, T, snaps, ortsoil = _run_with_canopy_stages(900, 9, start_doy)
+    cfg, T, snaps, ortsoil = _run_with_canopy_stages(900, 9, start_doy, switches)
+    litter, rev_corr = bool(cfg.litter), bool(cfg.l_rev_corr)
     zse1 = cfg.zse[0]
     bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.int32)
 
@@ -591,7 +597,7 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy):
         same(lwabv, S3["rad_lwabv"], tag + "rad%lwabv", dense); same(qstss, S3["ssnow_qstss"], tag + "ssnow%qstss")
         # potential evaporation + latent heat flux, first and second call, and the ground sensible heat flux after each
         for (Sa, Sb, call) in ((S3, S4, "1st"), (S6, S7, "2nd")):
-            potev = NC.potev_hdm(Sa, Sa["ssnow_qstss"], Sa["ssnow_rtsoil"], Sa["met_qv" if call == "1st" else "met_qvair"])
+            potev = NC.potev_hdm(Sa, Sa["ssnow_qstss"], Sa["ssnow_rtsoil"], Sa["met_qv" if call == "1st" else "met_qvair"], litter)
             wetfac, pwet, cls, fess, fesp, fes = NC.latent_heat_flux(DELS, Sa, zse1, potev, Sa["ssnow_wetfac"],
                                                                      bool(cfg.l_new_reduce_soilevp))
             if call == "1st":
@@ -601,19 +607,24 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy):
             for n, g in (("fess", fess), ("fesp", fesp), ("fes", fes)):
                 same(g, Sb["canopy_" + n], tag + f"canopy%{n} " + call)
             n_frost += int(((cls > 1) & (Sa["ssnow_snowd"] < 0.1)).sum()); n_snow += int((Sa["ssnow_snowd"] >= 0.1).sum())
-        fhs = S4["air_rho"] * NC.CAPP * (S4["ssnow_tss"] - S4["met_tvair"]) / S4["ssnow_rtsoil"]
+        rhlitt, relitt = NC.litter_resistances(S3) if litter else (None, None)             # cable_canopy.F90:471-476
+        assert not litter or (rhlitt.max() > 0 and relitt.max() > 0 and (rhlitt == 0).any())
+        if litter:                                                                         # :525-530 (met%tk here, met%tvair at :600)
+            fhs = S4["air_rho"] * NC.CAPP * (S4["ssnow_tss"] - S4["met_tk"]) / (S4["ssnow_rtsoil"] + rhlitt)
+        else:
+            fhs = S4["air_rho"] * NC.CAPP * (S4["ssnow_tss"] - S4["met_tvair"]) / S4["ssnow_rtsoil"]
         same(fhs, S5["canopy_fhs"], tag + "canopy%fhs 1st")
         # within_canopy
         on, tvair, qvair, dva = NC.within_canopy(S5, S5["w_gbhu"], S5["w_gbhf"], S5["w_rt0"], S5["rough_rt1"], S5["ssnow_potev"],
                                                  S5["ssnow_wetfac"], S5["ssnow_cls"], S5["ssnow_qstss"], S5["canopy_fhv"],
-                                                 S5["canopy_fhs"], S5["canopy_fev"], S5["canopy_fes"])
+                                                 S5["canopy_fhs"], S5["canopy_fev"], S5["canopy_fes"], rhlitt, relitt)
         n_on += int(on.sum())
         for n, g in (("tvair", tvair), ("qvair", qvair), ("dva", dva)):
             same(g, S6["met_" + n], tag + "met%" + n, on)
             same(S5["met_" + n], S6["met_" + n], tag + f"met%{n} untouched", ~on)
         # end of the iteration
-        potev2 = NC.potev_hdm(S6, S6["ssnow_qstss"], S6["ssnow_rtsoil"], S6["met_qvair"])
-        fhs = S6["air_rho"] * NC.CAPP * (S6["ssnow_tss"] - S6["met_tvair"]) / S6["ssnow_rtsoil"]
+        potev2 = NC.potev_hdm(S6, S6["ssnow_qstss"], S6["ssnow_rtsoil"], S6["met_qvair"], litter)
+        fhs = S6["air_rho"] * NC.CAPP * (S6["ssnow_tss"] - S6["met_tvair"]) / ((S6["ssnow_rtsoil"] + rhlitt) if litter else S6["ssnow_rtsoil"])
         same(fhs, S7["canopy_fhs"], tag + "canopy%fhs 2nd")
         ga, fe, fh, potev, fevw_pot, rnet, rniso, epot, wetfac_cs = NC.end_of_iteration(
             DELS, S6, S6["w_sum_rad_rniso"], S6["canopy_fns"], fhs, S7["canopy_fes"], S6["canopy_fev"], S6["canopy_fhv"],
@@ -637,7 +648,7 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy):
     # screen-level diagnostics, canopy water store, d(ground flux)/dT, balances and net radiation after the loop
     Sa, Sb = snaps[(4, 7)], snaps[(4, 8)]
     W = {n[2:]: a for n, a in Sa.items() if n.startswith("w_")}
-    got = NC.after_stability_loop(DELS, Sa, W, Sa["canopy_zetar"][3], Sa["canopy_zetar"][3])
+    got = NC.after_stability_loop(DELS, Sa, W, Sa["canopy_zetar"][3], Sa["canopy_zetar"][3], litter, rev_corr)
     assert len(got) == 23
     for n, g in got.items():
         same(g, Sb[n], "after the loop: " + n)
