@@ -138,16 +138,36 @@ def old_soil_conductivity(wblf, wbfice, ssat, cnsd, isoilm, snow_ccnsw):
     return out
 
 
+def total_soil_conductivity(wb, wbliq, wbice, tgg, isflag, snowd, isoilm, cnsd_vec, ssat_vec, sand_vec, watr, snow_ccnsw):
+    """cbl_conductivity.F90:11-89 (cable_user%soil_thermal_fix): Johansen-type conductivity, every local REAL(r_2), REAL
+    literals promoted.  (6, mp) f64: wb, wbliq, wbice, cnsd_vec, ssat_vec, sand_vec, watr; tgg (6, mp) f32 -> (6, mp) f64."""
+    L = lambda x: F64(F32(x))                                                           # a default-REAL literal, promoted
+    quartz = np.maximum(L(0.0), np.minimum(L(0.8), sand_vec * L(0.92)))
+    ko = np.where(quartz > L(0.2), 2.0, 3.0)
+    with np.errstate(all="ignore"):
+        ktmp = np.power(np.power(L(7.7), quartz) * np.power(ko, L(1.0) - quartz), L(1.0) - ssat_vec)
+        liq_frac = np.where(wb >= L(1.0e-15), np.minimum(1.0, np.maximum(0.0, wbliq / wb)), 0.0)
+        ksat = ktmp * np.power(L(2.2), ssat_vec * (L(1.0) - liq_frac)) * np.power(L(0.57), liq_frac)
+        sr = np.minimum(L(0.9999), np.maximum(L(0.), wb - watr) / (ssat_vec - watr))
+        ke = np.where(sr >= L(0.05), L(0.7) * np.log10(sr) + L(1.0), 0.0)
+    frozen = (wbice > 0.0) | (tgg < F32(273.16)) | (isflag != 0)[None, :] | (snowd >= F32(0.1))[None, :]
+    ke = np.where(frozen, sr, ke)
+    cond = ke * ksat + (L(1.0) - ke) * cnsd_vec
+    cond = np.minimum(ksat, np.maximum(cnsd_vec, cond))
+    return np.where((isoilm == 9)[None, :], F64(F32(snow_ccnsw)), cond)
+
+
 def stempv(dels, tgg, tggsn, gammzz, wblf, wbfice, isflag, snowd, ssdnn, ssdn, sdepth, sconds, ga, dgdtg, ssat, css, rhosoil,
-           cnsd, isoilm, hcll, zse, snow_ccnsw, max_sconds):
-    """cbl_stempv.F90:13-221 (soil_thermal_fix = .FALSE.).  (k, mp) arrays: tgg f32 (6), tggsn/ssdn/sdepth/sconds f32 (3),
+           cnsd, isoilm, hcll, zse, snow_ccnsw, max_sconds, ccnsw=None):
+    """cbl_stempv.F90:13-221 (ccnsw = None: soil_thermal_fix = .FALSE., old_soil_conductivity; else the (6, mp) result of
+    total_soil_conductivity).  (k, mp) arrays: tgg f32 (6), tggsn/ssdn/sdepth/sconds f32 (3),
     gammzz/wblf/wbfice f64 (6), hcll f32 (6); (mp): isflag i32, snowd/ssdnn/ga/ssat/css/rhosoil f32, dgdtg/cnsd f64; zse (6) f32.
     Returns dict(tgg, tggsn, gammzz, sconds, ghflux, sghflux)."""
     dels = F32(dels)
     ms, mp = tgg.shape
     tgg, tggsn, gammzz, sconds = tgg.copy(), tggsn.copy(), gammzz.copy(), sconds.copy()
     nos, sn = isflag == 0, isflag != 0
-    ccnsw = old_soil_conductivity(wblf, wbfice, ssat, cnsd, isoilm, snow_ccnsw)
+    ccnsw = old_soil_conductivity(wblf, wbfice, ssat, cnsd, isoilm, snow_ccnsw) if ccnsw is None else ccnsw.copy()
     # rows -2..ms of at/bt/ct/coeff live at index row + 2 (coeff has one more row, ms+1)
     at = np.zeros((ms + 3, mp), F64); bt = np.ones((ms + 3, mp), F64); ct = np.zeros((ms + 3, mp), F64)
     coeff = np.zeros((ms + 4, mp), F64)

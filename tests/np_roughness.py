@@ -18,14 +18,21 @@ def _cr(fn, x):
         return fn(np.asarray(x, np.float64)).astype(np.float32)
 
 
-def ruff_resist(hc, vlai, iveg, snowd, ssdnn, za_uv, za_tq):
+GRAV = F(9.8086)                                                                       # cable_phys_constants_mod.F90:34
+
+
+def ruff_resist(hc, vlai, iveg, snowd, ssdnn, za_uv, za_tq, us=None):
     """-> dict of the rough%* members, canopy%vlaiw / rghlai, and `veg` (the vegetated-surface branch mask; term2..term6a
     are only written there)."""
     o = {}
     hruff = np.maximum(F(10.0) * Z0SOILSN_MIN, hc - (F(1.2) * snowd / np.maximum(F(100.0), ssdnn)))
     vlaiw = vlai * (hruff / np.maximum(F(0.01), hc))
-    z0soil = F(0.0009) * np.minimum(F(1.0), vlaiw) + F(1.e-4)
-    z0soilsn = z0soil.copy()
+    if us is None:
+        z0soil = F(0.0009) * np.minimum(F(1.0), vlaiw) + F(1.e-4)
+        z0soilsn = z0soil.copy()
+    else:                                      # cable_user%l_new_roughness_soil (cable_roughness.F90:196-198), us = canopy%us
+        z0soil = F(0.01) * np.minimum(F(1.0), vlaiw) + F(0.02) * np.minimum(us * us / GRAV, F(1.0))
+        z0soilsn = np.maximum(F(1.e-7), z0soil)
     sn = snowd > F(0.01)
     z0soilsn = np.where(sn, np.maximum(Z0SOILSN_MIN, z0soil - z0soil * np.minimum(snowd, F(10.)) / F(10.)), z0soilsn).astype(F)
     z0soilsn = np.where(sn & (iveg == ICE), np.maximum(z0soilsn, Z0SOILSN_MIN_PF), z0soilsn).astype(F)

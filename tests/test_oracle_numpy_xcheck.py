@@ -172,11 +172,13 @@ def test_radiation_albedo_numpy_vs_oracle():
 
 
 # ---- stempv (soil + snow heat conduction, Thomas(9)) ----------------------------------------------------------------
-def test_stempv_numpy_vs_oracle():
+@pytest.mark.parametrize("soil_thermal_fix", [0, 1], ids=["old_conductivity", "soil_thermal_fix"])
+def test_stempv_numpy_vs_oracle(soil_thermal_fix):
     """tests/np_restatement.py::stempv against the oracle's stempv on states taken from a running winter simulation:
     tiles without snow layers (isflag = 0, with and without a thin pack), with three snow layers, permanent ice."""
-    from np_restatement import stempv as stempv_np
-    cfg, grid, T, F = make_case(1500, start_doy=15)
+    from np_restatement import stempv as stempv_np, total_soil_conductivity
+    cfg = lib.default_cfg(); cfg.soil_thermal_fix = soil_thermal_fix
+    cfg, grid, T, F = make_case(1500, cfg=cfg, start_doy=15)
     o = Oracle(T, cfg, cr_math=True)
     o._lib.oracle_run_stempv.argtypes = [C.c_void_p, C.c_float]
     o._lib.oracle_run_stempv.restype = None
@@ -192,11 +194,18 @@ def test_stempv_numpy_vs_oracle():
         # what soil_snow hands stempv: liquid / ice fractions rebuilt from wb, wbice (cbl_soilsnow_main.F90:102-108)
         T["ssnow_wblf"][...] = np.maximum(0.01, T["ssnow_wb"] - T["ssnow_wbice"]) / T["soil_ssat"][0].astype(np.float64)
         T["ssnow_wbfice"][...] = (T["ssnow_wbice"].astype(np.float32) / T["soil_ssat"][0]).astype(np.float64)
+        ccnsw = None
+        if soil_thermal_fix:                                    # cbl_stempv.F90:57-61, on the wbliq soil_snow refreshed at entry
+            T["ssnow_wbliq"][...] = T["ssnow_wb"] - T["ssnow_wbice"]
+            ccnsw = total_soil_conductivity(T["ssnow_wb"], T["ssnow_wbliq"], T["ssnow_wbice"], T["ssnow_tgg"], isflag,
+                                            T["ssnow_snowd"][0], T["soil_isoilm"][0], T["soil_cnsd_vec"], T["soil_ssat_vec"],
+                                            T["soil_sand_vec"], T["soil_watr"], cfg.snow_ccnsw)
+            assert np.ptp(ccnsw) > 0.5
         want = stempv_np(DELS, T["ssnow_tgg"], T["ssnow_tggsn"], T["ssnow_gammzz"], T["ssnow_wblf"], T["ssnow_wbfice"], isflag,
                          T["ssnow_snowd"][0], T["ssnow_ssdnn"][0], T["ssnow_ssdn"], T["ssnow_sdepth"], T["ssnow_sconds"],
                          T["canopy_ga"][0], T["canopy_dgdtg"][0], T["soil_ssat"][0], T["soil_css"][0], T["soil_rhosoil"][0],
                          T["soil_cnsd"][0], T["soil_isoilm"][0], T["soil_heat_cap_lower_limit"],
-                         np.array(list(cfg.zse), np.float32), cfg.snow_ccnsw, cfg.max_sconds)
+                         np.array(list(cfg.zse), np.float32), cfg.snow_ccnsw, cfg.max_sconds, ccnsw)
         before = T["ssnow_tgg"].copy()
         o._lib.oracle_run_stempv(o._h, DELS)
         np.testing.assert_allclose(T["ssnow_gammzz"], want["gammzz"], rtol=1e-14, err_msg="gammzz")
@@ -253,6 +262,25 @@ def test_ruff_resist_numpy_vs_oracle():
         for name in ("term2", "term3", "term5", "term6", "term6a"):      # written on the vegetated branch only
             assert np.array_equal(T["rough_" + name][0][veg].view(np.int32), r[name][veg].view(np.int32)), f"rough%{name} step {k + 1}"
     assert nveg > 10000 and nbare > 10000 and nsnow > 1000 and (T["veg_iveg"][0] == 17).any()
+
+
+def test_ruff_resist_new_roughness_soil_numpy_vs_oracle():
+    """cable_user%l_new_roughness_soil: ruff_resist is called again inside every stability iteration with the current
+    friction velocity (cable_canopy.F90:268-269), so the step's final rough%* come from the last iteration's canopy%us."""
+    import np_roughness as RR
+    cfg = lib.default_cfg(); cfg.l_new_roughness_soil = 1
+    cfg, grid, T, F = make_case(1200, cfg=cfg, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    for k in range(12):
+        F.fill(T, k)
+        snowd, ssdnn = T["ssnow_snowd"][0].copy(), T["ssnow_ssdnn"][0].copy()
+        o.cbm(k + 1, DELS)
+        r = RR.ruff_resist(T["veg_hc"][0], T["veg_vlai"][0], T["veg_iveg"][0], snowd, ssdnn, T["rough_za_uv"][0], T["rough_za_tq"][0],
+                           us=T["canopy_us"][0])
+        for name in ("hruff", "z0soil", "z0soilsn", "z0m", "disp", "zref_uv", "zref_tq", "usuh", "coexp", "rt0us", "zruffs",
+                     "rt1usa", "rt1usb"):
+            assert np.array_equal(T["rough_" + name][0].view(np.int32), r[name].view(np.int32)), f"rough%{name} step {k + 1}"
+    assert (T["rough_z0soil"][0] > np.float32(0.0101)).any() and (snowd > 0.01).sum() > 100
 
 
 def test_define_air_numpy_vs_oracle():
