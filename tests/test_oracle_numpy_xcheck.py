@@ -758,3 +758,31 @@ def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
         overflow += int((T["ssnow_rnof1"][0] > 0).sum())
     assert refilled > 10 and snowy > 300 and (T["ssnow_snowd"][0] > 0).sum() > 300 and puddles > 100 and overflow > 100, \
         (refilled, snowy, puddles, overflow)
+
+
+def test_post_step_numpy_vs_oracle():
+    """The post-step statements of the offline driver (tests/np_poststep.py, written from cable_serial.F90 / casa_sumcflux.F90 /
+    cable_checks.F90 alone) against the oracle driver's post_step on the same cbm() output, 14 steps (so that the ktau == 1
+    and ktau > 10 branches both run): every driver-side array and the scaled runoff fields bit-identical."""
+    import np_poststep as NP
+    from oracle.pyoracle import OracleDriver, DRIVER_ARRAYS
+    cfg, grid, T, F = make_case(700, start_doy=15)
+    o = Oracle(T, cfg, cr_math=True)
+    d = OracleDriver(o)
+    Dr = {n: a.copy() for n, a in d.arrays.items()}
+    skip = ("tscrn_max_daily", "tscrn_min_daily")                                # aggregator objects, checked in test_oracle.py
+    for k in range(14):
+        F.fill(T, k)
+        o.cbm(k + 1, DELS)
+        S = {n: a.copy() for n, a in T.items()}
+        d.post_step(k + 1, 1, DELS)
+        NP.scale_by_dels(S, DELS)
+        NP.sumcflux(S, Dr, k + 1, 1, DELS)
+        NP.mass_balance(S, Dr, k + 1, DELS)
+        NP.energy_balance(S, Dr)
+        for n in ("ssnow_smelt", "ssnow_rnof1", "ssnow_rnof2", "ssnow_runoff", "canopy_fnee"):
+            assert np.array_equal(S[n], T[n]), (n, k)
+        for n in DRIVER_ARRAYS:
+            if n not in skip:
+                assert Dr[n].dtype == d.arrays[n].dtype and np.array_equal(Dr[n], d.arrays[n]), (n, k + 1)
+    assert Dr["precip_tot"].any() and Dr["rnoff_tot"].any() and np.abs(Dr["wbal"][T["veg_iveg"][0] < 16]).max() < 2e-2
