@@ -40,7 +40,7 @@ def cbm_tail(T):
 def soil_snow(dels, T, zse, R, first_call=False):
     """cbl_soilsnow_main.F90:62-203 for cable_runtime%offline, redistrb = .FALSE.; R = the called routines, each working in
     place on T (first_call = the process's first call ever): snowcheck(), snowdensity(dels), snow_accum(dels), snow_melting(dels) -> snowmlt, snowl_adjust(),
-    stempv(dels), remove_trans(), soilfreeze(), surfbv(dels)."""
+    stempv(dels), remove_trans(), soilfreeze(), surfbv(dels) and, with redistrb, hydraulic_redistribution(dels)."""
     dels = F(dels)
     zse = np.asarray(zse, F)
     ms = zse.shape[0]
@@ -96,6 +96,8 @@ def soil_snow(dels, T, zse, R, first_call=False):
     s("ssnow_rnof1")[:] = rnof1
     s("ssnow_pudsto")[:] = pudsto - rnof1
     R["surfbv"](dels)
+    if "hydraulic_redistribution" in R:                                              # IF (redistrb) (:186-187)
+        R["hydraulic_redistribution"](dels)
     s("ssnow_smelt")[:] = s("ssnow_smelt") / dels
     s("ssnow_tss")[:] = surface_temp()
     T["ssnow_wbliq"][...] = T["ssnow_wb"] - T["ssnow_wbice"]
@@ -105,3 +107,74 @@ def soil_snow(dels, T, zse, R, first_call=False):
     for k in range(ms):
         wbtot = wbtot + (T["ssnow_wbliq"][k] * D(DENSITY_LIQ) + T["ssnow_wbice"][k] * D(DENSITY_ICE)) * D(zse[k])
     s("ssnow_wbtot")[:] = wbtot
+
+
+def hydraulic_redistribution(dels, T, zse, wilt_param, satu_param):
+    """cbl_hyd_redistrib.F90:13-221 (redistrb = .TRUE.): every working variable default REAL, ssnow%wb REAL(r_2); EXP / **
+    with a real exponent evaluated in float64 and rounded once.  Updates T['ssnow_wb'] in place."""
+    dels = F(dels)
+    zse = np.asarray(zse, F)
+    ms = zse.shape[0]
+    s = lambda n: T[n][0]
+    wb, wbice, froot = T["ssnow_wb"], T["ssnow_wbice"], T["veg_froot"]
+    swilt, sfc, ssat = s("soil_swilt"), s("soil_sfc"), s("soil_ssat")
+    n_hr, wpsy50, n_vg, alpha_vg, crt = F(3.22), F(-1.0), F(2.06), F(0.00423), F(125.0)
+    m_vg = F(1.0) - F(1.0) / n_vg
+    wilt_param, satu_param = F(wilt_param), F(satu_param)
+    pw = lambda x, y: np.power(np.asarray(x, D), D(y)).astype(F)
+    zsetot = F(0.)
+    for k in range(ms):
+        zsetot = zsetot + zse[k]
+    totalice = np.zeros(swilt.shape[0], F)
+    for k in range(ms):
+        totalice = (totalice.astype(D) + wbice[k] * D(zse[k]) / D(zsetot)).astype(F)
+    dtran = np.where((s("canopy_fevc") < 10.0) & (totalice < F(1.e-2)), F(1.0), F(0.0)).astype(F)
+    hr_pft = (s("veg_iveg") == 2) | (s("veg_iveg") == 7)               # evergreen_broadleaf, c4_grassland
+
+    def potentials():
+        wpsy, c_hr = [], []
+        for k in range(ms):
+            s_vg = np.minimum(F(1.0), np.maximum(F(1.0E-4), wb[k].astype(F) - swilt) / (ssat - swilt))
+            with np.errstate(all="ignore"):
+                w = -(F(1.0) / alpha_vg * pw(pw(s_vg, -(F(1.0) / m_vg)) - F(1.0), F(1) / n_vg) * F(100) * F(1.0E-6))
+                c = F(1.) / (F(1) + pw(w / wpsy50, n_hr))
+            wpsy.append(w); c_hr.append(c)
+        return wpsy, c_hr
+
+    def exchange(k, j, hr_term, avail_of):
+        hkj = hr_term * F(1.0E-2) / F(3600.0) * dels
+        hjk = F(-1.0) * hkj
+        hkj = hkj / zse[k]
+        hjk = hjk / zse[j]
+        hkj = np.where(hr_pft, hkj, F(0.0)).astype(F)
+        hjk = np.where(hr_pft, hjk, F(0.0)).astype(F)
+        down, up = hkj < F(0.0), ~(hkj < F(0.0)) & (hjk < F(0.0))
+        # WHERE (hr_perTime(:,k,j) < 0): layer k gives to layer j
+        t1 = np.maximum(np.maximum(hkj, F(-1.0) * wilt_param * avail_of(k)),
+                        F(-1.0) * satu_param * np.maximum(D(0.0), ssat.astype(D) - wb[j]).astype(F) * zse[j] / zse[k])
+        # ELSEWHERE (hr_perTime(:,j,k) < 0): layer j gives to layer k
+        t2 = np.maximum(np.maximum(hjk, F(-1.0) * wilt_param * avail_of(j)),
+                        F(-1.0) * satu_param * np.maximum(D(0.0), ssat.astype(D) - wb[k]).astype(F) * zse[k] / zse[j])
+        new_kj = np.where(down, t1, np.where(up, F(-1.0) * t2 * zse[j] / zse[k], hkj)).astype(F)
+        new_jk = np.where(down, F(-1.0) * t1 * zse[k] / zse[j], np.where(up, t2, hjk)).astype(F)
+        wb[k][:] = wb[k] + new_kj.astype(D)
+        wb[j][:] = wb[j] + new_jk.astype(D)
+
+    # deep -> shallow pairs, limited by a third of the way from wilting point to field capacity (:98-143)
+    wpsy, c_hr = potentials()
+    avail1 = lambda l: np.maximum(D(0.0), wb[l] - (swilt + (sfc - swilt) / F(3.)).astype(D)).astype(F)
+    for k in range(ms - 1, 1, -1):
+        for j in range(k - 1, 0, -1):
+            froot_x = np.maximum(F(0.01), np.maximum(froot[k], froot[j]))
+            hr_term = crt * (wpsy[j] - wpsy[k]) * np.maximum(c_hr[k], c_hr[j]) * (froot[k] * froot[j]) / (F(1) - froot_x) * dtran
+            exchange(k, j, hr_term, avail1)
+    # shallow -> deep pairs, only the water above field capacity moves (:146-219)
+    dtran = np.where(s("met_tk") < F(273.16) + F(5.), F(0.0), dtran).astype(F)
+    wpsy, c_hr = potentials()
+    avail2 = lambda l: np.maximum(D(0.0), wb[l] - sfc.astype(D)).astype(F)
+    for k in range(0, ms - 2):
+        for j in range(k + 1, ms - 1):
+            froot_x = np.maximum(F(0.01), np.maximum(froot[k], froot[j]))
+            hr_term = (crt * (wpsy[j] - wpsy[k]) * np.maximum(c_hr[k], c_hr[j])
+                       * (np.maximum(F(0.01), froot[k]) * np.maximum(F(0.01), froot[j])) / (F(1) - froot_x) * dtran)
+            exchange(k, j, hr_term, avail2)

@@ -683,14 +683,16 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
     assert (got["canopy_spill"] > 0).any() or (got["canopy_dewmm"] > 0).any()
 
 
-def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
+@pytest.mark.parametrize("redistrb", [0, 1], ids=["default", "redistrb"])
+def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle(redistrb):
     """The statements BETWEEN the calls in cbm and soil_snow (tests/np_orchestration.py, written from the Fortran alone):
     lake refill, the otss shuffle, albedo_T, owetfac, soil_snow's set-up, infiltration / puddle arithmetic and closing
     bookkeeping, and cbm's final flux sums and radiative temperature.  soil_snow is re-run on a copy of the state captured at
     the end of define_canopy, with the oracle's single-routine hooks (each cross-checked above) called in the Fortran's
     order from Python; every bound field must then equal the oracle's own step to the bit."""
     import np_orchestration as NO
-    cfg, grid, T, F = make_case(1200, start_doy=15)
+    cfg = lib.default_cfg(); cfg.redistrb = redistrb
+    cfg, grid, T, F = make_case(1200, cfg=cfg, start_doy=15)
     o = Oracle(T, cfg, cr_math=True)
     zse = np.array(list(cfg.zse), np.float32)
     HOOK = C.CFUNCTYPE(None, C.c_int, C.c_int, C.POINTER(C.c_void_p))
@@ -705,7 +707,7 @@ def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
     o._lib.oracle_set_dryleaf_hook(o._h, cb)
     after = ("ssnow_snage", "ssnow_deltss", "canopy_fev", "canopy_fe", "canopy_rnet", "rad_trad", "canopy_frp", "canopy_frpw",
              "canopy_frpr", "canopy_frs", "canopy_fnpp", "canopy_fgpp", "canopy_fnee", "canopy_fra", "bgc_cplant", "bgc_csoil")
-    refilled = snowy = puddles = overflow = 0
+    refilled = snowy = puddles = overflow = moved = 0
     for k in range(20):
         F.fill(T, k)
         if k == 5:                                              # dry out some lakes so that the refill has work to do
@@ -744,10 +746,16 @@ def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
         R = {nm: run0(nm) for nm in ("snowcheck", "snowl_adjust", "remove_trans", "soilfreeze")}
         R.update({nm: run1(nm) for nm in ("snowdensity", "snow_accum", "stempv", "surfbv")})
         R["snow_melting"] = melt
+        if redistrb:          # no single-routine hook in the oracle: the NumPy restatement (np_orchestration.py) stands in,
+            wb_in = []        # so this leg is a cross-check of hydraulic_redistribution itself; fp64 wb compared below
+            R["hydraulic_redistribution"] = lambda dels: (wb_in.append(P["ssnow_wb"].copy()),
+                                                          NO.hydraulic_redistribution(dels, P, zse, cfg.wiltParam, cfg.satuParam))[0]
         NO.soil_snow(DELS, P, zse, R, first_call=(k == 0))       # the first call ever initialises gammzz(:,1) (D3)
         assert calls == ["snowcheck", "snowdensity", "snow_accum", "snow_melting", "snowl_adjust", "stempv", "snow_melting",
                          "remove_trans", "soilfreeze", "surfbv"]
         ob.close()
+        if redistrb:
+            moved += int((np.abs(P["ssnow_wb"] - wb_in[0]) > 0).sum())
         for n in T:
             if n not in after:
                 assert np.array_equal(P[n], T[n], equal_nan=True), (n, k, float(np.abs(P[n].astype(np.float64) - T[n]).max()))
@@ -758,6 +766,7 @@ def test_cbm_and_soil_snow_orchestration_numpy_vs_oracle():
         overflow += int((T["ssnow_rnof1"][0] > 0).sum())
     assert refilled > 10 and snowy > 300 and (T["ssnow_snowd"][0] > 0).sum() > 300 and puddles > 100 and overflow > 100, \
         (refilled, snowy, puddles, overflow)
+    assert not redistrb or moved > 500, moved
 
 
 def test_post_step_numpy_vs_oracle():
