@@ -148,14 +148,14 @@ def photosynthesis(csx, cx1, cx2, gswmin, rdx, vcmxt3, vcmxt4, vx3, vx4, gs_coef
     return anx
 
 
-def dryleaf(dels, iter_, medlyn, I):
+def dryleaf(dels, iter_, medlyn, I, call_climate=False):
     """I: dict of inputs (copies).  Field names follow the registry; work arrays are 'w_<name>'.  Returns a dict with every
     array dryLeaf writes."""
     with np.errstate(all="ignore"):
-        return _dryleaf(F32(dels), iter_, medlyn, I)
+        return _dryleaf(F32(dels), iter_, medlyn, I, call_climate)
 
 
-def _dryleaf(dels, iter_, medlyn, I):
+def _dryleaf(dels, iter_, medlyn, I, call_climate=False):
     g = lambda n: I[n].copy()
     one = lambda n: I[n][0].copy()
     vlaiw, fwet, rlam, cmolar, psyc, dsatdk = one("canopy_vlaiw"), one("canopy_fwet"), one("air_rlam"), one("air_cmolar"), one("air_psyc"), one("air_dsatdk")
@@ -235,7 +235,22 @@ def _dryleaf(dels, iter_, medlyn, I):
         for l in range(2):
             vx3[l] = upd(vx3[l], ej3x(qcan[l] * jtomol * (F32(1.0) - frac4), alpha, convex, ejmxt3[l]))
             vx4[l] = upd(vx4[l], ej4x(qcan[l] * jtomol * frac4, alpha, convex, vcmxt4[l]))
-            rdx[l] = upd(rdx[l], cfrd * vcmxt3[l] + cfrd * vcmxt4[l])
+            if not call_climate:
+                rdx[l] = upd(rdx[l], cfrd * vcmxt3[l] + cfrd * vcmxt4[l])                # :396-397
+        if call_climate:                      # Atkin et al. (2015) leaf respiration, :340-393 (cable_user%call_climate)
+            iveg, qt = one("veg_iveg"), one("climate_qtemp_max_last_year")
+            inner = lambda c0: F32(c0) + F32(0.0116) * vcmax - F32(0.0334) * qt * F32(1.0e-6)
+            base = np.where(np.isin(iveg, (2, 4, 12, 13)), F32(0.60) * inner(1.2818e-6),       # broadleaf, aust_mesic / xeric
+                            np.where(np.isin(iveg, (1, 3)), F32(1.0) * inner(1.2877e-6),     # needleleaf
+                                     np.where(np.isin(iveg, (6, 8, 9)), F32(0.60) * inner(1.6737e-6),   # C3 grass, tundra, crop
+                                              F32(0.60) * inner(1.5758e-6)))).astype(F32)
+            xrdt = pow32(F32(3.09) - F32(0.043) * ((tlfx - F32(273.15)) + F32(25.)) / F32(2.0),
+                         (tlfx - F32(273.15) - F32(25.0)) / F32(10.0))                          # :852
+            for l in range(2):
+                r = base * xrdt * scalex[l]
+                par = jtomol * F32(1.0e6) * qcan[2 * l]       # qcan(i,1,1) and, for the shaded leaf, qcan(i,1,2) (:387-393)
+                light = F32(0.5) - F32(0.05) * np.log(par.astype(F64)).astype(F32)
+                rdx[l] = upd(rdx[l], np.where(par > F32(10.0), r * light, r).astype(F32))
         if not medlyn:                                                                # :404-409
             for l in range(2):
                 new = ((fwsoil.astype(F64) / (csx[l] - F64(co2cp3))) * (a1gs / (F32(1.0) + dsx / d0gs)).astype(F64)).astype(F32)
