@@ -674,6 +674,21 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
         same(g, Sb["canopy_" + n], "Surf_wetness_fact canopy%" + n)
     same(wetfac, Sb["ssnow_wetfac"], "Surf_wetness_fact ssnow%wetfac")
     assert (wcint > 0).any() and (Sa["ssnow_wbice"][0] > 0).any() and (Sa["veg_iveg"] == 16).any()
+    # the initialisations between Surf_wetness_fact and the loop (cable_canopy.F90:183-256), seen at the first dryLeaf call
+    P0, P1 = snaps[(0, -1)], snaps[(1, 0)]
+    tk, qv, pmb = P0["met_tk"], P0["met_qv"], P0["met_pmb"]
+    dva = (NC.qsatf(tk - NC.TFRZ, pmb) - qv) * NC.RMAIR / NC.RMH2O * pmb * np.float32(100.0)
+    tss = (1 - P0["ssnow_isflag"]).astype(np.float32) * P0["ssnow_tgg"][0] + P0["ssnow_isflag"].astype(np.float32) * P0["ssnow_tggsn"][0]
+    same(Sb["w_cansat"], P0["veg_canst1"] * P0["canopy_vlaiw"], "cansat")
+    same(P1["ssnow_tss"], tss, "ssnow%tss at entry"); same(P1["w_tss4"], (tss * tss) * (tss * tss), "tss4")
+    same(P1["w_dsx"], np.maximum(dva, np.float32(0.0)), "dsx")
+    same(snaps[(1, 2)]["w_sum_rad_rniso"], P1["rad_rniso"][0] + P1["rad_rniso"][1], "sum_rad_rniso")
+    same(snaps[(1, 2)]["w_sum_rad_gradis"], P1["rad_gradis"][0] + P1["rad_gradis"][1], "sum_rad_gradis")
+    assert np.array_equal(P1["w_tlfx"], tk) and np.array_equal(P1["w_tlfy"], tk)
+    assert np.array_equal(P1["w_csx"], np.stack([P0["met_ca"].astype(np.float64)] * 2))
+    assert np.all(P1["w_gbhf"] == np.float64(np.float32(1e-3))) and not P1["ssnow_evapfbl"].any()
+    assert np.all(P1["canopy_zetar"][0] == 0) and np.all(snaps[(1, 7)]["canopy_zetar"][1] == NC.ZETPOS + 1)
+    assert np.array_equal(P1["canopy_cansto"], Sb["canopy_cansto"]) and np.array_equal(P0["canopy_cansto"], P0["canopy_oldcansto"])
     # screen-level diagnostics, canopy water store, d(ground flux)/dT, balances and net radiation after the loop
     Sa, Sb = snaps[(4, 7)], snaps[(4, 8)]
     W = {n[2:]: a for n, a in Sa.items() if n.startswith("w_")}
