@@ -1,8 +1,8 @@
 """GPU debugging aid: run one switch case for a few steps and describe the tiles whose results differ from the oracle.
-usage: python tools/debug_switch.py soil_thermal_fix=1 [nsteps]"""
+usage: python tests/checks/debug_switch.py soil_thermal_fix=1 [nsteps]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np
 from cable_b200 import lib, synth
 from cable_b200.cbm import CableB200

@@ -1,8 +1,8 @@
 """Parity at a size that takes kernel A's 768-thread path (>= 148*768 tiles): device vs CR oracle, every output field.
-usage: python tools/parity_big.py [nland] [steps]"""
+usage: python tests/checks/parity_big.py [nland] [steps]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import numpy as np
 from cable_b200 import lib, synth
 from cable_b200.cbm import CableB200

@@ -1,7 +1,7 @@
 """Run oracle and CUDA path side by side on the same seeded inputs and print a per-field report.
-Usage: python tools/parity_report.py [nland] [nsteps] [gs_switch]"""
+Usage: python tests/checks/parity_report.py [nland] [nsteps] [gs_switch]"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from cable_b200 import lib, synth
 from cable_b200.cbm import CableB200

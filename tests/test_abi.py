@@ -96,3 +96,6 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 txt = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, fn
+    for fn in os.listdir(os.path.join(ROOT, "tools")):                      # developer tooling: checkers live in tests/checks/
+        txt = open(os.path.join(ROOT, "tools", fn), errors="ignore").read()
+        assert "pyoracle" not in txt and "liboracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn

@@ -2,7 +2,7 @@
 
   config 1  single site, half-hourly, one YEAR: annual totals within 1e-5 of the oracle (north star)
   config 2  regional 0.5 degree grid, 10 000 land points x 5 tiles: every field vs the oracle (takes kernel A's
-            256-thread path; tools/parity_big.py covers the 768-thread path at 125 000 tiles the same way)
+            256-thread path; tests/checks/parity_big.py covers the 768-thread path at 125 000 tiles the same way)
   config 3  the benchmark shard (62 000 land points x 5 tiles = 310 000 tiles) through size-independent properties:
             the reference's own closure checks (cable_checks.F90:472-618) evaluated ON THE DEVICE, finiteness,
             run-to-run determinism, and a checksum of the output block against a second run
