@@ -199,3 +199,53 @@ def test_driver_api_rejects_bad_arguments():
         F.fill(Tg, 0); h.set_forcing_async(0); h.step(1, DELS, 0); h.post_step(1, 1, DELS)
         h.output_fetch_async(out); h.output_wait()
         assert np.isfinite(out).all()
+
+
+def test_ragged_patch_counts_through_the_driver_stages():
+    """Land points with 1..5 active patches (landpt%cstart/cend, cable_input.F90:158-160): met expansion, cbm, post-step and
+    the patch -> grid-cell output reduction on the device against the oracle on the same ragged tile list."""
+    import ctypes as C
+    from util import ragged_case
+    cfg, grid, T, F, idx = ragged_case(500)
+    cfg.output_level = 2
+    cfg.n_forcing_slots = 2
+    T_gpu = {k: v.copy() for k, v in T.items()}
+    lat_tile = grid.lat[grid.tile2land]
+    o = Oracle(T, cfg, cr_math=True)
+    od = OracleDriver(o)
+    rows = [("canopy_fe", 0, "mean"), ("ssnow_tgg", 2, "mean"), ("ssnow_wb", 1, "mean"), ("canopy_tscrn", 0, "mean"),
+            ("bal_wbal", 0, "mean")]
+    out = np.zeros((len(rows), grid.nland), np.float32)
+    with _handle(cfg, grid, T_gpu) as h:
+        h.output_plan(rows)
+        for k in range(8):
+            land = F.land_slice(k)
+            pyoracle.met_expand(T, land, grid.cstart, grid.cend, lat_tile, cr_math=True, **CONVERT)
+            T["veg_vlai"][0] = F.lai(k)[idx]; T["met_tvrad"][0] = T["met_tk"][0]
+            o.cbm(k + 1, DELS)
+            od.post_step(k + 1, 1, DELS)
+            T_gpu["veg_vlai"][0] = F.lai(k)[idx]
+            h.upload_lai()
+            h.set_met_async(k % 2, land, lib.MetConvert(**CONVERT))
+            if k == 3:                                                   # the expanded forcing itself, tile by tile
+                h.sync()
+                for name in ("met_tk", "met_fsd", "met_precip", "met_precip_sn"):
+                    dev = np.empty((T[name].shape[0], grid.mp), np.float32)
+                    assert _cudart().cudaMemcpy(C.c_void_p(dev.ctypes.data), C.c_void_p(h.device_ptr(name, k % 2)),
+                                                C.c_size_t(dev.nbytes), 2) == 0
+                    assert np.array_equal(dev, T[name]), name
+            h.step(k + 1, DELS, k % 2)
+            h.post_step(k + 1, 1, DELS)
+            h.output_fetch_async(out); h.output_wait()                   # one sample per interval: the sample, reduced
+        h.sync()
+        wbal = h.driver_download(DRIVER_ABI_NAMES["wbal"])
+        h.download_state(); h.download_diag(star_only=False)
+    bad = {n: r for n, r in compare_tiles(T, T_gpu).items() if r[0] > r[1]}
+    assert not bad, bad
+    for r, (name, comp, _) in enumerate(rows):                           # exact reduction of the device's own fields ...
+        src = wbal if name == "bal_wbal" else T_gpu[name][comp].astype(np.float32)
+        assert np.array_equal(out[r], pyoracle.grid_reduce(src, grid.patchfrac, grid.cstart, grid.cend)), name
+    want = pyoracle.grid_reduce(T["canopy_fe"][0], grid.patchfrac, grid.cstart, grid.cend)                # ... and the oracle's
+    np.testing.assert_allclose(out[0], want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()))
+    n = grid.cend - grid.cstart + 1
+    assert n.min() == 1 and n.max() == 5

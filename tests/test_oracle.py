@@ -263,3 +263,37 @@ def test_post_step_closure_and_bookkeeping():
             assert not d.arrays["wbal_tot"].any() and not d.arrays["precip_tot"].any()
     assert d.arrays["precip_tot"].any()
     assert np.array_equal(T["canopy_fnee"][0], T["canopy_fpn"][0] + T["canopy_frs"][0] + T["canopy_frp"][0])
+
+
+def test_ragged_patch_counts_met_expand_and_grid_reduce():
+    """Land points with 1..5 active patches (landpt%cstart/cend, cable_input.F90:158-160): the oracle's met expansion puts
+    each land point's forcing on exactly its own tiles, and the patch -> grid-cell reduction is sum(x * patchfrac) over them."""
+    from oracle import pyoracle
+    from util import ragged_case
+    cfg, grid, T, F, idx = ragged_case(150)
+    n = grid.cend - grid.cstart + 1
+    assert n.min() == 1 and n.max() == 5 and grid.mp == n.sum() == T["met_tk"].shape[1] and len(set(n)) == 5
+    assert np.array_equal(np.repeat(np.arange(grid.nland), n), grid.tile2land)
+    tot = np.zeros(grid.nland); np.add.at(tot, grid.tile2land, grid.patchfrac)
+    np.testing.assert_allclose(tot, 1.0, atol=3e-7)
+    land = F.land_slice(4)
+    conv = dict(tair_offset=0.0, psurf_scale=0.01, rainf_scale=DELS, co2_scale=1.0e-6, snowf_from_tair=1)
+    pyoracle.met_expand(T, land, grid.cstart, grid.cend, grid.lat[grid.tile2land], cr_math=True, **conv)
+    assert np.array_equal(T["met_tk"][0], land[1][grid.tile2land]) and np.array_equal(T["met_ua"][0], land[4][grid.tile2land])
+    x = T["met_tk"][0] * np.float32(0.5)
+    got = pyoracle.grid_reduce(x, grid.patchfrac, grid.cstart, grid.cend)
+    want = np.zeros(grid.nland, np.float32)
+    for l in range(grid.nland):
+        s = np.float32(0.0)
+        for i in range(grid.cstart[l], grid.cend[l] + 1):
+            s = np.float32(s + x[i] * grid.patchfrac[i])
+        want[l] = s
+    assert np.array_equal(got, want)
+    # and a step of cbm on the ragged tiles closes like any other
+    o = Oracle(T, cfg, cr_math=True)
+    for k in range(3):
+        pyoracle.met_expand(T, F.land_slice(k), grid.cstart, grid.cend, grid.lat[grid.tile2land], cr_math=True, **conv)
+        T["veg_vlai"][0] = F.lai(k)[idx]; T["met_tvrad"][0] = T["met_tk"][0]
+        o.cbm(k + 1, DELS)
+    radbal, ebalsoil, ebalveg, ebal = energy_balances(T)
+    assert np.abs(ebal).max() < 5e-3 and np.abs(radbal).max() < 5e-3

@@ -41,6 +41,26 @@ def test_tiles_of_a_land_point_stay_together():
     assert seen == grid.mp
 
 
+def test_ragged_patch_counts_shard_on_land_point_boundaries():
+    """With 1..5 active patches per land point the ranks' tile ranges still tile the whole list, start and end on land-point
+    boundaries, and the local cstart/cend/tile2land are rebased to the rank's first tile and first land point."""
+    from util import ragged_case
+    cfg, grid, T, F, idx = ragged_case(41)
+    seen_t = seen_l = 0
+    for r in range(3):
+        g, Tl = shard_grid(grid, T, r, 3)
+        l0, nl = array_partition(grid.nland, 3, r)
+        assert l0 == seen_l and g.nland == nl and g.cstart[0] == 0 and g.cend[-1] == g.mp - 1
+        assert np.array_equal(g.cend - g.cstart, grid.cend[l0:l0 + nl] - grid.cstart[l0:l0 + nl])
+        assert np.array_equal(g.cstart[1:], g.cend[:-1] + 1)
+        assert np.array_equal(g.tile2land, np.repeat(np.arange(nl), g.cend - g.cstart + 1))
+        assert Tl["ssnow_tgg"].shape[1] == g.mp and np.array_equal(Tl["veg_iveg"][0], T["veg_iveg"][0][seen_t:seen_t + g.mp])
+        tot = np.zeros(nl); np.add.at(tot, g.tile2land, g.patchfrac)
+        np.testing.assert_allclose(tot, 1.0, atol=3e-7)
+        seen_t += g.mp; seen_l += nl
+    assert seen_t == grid.mp and seen_l == grid.nland
+
+
 def _free_port() -> int:
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

@@ -69,3 +69,24 @@ def energy_balances(T):
             - sb * T["canopy_tv"][0].astype(np.float64) ** 4 * (1 - T["rad_transd"][0]) - T["rad_flws"][0] * T["rad_transd"][0]
             - T["canopy_fev"][0] - T["canopy_fes"][0] - T["canopy_fh"][0] - T["canopy_ga"][0])
     return radbal, ebalsoil, ebalveg, ebal
+
+
+def ragged_case(nland=200, seed=7, **kw):
+    """A case whose land points keep 1..5 active patches, as landpt(:)%cstart/cend are in the reference (nap = number of
+    active patches of a point, src/offline/cable_input.F90:158-160): tiles dropped from the tail of each point of a uniform
+    case, patch fractions renormalised per point.  -> cfg, grid, tiles, forcing, idx (kept tiles of the uniform case, for the
+    per-tile LAI the forcing generator returns)."""
+    import dataclasses
+    cfg, grid, T, F = make_case(nland, **kw)
+    rng = np.random.default_rng(seed)
+    keep_n = rng.integers(1, grid.nap + 1, grid.nland)
+    idx = np.flatnonzero((np.arange(grid.mp) - grid.cstart[grid.tile2land]) < keep_n[grid.tile2land])
+    T2 = {n: np.ascontiguousarray(a[:, idx]) for n, a in T.items()}
+    cend = (np.cumsum(keep_n) - 1).astype(np.int32)
+    cstart = (cend - keep_n + 1).astype(np.int32)
+    tl = grid.tile2land[idx].astype(np.int32)
+    pf = grid.patchfrac[idx].astype(np.float64)
+    tot = np.zeros(grid.nland)
+    np.add.at(tot, tl, pf)
+    g2 = dataclasses.replace(grid, mp=int(idx.size), tile2land=tl, cstart=cstart, cend=cend, patchfrac=(pf / tot[tl]).astype(np.float32))
+    return cfg, g2, T2, F, idx
