@@ -161,6 +161,19 @@ def potev_hdm(S, qstss, rtsoil, q_air, litter=False):
     return S["air_rho"] * S["air_rlam"] * dq / rtsoil
 
 
+def potev_pm(S, litter=False):
+    """Penman_Monteith (cbl_pot_evap_snow.F90:11-76, cable_user%ssnow_POTEV = 'P-M'), both calls of an iteration: the current
+    met%tvair / qvair, this iteration's canopy%fns and the previous canopy%ga."""
+    sss = S["air_dsatdk"]
+    cc1 = sss / (sss + S["air_psyc"])
+    cc2 = S["air_psyc"] / (sss + S["air_psyc"])
+    qs = qsatf(S["met_tvair"] - TFRZ, S["met_pmb"])
+    res = S["ssnow_rtsoil"]
+    if litter:
+        res = res + (1 - S["ssnow_isflag"]).astype(F) * S["veg_clitt"].astype(F) * F(0.003) / F(DVLITT)
+    return cc1 * (S["canopy_fns"] - S["canopy_ga"]) + cc2 * S["air_rho"] * S["air_rlam"] * (qs - S["met_qvair"]) / res
+
+
 def latent_heat_flux(dels, S, zse1, potev, wetfac, l_new_reduce_soilevp=False):
     """cbl_latent_heat.F90:15-285 -> wetfac, pwet, cls, fess, fesp, fes (float64)."""
     dels = F(dels)

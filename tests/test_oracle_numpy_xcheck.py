@@ -576,8 +576,8 @@ def _run_with_canopy_stages(ntiles_land, steps, start_doy, switches=None):
 
 
 @pytest.mark.parametrize("start_doy,switches", [(15, {}), (196, {}), (15, dict(litter=1, l_rev_corr=1)), (196, dict(litter=1)),
-                                                (15, dict(l_rev_corr=1))],
-                         ids=["january", "july", "january-litter-revcorr", "july-litter", "january-revcorr"])
+                                                (15, dict(l_rev_corr=1)), (15, dict(ssnow_potev=1)), (196, dict(ssnow_potev=1, litter=1))],
+                         ids=["january", "july", "january-litter-revcorr", "july-litter", "january-revcorr", "january-PM", "july-PM-litter"])
 def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
     """tests/np_canopy.py (written from the Fortran alone) against every stage of the four stability iterations of one
     timestep: friction velocity, resistances and boundary-layer conductances, wetLeaf, canopy flux sums and radiative
@@ -585,7 +585,7 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
     update_zetar.  fp32 fields to the bit, fp64 fields to 1e-14 relative."""
     import np_canopy as NC
     cfg, T, snaps, ortsoil = _run_with_canopy_stages(900, 9, start_doy, switches)
-    litter, rev_corr = bool(cfg.litter), bool(cfg.l_rev_corr)
+    litter, rev_corr, pm = bool(cfg.litter), bool(cfg.l_rev_corr), bool(cfg.ssnow_potev)
     zse1 = cfg.zse[0]
     bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.int32)
 
@@ -626,7 +626,8 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
         same(lwabv, S3["rad_lwabv"], tag + "rad%lwabv", dense); same(qstss, S3["ssnow_qstss"], tag + "ssnow%qstss")
         # potential evaporation + latent heat flux, first and second call, and the ground sensible heat flux after each
         for (Sa, Sb, call) in ((S3, S4, "1st"), (S6, S7, "2nd")):
-            potev = NC.potev_hdm(Sa, Sa["ssnow_qstss"], Sa["ssnow_rtsoil"], Sa["met_qv" if call == "1st" else "met_qvair"], litter)
+            potev = (NC.potev_pm(Sa, litter) if pm else
+                     NC.potev_hdm(Sa, Sa["ssnow_qstss"], Sa["ssnow_rtsoil"], Sa["met_qv" if call == "1st" else "met_qvair"], litter))
             wetfac, pwet, cls, fess, fesp, fes = NC.latent_heat_flux(DELS, Sa, zse1, potev, Sa["ssnow_wetfac"],
                                                                      bool(cfg.l_new_reduce_soilevp))
             if call == "1st":
@@ -652,7 +653,7 @@ def test_canopy_iteration_numpy_vs_oracle(start_doy, switches):
             same(g, S6["met_" + n], tag + "met%" + n, on)
             same(S5["met_" + n], S6["met_" + n], tag + f"met%{n} untouched", ~on)
         # end of the iteration
-        potev2 = NC.potev_hdm(S6, S6["ssnow_qstss"], S6["ssnow_rtsoil"], S6["met_qvair"], litter)
+        potev2 = NC.potev_pm(S6, litter) if pm else NC.potev_hdm(S6, S6["ssnow_qstss"], S6["ssnow_rtsoil"], S6["met_qvair"], litter)
         fhs = S6["air_rho"] * NC.CAPP * (S6["ssnow_tss"] - S6["met_tvair"]) / ((S6["ssnow_rtsoil"] + rhlitt) if litter else S6["ssnow_rtsoil"])
         same(fhs, S7["canopy_fhs"], tag + "canopy%fhs 2nd")
         ga, fe, fh, potev, fevw_pot, rnet, rniso, epot, wetfac_cs = NC.end_of_iteration(
