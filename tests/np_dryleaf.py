@@ -75,6 +75,31 @@ def fwsoil_calc_std(froot, wbliq, swilt_vec, sfc_vec, vbeta, medlyn):           
     return np.maximum(F32(1.0e-9), np.minimum(F32(1.0), vbeta * rwater))
 
 
+def fwsoil_calc_non_linear(froot, wbliq, swilt, sfc):                                  # cbl_fwsoil.F90:42-85
+    terms = froot * np.maximum(F32(0.0), np.minimum(F32(1.0), (wbliq - swilt.astype(F64)[None, :]).astype(F32)))
+    s = np.zeros_like(swilt)
+    for k in range(MS):
+        s = s + terms[k]
+    rwater = np.maximum(F32(1.0e-9), s / (sfc - swilt))
+    rwater = swilt + rwater * (sfc - swilt)
+    x1, x2, x3 = swilt, swilt + (sfc - swilt) / F32(2.0), sfc
+    s1 = (rwater - x2) / (x1 - x2) * (rwater - x3) / (x1 - x3)
+    s2 = (rwater - x1) / (x2 - x1) * (rwater - x3) / (x2 - x3)
+    s3 = (rwater - x1) / (x3 - x1) * (rwater - x2) / (x3 - x2)
+    interp = np.maximum(F32(0.), np.minimum(F32(1.), F32(0.) * s1 + F32(0.9) * s2 + F32(1.0) * s3))
+    return np.where(rwater < sfc - F32(0.02), interp, F32(1.)).astype(F32)
+
+
+def fwsoil_calc_lai_ktaul(wbliq, swilt_vec, ssat_vec):                                 # cbl_fwsoil.F90:89-118
+    rootgamma = F32(0.01)
+    fwsoil = np.zeros(wbliq.shape[1], F32)
+    for k in range(MS):
+        dummy = (F64(rootgamma) / np.maximum(F64(1.0e-3), wbliq[k] - swilt_vec[k])).astype(F32)      # 1.0e-3_r_2: a double literal
+        frwater = np.fmax(F64(1.0e-4), np.power((wbliq[k] - swilt_vec[k]) / ssat_vec[k], dummy.astype(F64))).astype(F32)
+        fwsoil = np.minimum(F32(1.0), np.maximum(fwsoil, frwater))
+    return fwsoil
+
+
 def transp_soil_water(dels, swilt, froot, zse, fevc, wbliq):                          # cbl_remove_trans.F90:43-93
     """all (ms, n) float64 except froot float32; fevc (n,) float64 > 0"""
     evap = np.zeros_like(wbliq)
@@ -148,14 +173,14 @@ def photosynthesis(csx, cx1, cx2, gswmin, rdx, vcmxt3, vcmxt4, vx3, vx4, gs_coef
     return anx
 
 
-def dryleaf(dels, iter_, medlyn, I, call_climate=False):
+def dryleaf(dels, iter_, medlyn, I, call_climate=False, fwsoil_switch=0):
     """I: dict of inputs (copies).  Field names follow the registry; work arrays are 'w_<name>'.  Returns a dict with every
     array dryLeaf writes."""
     with np.errstate(all="ignore"):
-        return _dryleaf(F32(dels), iter_, medlyn, I, call_climate)
+        return _dryleaf(F32(dels), iter_, medlyn, I, call_climate, fwsoil_switch)
 
 
-def _dryleaf(dels, iter_, medlyn, I, call_climate=False):
+def _dryleaf(dels, iter_, medlyn, I, call_climate=False, fwsoil_switch=0):
     g = lambda n: I[n].copy()
     one = lambda n: I[n][0].copy()
     vlaiw, fwet, rlam, cmolar, psyc, dsatdk = one("canopy_vlaiw"), one("canopy_fwet"), one("air_rlam"), one("air_cmolar"), one("air_psyc"), one("air_dsatdk")
@@ -178,7 +203,12 @@ def _dryleaf(dels, iter_, medlyn, I, call_climate=False):
     gs_coeff = [np.zeros(mp, F32), np.zeros(mp, F32)]                                 # :166
     canopy_fwsoil = one("canopy_fwsoil")
     if iter_ == 1:                                                                    # :169-186
-        fwsoil = fwsoil_calc_std(froot, wbliq, swilt_vec, sfc_vec, vbeta, medlyn)
+        if fwsoil_switch == 0:                                                        # 'standard'
+            fwsoil = fwsoil_calc_std(froot, wbliq, swilt_vec, sfc_vec, vbeta, medlyn)
+        elif fwsoil_switch == 1:                                                      # 'non-linear extrapolation'
+            fwsoil = fwsoil_calc_non_linear(froot, wbliq, one("soil_swilt"), one("soil_sfc"))
+        else:                                                                         # 'Lai and Ktaul 2000'
+            fwsoil = fwsoil_calc_lai_ktaul(wbliq, swilt_vec, g("soil_ssat_vec"))
         canopy_fwsoil = fwsoil.copy()
     gswmin = [np.maximum(F32(1.0e-6), scalex[l] * one("veg_gswmin")) for l in range(2)]   # :189-193
     z32 = lambda: np.zeros(mp, F32)

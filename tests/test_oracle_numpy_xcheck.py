@@ -65,15 +65,15 @@ DRYLEAF_FIELDS_IN = ("canopy_vlaiw", "canopy_fwet", "air_rlam", "air_cmolar", "a
                      "veg_conko0", "veg_eko", "veg_alpha", "veg_convex", "veg_cfrd", "veg_a1gs", "veg_d0gs", "veg_g0", "veg_g1",
                      "veg_vbeta", "veg_gswmin", "veg_froot", "rad_fvlai", "rad_scalex", "rad_gradis", "rad_rniso", "rad_qcan",
                      "ssnow_wbliq", "soil_swilt_vec", "soil_sfc_vec", "soil_zse_vec", "canopy_gswx", "canopy_fwsoil", "veg_iveg",
-                     "climate_qtemp_max_last_year")
+                     "climate_qtemp_max_last_year", "soil_swilt", "soil_sfc", "soil_ssat_vec")
 DRYLEAF_FIELDS_OUT = ("canopy_fevc", "ssnow_evapfbl", "canopy_gswx", "canopy_frday", "canopy_fpn", "canopy_fwsoil")
 DRYLEAF_WORK_OUT = ("dsx", "fwsoil", "tlfx", "tlfy", "ecy", "hcy", "rny", "ghwet", "gbhf", "csx")
 
 
-def _run_with_dryleaf_capture(gs_switch, ntiles_land=400, steps=7, call_climate=0):
+def _run_with_dryleaf_capture(gs_switch, ntiles_land=400, steps=7, call_climate=0, fwsoil_switch=0):
     """cbm on the oracle for `steps` steps; on the last one every dryLeaf call (4 stability iterations) is captured:
     inputs before, outputs after."""
-    cfg = lib.default_cfg(); cfg.gs_switch = gs_switch; cfg.call_climate = call_climate
+    cfg = lib.default_cfg(); cfg.gs_switch = gs_switch; cfg.call_climate = call_climate; cfg.fwsoil_switch = fwsoil_switch
     cfg, grid, T, F = make_case(ntiles_land, cfg=cfg, start_doy=172)
     o = Oracle(T, cfg, cr_math=True)
     mp = grid.mp
@@ -112,18 +112,19 @@ def _run_with_dryleaf_capture(gs_switch, ntiles_land=400, steps=7, call_climate=
     return captured, o.warnings()
 
 
-@pytest.mark.parametrize("gs_switch,call_climate", [(0, 0), (1, 0), (0, 1)], ids=["leuning", "medlyn", "leuning-call_climate"])
-def test_dryleaf_numpy_vs_oracle(gs_switch, call_climate):
+@pytest.mark.parametrize("gs_switch,call_climate,fwsoil_switch", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 2)],
+                         ids=["leuning", "medlyn", "leuning-call_climate", "leuning-fwsoil-non-linear", "medlyn-fwsoil-Lai-Ktaul"])
+def test_dryleaf_numpy_vs_oracle(gs_switch, call_climate, fwsoil_switch):
     """Same inputs -> same outputs, for every dryLeaf call of one timestep (four stability iterations): leaf temperature,
     fluxes, conductances, leaf-surface CO2, root water extraction, photosynthesis.  Both restatements evaluate EXP and **
     in fp64 rounded once, so they agree to the last bit except where numpy's and g++'s fp64 pow/exp differ by an ulp
     before that rounding (never observed); tolerance 1e-6 relative on REAL, 1e-12 on REAL(r_2)."""
     from np_dryleaf import dryleaf
-    captured, _ = _run_with_dryleaf_capture(gs_switch, call_climate=call_climate)
+    captured, _ = _run_with_dryleaf_capture(gs_switch, call_climate=call_climate, fwsoil_switch=fwsoil_switch)
     assert [c["iter"] for c in captured] == [1, 2, 3, 4]
     total_passes = 0
     for c in captured:
-        got = dryleaf(DELS, c["iter"], bool(gs_switch), c["inp"], bool(call_climate))
+        got = dryleaf(DELS, c["iter"], bool(gs_switch), c["inp"], bool(call_climate), fwsoil_switch)
         total_passes += int(got["npass"].sum())
         for name, want in c["out"].items():
             g = np.asarray(got[name]).reshape(want.shape)
