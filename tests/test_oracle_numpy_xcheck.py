@@ -1,8 +1,17 @@
 """CPU: the C++ oracle against INDEPENDENT NumPy restatements of the same Fortran, routine by routine
-on states taken from a running simulation: smoisturev / trimb (tests/np_restatement.py; frozen and saturated layers
-included) and dryLeaf + photosynthesis + fwsoil_calc_std + transp_soil_water (tests/np_dryleaf.py; every call of one
-timestep, captured through the oracle's test hook).  Same kinds, same operation order, same fp64 libm -> they must agree
-to rounding; on this image all 192 000 compared dryLeaf outputs per stomatal model are bit-identical."""
+on states taken from a running simulation.  Every routine of SURVEY.md 8a, the orchestration of cbm / define_canopy /
+soil_snow, every switch cable_cfg accepts and the post-step driver statements have one:
+  np_restatement.py   trimb, smoisturev, surfbv tail, stempv + old / total soil conductivity, snow_aging, remove_trans, soilfreeze
+  np_snow.py          snowcheck, snowdensity, snow_accum, snow_melting, snowl_adjust
+  np_dryleaf.py       dryLeaf + photosynthesis + fwsoil (standard / non-linear / Lai-Ktaul) + transp_soil_water (+ call_climate)
+  np_radiation.py     init_radiation, Albedo, surface_albedosn, spitter, radiation
+  np_roughness.py     ruff_resist (+ l_new_roughness_soil), HgtAboveSnow, LAI_eff, define_air
+  np_canopy.py        define_canopy around dryLeaf, stage by stage through the oracle's stage hook (+ litter, l_rev_corr, P-M)
+  np_carbon.py        plantcarb, soilcarb, carbon_pl
+  np_orchestration.py cbm head / tail, soil_snow's own statements (+ hydraulic_redistribution)
+  np_poststep.py      dels scaling, sumcflux, mass_balance, energy_balance
+Same kinds, same operation order, EXP / LOG / ** evaluated in fp64 and rounded once like the oracle's correctly rounded
+build -> fp32 results agree to the last bit, fp64 ones to 1e-12 .. 1e-14 (NumPy's and g++'s fp64 pow/exp may differ by an ulp)."""
 import ctypes as C
 
 import numpy as np
