@@ -99,3 +99,102 @@ def test_product_never_touches_the_oracle():
     for fn in os.listdir(os.path.join(ROOT, "tools")):                      # developer tooling: checkers live in tests/checks/
         txt = open(os.path.join(ROOT, "tools", fn), errors="ignore").read()
         assert "pyoracle" not in txt and "liboracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def _shim_blocks(path):
+    """Parse a Fortran source with f2py's front end (no compiler needed) -> list of (kind, name, args)."""
+    import contextlib
+    import io
+    import numpy.f2py.crackfortran as cf
+    out = []
+
+    def walk(blocks):
+        for b in blocks:
+            if b.get("block") in ("module", "subroutine", "function"):
+                out.append((b["block"], b.get("name", "").lower(), [a.lower() for a in b.get("args", [])]))
+            walk(b.get("body", []))
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        cf.verbose, cf.quiet = 0, 1
+        walk(cf.crackfortran([path]))
+    return out
+
+
+def _c_prototypes():
+    """name -> number of parameters, from include/cable_b200.h."""
+    import re
+    txt = open(os.path.join(ROOT, "include", "cable_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(cable_b200_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def test_fortran_shims_parse_and_match_the_c_abi_and_the_reference_signature():
+    """No Fortran compiler in this image, so the ISO_C_BINDING shims are checked with f2py's parser: both files parse, the
+    drop-in module has the reference's name and `cbm` its 17 dummy arguments in the reference's order
+    (cbl_model_driver_offline.F90:38-40), and every BIND(C) interface names an exported symbol of the library with the
+    parameter count of its prototype in include/cable_b200.h."""
+    protos = _c_prototypes()
+    assert set(lib.EXPORTS) <= set(protos), set(lib.EXPORTS) - set(protos)
+    cbm_shim = _shim_blocks(os.path.join(ROOT, "fortran", "cable_cbm_b200.F90"))
+    drv_shim = _shim_blocks(os.path.join(ROOT, "fortran", "cable_driver_b200.F90"))
+    assert ("module", "cable_cbm_module", []) in cbm_shim
+    cbm = [b for b in cbm_shim if b[0] == "subroutine" and b[1] == "cbm"]
+    assert len(cbm) == 1 and cbm[0][2] == ["ktau", "dels", "air", "bgc", "canopy", "met", "bal", "rad", "rough", "soil", "ssnow",
+                                           "sum_flux", "veg", "climate", "xk", "c1", "rhoch"]
+    bound = [b for b in cbm_shim + drv_shim if b[1].startswith("cable_b200_") and b[0] in ("function", "subroutine")]
+    assert len(bound) >= 15
+    for kind, name, args in bound:
+        assert name in lib.EXPORTS, name
+        assert len(args) == protos[name], (name, args, protos[name])
+
+
+def _shim_types(path):
+    """BIND(C) derived types of a shim -> {type name: [(component, 'integer'|'real', n elements)]} in declaration order."""
+    import contextlib
+    import io
+    import numpy.f2py.crackfortran as cf
+    out = {}
+
+    def walk(blocks):
+        for b in blocks:
+            if b.get("block") == "type":
+                comps = []
+                for v in b["sortvars"]:
+                    d = b["vars"][v]
+                    n = 1
+                    for ext in d.get("dimension") or []:
+                        n *= int(ext)
+                    comps.append((v.lower(), d["typespec"], d.get("kindselector", {}).get("kind", "").lower(), n))
+                out[b["name"].lower()] = comps
+            walk(b.get("body", []))
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        cf.verbose, cf.quiet = 0, 1
+        walk(cf.crackfortran([path]))
+    return out
+
+
+def test_fortran_bind_c_types_mirror_the_c_structs():
+    """TYPE, BIND(C) :: cable_cfg / cable_met_convert of the shims against the ctypes mirrors of include/cable_b200.h (which
+    test_default_cfg_is_shipped_namelist / the library's struct_bytes check tie to the header): same components, same
+    order, same C kinds, same array extents -- a reordered component would be a silent ABI break."""
+    import ctypes as C
+    kinds = {C.c_int: ("integer", "c_int"), C.c_float: ("real", "c_float"), C.c_double: ("real", "c_double")}
+
+    def mirror(struct):
+        out = []
+        for name, ct in struct._fields_:
+            n = 1
+            while hasattr(ct, "_length_"):
+                n *= ct._length_; ct = ct._type_
+            out.append((name.lower(),) + kinds[ct] + (n,))
+        return out
+
+    t = _shim_types(os.path.join(ROOT, "fortran", "cable_cbm_b200.F90"))
+    assert t["cable_cfg"] == mirror(lib.CableCfg)
+    t = _shim_types(os.path.join(ROOT, "fortran", "cable_driver_b200.F90"))
+    assert t["cable_met_convert"] == mirror(lib.MetConvert)
