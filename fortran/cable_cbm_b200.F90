@@ -127,20 +127,8 @@ CONTAINS
        cfg%zse = soil%zse;  cfg%zshh = soil%zshh;  cfg%ratecp = bgc%ratecp;  cfg%ratecs = bgc%ratecs
        cfg%caller_duties = 0        ! the Fortran driver keeps doing canopy%oldcansto = canopy%cansto itself
        rc = cable_b200_create(INT(mp, C_INT), cfg, -1_C_INT, handle);  CALL check(rc)
-       ! one bind per registry row (include/cable_b200_fields.def); abbreviated here, the full list is generated
-       CALL bind('met_fsd',   C_LOC(met%fsd));     CALL bind('met_tk',     C_LOC(met%tk))
-       CALL bind('met_pmb',   C_LOC(met%pmb));     CALL bind('met_qv',     C_LOC(met%qv))
-       CALL bind('met_ua',    C_LOC(met%ua));      CALL bind('met_precip', C_LOC(met%precip))
-       CALL bind('met_precip_sn', C_LOC(met%precip_sn)); CALL bind('met_fld', C_LOC(met%fld))
-       CALL bind('met_ca',    C_LOC(met%ca));      CALL bind('met_coszen', C_LOC(met%coszen))
-       CALL bind('met_doy',   C_LOC(met%doy));     CALL bind('veg_vlai',   C_LOC(veg%vlai))
-       CALL bind('ssnow_tgg', C_LOC(ssnow%tgg));   CALL bind('ssnow_wb',   C_LOC(ssnow%wb))
-       CALL bind('canopy_fe', C_LOC(canopy%fe));   CALL bind('scr_xk',     C_LOC(xk))
-       ! inputs of non-default switches (registry flag OPTIN): bound always, uploaded when the switch is set
-       CALL bind('veg_clitt', C_LOC(veg%clitt));   CALL bind('soil_watr',  C_LOC(soil%watr))
-       CALL bind('soil_cnsd_vec', C_LOC(soil%cnsd_vec)); CALL bind('soil_sand_vec', C_LOC(soil%sand_vec))
-       CALL bind('climate_qtemp_max_last_year', C_LOC(climate%qtemp_max_last_year))
-       ! ... (every remaining row of the registry, same pattern) ...
+       ! one bind per registry row (include/cable_b200_fields.def), generated by tools/gen_fortran_binds.py
+#include "cable_b200_binds.inc"
        rc = cable_b200_upload(handle, 2_C_INT);  CALL check(rc)     ! CABLE_ROLE_PARAM
        rc = cable_b200_upload(handle, 4_C_INT);  CALL check(rc)     ! CABLE_ROLE_STATE
     END IF

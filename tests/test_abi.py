@@ -198,3 +198,38 @@ def test_fortran_bind_c_types_mirror_the_c_structs():
     assert t["cable_cfg"] == mirror(lib.CableCfg)
     t = _shim_types(os.path.join(ROOT, "fortran", "cable_driver_b200.F90"))
     assert t["cable_met_convert"] == mirror(lib.MetConvert)
+
+
+def test_fortran_bind_list_is_generated_from_the_registry_and_names_real_members():
+    """fortran/cable_b200_binds.inc is what tools/gen_fortran_binds.py renders from the registry (one bind per row), and --
+    where the reference tree is present (this container, not the GPU box) -- every `type%member` it takes C_LOC of is a
+    component of that derived type in the reference (cable_define_types.F90, cable_climate_type_mod.F90)."""
+    import re
+    import subprocess
+    import sys
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_fortran_binds.py"), "--check"]) == 0
+    inc = open(os.path.join(ROOT, "fortran", "cable_b200_binds.inc")).read()
+    binds = re.findall(r"CALL bind\('(\w+)', C_LOC\(([\w%]+)\)\)", inc)
+    assert len(binds) == len(FIELDS) and [b[0] for b in binds] == [f.name for f in FIELDS]
+    shim = open(os.path.join(ROOT, "fortran", "cable_cbm_b200.F90")).read()
+    assert '#include "cable_b200_binds.inc"' in shim
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    src = open(os.path.join(ref, "offline", "cable_define_types.F90")).read() + \
+        open(os.path.join(ref, "util", "cable_climate_type_mod.F90")).read()
+    src = re.sub(r"!.*", "", src).lower()
+    type_of = {"met": "met_type", "air": "air_type", "veg": "veg_parameter_type", "soil": "soil_parameter_type",
+               "ssnow": "soil_snow_type", "canopy": "canopy_type", "rad": "radiation_type", "rough": "roughness_type",
+               "bal": "balances_type", "bgc": "bgc_pool_type", "climate": "climate_type"}
+    members = {}
+    for var, tname in type_of.items():
+        m = re.search(r"\n\s*type\s+" + tname + r"\b(.*?)\n\s*end\s*type", src, flags=re.S)
+        assert m, tname
+        members[var] = set(re.findall(r"[a-z_]\w*", m.group(1)))
+    for name, target in binds:
+        if "%" in target:
+            var, member = target.split("%")
+            assert member.lower() in members[var], (name, target)
+        else:
+            assert target in ("xk", "c1", "rhoch"), target
