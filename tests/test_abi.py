@@ -233,3 +233,18 @@ def test_fortran_bind_list_is_generated_from_the_registry_and_names_real_members
             assert member.lower() in members[var], (name, target)
         else:
             assert target in ("xk", "c1", "rhoch"), target
+
+
+def test_generated_host_mirror_types_are_up_to_date():
+    """cable_b200/csrc/host_mirror_types.inc (the C++ mirror of the reference's derived types) is what
+    tools/gen_host_mirror.py renders from the registry today."""
+    import subprocess
+    import sys
+    path = os.path.join(ROOT, "cable_b200", "csrc", "host_mirror_types.inc")
+    before, st = open(path).read(), os.stat(path)
+    try:
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_host_mirror.py")], stdout=subprocess.DEVNULL)
+        assert open(path).read() == before
+    finally:
+        open(path, "w").write(before)
+        os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns))            # keep make from rebuilding the library
