@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2]): global 0.5 degree GSWP3-shape synthetic forcing, 62 000 land points x 5
-tiles = 310 000 tiles per GPU, 3-hourly (dels = 10 800 s).  A "step" is one cbm() pass over every tile of this
-rank.  Land points shard across GPUs with no data-path collective (weak scaling: every rank owns its own
-62 000-point block); NCCL only gathers grid-cell-reduced diagnostics to rank 0 once per output interval
-(= once per timed region).
+Workload (BASELINE.json configs[2]): global 0.5 degree GSWP3-shape synthetic forcing, ONE grid of 62 000 land
+points x 5 tiles = 310 000 tiles, 3-hourly (dels = 10 800 s), sharded over the N GPUs as contiguous land-point
+blocks (rule of master_decomp, src/offline/cable_mpimaster.F90:1428-1463) -- strong scaling: 310 k / 155 k / 78 k /
+39 k tiles per GPU at N = 1 / 2 / 4 / 8.  `--nland 250000` is configs[3] (1.25 M tiles, 156 k per GPU at N = 8).
+`--scaling weak` gives every rank its own --nland-point grid instead.  A "step" is one cbm() pass over every tile
+of the grid.  There is no data-path collective: NCCL only gathers grid-cell-reduced diagnostics to rank 0 once
+per output interval (= once per timed region).
 
 value : device-resident rate -- a year-shaped forcing ring already in HBM, one fused kernel launch per step.
 e2e   : the reference-facing call cable_b200_cbm() with HOST buffers -- per step the forcing goes H2D from
@@ -34,7 +36,7 @@ import numpy as np
 
 DELS = 10800.0
 ALGO_BYTES_PER_TILE_STEP = 648          # forcing 68 + state 252 r + 252 w + per-tile params 76
-NLAND_PER_GPU = 62000
+NLAND = 62000                           # configs[2]: the 0.5 degree global grid
 NAP = 5
 RING = 8                                # forcing ring = one model day of 3-hourly steps
 # rows the output module writes by default (src/offline/cable_diagnostics.F90 registrations): (field, component, method)
@@ -75,6 +77,7 @@ def profiled_metrics() -> dict | None:
         return {"file": os.path.relpath(files[-1], ROOT), "tiles": m.get("tiles"),
                 "flops_per_tile_step": m.get("flops_per_tile_step"),
                 "traffic_bytes_per_step": sum(k["dram_bytes"] for k in ks),
+                "warp_inst_per_step": sum(k.get("warp_inst_executed") or 0.0 for k in ks),
                 "kernels": [{k2: k[k2] for k2 in ("kernel", "duration_ms", "dram_bytes", "issue_active_pct", "pipe_fp64_pct",
                                                     "pipe_fma_fp32_pct", "pipe_alu_pct", "pipe_xu_pct", "dram_pct_of_peak",
                                                     "active_threads_per_warp_inst", "icache_hit_pct")} for k in ks]}
@@ -96,6 +99,23 @@ def pipe_roof(prof: dict | None, tile_steps_per_s_per_gpu: float, clocks: dict |
     return {"flops_per_tile_step_fp64": f["fp64"], "flops_per_tile_step_fp32": f["fp32"], "counted": f.get("how"),
             "fp64": {"achieved": a64, "peak": peak64, "unit": "TFLOP/s", "frac": a64 / peak64},
             "fp32": {"achieved": a32, "peak": peak32, "unit": "TFLOP/s", "frac": a32 / peak32}}
+
+
+def issue_roof(prof: dict | None, mp: int, kern_ms: float, clocks: dict | None) -> dict | None:
+    """The bound that actually bites: warp-instruction issue slots.  Executed warp instructions per
+    tile-step COUNTED by ncu in the committed capture (smsp__inst_executed.sum over the step's launches / tiles of that
+    capture) x this run's tiles per step / this run's event-timed step, against 148 SMs x 4 schedulers x 1 warp
+    instruction per cycle at the SM clock sampled during the timed region."""
+    if not prof or not prof.get("warp_inst_per_step") or not prof.get("tiles") or kern_ms <= 0:
+        return None
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    per_tile = prof["warp_inst_per_step"] / prof["tiles"]
+    peak = 148 * 4 * mhz * 1e6
+    achieved = per_tile * mp / (kern_ms * 1e-3)
+    return {"warp_inst_per_tile_step": per_tile, "warp_inst_per_step": per_tile * mp, "achieved": achieved, "peak": peak,
+            "unit": "warp-inst/s", "frac": achieved / peak, "sm_mhz": mhz,
+            "floor_ms_at_this_instruction_count": per_tile * mp / peak * 1e3,
+            "counted": f"ncu smsp__inst_executed.sum, {prof.get('file')}"}
 
 
 class ClockSampler(threading.Thread):
@@ -140,30 +160,43 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def workload_text(nland_total: int, tiles_total: int) -> str:
+    res = "0.5deg" if nland_total <= 100000 else "0.25deg"
+    return (f"global {res} GSWP3-shape synthetic forcing: ONE grid of {nland_total} land points x {NAP} tiles = {tiles_total} "
+            f"tiles, dels={int(DELS)}s, leuning/standard/HDM/icycle=0 (cable.nml)")
+
+
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(nland_w: int, nsteps: int, nproc: int, warm: int = 1) -> tuple[float, float]:
-    """Oracle throughput on `nproc` host processes, each stepping its own block of `nland_w` land points
-    (the reference MPI driver's decomposition: contiguous land-point blocks, one worker per core)."""
+def cpu_oracle_rate(nland: int, nsteps: int, nproc: int, warm: int = 1) -> tuple[float, float, int]:
+    """Oracle throughput on `nproc` host processes stepping ONE `nland`-point grid (the b200 arm's grid: same seed,
+    same forcing), split into contiguous land-point blocks exactly like the reference MPI driver does it (master_decomp,
+    cable_mpimaster.F90:1428-1445), one worker per core.  -> (tile-steps/s, seconds, tiles per step)."""
     import multiprocessing as mp_
     ctx = mp_.get_context("fork")
     with ctx.Pool(nproc) as pool:
-        res = pool.starmap(_cpu_worker, [(r, nland_w, nsteps, warm) for r in range(nproc)])
+        res = pool.starmap(_cpu_worker, [(r, nproc, nland, nsteps, warm) for r in range(nproc)])
     tmax = max(t for t, _ in res)
     tiles = sum(n for _, n in res)
-    return tiles * nsteps / tmax, tmax
+    return tiles * nsteps / tmax, tmax, tiles
 
 
-def _cpu_worker(rank: int, nland_w: int, nsteps: int, warm: int):
+def _cpu_worker(rank: int, nproc: int, nland: int, nsteps: int, warm: int):
     from cable_b200 import lib, synth
+    from cable_b200.sharding import shard_grid
+    from cable_b200.partition import array_partition, land_to_tile_range
     from oracle.pyoracle import Oracle
     cfg = lib.default_cfg()
-    grid = synth.make_grid(nland_w, NAP, seed=synth.SEED + 1000 + rank)
-    tiles = synth.make_tiles(grid, cfg)
-    forcing = synth.Forcing(grid, tiles, DELS, start_doy=172)
+    full = synth.make_grid(nland, NAP, seed=synth.SEED)
+    tiles_full = synth.make_tiles(full, cfg)
+    forcing = synth.Forcing(full, tiles_full, DELS, start_doy=172)
+    l0, nl = array_partition(full.nland, nproc, rank)
+    t0, t1 = land_to_tile_range(full.cstart, full.cend, l0, nl)
     sets = []
     for k in range(RING):
-        forcing.fill(tiles, k)
-        sets.append({n: tiles[n].copy() for n in synth.FORCING_FIELDS})
+        forcing.fill(tiles_full, k)
+        sets.append({n: np.ascontiguousarray(tiles_full[n][:, t0:t1]) for n in synth.FORCING_FIELDS})
+    grid, tiles = shard_grid(full, tiles_full, rank, nproc)
+    del tiles_full
     o = Oracle(tiles, cfg, cr_math=False)
     for k in range(warm):
         for n, a in sets[k % RING].items():
@@ -184,24 +217,24 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nland_w = 2000                                      # 10 000 tiles per worker per step
     t0 = time.perf_counter()
-    rate, tmax = cpu_oracle_rate(nland_w, args.steps, cores, warm=args.warmup)
+    # the b200 arm's own grid (same seed, same forcing ring, every tile of it each step); a bounded number of steps
+    nland_total = args.nland * (args.gpus if args.scaling == "weak" else 1)
+    rate, tmax, tiles_step = cpu_oracle_rate(nland_total, args.steps, cores, warm=args.warmup)
     ms = tmax / max(args.steps, 1) * 1e3
     line = {
         "impl": "reference", "metric": "tile-timesteps/sec for cbm()", "value": rate, "unit": "tile-timesteps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        # the b200 arm's workload (same text, same sizes); each CPU step is a bounded sample of it
-        "config": {"workload": f"global 0.5deg GSWP3-shape synthetic forcing: {args.nland} land points x {NAP} tiles "
-                               f"= {args.nland * NAP} tiles per GPU, dels={int(DELS)}s, leuning/standard/HDM/icycle=0 (cable.nml)",
-                   "tiles_per_gpu": args.nland * NAP, "global_tiles": args.nland * NAP * args.gpus,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        # the b200 arm's workload: same grid, same seed, every tile of it each step
+        "config": {"workload": workload_text(nland_total, nland_total * NAP),
+                   "global_tiles": nland_total * NAP, "tiles_per_step": tiles_step,
                    "parallelism": f"land-point blocks x{cores} host processes (master_decomp rule)",
-                   "sample": f"each step = {nland_w * NAP * cores} tiles of that grid ({cores} blocks of {nland_w} land points)",
-                   "sample_tiles_per_step": nland_w * NAP * cores},
+                   "sample": f"every step = all {tiles_step} tiles of that grid; {args.steps} steps (bounded), {args.warmup} warm-up"},
         "cpu_baseline": {"value": rate, "unit": "tile-timesteps/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores} workers x {nland_w} land points x {NAP} tiles x {args.steps} steps, "
-                                   "C++ restatement of the reference (not the Fortran binary), forcing in memory"},
+                         "sample": f"{cores} workers x {tiles_step // cores}+ tiles ({nland_total} land points split by "
+                                   f"master_decomp) x {args.steps} steps, C++ restatement of the reference (not the Fortran "
+                                   "binary), forcing in memory"},
         "e2e": {"value": rate, "unit": "tile-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -228,15 +261,30 @@ def run_b200(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, max(args.warmup, 3)
 
-    # ---- this rank's shard: its own contiguous block of land points (no halo, no inter-GPU traffic in a step)
-    nland = args.nland
+    # ---- this rank's shard: a contiguous block of land points (no halo, no inter-GPU traffic in a step)
+    from cable_b200.partition import array_partition, land_to_tile_range
+    from cable_b200.sharding import shard_grid, gather_land_blocks
     cfg = lib.default_cfg()
     cfg.n_forcing_slots = RING
     cfg.output_level = 1
-    grid = synth.make_grid(nland, NAP, seed=synth.SEED + rank)
-    tiles = synth.make_tiles(grid, cfg)
+    strong = args.scaling == "strong"
+    if strong:
+        # ONE grid (seed = SEED) cut by the reference's decomposition rule; every rank generates the whole synthetic grid
+        # and forcing on its host (cheap) and keeps its block -- the master's scatter is outside the timed region anyway
+        full = synth.make_grid(args.nland, NAP, seed=synth.SEED)
+        tiles_full = synth.make_tiles(full, cfg)
+        l0, nland = array_partition(full.nland, world, rank)
+        t0_, t1_ = land_to_tile_range(full.cstart, full.cend, l0, nland)
+        grid, tiles = shard_grid(full, tiles_full, rank, world)
+        nland_total, mp_total = full.nland, full.mp
+    else:
+        full = synth.make_grid(args.nland, NAP, seed=synth.SEED + rank)
+        tiles_full = synth.make_tiles(full, cfg)
+        l0, nland, t0_, t1_ = 0, full.nland, 0, full.mp
+        grid, tiles = full, tiles_full
+        nland_total, mp_total = full.nland * world, full.mp * world
     mp = grid.mp
-    forcing = synth.Forcing(grid, tiles, DELS, start_doy=172)
+    forcing = synth.Forcing(full, tiles_full, DELS, start_doy=172)      # generated on the whole grid, sliced per rank
 
     # pinned host buffers for everything that moves per step (forcing ring, state, STAR diagnostics)
     def pinned_like(a):
@@ -251,11 +299,15 @@ def run_b200(args) -> None:
             t = pinned_like(tiles[f.name]); keep.append(t); tiles[f.name] = t.numpy()
     fsets = []
     for k in range(RING):
-        forcing.fill(tiles, k)
+        forcing.fill(tiles_full, k)
         s = {}
         for n in synth.FORCING_FIELDS:
-            t = pinned_like(tiles[n]); keep.append(t); s[n] = t.numpy()
+            t = pinned_like(np.ascontiguousarray(tiles_full[n][:, t0_:t1_])); keep.append(t); s[n] = t.numpy()
         fsets.append(s)
+    for n in synth.FORCING_FIELDS:
+        tiles[n] = fsets[0][n].copy()
+    if strong:
+        del tiles_full
     state0 = {f.name: tiles[f.name].copy() for f in FIELDS if f.role == ROLE["STATE"]}
 
     h = CableB200(mp, cfg, device=local)
@@ -291,6 +343,9 @@ def run_b200(args) -> None:
             h.grid_reduce(n, 0, d_pf.data_ptr(), d_cs.data_ptr(), d_ce.data_ptr(), nland, d_out[j].data_ptr())
         h.sync()
         if world > 1:
+            if strong:       # uneven land-point blocks (sizes differ by <= 1) -> [ndiag, nland_total] on rank 0
+                g = gather_land_blocks(d_out, nland_total, dst=0)
+                return [g] if rank == 0 else None
             bufs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
             dist.gather(d_out, bufs, dst=0)
             return bufs
@@ -306,20 +361,33 @@ def run_b200(args) -> None:
     sampler = ClockSampler(local); sampler.start()
     time.sleep(0.25)
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Timing rule: inputs larger than L2, or L2 flushed between timed iterations.  A rank's resident working set
+    # (parameters + state + diagnostics + the 8-slot forcing ring ~ 1.7 KB per tile) exceeds the 126 MB L2 only for
+    # shards above ~150 k tiles; below 2 x L2 every timed step is preceded by a 256 MB memset and the steps are timed
+    # one by one with the library's CUDA events on its compute stream (the flush is outside the events), summed.
+    ws_bytes = mp * 1700
+    flush = ws_bytes < 2 * 126e6 and not args.no_flush
+    fl = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if flush else None
     t0 = time.perf_counter()
     for k in range(W, W + K):
+        if flush:
+            h.sync(); fl.zero_(); torch.cuda.synchronize()
         h.step(k + 1, DELS, k % RING)
+    h.sync()
+    tg0 = time.perf_counter()
     gathered = gather_diags()
     barrier()
-    t_res = time.perf_counter() - t0
+    t_gather = time.perf_counter() - tg0
+    t_wall = time.perf_counter() - t0
     clocks = sampler.stop()
     ctr = h.counters()
     h.profile(False)
-    t_res = max_over_ranks(t_res)
     kern_ms = ctr.kernel_ms / max(ctr.kernel_ms_count, 1)
+    # flushed: sum of the K event-timed steps + the gather; otherwise the wall clock between the two barriers
+    t_res = max_over_ranks(ctr.kernel_ms * 1e-3 + t_gather if flush else t_wall)
+    t_wall = max_over_ranks(t_wall)
     launches = int(ctr.kernel_launches)
-    value = world * mp * K / t_res
+    value = mp_total * K / t_res
     finite = bool(torch.isfinite(gathered[0]).all().item()) if rank == 0 else True
 
     # ---- (2) end-to-end through the C ABI with HOST buffers: the offline driver's time loop --------------------------
@@ -345,11 +413,11 @@ def run_b200(args) -> None:
     slices = []
     for k in range(RING):
         t = torch.empty((len(lib.MET_ROWS), nland), dtype=torch.float32, pin_memory=True)
-        forcing.land_slice(k, out=t.numpy()); keep.append(t); slices.append(t.numpy())
+        t.numpy()[...] = forcing.land_slice(k)[:, l0:l0 + nland]; keep.append(t); slices.append(t.numpy())
     rows = OUTPUT_ROWS
     h.output_plan(rows)
     outs = [torch.zeros((len(rows), nland), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    tiles["veg_vlai"][0] = forcing.lai(0)
+    tiles["veg_vlai"][0] = forcing.lai(0)[t0_:t1_]
     h.upload_lai()
     checksum = 0.0
 
@@ -375,7 +443,7 @@ def run_b200(args) -> None:
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     ce = h.counters()
-    e2e = world * mp * Ke / t_e2e
+    e2e = mp_total * Ke / t_e2e
     h2d_step, d2h_step = ce.h2d_bytes / Ke, ce.d2h_bytes / Ke
     e2e_launches = int(ce.kernel_launches)
     last = outs[(3 + Ke - 1) % 2].numpy()
@@ -398,7 +466,7 @@ def run_b200(args) -> None:
     barrier()
     t_mir = max_over_ranks(time.perf_counter() - t0)
     cm = h.counters()
-    mirror = {"value": world * mp * Km / t_mir, "unit": "tile-timesteps/s", "h2d_bytes_per_step": cm.h2d_bytes / Km,
+    mirror = {"value": mp_total * Km / t_mir, "unit": "tile-timesteps/s", "h2d_bytes_per_step": cm.h2d_bytes / Km,
               "d2h_bytes_per_step": cm.d2h_bytes / Km, "steps": Km,
               "api": "cable_b200_cbm, output_level=1: every prognostic + driver-visible array mirrored to the host each step"}
 
@@ -406,11 +474,12 @@ def run_b200(args) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        nland_w, nst = 2000, 160                        # ~10-20 s of CPU work per core
-        rate, tmax = cpu_oracle_rate(nland_w, nst, cores)
+        nst = max(8, min(160, int(15.0 * 3.0e6 / mp_total)))      # ~10-20 s of CPU work on the same grid
+        rate, tmax, tiles_step = cpu_oracle_rate(nland_total, nst, cores)
         cpu = {"value": rate, "unit": "tile-timesteps/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} workers x {nland_w} land points x {NAP} tiles x {nst} steps ({tmax:.1f} s), C++ restatement "
-                         "of the reference (not the Fortran binary), forcing in memory"}
+               "sample": f"the same {nland_total}-point grid ({tiles_step} tiles per step) split over {cores} workers by "
+                         f"master_decomp x {nst} steps ({tmax:.1f} s), C++ restatement of the reference (not the Fortran "
+                         "binary), forcing in memory"}
 
     if rank == 0:
         peak, which = measured_peak_hbm()
@@ -421,12 +490,19 @@ def run_b200(args) -> None:
             traffic = prof["traffic_bytes_per_step"]
         line = {
             "metric": "tile-timesteps/sec for cbm()", "value": value, "unit": "tile-timesteps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": t_res / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": t_res / K * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": f"global 0.5deg GSWP3-shape synthetic forcing: {nland} land points x {NAP} tiles "
-                                   f"= {mp} tiles per GPU, dels={int(DELS)}s, leuning/standard/HDM/icycle=0 (cable.nml)",
-                       "tiles_per_gpu": mp, "global_tiles": mp * world, "parallelism": f"land-point blocks x{world}",
-                       "l2": "per-step working set (state+params+forcing ~ 0.2 GB) exceeds the 126 MB L2; no flush needed",
+            "config": {"workload": workload_text(nland_total, mp_total) if strong else
+                                   f"weak scaling: every GPU its own grid of {nland} land points x {NAP} tiles = {mp} tiles, "
+                                   f"dels={int(DELS)}s, leuning/standard/HDM/icycle=0 (cable.nml)",
+                       "tiles_per_gpu": mp, "global_tiles": mp_total, "land_points_per_gpu": nland,
+                       "parallelism": f"contiguous land-point blocks x{world} (master_decomp rule, cable_mpimaster.F90:1428-1463)",
+                              "l2": (f"resident set of a rank ~ {ws_bytes / 1e6:.0f} MB (1.7 KB/tile incl. the 8-slot forcing ring) "
+                              + ("< 2 x the 126 MB L2: L2 flushed (256 MB memset) before every timed step, steps timed one by "
+                                 "one with CUDA events on the library's compute stream and summed (+ the gather)"
+                                 if flush else "> 2 x the 126 MB L2: inputs larger than L2, no flush; wall clock between barriers")),
+                       "timing": "events+flush" if flush else "wall",
+                       "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
                        "forcing_ring_steps": RING, "outputs_finite": finite},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel_ms": kern_ms,
@@ -438,6 +514,7 @@ def run_b200(args) -> None:
                                    "timed with CUDA events on the library's streams",
                          "ncu": prof,
                          "pipe": pipe_roof(prof, value / world, clocks),
+                         "issue": issue_roof(prof, mp, kern_ms, clocks),
                          "note": "instruction-issue / latency-bound step (fp64 islands, ~300 correctly rounded transcendentals "
                                  "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 48 %, FP64 pipe 21-25 %, "
                                  "DRAM 5-23 % in the ncu capture; the HBM fraction is reported because it is the official "
@@ -468,7 +545,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nland", type=int, default=NLAND_PER_GPU, help="land points per GPU")
+    ap.add_argument("--nland", type=int, default=NLAND, help="land points of the grid (strong) / per GPU (weak); "
+                    "62000 = BASELINE configs[2], 250000 = configs[3]")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-flush", action="store_true", help="small shards: do not flush L2 between timed steps")
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

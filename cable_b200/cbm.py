@@ -104,6 +104,16 @@ class CableB200:
     def sync(self) -> None:
         _lib.check(self._lib.cable_b200_sync(self._h))
 
+    def mark_dirty(self, *names: str) -> None:
+        """The host wrote these resident (PARAM / STATE) arrays: the next step uploads them first."""
+        for n in names:
+            _lib.check(self._lib.cable_b200_mark_dirty(self._h, BY_NAME[n].id))
+
+    def set_output_mask(self, names) -> None:
+        """Restrict what cbm() mirrors to the host every step to these fields (empty: the output_level default)."""
+        ids = np.asarray([BY_NAME[n].id for n in names], np.int32)
+        _lib.check(self._lib.cable_b200_set_output_mask(self._h, ids.ctypes.data if ids.size else None, int(ids.size)))
+
     # -- device access / measurement ----------------------------------------------------------
     def device_ptr(self, name: str, slot: int = 0) -> int:
         p = self._lib.cable_b200_device_ptr(self._h, BY_NAME[name].id, slot)

@@ -20,9 +20,8 @@
 using namespace cbl;
 
 // cable_fast.cu: kernel A compiled with CBL_FASTDIV=1 in its own namespace (own copy of the constant-memory config)
-int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, int mp, int i0, int i1, float dels, int first, unsigned long long *warn,
-                  int *redo, int big, int lvl, int max_l1, cudaStream_t st);
-int cblf_set_cfg(const void *cfg, size_t bytes, cudaStream_t st);
+int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, const void *cfg, size_t cfg_bytes, int mp, int i0, int i1, float dels,
+                  int first, unsigned long long *warn, int *redo, int big, int lvl, int max_l1, cudaStream_t st);
 void cblf_debug_dump();
 
 // scratch rows / shared memory of kernel A's dryLeaf pass pool (0 when the pool is compiled out)
@@ -56,7 +55,6 @@ constexpr size_t pool_smem_bytes(int) { return 0; }
 namespace {
 
 thread_local std::string g_err;
-const void *g_cfg_owner = nullptr;    // which handle's DevCfg currently sits in __constant__ c_cfg
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #define CUDA_TRY(expr)                                                                          \
   do { cudaError_t e_ = (expr);                                                                 \
@@ -110,6 +108,11 @@ struct cable_handle {
   size_t off[NFIELDS]{};             // arena offset of each field (forcing: offset inside a slot)
   size_t bytes[NFIELDS]{};
   size_t forcing_slot_bytes = 0, forcing_base = 0;
+  size_t off_tvair_in = 0, off_oldcansto_in = 0;   // per-slot copies of the two inputs that are not FORCING rows
+  bool dirty[NFIELDS]{};             // cable_b200_mark_dirty: host-side writes to resident fields, uploaded by the next cbm()
+  bool any_dirty = false;
+  bool out_mask_on = false;          // cable_b200_set_output_mask: what cable_b200_cbm() mirrors to the host each step
+  bool out_mask[NFIELDS]{};
   int nslots = 2;
   void *host[NFIELDS]{};
   bool host_pinned[NFIELDS]{};
@@ -160,9 +163,13 @@ namespace {
 
 void driver_free(cable_handle *h);      // driver stages, end of this file
 
+// what the caller sets before every CALL cbm: the FORCING rows, met%tvair/tvrad when the caller's values are to be
+// honoured (met_tv_is_tk = 0), and canopy%oldcansto when the caller keeps its own `oldcansto = cansto` statement
+// (caller_duties = 0, cable_serial.F90:573)
 bool is_forcing_input(const cable_handle *h, int id) {
   const cable_field_info &f = g_fields[id];
   if (id == FID_met_tvair || id == FID_met_tvrad) return !h->cfg.met_tv_is_tk;
+  if (id == FID_canopy_oldcansto) return !h->cfg.caller_duties;
   return f.role == FORCING && !(f.flags & CABLE_FLAG_HOSTONLY);
 }
 
@@ -173,12 +180,22 @@ void *dev_ptr(const cable_handle *h, int id, int slot) {
   return h->arena + h->off[id];
 }
 
+// where a per-step input lands on the device: its forcing-slot block, or the slot's side copy for the two inputs
+// whose registry row is a resident (slot-independent) field
+void *dev_in_ptr(const cable_handle *h, int id, int slot) {
+  char *slot_base = h->arena + h->forcing_base + (size_t)slot * h->forcing_slot_bytes;
+  if (id == FID_met_tvair) return slot_base + h->off_tvair_in;
+  if (id == FID_canopy_oldcansto) return slot_base + h->off_oldcansto_in;
+  return dev_ptr(h, id, slot);
+}
+
 DevPtrs make_ptrs(const cable_handle *h, int slot) {
   DevPtrs d;
   int id = 0;
 #define CABLE_FA(T, m, ct, n1, n2, role, flags) d.T##_##m = (ct *)dev_ptr(h, id, slot); id++;
 #include "../../include/cable_b200_fields.def"
-  // met%tvair doubles as an opt-in input: when uploaded it lives in its DIAG block (slot independent)
+  d.met_tvair_in = (const float *)dev_in_ptr(h, FID_met_tvair, slot);
+  d.canopy_oldcansto_in = (const float *)dev_in_ptr(h, FID_canopy_oldcansto, slot);
   d.leaf_scr_d = h->leaf_scr_d; d.leaf_scr_f = h->leaf_scr_f;
   d.tile_order = nullptr;                          // set per launch (launch_range)
   return d;
@@ -187,7 +204,7 @@ DevPtrs make_ptrs(const cable_handle *h, int slot) {
 // copy tiles [i0, i1) of one field: every component is a contiguous run, the components are mp elements apart
 int copy_field_range(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s, int i0, int i1) {
   if (!h->host[id] || i1 <= i0) return CABLE_OK;
-  char *dp = (char *)dev_ptr(h, id, slot);
+  char *dp = (char *)(to_device && slot >= 0 ? dev_in_ptr(h, id, slot) : dev_ptr(h, id, slot < 0 ? 0 : slot));
   if (!dp) return CABLE_OK;
   const cable_field_info &f = g_fields[id];
   const size_t es = elem_size(f.dtype), pitch = (size_t)h->mp * es, width = (size_t)(i1 - i0) * es, rows = (size_t)f.n1 * f.n2;
@@ -200,7 +217,7 @@ int copy_field_range(cable_handle *h, int id, int slot, bool to_device, cudaStre
 
 int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s) {
   if (!h->host[id]) return CABLE_OK;
-  void *dp = dev_ptr(h, id, slot);
+  void *dp = to_device && slot >= 0 ? dev_in_ptr(h, id, slot) : dev_ptr(h, id, slot < 0 ? 0 : slot);
   if (!dp) return CABLE_OK;
   if (to_device) { CUDA_TRY(cudaMemcpyAsync(dp, h->host[id], h->bytes[id], cudaMemcpyHostToDevice, s)); h->ctr.h2d_bytes += (long long)h->bytes[id]; }
   else { CUDA_TRY(cudaMemcpyAsync(h->host[id], dp, h->bytes[id], cudaMemcpyDeviceToHost, s)); h->ctr.d2h_bytes += (long long)h->bytes[id]; }
@@ -219,16 +236,17 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
 #define CBL_LAUNCH_X(PH, BL, MB, LV, XS) {                                                                                     \
     const size_t sm_ = ((PH) & 1) ? pool_smem_bytes(BL) : 0;                                                                 \
     {                                                                                                                          \
-      static bool once_ = false;   /* per instantiation */                                                                    \
-      if (!once_) {                                                                                                            \
+      static bool once_[64] = {};   /* per instantiation and device */                                                        \
+      const int dv_ = h->device & 63;                                                                                          \
+      if (!once_[dv_]) {                                                                                                       \
         if (sm_ > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
         /* no shared memory in the default build: give the whole unified array to L1, which holds the spill slots */          \
         if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); \
         cudaGetLastError();                                                                                                    \
-        once_ = true;                                                                                                          \
+        once_[dv_] = true;                                                                                                     \
       }                                                                                                                        \
     }                                                                                                                          \
-    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->mp, i0, i1, dels, first, h->d_warn, redo_); }
+    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->dcfg, h->mp, i0, i1, dels, first, h->d_warn, redo_); }
 #define CBL_LAUNCH(PH, BL, MB, LV) CBL_LAUNCH_X(PH, BL, MB, LV, 0)
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
   switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
@@ -250,8 +268,9 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
     const bool big = i1 - i0 >= h->sms * CBL_BLOCK_A;
     if (h->fastdiv) {
       const int bl = big ? CBL_BLOCK_A : 256, nblk = (i1 - i0 + bl - 1) / bl;
+      if (i0 % 256) return fail(CABLE_E_ARG, "launch_range: range start must be a multiple of 256 (redo-flag slices)");
       redo_ = h->d_redo + (size_t)(i0 / 256);              // disjoint slices for ranges launched concurrently
-      const int rc = cblf_launch_A(&d, sizeof(d), h->mp, i0, i1, dels, first, h->d_warn, redo_, big ? 1 : 0, h->cfg.output_level, h->max_l1, st);
+      const int rc = cblf_launch_A(&d, sizeof(d), &h->dcfg, sizeof(h->dcfg), h->mp, i0, i1, dels, first, h->d_warn, redo_, big ? 1 : 0, h->cfg.output_level, h->max_l1, st);
       if (rc) return fail(CABLE_E_CUDA, std::string("fast kernel A launch: ") + cudaGetErrorString((cudaError_t)rc));
       if (getenv("CABLE_B200_FASTDIV_DEBUG")) {             // debugging aid: how many blocks the fast build handed back
         std::vector<int> fl(nblk);
@@ -285,6 +304,7 @@ bool wanted_output(const cable_handle *h, int id) {
   const cable_field_info &f = g_fields[id];
   if (f.flags & CABLE_FLAG_HOSTONLY) return false;
   const int lvl = h->cfg.output_level;
+  if (h->out_mask_on) return h->out_mask[id];
   if (lvl < 1) return false;
   return (f.role == STATE) || (f.role == DIAG && (lvl >= 2 || (f.flags & CABLE_FLAG_STAR)));
 }
@@ -316,6 +336,18 @@ int check_spreads(cable_handle *h) {
         if (v[(size_t)i + (size_t)mp * k] != (double)h->cfg.zse[k]) return fail(CABLE_E_PARAM, "soil_zse_vec is not SPREAD(soil%zse)");
   if (const double *v = (const double *)h->host[FID_canopy_fes_cor])
     for (int i = 0; i < mp; i++) if (v[i] != 0.0) return fail(CABLE_E_PARAM, "canopy_fes_cor must be 0 offline (cable_serial.F90:440)");
+  return CABLE_OK;
+}
+
+// host-side writes to resident fields announced with cable_b200_mark_dirty go up before the next step reads them
+int flush_dirty(cable_handle *h) {
+  if (!h->any_dirty) return CABLE_OK;
+  for (int id = 0; id < NFIELDS; id++) {
+    if (!h->dirty[id]) continue;
+    int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc;
+    h->dirty[id] = false;
+  }
+  h->any_dirty = false;
   return CABLE_OK;
 }
 
@@ -441,6 +473,8 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
     if (f.role != FORCING || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
     h->off[id] = fcur; fcur = align_up(fcur + h->bytes[id], 256);
   }
+  h->off_tvair_in = fcur; fcur = align_up(fcur + (size_t)mp * sizeof(float), 256);
+  h->off_oldcansto_in = fcur; fcur = align_up(fcur + (size_t)mp * sizeof(float), 256);
   h->forcing_slot_bytes = fcur;
   h->arena_bytes = cur + fcur * (size_t)h->nslots;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
@@ -477,9 +511,11 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   }
   if (const char *e = getenv("CABLE_B200_CHUNKS")) {        // explicit override: equal chunks
     h->nchunks = atoi(e) > 0 ? atoi(e) : 1;
-    h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + 127) / 128 * 128;
+    h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + CBL_ORDER_WINDOW - 1) / CBL_ORDER_WINDOW * CBL_ORDER_WINDOW;
   }
-  if (h->nchunks > 64) { h->nchunks = 64; h->chunk_tiles = ((mp + 63) / 64 + 127) / 128 * 128; }
+  if (h->nchunks > 64) { h->nchunks = 64; h->chunk_tiles = ((mp + 63) / 64 + CBL_ORDER_WINDOW - 1) / CBL_ORDER_WINDOW * CBL_ORDER_WINDOW; }
+  // chunk edges are multiples of 768 = 3 x 256: two concurrently launched ranges never share a 256-tile redo-flag entry
+  // (launch_range checks it)
   if (const char *e = getenv("CABLE_B200_GRAPH")) h->use_graph = atoi(e);
   if (const char *e = getenv("CABLE_B200_TRACE")) { h->trace = atoi(e); if (h->trace) h->use_graph = 0; }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -495,11 +531,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
     cudaEventCreateWithFlags(&h->ev_forcing_ready[s], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_slot_free[s], cudaEventDisableTiming);
   }
-  e = cudaMemcpyToSymbol(c_cfg, &h->dcfg, sizeof(DevCfg));
-  if (e == cudaSuccess) e = (cudaError_t)cblf_set_cfg(&h->dcfg, sizeof(DevCfg), nullptr);
-  if (e != cudaSuccess) { cable_b200_destroy(h); return fail(CABLE_E_CUDA, std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(e)); }
   CUDA_TRY(cudaDeviceSynchronize());
-  g_cfg_owner = h;
   *out = h;
   return CABLE_OK;
 }
@@ -508,7 +540,6 @@ int cable_b200_destroy(cable_handle *h) {
   if (!h) return CABLE_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  if (g_cfg_owner == h) g_cfg_owner = nullptr;
   for (int id = 0; id < NFIELDS; id++) if (h->host_pinned[id]) cudaHostUnregister(h->host[id]);
   for (auto ev : h->ev_forcing_ready) cudaEventDestroy(ev);
   for (auto ev : h->ev_slot_free) cudaEventDestroy(ev);
@@ -588,16 +619,16 @@ int cable_b200_upload(cable_handle *h, unsigned role_mask) {
     if (!(f.role & role_mask) || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
     if (f.role == FORCING) continue;                       // forcing goes through set_forcing_async
     if (f.role == PARAM && (f.flags & CABLE_FLAG_OPTIN) && !optin_param_needed(h, id)) {
-      if (h->host[id]) { int rc = copy_field(h, id, 0, true, h->s_compute); if (rc) return rc; }
+      if (h->host[id]) { int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc; }
       continue;
     }
     if ((f.role & (PARAM | STATE)) && !h->host[id])
       return fail(CABLE_E_UNBOUND, std::string("field not bound: ") + f.name);
-    int rc = copy_field(h, id, 0, true, h->s_compute); if (rc) return rc;
+    int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc;
   }
   if ((role_mask & STATE) && h->cfg.l_new_roughness_soil) {     // canopy%us feeds the next ruff_resist (cable_roughness.F90:197)
     if (!h->host[FID_canopy_us]) return fail(CABLE_E_UNBOUND, "field not bound: canopy_us (l_new_roughness_soil)");
-    int rc = copy_field(h, FID_canopy_us, 0, true, h->s_compute); if (rc) return rc;
+    int rc = copy_field(h, FID_canopy_us, -1, true, h->s_compute); if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
   if (role_mask & PARAM) { int rc = build_tile_order(h); if (rc) return rc; }
@@ -614,6 +645,42 @@ int cable_b200_download(cable_handle *h, unsigned role_mask, unsigned flag_mask)
     int rc = copy_field(h, id, 0, false, h->s_compute); if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
+int cable_b200_mark_dirty(cable_handle *h, int id) {
+  if (!h || id < 0 || id >= NFIELDS) return fail(CABLE_E_ARG, "mark_dirty: bad handle or id");
+  const cable_field_info &f = g_fields[id];
+  if ((f.flags & CABLE_FLAG_HOSTONLY) || f.role == FORCING || f.role == DIAG)
+    return fail(CABLE_E_ARG, std::string("mark_dirty: not a resident PARAM/STATE field: ") + f.name);
+  if (!h->host[id]) return fail(CABLE_E_UNBOUND, std::string("field not bound: ") + f.name);
+  h->dirty[id] = true; h->any_dirty = true;
+  return CABLE_OK;
+}
+
+int cable_b200_set_output_mask(cable_handle *h, const int *field_ids, int n) {
+  if (!h || n < 0 || (n > 0 && !field_ids)) return fail(CABLE_E_ARG, "set_output_mask: bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  bool m[NFIELDS] = {};
+  for (int k = 0; k < n; k++) {
+    const int id = field_ids[k];
+    if (id < 0 || id >= NFIELDS) return fail(CABLE_E_ARG, "set_output_mask: unknown field id");
+    const cable_field_info &f = g_fields[id];
+    if ((f.flags & CABLE_FLAG_HOSTONLY) || f.role == FORCING || f.role == PARAM)
+      return fail(CABLE_E_ARG, std::string("set_output_mask: not an output of cbm: ") + f.name);
+    if (f.role == DIAG && !(f.flags & CABLE_FLAG_STAR) && h->cfg.output_level < 2)
+      return fail(CABLE_E_ARG, std::string("set_output_mask: ") + f.name + " is only written at output_level 2");
+    if (f.role == DIAG && h->cfg.output_level < 1)
+      return fail(CABLE_E_ARG, std::string("set_output_mask: ") + f.name + " needs output_level >= 1");
+    if (!h->host[id]) return fail(CABLE_E_UNBOUND, std::string("field not bound: ") + f.name);
+    m[id] = true;
+  }
+  h->out_mask_on = n > 0;
+  memcpy(h->out_mask, m, sizeof(m));
+  // the captured drop-in pipelines copy the previous selection
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+  h->graphs.clear();
   return CABLE_OK;
 }
 
@@ -638,11 +705,7 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
   if (!(dels > 0.f)) return fail(CABLE_E_ARG, "step: dels must be > 0");
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->slot_has_data[slot]) CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_forcing_ready[slot], 0));
-  if (g_cfg_owner != h) {      // several handles (e.g. differing switches) may share the device
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->s_compute));
-    CUDA_TRY((cudaError_t)cblf_set_cfg(&h->dcfg, sizeof(DevCfg), h->s_compute));
-    g_cfg_owner = h;
-  }
+  { int rc = flush_dirty(h); if (rc) return rc; }
   const DevPtrs d = make_ptrs(h, slot);
   const int first = (h->soil_snow_calls == 0) ? 1 : 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -746,15 +809,11 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
   const int slot = (int)(h->ctr.steps % h->nslots);
   for (int id = 0; id < NFIELDS; id++)
     if (is_forcing_input(h, id) && !h->host[id]) return fail(CABLE_E_UNBOUND, std::string("forcing field not bound: ") + g_fields[id].name);
-  if (g_cfg_owner != h) {
-    CUDA_TRY(cudaMemcpyToSymbolAsync(c_cfg, &h->dcfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, h->s_compute));
-    CUDA_TRY((cudaError_t)cblf_set_cfg(&h->dcfg, sizeof(DevCfg), h->s_compute));
-    g_cfg_owner = h;
-  }
   const DevPtrs d = make_ptrs(h, slot);
   const int first = (h->soil_snow_calls == 0) ? 1 : 0;
   // a previous asynchronous user of this slot (set_forcing_async/step) must have drained
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
+  { int rc = flush_dirty(h); if (rc) return rc; }
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
   const long long launches0 = h->ctr.kernel_launches, h2d0 = h->ctr.h2d_bytes, d2h0 = h->ctr.d2h_bytes;
   if (h->use_graph && !first) {
@@ -1022,6 +1081,8 @@ int cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels, int 
   post_step_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(p, h->drv.arr, h->mp, ktau, kstart, dels, do_mass_bal, do_energy_bal);
   CUDA_TRY(cudaGetLastError());
   h->ctr.kernel_launches++;
+  // this kernel is the slot's last reader (met%precip/fsd/fld): a prefetch into the slot must wait for it, not only for the step
+  CUDA_TRY(cudaEventRecord(h->ev_slot_free[h->last_slot], h->s_compute));
   return CABLE_OK;
 }
 

@@ -3,8 +3,8 @@
 // Same sources as the ordinary build (cbm_kernel.cuh and everything it includes); the only difference is how
 // dv() / f_sqrt() / d_sqrt() / x**0.25 are expanded (cbm_consts.cuh, CBL_FASTDIV): the IEEE fast-path FMA chains run
 // straight-line, operands outside a conservative exponent window raise a per-block flag, and flagged blocks are left to
-// the ordinary kernel.  The whole namespace is renamed so that both builds live in one library, each with its own copy
-// of the constant-memory configuration.
+// the ordinary kernel.  The whole namespace is renamed so that both builds live in one library, the configuration
+// travels with each launch as a kernel parameter.
 #define CBL_FASTDIV 1
 #define cbl cblf
 #include <cstdio>
@@ -19,35 +19,32 @@ using namespace cblf;
 #define CBL_BLOCK_A 768
 #endif
 
-int cblf_set_cfg(const void *cfg, size_t bytes, cudaStream_t st) {
-  if (bytes != sizeof(DevCfg)) return (int)cudaErrorInvalidValue;
-  return (int)(st ? cudaMemcpyToSymbolAsync(c_cfg, cfg, sizeof(DevCfg), 0, cudaMemcpyHostToDevice, st)
-                  : cudaMemcpyToSymbol(c_cfg, cfg, sizeof(DevCfg)));
-}
-
 template <int BL, int MB, int LV>
-static int launch(const DevPtrs &d, int mp, int i0, int i1, float dels, int first, unsigned long long *warn, int *redo, int max_l1,
-                  cudaStream_t st) {
-  static bool once = false;
-  if (!once) {
+static int launch(const DevPtrs &d, const DevCfg &c, int mp, int i0, int i1, float dels, int first, unsigned long long *warn,
+                  int *redo, int max_l1, cudaStream_t st) {
+  static bool once[64] = {};             // function attributes are per device
+  int dev = 0; cudaGetDevice(&dev); dev &= 63;
+  if (!once[dev]) {
     if (max_l1) cudaFuncSetAttribute(cbm_kernel<1, BL, MB, LV, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaGetLastError();
-    once = true;
+    once[dev] = true;
   }
-  cbm_kernel<1, BL, MB, LV, 0><<<(i1 - i0 + BL - 1) / BL, BL, 0, st>>>(d, mp, i0, i1, dels, first, warn, redo);
+  cbm_kernel<1, BL, MB, LV, 0><<<(i1 - i0 + BL - 1) / BL, BL, 0, st>>>(d, c, mp, i0, i1, dels, first, warn, redo);
   return (int)cudaGetLastError();
 }
 
-int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, int mp, int i0, int i1, float dels, int first, unsigned long long *warn,
-                  int *redo, int big, int lvl, int max_l1, cudaStream_t st) {
-  if (devptrs_bytes != sizeof(DevPtrs)) return (int)cudaErrorInvalidValue;
+int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, const void *cfg, size_t cfg_bytes, int mp, int i0, int i1, float dels,
+                  int first, unsigned long long *warn, int *redo, int big, int lvl, int max_l1, cudaStream_t st) {
+  if (devptrs_bytes != sizeof(DevPtrs) || cfg_bytes != sizeof(DevCfg)) return (int)cudaErrorInvalidValue;
   DevPtrs d;
   memcpy(&d, devptrs, sizeof(d));
+  DevCfg c;
+  memcpy(&c, cfg, sizeof(c));
   d.tile_order = nullptr;
 #define CBLF_LVL(BL, MB)                                                                           \
-  switch (lvl) { case 0: return launch<BL, MB, 0>(d, mp, i0, i1, dels, first, warn, redo, max_l1, st); \
-                 case 1: return launch<BL, MB, 1>(d, mp, i0, i1, dels, first, warn, redo, max_l1, st); \
-                 default: return launch<BL, MB, 2>(d, mp, i0, i1, dels, first, warn, redo, max_l1, st); }
+  switch (lvl) { case 0: return launch<BL, MB, 0>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); \
+                 case 1: return launch<BL, MB, 1>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); \
+                 default: return launch<BL, MB, 2>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); }
   if (big) { CBLF_LVL(CBL_BLOCK_A, CBL_MINB_A) }
   CBLF_LVL(256, 3)
 #undef CBLF_LVL

@@ -14,8 +14,6 @@
 
 namespace cbl {
 
-__constant__ DevCfg c_cfg;
-
 #define CBL_ROLE_FORCING CABLE_ROLE_FORCING
 #define CBL_ROLE_PARAM   CABLE_ROLE_PARAM
 #define CBL_ROLE_STATE   CABLE_ROLE_STATE
@@ -68,8 +66,11 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
 // unchanged by their existence.
 template <int PHASE, int BLOCK, int MINB, int LVL, int XSW>
 __global__ void __launch_bounds__(BLOCK, MINB)
-cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const float dels, const int first_call,
-           unsigned long long *warn_counter, int *redo) {
+cbm_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ DevCfg c, const int mp, const int i0, const int i1,
+           const float dels, const int first_call, unsigned long long *warn_counter, int *redo) {
+  // `c` (every module-scope input of the reference cbm, cbm_types.cuh) travels as a kernel parameter: it sits in the
+  // constant bank like a __constant__ symbol would, but belongs to the launch, so handles with different switches can
+  // share a device and overlap on their own streams.
   // `redo` (one int per block of this launch geometry, or null): the CBL_FASTDIV build of kernel A (cable_fast.cu) writes 1
   // for a block in which some division / square root met an operand outside the fast path's window and stores nothing for
   // that block; the ordinary build, launched right after with the same geometry and the same array, computes exactly
@@ -88,7 +89,6 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
   // vegetation (1-20 dryLeaf passes), and a static even split of the range over the SMs measured 35 % slower.
   // A thread past the end of the range shadows the last tile (its stores are suppressed) instead of leaving:
   // kernel A's block-wide phase barriers (define_canopy) need every thread of the block.
-  const DevCfg &c = c_cfg;
   const size_t smp = (size_t)mp;
   const int i_raw = i0 + blockIdx.x * BLOCK + threadIdx.x;
   const bool valid = i_raw < i1;
@@ -113,9 +113,10 @@ cbm_kernel(const DevPtrs d, const int mp, const int i0, const int i1, const floa
   if (PHASE & 1) {
     // opt-in inputs
     if (c.met_tv_is_tk) { t.met_tvair = t.met_tk; t.met_tvrad = t.met_tk; }     // cable_input.F90:2679-2680
-    else { t.met_tvair = d.met_tvair[i]; t.met_tvrad = d.met_tvrad[i]; }
+    else { t.met_tvair = d.met_tvair_in[i]; t.met_tvrad = d.met_tvrad[i]; }
     if (c.ssnow_potev == CABLE_POTEV_PM) t.canopy_ga = d.canopy_ga[i];           // cable_canopy.F90:487
     if (c.caller_duties) t.canopy_oldcansto = t.canopy_cansto;                   // cable_serial.F90:573
+    else t.canopy_oldcansto = d.canopy_oldcansto_in[i];                          // the caller's own statement, this step's value
     if (XSW && c.litter) t.veg_clitt = d.veg_clitt[i];                           // cable_canopy.F90:472
     if (XSW && c.call_climate) t.climate_qtemp_max_last_year = d.climate_qtemp_max_last_year[i];   // cbl_dryLeaf.F90:349
     if (XSW && c.l_new_roughness_soil) t.canopy_us = d.canopy_us[i];             // cable_roughness.F90:197: last step's us

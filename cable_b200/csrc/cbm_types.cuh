@@ -31,6 +31,11 @@ struct DevPtrs {
   // kernel A only: thread -> tile map, a permutation inside every aligned window of CBL_ORDER_WINDOW tiles that puts
   // tiles of one vegetation type side by side (null: identity).  See cable_capi.cu build_tile_order().
   const int *__restrict__ tile_order;
+  // per-slot copies of the two inputs that are not FORCING rows: met%tvair as set by the caller (met_tv_is_tk = 0) and
+  // canopy%oldcansto as set by the caller (caller_duties = 0, cable_serial.F90:573).  They ride in the forcing slot so a
+  // prefetched step never overwrites what a running step still reads.
+  const float *__restrict__ met_tvair_in;
+  const float *__restrict__ canopy_oldcansto_in;
 };
 #define CBL_ORDER_WINDOW 768
 

@@ -7,8 +7,8 @@
 !!   1. on the first call creates a handle, binds every member array of the derived types with
 !!      C_LOC (the arrays are (mp[,k[,b]]) column-major = the library's SoA layout), uploads
 !!      parameters and prognostic state;
-!!   2. on every call runs cable_b200_cbm(handle, ktau, dels): forcing H2D, one fused step,
-!!      state + driver-visible diagnostics D2H, synchronise;
+!!   2. on every call runs cable_b200_cbm(handle, ktau, dels): forcing (+ the caller's canopy%oldcansto) H2D, one
+!!      fused step, state + driver-visible diagnostics D2H (or the cable_b200_set_output_mask selection), synchronise;
 !!   3. turns a non-zero status into the reference's own abort (src/offline/cable_abort.F90).
 !!
 !! NOTE: this image has no Fortran compiler (gfortran/flang/nvfortran/ifx all absent), so this shim
@@ -66,6 +66,17 @@ MODULE cable_cbm_module
        TYPE(C_PTR), VALUE :: handle
        INTEGER(C_INT), VALUE :: ktau
        REAL(C_FLOAT), VALUE :: dels
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION cable_b200_mark_dirty(handle, id) BIND(C, NAME="cable_b200_mark_dirty")
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: handle
+       INTEGER(C_INT), VALUE :: id
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION cable_b200_set_output_mask(handle, field_ids, n) BIND(C, NAME="cable_b200_set_output_mask")
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: handle
+       INTEGER(C_INT), INTENT(IN) :: field_ids(*)
+       INTEGER(C_INT), VALUE :: n
      END FUNCTION
      FUNCTION cable_b200_last_error() BIND(C, NAME="cable_b200_last_error")
        IMPORT :: C_PTR
@@ -125,13 +136,22 @@ CONTAINS
        cfg%max_ssdn = max_ssdn;  cfg%max_sconds = max_sconds;  cfg%frozen_limit = frozen_limit
        cfg%wiltParam = wiltParam;  cfg%satuParam = satuParam       ! cable_runtime_opts_mod.F90:6-7
        cfg%zse = soil%zse;  cfg%zshh = soil%zshh;  cfg%ratecp = bgc%ratecp;  cfg%ratecs = bgc%ratecs
-       cfg%caller_duties = 0        ! the Fortran driver keeps doing canopy%oldcansto = canopy%cansto itself
+       ! The Fortran driver keeps doing  canopy%oldcansto = canopy%cansto  itself (cable_serial.F90:573): with
+       ! caller_duties = 0 the library treats canopy%oldcansto as a per-step INPUT and uploads the bound array with the
+       ! forcing on every call (4 bytes per tile), so cable_canopy.F90:169 sees exactly what the reference would.
+       cfg%caller_duties = 0
        rc = cable_b200_create(INT(mp, C_INT), cfg, -1_C_INT, handle);  CALL check(rc)
        ! one bind per registry row (include/cable_b200_fields.def), generated by tools/gen_fortran_binds.py
 #include "cable_b200_binds.inc"
        rc = cable_b200_upload(handle, 2_C_INT);  CALL check(rc)     ! CABLE_ROLE_PARAM
        rc = cable_b200_upload(handle, 4_C_INT);  CALL check(rc)     ! CABLE_ROLE_STATE
     END IF
+    ! xk, c1, rhoch are explicit-shape dummies: a compiler may hand cbm a contiguous temporary whose address changes
+    ! from call to call, so (unlike the POINTER components of the derived types) they are re-bound on every call.
+    ! They are scratch of init_radiation, written back only at output_level = 2; re-binding is three table writes.
+    CALL bind('scr_xk', C_LOC(xk));  CALL bind('scr_c1', C_LOC(c1));  CALL bind('scr_rhoch', C_LOC(rhoch))
+    ! Any OTHER host-side write to a resident array between two calls (restart read, casa feedback into veg%vcmax, a
+    ! parameter perturbation ...) must be announced:  rc = cable_b200_mark_dirty(handle, cable_b200_field_id(name)).
     rc = cable_b200_cbm(handle, INT(ktau, C_INT), REAL(dels, C_FLOAT));  CALL check(rc)
 
   CONTAINS

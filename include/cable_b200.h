@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CABLE_B200_ABI_VERSION 2
+#define CABLE_B200_ABI_VERSION 3
 
 /* dims fixed by the reference (cable_define_types.F90:62-71) */
 #define CABLE_MS    6   /* soil layers            */
@@ -176,6 +176,18 @@ int          cable_b200_bind_field(cable_handle *h, int field_id, void *host);
 int          cable_b200_upload(cable_handle *h, unsigned role_mask);
 int          cable_b200_download(cable_handle *h, unsigned role_mask,
                                  unsigned flag_mask);
+
+/* A host-side write to a resident field (PARAM or STATE) between two steps -- a restart read, a parameter the
+ * driver changes mid-run, casa feedback into veg%vcmax ... -- is announced per field; the next cable_b200_cbm() /
+ * cable_b200_step() uploads the bound array before it runs.  (The reference cbm reads the host arrays every call;
+ * the device copy cannot see a write it is not told about.)                                                       */
+int          cable_b200_mark_dirty(cable_handle *h, int field_id);
+
+/* SURVEY.md 8b sync_outputs(handle, mask): restrict what cable_b200_cbm() mirrors back to the bound host arrays
+ * every step to these fields (STATE or DIAG; non-STAR DIAG fields need output_level 2).  n = 0 restores the
+ * default selection of cfg.output_level.  Prognostic state left out of the mask stays current on the device and
+ * comes back with cable_b200_download(h, CABLE_ROLE_STATE, 0) whenever the caller wants it (restart, end of run). */
+int          cable_b200_set_output_mask(cable_handle *h, const int *field_ids, int n);
 
 /* forcing: pack the bound FORCING arrays into pinned memory and start an
  * asynchronous H2D copy into ring slot `slot` on the side stream.            */

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/cable_b200.h but not exported"
     assert sorted(lib.EXPORTS) == declared
-    assert L.cable_b200_abi_version() == 2
+    assert L.cable_b200_abi_version() == 3
 
 
 def test_registry_matches_def_file():
