@@ -51,6 +51,15 @@ constexpr size_t pool_smem_bytes(int) { return 0; }
 #ifndef CBL_BLOCK_B
 #define CBL_BLOCK_B 128
 #endif
+// kernel A's geometry for ranges that do not fill the chip with 768-thread blocks (a shard of a strong-scaling run, a
+// pipeline chunk, the remainder chain): such a launch is bound by the latency of one warp's dependent chain, not by
+// issue slots, so it gets small blocks and a high register cap (no spill traffic on the chain)
+#ifndef CBL_SMALL_BLOCK
+#define CBL_SMALL_BLOCK 128
+#endif
+#ifndef CBL_SMALL_MINB
+#define CBL_SMALL_MINB 3
+#endif
 
 namespace {
 
@@ -267,9 +276,9 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
     // scaffolding); the ordinary build that follows only computes the blocks that build flagged (normally none)
     const bool big = i1 - i0 >= h->sms * CBL_BLOCK_A;
     if (h->fastdiv) {
-      const int bl = big ? CBL_BLOCK_A : 256, nblk = (i1 - i0 + bl - 1) / bl;
+      const int bl = big ? CBL_BLOCK_A : CBL_SMALL_BLOCK, nblk = (i1 - i0 + bl - 1) / bl;
       if (i0 % 256) return fail(CABLE_E_ARG, "launch_range: range start must be a multiple of 256 (redo-flag slices)");
-      redo_ = h->d_redo + (size_t)(i0 / 256);              // disjoint slices for ranges launched concurrently
+      redo_ = h->d_redo + (size_t)(i0 / 64);               // one entry per block (>= 64 threads): disjoint slices for ranges launched concurrently
       const int rc = cblf_launch_A(&d, sizeof(d), &h->dcfg, sizeof(h->dcfg), h->mp, i0, i1, dels, first, h->d_warn, redo_, big ? 1 : 0, h->cfg.output_level, h->max_l1, st);
       if (rc) return fail(CABLE_E_CUDA, std::string("fast kernel A launch: ") + cudaGetErrorString((cudaError_t)rc));
       if (getenv("CABLE_B200_FASTDIV_DEBUG")) {             // debugging aid: how many blocks the fast build handed back
@@ -283,7 +292,7 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
       h->ctr.kernel_launches++;
     }
     if (big) { CBL_DISPATCH(1, CBL_BLOCK_A, CBL_MINB_A); }
-    else { CBL_DISPATCH(1, 256, 3); }
+    else { CBL_DISPATCH(1, CBL_SMALL_BLOCK, CBL_SMALL_MINB); }
     redo_ = nullptr;
     CUDA_TRY(cudaGetLastError());
     CBL_DISPATCH(2, CBL_BLOCK_B, CBL_MINB_B);
@@ -484,8 +493,8 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaMalloc(&h->leaf_scr_f, (size_t)mp * SF_ROWS * sizeof(float));
   cudaMemset(h->leaf_scr_d, 0, (size_t)mp * SD_ROWS * sizeof(double));
   cudaMemset(h->leaf_scr_f, 0, (size_t)mp * SF_ROWS * sizeof(float));
-  cudaMalloc(&h->d_redo, ((size_t)mp / 256 + 2) * sizeof(int));
-  cudaMemset(h->d_redo, 0, ((size_t)mp / 256 + 2) * sizeof(int));
+  cudaMalloc(&h->d_redo, ((size_t)mp / 64 + 2) * sizeof(int));
+  cudaMemset(h->d_redo, 0, ((size_t)mp / 64 + 2) * sizeof(int));
   cudaMalloc(&h->d_warn, 2 * sizeof(unsigned long long));       // [0] dryLeaf soft warnings, [1] blocks recomputed after a fast-path miss
   cudaMemset(h->d_warn, 0, 2 * sizeof(unsigned long long));
   {

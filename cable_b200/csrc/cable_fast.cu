@@ -18,6 +18,12 @@ using namespace cblf;
 #ifndef CBL_BLOCK_A
 #define CBL_BLOCK_A 768
 #endif
+#ifndef CBL_SMALL_BLOCK
+#define CBL_SMALL_BLOCK 128
+#endif
+#ifndef CBL_SMALL_MINB
+#define CBL_SMALL_MINB 3
+#endif
 
 template <int BL, int MB, int LV>
 static int launch(const DevPtrs &d, const DevCfg &c, int mp, int i0, int i1, float dels, int first, unsigned long long *warn,
@@ -46,7 +52,7 @@ int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, const void *cfg, si
                  case 1: return launch<BL, MB, 1>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); \
                  default: return launch<BL, MB, 2>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); }
   if (big) { CBLF_LVL(CBL_BLOCK_A, CBL_MINB_A) }
-  CBLF_LVL(256, 3)
+  CBLF_LVL(CBL_SMALL_BLOCK, CBL_SMALL_MINB)
 #undef CBLF_LVL
 }
 

@@ -182,10 +182,20 @@ CBL_DEV float fwsoil_calc(const Tile &t, const DevCfg &c) {
   }
 }
 
+// CBL_INLINE_LEAF=1 (latency-oriented builds for ranges that leave most issue slots idle): inline the leaf-level helpers
+// so that the scheduler can interleave their independent dependent chains
+#ifndef CBL_INLINE_LEAF
+#define CBL_INLINE_LEAF 1
+#endif
+#if CBL_INLINE_LEAF
+#define CBL_LEAFFN CBL_DEV
+#else
+#define CBL_LEAFFN CBL_NOINLINE
+#endif
 // leaf-level response functions: cbl_dryLeaf.F90:779-877
 // (divisions and square roots in everything the iteration loops execute go through dv()/f_sqrt()/d_sqrt():
 //  one shared out-of-line copy instead of an inline expansion per use -- see cbm_consts.cuh)
-CBL_NOINLINE float ejx_root(float parx, float alpha, float convex, float x) {
+CBL_LEAFFN float ejx_root(float parx, float alpha, float convex, float x) {
   const float ap = alpha * parx;
   return dv(ap + x - f_sqrt(p2(ap + x) - 4.0f * convex * alpha * parx * x), 2.0f * convex);
 }
@@ -195,7 +205,7 @@ CBL_DEV float xvcmxt4(float x) {
 // xvcmxt3 / xejmxt3 (:821-877).  `arr` = 1 - trefk/x is what the caller already needs for conkct/conkot, and
 // `eha_rt` = eha/(rgas*trefk) is a ratio of literals that the compiler folds (correctly rounded): the same values the
 // reference's expressions produce, without repeating three divisions per call.
-CBL_NOINLINE float arrhenius_peaked(float x, float arr, float coef, float eha_rt, float ehd, float entrop) {
+CBL_LEAFFN float arrhenius_peaked(float x, float arr, float coef, float eha_rt, float ehd, float entrop) {
   float num = coef * m_exp(eha_rt * arr);
   float den = 1.0f + m_exp(dv(entrop * x - ehd, K::rgas * x));
   return mx(0.0f, dv(num, den));
@@ -204,7 +214,7 @@ CBL_NOINLINE float arrhenius_peaked(float x, float arr, float coef, float eha_rt
 // One root of the Ci quadratic as the reference selects it (cbl_photosynthesis.F90:78-119 etc.)
 // kind 0: Rubisco (sentinel only if |coef2|>1e-9 & |coef1|<1e-9, later overwritten),
 // kind 1: RuBP (default sentinel 99999), kind 2: sink (value is ci itself).
-CBL_NOINLINE double an_limited(int kind, double coef2, double coef1, double coef0,
+CBL_LEAFFN double an_limited(int kind, double coef2, double coef1, double coef0,
                           float vmax, float cxa, float cxb, float v4, float rdx) {
   const double tiny = (double)1.0e-9f;
   double an = (kind == 1) ? (double)99999.0f : 0.0;

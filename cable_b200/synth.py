@@ -196,7 +196,7 @@ def make_tiles(grid: Grid, cfg=None, single_pft: int | None = None) -> dict[str,
         T["veg_" + name][0] = PFT[name][iv]
     T["veg_dleaf"][0] = np.sqrt(PFT["width"] * PFT["length"])[iv]            # cable_pft_params.F90
     T["veg_ejmax"][0] = np.float32(2.0) * T["veg_vcmax"][0]                   # cable_parameters.F90:1543
-    for b, (r, tl) in enumerate((("refl1", "taul1"), ("refl2", "taul2"), ("refl3", "taul3"))):
+    for b, (r, tl) in enumerate((("refl1", "taul1"), ("refl2", "taul2"))):        # (mp,2) offline, cable_define_types.F90:1083
         T["veg_refl"][b] = PFT[r][iv]
         T["veg_taul"][b] = PFT[tl][iv]
     # froot from rootbeta (cable_parameters.F90:3335-3343), float32 like the reference

@@ -1,0 +1,89 @@
+"""CPU: the C++ oracle against golden vectors produced by the REFERENCE ITSELF -- /root/reference's SUBROUTINE cbm,
+executed from its unmodified Fortran source by oracle/frun (tests/golden/make_fortran_golden.py; no Fortran compiler
+exists in this image or on the GPU box).  This is what pins the oracle: every state and diagnostic field after the last
+step of every case, and a per-step trace of fluxes and stores.
+
+Bar: binary32 fields bit-identical; binary64 fields to 1e-12 relative (they are bit-identical in practice: both sides call
+the C library's pow / exp / log in binary64)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_fortran_golden as G           # noqa: E402
+from cable_b200.registry import FIELDS     # noqa: E402
+from oracle.pyoracle import Oracle         # noqa: E402
+
+GOLD = os.path.join(HERE, "golden", "fortran_cbm_v1.npz")
+
+
+def _gold():
+    if not os.path.exists(GOLD):
+        pytest.fail("tests/golden/fortran_cbm_v1.npz is missing: run tests/golden/make_fortran_golden.py")
+    return np.load(GOLD)
+
+
+def _check(name, got, want, where):
+    if want.dtype == np.float64:
+        floor = 1e-3 * max(float(np.abs(want).max()), 1e-300)
+        rel = np.abs(got - want) / np.maximum(np.maximum(np.abs(got), np.abs(want)), floor)
+        assert float(rel.max()) <= 1e-12, (where, name, float(rel.max()))
+    else:
+        same = (got == want) | (np.isnan(got) & np.isnan(want)) if want.dtype.kind == "f" else (got == want)
+        assert bool(np.all(same)), (where, name, int((~same).sum()), "elements differ from the Fortran run")
+
+
+@pytest.mark.parametrize("case", list(G.CASES))
+def test_oracle_reproduces_the_fortran_run(case):
+    z = _gold()
+    nland, nsteps, doy, dels, site_lat, sw = G.CASES[case]
+    cfg, grid, T, F = G.case_inputs(case)
+    o = Oracle(T, cfg, cr_math=True)
+    for k in range(nsteps):
+        G.caller_step(case, T, F, k)
+        o.cbm(k + 1, dels)
+        for n in G.TRACE:
+            _check(n, T[n], z[f"{case}/trace/{n}"][k], f"{case} step {k + 1}")
+    nfields = 0
+    for f in FIELDS:
+        key = f"{case}/final/{f.name}"
+        if key in z.files:
+            _check(f.name, T[f.name], z[key], f"{case} final")
+            nfields += 1
+    assert nfields >= 170
+
+
+def test_golden_cases_cover_the_branches_we_claim():
+    """The Fortran run must have been through snow (one- and three-layer), permanent ice, lakes, frozen soil,
+    vegetated and bare tiles, day and night."""
+    z = _gold()
+    snow = three = ice = lakes = frozen = night = day = 0
+    for case in G.CASES:
+        cfg, grid, T, F = G.case_inputs(case)
+        ice += int((T["soil_isoilm"] == 9).sum()); lakes += int((T["veg_iveg"] == 16).sum())
+        snow += int((z[f"{case}/final/ssnow_snowd"] > 0).sum()); three += int((z[f"{case}/trace/ssnow_isflag"] == 1).sum())
+        frozen += int((z[f"{case}/final/ssnow_wbice"] > 0).sum())
+        q = z[f"{case}/final/rad_qcan"]
+        day += int((q[0] > 0).sum()); night += int((q[0] == 0).sum())
+    assert min(snow, three, ice, lakes, frozen, night, day) > 0, dict(snow=snow, three=three, ice=ice, lakes=lakes, frozen=frozen,
+                                                                    night=night, day=day)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present (GPU box)")
+def test_interpreter_still_reproduces_the_fixture_live():
+    """Where the reference is present: execute two steps of the reference source now and compare with the committed trace
+    (guards the generator and the interpreter against drift; ~20 s)."""
+    from oracle.frun.run_cbm import FortranCbm
+    z = _gold()
+    case = "site_half_hourly"
+    cfg, grid, T, F = G.case_inputs(case)
+    fc = FortranCbm(T, cfg, FIELDS)
+    for k in range(2):
+        G.caller_step(case, T, F, k)
+        fc.cbm(k + 1, G.CASES[case][3])
+        for n in G.TRACE:
+            assert np.array_equal(T[n], z[f"{case}/trace/{n}"][k], equal_nan=True), (n, k)
+    assert fc.I.nstmt > 10000
