@@ -54,6 +54,16 @@ OUTPUT_ROWS = (
     + [("ssnow_tgg", k, "mean") for k in range(6)] + [("ssnow_wb", k, "mean") for k in range(6)])
 
 
+# what an UNCHANGED serialdrv reads back after CALL cbm (cable_b200_set_output_mask): the fields its output module registers
+# (OUTPUT_ROWS) + the inputs of mass_balance / energy_balance (cable_checks.F90:472-618) + runoff scaling (cable_serial.F90:602-605)
+DRIVER_READS = sorted({r[0] for r in OUTPUT_ROWS if not r[0].startswith("bal_")} | {
+    "ssnow_smelt", "ssnow_rnof1", "ssnow_rnof2", "ssnow_runoff", "canopy_tscrn", "canopy_fpn", "canopy_frday", "canopy_frp",
+    "canopy_frpw", "canopy_frpr", "canopy_frs", "canopy_fnee", "canopy_delwc", "ssnow_snowd", "ssnow_osnowd", "canopy_fevw",
+    "canopy_fev", "ssnow_cls", "air_rlam", "rad_albedo", "rad_transd", "ssnow_otss", "canopy_tv", "canopy_fnv", "canopy_fns",
+    "canopy_fhs", "canopy_ga", "canopy_fhv", "canopy_fh", "rad_qcan", "rad_qssabs", "rad_flws", "ssnow_wbtot", "canopy_fevc",
+    "canopy_fes", "canopy_cansto"})
+
+
 def measured_peak_hbm() -> tuple[float, str]:
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -263,7 +273,7 @@ def run_b200(args) -> None:
 
     # ---- this rank's shard: a contiguous block of land points (no halo, no inter-GPU traffic in a step)
     from cable_b200.partition import array_partition, land_to_tile_range
-    from cable_b200.sharding import shard_grid, gather_land_blocks
+    from cable_b200.sharding import shard_grid, shard_grid_points, interleaved_land_points
     cfg = lib.default_cfg()
     cfg.n_forcing_slots = RING
     cfg.output_level = 1
@@ -273,14 +283,19 @@ def run_b200(args) -> None:
         # and forcing on its host (cheap) and keeps its block -- the master's scatter is outside the timed region anyway
         full = synth.make_grid(args.nland, NAP, seed=synth.SEED)
         tiles_full = synth.make_tiles(full, cfg)
-        l0, nland = array_partition(full.nland, world, rank)
-        t0_, t1_ = land_to_tile_range(full.cstart, full.cend, l0, nland)
-        grid, tiles = shard_grid(full, tiles_full, rank, world)
+        if args.decomp == "block" or world == 1:      # the reference's rule: contiguous blocks, sizes differ by <= 1
+            l0, nland = array_partition(full.nland, world, rank)
+            land_idx = np.arange(l0, l0 + nland)
+        else:                                         # chunks of 64 land points dealt round-robin (load balance)
+            land_idx = interleaved_land_points(full.nland, world, rank)
+            nland = int(land_idx.size)
+        grid, tiles, tile_idx = shard_grid_points(full, tiles_full, land_idx)
         nland_total, mp_total = full.nland, full.mp
     else:
         full = synth.make_grid(args.nland, NAP, seed=synth.SEED + rank)
         tiles_full = synth.make_tiles(full, cfg)
-        l0, nland, t0_, t1_ = 0, full.nland, 0, full.mp
+        nland = full.nland
+        land_idx, tile_idx = np.arange(full.nland), np.arange(full.mp)
         grid, tiles = full, tiles_full
         nland_total, mp_total = full.nland * world, full.mp * world
     mp = grid.mp
@@ -302,7 +317,7 @@ def run_b200(args) -> None:
         forcing.fill(tiles_full, k)
         s = {}
         for n in synth.FORCING_FIELDS:
-            t = pinned_like(np.ascontiguousarray(tiles_full[n][:, t0_:t1_])); keep.append(t); s[n] = t.numpy()
+            t = pinned_like(np.ascontiguousarray(tiles_full[n][:, tile_idx])); keep.append(t); s[n] = t.numpy()
         fsets.append(s)
     for n in synth.FORCING_FIELDS:
         tiles[n] = fsets[0][n].copy()
@@ -331,25 +346,36 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # output-interval diagnostics: device-side patch -> grid-cell reduction, gathered to rank 0 over NCCL
-    d_pf = torch.from_numpy(grid.patchfrac).cuda()
-    d_cs = torch.from_numpy(grid.cstart).cuda()
-    d_ce = torch.from_numpy(grid.cend).cuda()
-    diag_names = ["canopy_fe", "canopy_fh", "ssnow_runoff", "canopy_fpn"]
-    d_out = torch.zeros((len(diag_names), nland), device="cuda", dtype=torch.float32)
+    # output-interval diagnostics: device-side patch -> grid-cell reduction of the output module's rows, gathered to rank 0
+    # INSIDE the library (ncclSend / ncclRecv of uneven land-point blocks, cable_b200_output_gather_async); torch only
+    # carries the 128-byte NCCL id from rank 0 to the others, as the Fortran driver's MPI_Bcast would
+    if not strong:
+        counts = np.asarray([nland] * world, np.int32)
+    elif args.decomp == "block" or world == 1:
+        counts = np.asarray([array_partition(nland_total, world, r)[1] for r in range(world)], np.int32)
+    else:
+        counts = np.asarray([interleaved_land_points(nland_total, world, r).size for r in range(world)], np.int32)
+    def new_comm_id():
+        """a fresh NCCL id per communicator (one per handle), created on rank 0 and broadcast"""
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(CableB200.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        return bytes(idt.cpu().numpy().tobytes())
+    gathered_host = torch.zeros((len(OUTPUT_ROWS), int(counts.sum())), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+
+    def attach_driver(hh):
+        hh.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+        hh.output_plan(OUTPUT_ROWS)
+        if world > 1:
+            hh.comm_init(new_comm_id(), rank, world)
 
     def gather_diags():
-        for j, n in enumerate(diag_names):
-            h.grid_reduce(n, 0, d_pf.data_ptr(), d_cs.data_ptr(), d_ce.data_ptr(), nland, d_out[j].data_ptr())
-        h.sync()
-        if world > 1:
-            if strong:       # uneven land-point blocks (sizes differ by <= 1) -> [ndiag, nland_total] on rank 0
-                g = gather_land_blocks(d_out, nland_total, dst=0)
-                return [g] if rank == 0 else None
-            bufs = [torch.empty_like(d_out) for _ in range(world)] if rank == 0 else None
-            dist.gather(d_out, bufs, dst=0)
-            return bufs
-        return [d_out]
+        h.output_gather_async(0, gathered_host.numpy() if rank == 0 else None, counts)
+        h.output_wait()
+        return [gathered_host] if rank == 0 else None
+
+    attach_driver(h)
 
     # ---- (1) device-resident rate ----------------------------------------------------------------------------
     for k in range(W):
@@ -386,6 +412,12 @@ def run_b200(args) -> None:
     # flushed: sum of the K event-timed steps + the gather; otherwise the wall clock between the two barriers
     t_res = max_over_ranks(ctr.kernel_ms * 1e-3 + t_gather if flush else t_wall)
     t_wall = max_over_ranks(t_wall)
+    per_rank_ms = [kern_ms]
+    if world > 1:
+        tt = torch.tensor([kern_ms], device="cuda", dtype=torch.float64)
+        allk = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allk, tt)
+        per_rank_ms = [float(x.item()) for x in allk]
     launches = int(ctr.kernel_launches)
     value = mp_total * K / t_res
     finite = bool(torch.isfinite(gathered[0]).all().item()) if rank == 0 else True
@@ -409,15 +441,20 @@ def run_b200(args) -> None:
     fresh_handle()
     Ke = max(3, min(K, args.e2e_steps))
     h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+    if world > 1:
+        h.comm_init(new_comm_id(), rank, world)
     conv = lib.MetConvert(tair_offset=0.0, psurf_scale=0.01, rainf_scale=DELS, co2_scale=1.0e-6, snowf_from_tair=1)
     slices = []
     for k in range(RING):
         t = torch.empty((len(lib.MET_ROWS), nland), dtype=torch.float32, pin_memory=True)
-        t.numpy()[...] = forcing.land_slice(k)[:, l0:l0 + nland]; keep.append(t); slices.append(t.numpy())
+        t.numpy()[...] = forcing.land_slice(k)[:, land_idx]; keep.append(t); slices.append(t.numpy())
     rows = OUTPUT_ROWS
     h.output_plan(rows)
-    outs = [torch.zeros((len(rows), nland), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-    tiles["veg_vlai"][0] = forcing.lai(0)[t0_:t1_]
+    # every step's output block goes to rank 0 (the reference master receives every worker's fields every step,
+    # cable_mpimaster.F90:8066-8072): [rows, all land points] on rank 0, nothing on the others
+    nout = int(counts.sum()) if world > 1 else nland
+    outs = [torch.zeros((len(rows), nout), dtype=torch.float32, pin_memory=True) for _ in range(2)] if (rank == 0 or world == 1) else [None, None]
+    tiles["veg_vlai"][0] = forcing.lai(0)[tile_idx]
     h.upload_lai()
     checksum = 0.0
 
@@ -427,9 +464,12 @@ def run_b200(args) -> None:
         h.step(k + 1, DELS, k % RING)                           # cbm
         h.post_step(k + 1, 1, DELS)                             # runoff*dels, sumcflux, mass/energy balance
         h.output_wait()                                         # step k-1's output block is now on the host
-        if k > 0:
+        if k > 0 and outs[0] is not None:
             checksum += float(outs[(k - 1) % 2].numpy()[0, ::997].sum())     # the host consumes it
-        h.output_fetch_async(outs[k % 2].numpy())               # reduce -> D2H of this step's rows
+        if world > 1:                                           # reduce -> NCCL gather to rank 0 -> D2H there
+            h.output_gather_async(0, outs[k % 2].numpy() if rank == 0 else None, counts)
+        else:
+            h.output_fetch_async(outs[k % 2].numpy())           # reduce -> D2H of this step's rows
 
     for k in range(3):
         driver_step(k)
@@ -446,29 +486,38 @@ def run_b200(args) -> None:
     e2e = mp_total * Ke / t_e2e
     h2d_step, d2h_step = ce.h2d_bytes / Ke, ce.d2h_bytes / Ke
     e2e_launches = int(ce.kernel_launches)
-    last = outs[(3 + Ke - 1) % 2].numpy()
+    last = outs[(3 + Ke - 1) % 2].numpy() if outs[0] is not None else np.zeros((len(rows), 1), np.float32)
     bad_rows = [f"{rows[r][0]}[{rows[r][1]}]" for r in range(len(rows)) if not np.isfinite(last[r]).all()]
     e2e_finite = (not bad_rows) and bool(np.isfinite(checksum))
     if bad_rows:
         print("non-finite output rows:", bad_rows, file=sys.stderr)
 
-    # ---- (2b) the most conservative drop-in mode: cable_b200_cbm() mirrors every state + STAR array to the host each step
-    fresh_handle()
-    Km = max(3, min(Ke, 12))
-    for k in range(2):
-        h.bind(fsets[k % RING]); h.cbm(k + 1, DELS)
-    h.reset_counters()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(2, 2 + Km):
-        h.bind(fsets[k % RING])          # the driver fills met%* for this step (buffers already pinned)
-        h.cbm(k + 1, DELS)               # H2D forcing + kernel + D2H state/diagnostics + sync
-    barrier()
-    t_mir = max_over_ranks(time.perf_counter() - t0)
-    cm = h.counters()
-    mirror = {"value": mp_total * Km / t_mir, "unit": "tile-timesteps/s", "h2d_bytes_per_step": cm.h2d_bytes / Km,
-              "d2h_bytes_per_step": cm.d2h_bytes / Km, "steps": Km,
-              "api": "cable_b200_cbm, output_level=1: every prognostic + driver-visible array mirrored to the host each step"}
+    # ---- (2b) the unchanged-caller drop-in: cable_b200_cbm() per step, host arrays in, host arrays out.  First with the
+    # output mask an unchanged serialdrv needs (what its output module and balance checks read), then mirroring every
+    # prognostic + driver-visible array (the most conservative mode)
+    def dropin_leg(mask):
+        fresh_handle()
+        if mask:
+            h.set_output_mask(mask)
+        Km = max(3, min(Ke, 12))
+        for k in range(2):
+            h.bind(fsets[k % RING]); h.cbm(k + 1, DELS)
+        h.reset_counters()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(2, 2 + Km):
+            h.bind(fsets[k % RING])          # the driver fills met%* for this step (buffers already pinned)
+            h.cbm(k + 1, DELS)               # H2D forcing + kernel + D2H of the selection + sync
+        barrier()
+        t_mir = max_over_ranks(time.perf_counter() - t0)
+        cm = h.counters()
+        return {"value": mp_total * Km / t_mir, "unit": "tile-timesteps/s", "h2d_bytes_per_step": cm.h2d_bytes / Km,
+                "d2h_bytes_per_step": cm.d2h_bytes / Km, "steps": Km}
+    mirror = dropin_leg(DRIVER_READS)
+    mirror["api"] = (f"cable_b200_cbm + cable_b200_set_output_mask({len(DRIVER_READS)} fields: what cable_diagnostics registers and "
+                     "mass_balance / energy_balance read); the rest of the state stays on the device")
+    mirror_all = dropin_leg(None)
+    mirror_all["api"] = "cable_b200_cbm, output_level=1, no mask: every prognostic + driver-visible array mirrored to the host each step"
 
     # ---- (3) CPU baseline on this box's host cores (rank 0, N=1 only) -----------------------------------------
     cpu = None
@@ -496,12 +545,17 @@ def run_b200(args) -> None:
                                    f"weak scaling: every GPU its own grid of {nland} land points x {NAP} tiles = {mp} tiles, "
                                    f"dels={int(DELS)}s, leuning/standard/HDM/icycle=0 (cable.nml)",
                        "tiles_per_gpu": mp, "global_tiles": mp_total, "land_points_per_gpu": nland,
-                       "parallelism": f"contiguous land-point blocks x{world} (master_decomp rule, cable_mpimaster.F90:1428-1463)",
+                       "parallelism": (f"contiguous land-point blocks x{world} (master_decomp rule, cable_mpimaster.F90:1428-1463)"
+                                       if (args.decomp == "block" or world == 1 or not strong) else
+                                       f"chunks of 64 land points dealt round-robin to {world} GPUs (load balance; tiles of a land point "
+                                       "stay together; --decomp block = the reference's contiguous master_decomp blocks)"),
+                       "decomp": args.decomp if (strong and world > 1) else "block",
                               "l2": (f"resident set of a rank ~ {ws_bytes / 1e6:.0f} MB (1.7 KB/tile incl. the 8-slot forcing ring) "
                               + ("< 2 x the 126 MB L2: L2 flushed (256 MB memset) before every timed step, steps timed one by "
                                  "one with CUDA events on the library's compute stream and summed (+ the gather)"
                                  if flush else "> 2 x the 126 MB L2: inputs larger than L2, no flush; wall clock between barriers")),
                        "timing": "events+flush" if flush else "wall",
+                       "kernel_ms_per_rank": per_rank_ms,
                        "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
                        "forcing_ring_steps": RING, "outputs_finite": finite},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -527,6 +581,7 @@ def run_b200(args) -> None:
                            "tile expansion) -> cable_b200_step -> cable_b200_post_step -> cable_b200_output_fetch_async "
                            "(grid-cell output rows D2H every step, output%averaging='all')"},
             "e2e_dropin_mirror": mirror,
+            "e2e_dropin_mirror_all": mirror_all,
             "gpu_launches": launches,
             "clocks": clocks,
             "dryleaf_soft_warnings": int(ctr.n_dryleaf_warn),
@@ -548,6 +603,8 @@ def main() -> None:
     ap.add_argument("--nland", type=int, default=NLAND, help="land points of the grid (strong) / per GPU (weak); "
                     "62000 = BASELINE configs[2], 250000 = configs[3]")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--decomp", default="interleaved", choices=["interleaved", "block"],
+                    help="strong scaling: deal 64-point chunks round-robin (default) or the reference's contiguous blocks")
     ap.add_argument("--no-flush", action="store_true", help="small shards: do not flush L2 between timed steps")
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -184,6 +184,27 @@ class CableB200:
         assert host_out.dtype == np.float32 and host_out.size == self.nrows * self.nland and host_out.flags["C_CONTIGUOUS"]
         _lib.check(self._lib.cable_b200_output_fetch_async(self._h, host_out.ctypes.data))
 
+    # -- multi-GPU gather of the output block (NCCL inside the library; no torch involved) ----------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0 creates it; the caller broadcasts the 128 bytes with whatever it has (MPI_Bcast in the Fortran driver)."""
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().cable_b200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int) -> None:
+        assert len(unique_id) == 128
+        self.rank, self.nranks = int(rank), int(nranks)
+        _lib.check(self._lib.cable_b200_comm_init(self._h, C.create_string_buffer(unique_id, 128), self.rank, self.nranks))
+
+    def output_gather_async(self, root: int, host_out, nland_of_rank) -> None:
+        """host_out: float32 [nrows, sum(nland_of_rank)] on the root (pinned memory recommended), None elsewhere."""
+        counts = np.ascontiguousarray(nland_of_rank, np.int32)
+        if host_out is not None:
+            assert host_out.dtype == np.float32 and host_out.size == self.nrows * int(counts.sum()) and host_out.flags["C_CONTIGUOUS"]
+        _lib.check(self._lib.cable_b200_output_gather_async(self._h, int(root), host_out.ctypes.data if host_out is not None else None,
+                                                            counts.ctypes.data))
+
     def output_wait(self) -> None:
         _lib.check(self._lib.cable_b200_output_wait(self._h))
 

@@ -14,6 +14,7 @@
 #include <unordered_map>
 #include <cstdint>
 #include <algorithm>
+#include <dlfcn.h>
 #include "cbm_kernel.cuh"
 #include "cbm_driver.cuh"
 
@@ -162,6 +163,12 @@ struct cable_handle {
     float *d_out[2] = {nullptr, nullptr}; cudaEvent_t ev_out_free[2] = {nullptr, nullptr}; int out_buf = 0;
     cudaEvent_t ev_reduced = nullptr;
   } drv;
+  // multi-GPU gather of the output block (cable_b200_comm_init / cable_b200_output_gather_async)
+  struct Comm {
+    void *comm = nullptr;            // ncclComm_t
+    int rank = 0, nranks = 1;
+    float *d_recv = nullptr; size_t recv_floats = 0;    // root: the other ranks' blocks, rank after rank
+  } comm;
   // measurement
   cable_counters ctr{};
   bool profile = false;
@@ -549,6 +556,7 @@ int cable_b200_destroy(cable_handle *h) {
   if (!h) return CABLE_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  cable_b200_comm_destroy(h);          // while the streams still exist
   for (int id = 0; id < NFIELDS; id++) if (h->host_pinned[id]) cudaHostUnregister(h->host[id]);
   for (auto ev : h->ev_forcing_ready) cudaEventDestroy(ev);
   for (auto ev : h->ev_slot_free) cudaEventDestroy(ev);
@@ -1150,9 +1158,13 @@ int cable_b200_output_accumulate(cable_handle *h) {
   return CABLE_OK;
 }
 
-int cable_b200_output_fetch_async(cable_handle *h, float *host_out) {
-  if (!h || !h->drv.on || h->drv.rows.empty() || !host_out) return fail(CABLE_E_ARG, "output_fetch_async: no output plan / null buffer");
-  CUDA_TRY(cudaSetDevice(h->device));
+}  // extern "C"
+
+namespace {
+
+// end of an output interval on this rank: reduce every row patch -> grid cell into staging buffer `b` (compute stream), reset
+// the aggregators, and make the D2H stream wait for it.  The caller then moves the block (D2H, or NCCL + D2H).
+int reduce_rows(cable_handle *h, int &b_out) {
   auto &v = h->drv;
   const int nrows = (int)v.rows.size(), b = v.out_buf;
   // the D2H that last used this staging buffer must have drained
@@ -1170,11 +1182,135 @@ int cable_b200_output_fetch_async(cable_handle *h, float *host_out) {
   }
   CUDA_TRY(cudaEventRecord(v.ev_reduced, h->s_compute));
   CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, v.ev_reduced, 0));
-  const size_t bytes = (size_t)nrows * v.nland * sizeof(float);
+  b_out = b;
+  v.out_buf ^= 1;
+  return CABLE_OK;
+}
+
+// ---- NCCL, bound at run time (dlopen): the library has no link-time dependency on it, a single-GPU caller never loads it,
+// and a process that already carries a libnccl.so.2 (e.g. torch's) shares that copy -------------------------------------
+struct ncclUniqueId_ { char internal[128]; };
+typedef void *ncclComm_t_;
+struct Nccl {
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_ *) = nullptr;
+  int (*CommInitRank)(ncclComm_t_ *, int, ncclUniqueId_, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t_) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+constexpr int NCCL_FLOAT32 = 7;       // ncclFloat32 (nccl.h: ncclInt8 = 0 ... ncclFloat16 = 6, ncclFloat32 = 7)
+
+int nccl_load() {
+  if (g_nccl.lib) return CABLE_OK;
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(CABLE_E_UNSUPPORTED, std::string("NCCL not found: ") + dlerror());
+#define NCCL_SYM(field, name) *(void **)(&g_nccl.field) = dlsym(lib, name); if (!g_nccl.field) return fail(CABLE_E_UNSUPPORTED, "NCCL symbol missing: " name)
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank"); NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd"); NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv");
+  NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+  g_nccl.lib = lib;
+  return CABLE_OK;
+}
+#define NCCL_TRY(expr) do { int r_ = (expr); if (r_ != 0) return fail(CABLE_E_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int cable_b200_output_fetch_async(cable_handle *h, float *host_out) {
+  if (!h || !h->drv.on || h->drv.rows.empty() || !host_out) return fail(CABLE_E_ARG, "output_fetch_async: no output plan / null buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  auto &v = h->drv;
+  int b = 0;
+  { int rc = reduce_rows(h, b); if (rc) return rc; }
+  const size_t bytes = (size_t)v.rows.size() * v.nland * sizeof(float);
   CUDA_TRY(cudaMemcpyAsync(host_out, v.d_out[b], bytes, cudaMemcpyDeviceToHost, h->s_d2h));
   CUDA_TRY(cudaEventRecord(v.ev_out_free[b], h->s_d2h));
   h->ctr.d2h_bytes += (long long)bytes;
-  v.out_buf ^= 1;
+  return CABLE_OK;
+}
+
+int cable_b200_comm_unique_id(void *id128) {
+  if (!id128) return fail(CABLE_E_ARG, "comm_unique_id: null buffer");
+  { int rc = nccl_load(); if (rc) return rc; }
+  NCCL_TRY(g_nccl.GetUniqueId((ncclUniqueId_ *)id128));
+  return CABLE_OK;
+}
+
+int cable_b200_comm_init(cable_handle *h, const void *id128, int rank, int nranks) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(CABLE_E_ARG, "comm_init: bad argument");
+  { int rc = nccl_load(); if (rc) return rc; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cable_b200_comm_destroy(h);
+  ncclUniqueId_ id; memcpy(&id, id128, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&h->comm.comm, nranks, id, rank));
+  h->comm.rank = rank; h->comm.nranks = nranks;
+  return CABLE_OK;
+}
+
+int cable_b200_comm_destroy(cable_handle *h) {
+  if (!h) return CABLE_OK;
+  if (h->comm.comm) { cudaSetDevice(h->device); cudaStreamSynchronize(h->s_d2h); g_nccl.CommDestroy(h->comm.comm); h->comm.comm = nullptr; }
+  if (h->comm.d_recv) { cudaFree(h->comm.d_recv); h->comm.d_recv = nullptr; h->comm.recv_floats = 0; }
+  h->comm.nranks = 1; h->comm.rank = 0;
+  return CABLE_OK;
+}
+
+int cable_b200_output_gather_async(cable_handle *h, int root, float *host_out_root, const int *nland_of_rank) {
+  if (!h || !h->drv.on || h->drv.rows.empty() || !nland_of_rank) return fail(CABLE_E_ARG, "output_gather_async: no output plan / null argument");
+  auto &v = h->drv; auto &c = h->comm;
+  if (c.nranks > 1 && !c.comm) return fail(CABLE_E_ARG, "output_gather_async: call cable_b200_comm_init first");
+  if (root < 0 || root >= c.nranks || nland_of_rank[c.rank] != v.nland) return fail(CABLE_E_ARG, "output_gather_async: root / nland_of_rank do not match this rank");
+  if (c.rank == root && !host_out_root) return fail(CABLE_E_ARG, "output_gather_async: the root needs a host buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int nrows = (int)v.rows.size();
+  long long total = 0, others = 0;
+  for (int r = 0; r < c.nranks; r++) { if (nland_of_rank[r] < 0) return fail(CABLE_E_ARG, "output_gather_async: negative count"); total += nland_of_rank[r]; if (r != root) others += nland_of_rank[r]; }
+  int b = 0;
+  { int rc = reduce_rows(h, b); if (rc) return rc; }
+  if (c.rank == root) {
+    const size_t need = (size_t)others * nrows;
+    if (need > c.recv_floats) {
+      CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+      if (c.d_recv) cudaFree(c.d_recv);
+      CUDA_TRY(cudaMalloc(&c.d_recv, need * sizeof(float)));
+      c.recv_floats = need;
+    }
+    // uneven blocks (land-point counts differ by <= 1 under master_decomp): one grouped receive per peer
+    if (c.nranks > 1) {
+      NCCL_TRY(g_nccl.GroupStart());
+      size_t off = 0;
+      for (int r = 0; r < c.nranks; r++) {
+        if (r == root) continue;
+        const size_t n = (size_t)nland_of_rank[r] * nrows;
+        if (n) NCCL_TRY(g_nccl.Recv(c.d_recv + off, n, NCCL_FLOAT32, r, c.comm, h->s_d2h));
+        off += n;
+      }
+      NCCL_TRY(g_nccl.GroupEnd());
+    }
+    // every block lands in its columns of the [nrows][total] host array (rank order = land-point order)
+    size_t off = 0; long long col = 0;
+    for (int r = 0; r < c.nranks; r++) {
+      const float *src = (r == root) ? v.d_out[b] : c.d_recv + off;
+      const size_t w = (size_t)nland_of_rank[r] * sizeof(float);
+      if (w) CUDA_TRY(cudaMemcpy2DAsync(host_out_root + col, (size_t)total * sizeof(float), src, w, w, nrows, cudaMemcpyDeviceToHost, h->s_d2h));
+      if (r != root) off += (size_t)nland_of_rank[r] * nrows;
+      col += nland_of_rank[r];
+    }
+    h->ctr.d2h_bytes += (long long)total * nrows * (long long)sizeof(float);
+  } else {
+    const size_t n = (size_t)v.nland * nrows;
+    NCCL_TRY(g_nccl.GroupStart());
+    if (n) NCCL_TRY(g_nccl.Send(v.d_out[b], n, NCCL_FLOAT32, root, c.comm, h->s_d2h));
+    NCCL_TRY(g_nccl.GroupEnd());
+  }
+  CUDA_TRY(cudaEventRecord(v.ev_out_free[b], h->s_d2h));
   return CABLE_OK;
 }
 

@@ -59,6 +59,8 @@ EXPORTS = [
     "cable_b200_driver_init", "cable_b200_set_met_async", "cable_b200_upload_lai", "cable_b200_post_step",
     "cable_b200_output_plan", "cable_b200_driver_field_id", "cable_b200_output_accumulate",
     "cable_b200_output_fetch_async", "cable_b200_output_wait", "cable_b200_driver_download",
+    # multi-GPU gather of the output block (NCCL, bound at run time)
+    "cable_b200_comm_unique_id", "cable_b200_comm_init", "cable_b200_comm_destroy", "cable_b200_output_gather_async",
 ]
 
 MET_ROWS = ("SWdown", "Tair", "Qair", "PSurf", "Wind", "Rainf", "Snowf", "LWdown", "CO2air", "hod", "doy")
@@ -120,6 +122,10 @@ def load() -> C.CDLL:
     lib.cable_b200_output_fetch_async.argtypes = [H, C.c_void_p]
     lib.cable_b200_output_wait.argtypes = [H]
     lib.cable_b200_driver_download.argtypes = [H, C.c_char_p, C.c_void_p]
+    lib.cable_b200_comm_unique_id.argtypes = [C.c_void_p]
+    lib.cable_b200_comm_init.argtypes = [H, C.c_void_p, C.c_int, C.c_int]
+    lib.cable_b200_comm_destroy.argtypes = [H]
+    lib.cable_b200_output_gather_async.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is None and name != "cable_b200_default_cfg":

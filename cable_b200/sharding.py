@@ -29,6 +29,44 @@ def shard_grid(grid, tiles: dict, rank: int, world: int):
     return g, local
 
 
+def interleaved_land_points(nland: int, world: int, rank: int, chunk: int = 64) -> np.ndarray:
+    """Land points of `rank` when chunks of `chunk` consecutive land points are dealt to the ranks round-robin.
+
+    Why not only the reference's contiguous blocks (array_partition): land points are numbered in raster order from the
+    north, so a contiguous block is a latitude band, and the cost of a tile depends on season and time of day (the number
+    of dryLeaf passes) -- at N = 2 the northern-summer half of the 0.5 degree grid takes 24 % longer per step than the other
+    (profiles/r02_*).  Dealing chunks gives every GPU a sample of the whole globe; tiles of a land point stay together and
+    a chunk (320 tiles at 5 tiles per point) keeps neighbours in space neighbours in memory.  Rank 0 receives the blocks in
+    rank order and addresses land points through the concatenated index lists, exactly as the reference's master addresses
+    its workers' land points through landpt(:)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank")
+    nchunk = (nland + chunk - 1) // chunk
+    mine = np.arange(rank, nchunk, world)
+    idx = (mine[:, None] * chunk + np.arange(chunk)[None, :]).ravel()
+    return idx[idx < nland].astype(np.int64)
+
+
+def shard_grid_points(grid, tiles: dict, land_idx: np.ndarray):
+    """-> (grid_local, tiles_local, tile_idx) for an arbitrary (increasing) list of land points; tiles of a point stay together."""
+    import copy
+    land_idx = np.asarray(land_idx, np.int64)
+    counts = (grid.cend[land_idx] - grid.cstart[land_idx] + 1).astype(np.int64)
+    starts = grid.cstart[land_idx].astype(np.int64)
+    tile_idx = np.repeat(starts - np.concatenate(([0], np.cumsum(counts)[:-1])), counts) + np.arange(int(counts.sum()))
+    g = copy.copy(grid)
+    g.nland, g.mp = int(land_idx.size), int(tile_idx.size)
+    for name in ("lat", "lon", "elev", "tmean", "tamp"):
+        setattr(g, name, getattr(grid, name)[land_idx].copy())
+    cend = (np.cumsum(counts) - 1).astype(np.int32)
+    g.cstart = (cend - counts + 1).astype(np.int32)
+    g.cend = cend
+    g.tile2land = np.repeat(np.arange(g.nland, dtype=np.int32), counts)
+    g.patchfrac = grid.patchfrac[tile_idx].copy()
+    local = {k: np.ascontiguousarray(v[:, tile_idx]) for k, v in tiles.items()}
+    return g, local, tile_idx
+
+
 def gather_land_blocks(local, nland_total: int, dst: int = 0, group=None):
     """Gather per-rank [nfields, nland_local] tensors (uneven nland_local) to `dst` -> [nfields, nland_total].
     Blocks are padded to the largest block so one collective serves NCCL and gloo alike."""

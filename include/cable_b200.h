@@ -314,6 +314,28 @@ int          cable_b200_output_accumulate(cable_handle *h);
  * rows are sampled and reduced in one pass.                                    */
 int          cable_b200_output_fetch_async(cable_handle *h, float *host_out);
 int          cable_b200_output_wait(cable_handle *h);
+/* ---------------------------------------------------------------------------
+ * Multi-GPU: land points shard across ranks as contiguous blocks (master_decomp, src/offline/cable_mpimaster.F90:
+ * 1428-1463), one process and one handle per GPU, nothing is exchanged inside a step.  Once per output interval the
+ * grid-cell output block is gathered to one rank over NCCL -- this replaces the reference workers' per-step MPI_Send of
+ * ~225 fields (src/offline/cable_mpiworker.F90:552) and the master's matching receives (cable_mpimaster.F90:8066-8072).
+ * NCCL is bound at run time (dlopen of libnccl.so.2): single-GPU callers never load it.
+ *
+ *   rank 0:   cable_b200_comm_unique_id(id)      then the driver's own MPI_Bcast(id, 128, MPI_BYTE, 0, comm)
+ *   all:      cable_b200_comm_init(h, id, rank, nranks)
+ *   all:      cable_b200_output_gather_async(h, root, host_out, nland_of_rank)   instead of output_fetch_async
+ *   root:     cable_b200_output_wait(h);  host_out is [nrows][sum(nland_of_rank)], blocks in rank order
+ * ------------------------------------------------------------------------- */
+#define CABLE_B200_COMM_ID_BYTES 128
+int          cable_b200_comm_unique_id(void *id128);
+int          cable_b200_comm_init(cable_handle *h, const void *id128, int rank, int nranks);
+int          cable_b200_comm_destroy(cable_handle *h);
+/* end of an output interval on every rank: reduce the plan's rows patch -> grid cell on the device, then send the
+ * [nrows][nland_of_rank[rank]] block to `root`, which receives every block and copies them (asynchronously, D2H stream)
+ * into host_out_root.  nland_of_rank[r] = land points of rank r; host_out_root may be NULL on the other ranks.  With a
+ * single rank (no comm_init) it is output_fetch_async.                                                             */
+int          cable_b200_output_gather_async(cable_handle *h, int root, float *host_out_root, const int *nland_of_rank);
+
 /* copy a driver array (float, or double for "bal_owb") to the host; synchronous */
 int          cable_b200_driver_download(cable_handle *h, const char *name, void *host);
 

@@ -113,3 +113,40 @@ def test_world_size_2_gloo_matches_single_process():
                      for n in ("canopy_fe", "canopy_fh", "ssnow_runoff")])
     assert got.shape == (3, nland)
     np.testing.assert_array_equal(got, want)            # independent tiles => bitwise identical
+
+
+def test_interleaved_decomposition_partitions_the_grid_and_keeps_points_whole():
+    """Chunks of 64 land points dealt round-robin: every land point on exactly one rank, counts within one chunk of each
+    other, tiles of a point together, local cstart/cend contiguous, and shard_grid_points on a contiguous range equals
+    the reference-rule shard."""
+    from cable_b200.sharding import interleaved_land_points, shard_grid_points
+    cfg, grid, T, F = make_case(1000, nap=5)
+    for world in (1, 2, 3, 8):
+        seen = np.zeros(grid.nland, int)
+        sizes = []
+        for r in range(world):
+            idx = interleaved_land_points(grid.nland, world, r)
+            assert np.all(np.diff(idx) > 0)
+            seen[idx] += 1; sizes.append(idx.size)
+            g, Tl, tile_idx = shard_grid_points(grid, T, idx)
+            assert g.mp == tile_idx.size == idx.size * 5 and g.cstart[0] == 0 and g.cend[-1] == g.mp - 1
+            assert np.array_equal(g.cstart[1:], g.cend[:-1] + 1)
+            assert np.array_equal(grid.tile2land[tile_idx], np.repeat(idx, 5))
+            assert np.array_equal(Tl["veg_iveg"][0], T["veg_iveg"][0][tile_idx]) and np.array_equal(g.lat, grid.lat[idx])
+        assert np.all(seen == 1) and max(sizes) - min(sizes) <= 64
+    # a contiguous index range reproduces shard_grid
+    l0, nl = array_partition(grid.nland, 3, 1)
+    g1, T1 = shard_grid(grid, T, 1, 3)
+    g2, T2, _ = shard_grid_points(grid, T, np.arange(l0, l0 + nl))
+    assert g1.mp == g2.mp and np.array_equal(g1.cstart, g2.cstart) and np.array_equal(g1.patchfrac, g2.patchfrac)
+    assert all(np.array_equal(T1[k], T2[k]) for k in T1)
+    # ragged patch counts
+    from util import ragged_case
+    cfg, gr, Tr, Fr, _ = ragged_case(300)
+    tot = 0
+    for r in range(4):
+        idx = interleaved_land_points(gr.nland, 4, r, chunk=16)
+        g, Tl, tile_idx = shard_grid_points(gr, Tr, idx)
+        assert np.array_equal(g.cend - g.cstart, gr.cend[idx] - gr.cstart[idx])
+        tot += g.mp
+    assert tot == gr.mp
