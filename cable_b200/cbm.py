@@ -104,6 +104,10 @@ class CableB200:
     def sync(self) -> None:
         _lib.check(self._lib.cable_b200_sync(self._h))
 
+    def param_table_classes(self) -> int:
+        """bit 0: veg%* served from per-PFT tables in shared memory, bit 1: soil%* from per-soil-type tables"""
+        return int(self._lib.cable_b200_param_table_classes(self._h))
+
     def mark_dirty(self, *names: str) -> None:
         """The host wrote these resident (PARAM / STATE) arrays: the next step uploads them first."""
         for n in names:

@@ -46,9 +46,6 @@ constexpr size_t pool_smem_bytes(int) { return 0; }
 #define CBL_MINB_FUSED 8
 #endif
 // threads per block of kernel A / B (A's phase barriers make its block the unit that shares instruction fetches)
-#ifndef CBL_BLOCK_A
-#define CBL_BLOCK_A 768
-#endif
 #ifndef CBL_BLOCK_B
 #define CBL_BLOCK_B 128
 #endif
@@ -82,6 +79,20 @@ const cable_field_info g_fields[] = {
 #include "../../include/cable_b200_fields.def"
 };
 static_assert(sizeof(g_fields) / sizeof(g_fields[0]) == NFIELDS, "registry size");
+
+// parameter-table slot / class of every field (-1 / 0: not tabulated), from the same predicate the kernels use
+const int g_tbl_slot[] = {
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) (CBL_TBL_ON(T, m, ct, role, flags) ? (int)TBL_##T##_##m : -1),
+#include "../../include/cable_b200_fields.def"
+};
+const int g_tbl_drow[] = {      // row of DevPtrs::tbl_d for the REAL(r_2) soil members, else -1
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) (CBL_TBLD_ON(T, m, ct, role, flags) ? CBL_TBLD_ROW(m) : -1),
+#include "../../include/cable_b200_fields.def"
+};
+const int g_tbl_class[] = {
+#define CABLE_FA(T, m, ct, n1, n2, role, flags) CBL_CLASS_##T,
+#include "../../include/cable_b200_fields.def"
+};
 
 size_t elem_size(int dt) { return dt == CABLE_DT_F64 ? 8 : 4; }
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -121,6 +132,12 @@ struct cable_handle {
   size_t off_tvair_in = 0, off_oldcansto_in = 0;   // per-slot copies of the two inputs that are not FORCING rows
   bool dirty[NFIELDS]{};             // cable_b200_mark_dirty: host-side writes to resident fields, uploaded by the next cbm()
   bool any_dirty = false;
+  float *d_tbl = nullptr; double *d_tbl_d = nullptr;   // per-PFT / per-soil-type parameter tables (cbm_types.cuh)
+  int tbl_classes = 0, tbl_enable = 1;
+  // preferred shared-memory share of the unified L1 array, per cent.  -1 = the driver's default.  The kernels hold ~3.5 KB of
+  // static shared memory (parameter tables): a preference BELOW what they need (0 = all to L1, as in round 1 when they had
+  // none) costs 45 % of the step on B200 (1.47 vs 1.00 ms, profiles/r02_carveout_sweep.txt); 8-15 % and the default tie.
+  int carveout = -1;
   bool out_mask_on = false;          // cable_b200_set_output_mask: what cable_b200_cbm() mirrors to the host each step
   bool out_mask[NFIELDS]{};
   int nslots = 2;
@@ -210,6 +227,7 @@ DevPtrs make_ptrs(const cable_handle *h, int slot) {
   int id = 0;
 #define CABLE_FA(T, m, ct, n1, n2, role, flags) d.T##_##m = (ct *)dev_ptr(h, id, slot); id++;
 #include "../../include/cable_b200_fields.def"
+  d.tbl = h->d_tbl; d.tbl_d = h->d_tbl_d; d.tbl_classes = h->tbl_classes;
   d.met_tvair_in = (const float *)dev_in_ptr(h, FID_met_tvair, slot);
   d.canopy_oldcansto_in = (const float *)dev_in_ptr(h, FID_canopy_oldcansto, slot);
   d.leaf_scr_d = h->leaf_scr_d; d.leaf_scr_f = h->leaf_scr_f;
@@ -257,7 +275,7 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
       if (!once_[dv_]) {                                                                                                       \
         if (sm_ > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
         /* no shared memory in the default build: give the whole unified array to L1, which holds the spill slots */          \
-        if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); \
+        if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout); \
         cudaGetLastError();                                                                                                    \
         once_[dv_] = true;                                                                                                     \
       }                                                                                                                        \
@@ -286,7 +304,7 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
       const int bl = big ? CBL_BLOCK_A : CBL_SMALL_BLOCK, nblk = (i1 - i0 + bl - 1) / bl;
       if (i0 % 256) return fail(CABLE_E_ARG, "launch_range: range start must be a multiple of 256 (redo-flag slices)");
       redo_ = h->d_redo + (size_t)(i0 / 64);               // one entry per block (>= 64 threads): disjoint slices for ranges launched concurrently
-      const int rc = cblf_launch_A(&d, sizeof(d), &h->dcfg, sizeof(h->dcfg), h->mp, i0, i1, dels, first, h->d_warn, redo_, big ? 1 : 0, h->cfg.output_level, h->max_l1, st);
+      const int rc = cblf_launch_A(&d, sizeof(d), &h->dcfg, sizeof(h->dcfg), h->mp, i0, i1, dels, first, h->d_warn, redo_, big ? 1 : 0, h->cfg.output_level, h->max_l1 ? h->carveout : -2, st);
       if (rc) return fail(CABLE_E_CUDA, std::string("fast kernel A launch: ") + cudaGetErrorString((cudaError_t)rc));
       if (getenv("CABLE_B200_FASTDIV_DEBUG")) {             // debugging aid: how many blocks the fast build handed back
         std::vector<int> fl(nblk);
@@ -355,15 +373,70 @@ int check_spreads(cable_handle *h) {
   return CABLE_OK;
 }
 
+// Per-PFT / per-soil-type tables: a class (veg%* keyed by veg%iveg, soil%* keyed by soil%isoilm) is served from tables when
+// every tabulated member of it is a pure function of the key over all tiles of this handle (bit-for-bit), which is how the
+// offline driver fills them from pft_params.nml / cable_soilparm.nml.  Otherwise the class stays per-tile.
+int build_param_tables(cable_handle *h) {
+  h->tbl_classes = 0;
+  if (!h->tbl_enable) return CABLE_OK;
+  const int mp = h->mp;
+  std::vector<float> tbl((size_t)TBL_COUNT * CBL_TBL_KEYS, 0.f);
+  std::vector<double> tbld((size_t)2 * CBL_TBL_KEYS, 0.0);
+  for (int cls = 1; cls <= 2; cls++) {
+    const int *key = (const int *)h->host[cls == 1 ? FID_veg_iveg : FID_soil_isoilm];
+    if (!key) continue;
+    bool ok = true;
+    std::vector<char> seen(CBL_TBL_KEYS);
+    for (int i = 0; i < mp && ok; i++) ok = key[i] >= 0 && key[i] < CBL_TBL_KEYS;
+    for (int id = 0; id < NFIELDS && ok; id++) {
+      if (g_tbl_class[id] != cls || (g_tbl_slot[id] < 0 && g_tbl_drow[id] < 0)) continue;
+      if (!h->host[id]) { ok = false; break; }
+      const cable_field_info &f = g_fields[id];
+      for (int k = 0; k < f.n1 * f.n2 && ok; k++) {
+        std::fill(seen.begin(), seen.end(), 0);
+        if (g_tbl_slot[id] >= 0) {
+          const uint32_t *v = (const uint32_t *)h->host[id] + (size_t)k * mp;
+          uint32_t *row = (uint32_t *)&tbl[(size_t)(g_tbl_slot[id] + k) * CBL_TBL_KEYS];
+          for (int i = 0; i < mp; i++) {
+            const int q = key[i];
+            if (!seen[q]) { seen[q] = 1; row[q] = v[i]; }
+            else if (row[q] != v[i]) { ok = false; break; }
+          }
+        } else {
+          const uint64_t *v = (const uint64_t *)h->host[id];
+          uint64_t *row = (uint64_t *)&tbld[(size_t)g_tbl_drow[id] * CBL_TBL_KEYS];
+          for (int i = 0; i < mp; i++) {
+            const int q = key[i];
+            if (!seen[q]) { seen[q] = 1; row[q] = v[i]; }
+            else if (row[q] != v[i]) { ok = false; break; }
+          }
+        }
+      }
+    }
+    if (ok) h->tbl_classes |= cls;
+  }
+  if (!h->d_tbl) {
+    CUDA_TRY(cudaMalloc(&h->d_tbl, tbl.size() * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->d_tbl_d, tbld.size() * sizeof(double)));
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_tbl, tbl.data(), tbl.size() * sizeof(float), cudaMemcpyHostToDevice, h->s_compute));
+  CUDA_TRY(cudaMemcpyAsync(h->d_tbl_d, tbld.data(), tbld.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  return CABLE_OK;
+}
+
 // host-side writes to resident fields announced with cable_b200_mark_dirty go up before the next step reads them
 int flush_dirty(cable_handle *h) {
   if (!h->any_dirty) return CABLE_OK;
+  bool param = false;
   for (int id = 0; id < NFIELDS; id++) {
     if (!h->dirty[id]) continue;
     int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc;
     h->dirty[id] = false;
+    param = param || g_fields[id].role == PARAM;
   }
   h->any_dirty = false;
+  if (param) { int rc = build_param_tables(h); if (rc) return rc; }      // a changed parameter may leave (or re-enter) its table
   return CABLE_OK;
 }
 
@@ -442,6 +515,8 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   if (const char *e = getenv("CABLE_B200_STEP_CHAINS")) h->step_chains = atoi(e);
   if (const char *e = getenv("CABLE_B200_TILE_ORDER")) h->tile_order = atoi(e);
   if (const char *e = getenv("CABLE_B200_FASTDIV")) h->fastdiv = atoi(e);
+  if (const char *e = getenv("CABLE_B200_TABLES")) h->tbl_enable = atoi(e);
+  if (const char *e = getenv("CABLE_B200_CARVEOUT")) h->carveout = atoi(e);
   // device-side config + host-evaluated constants
   DevCfg &d = h->dcfg;
   d.gs_switch = cfg->gs_switch; d.fwsoil_switch = cfg->fwsoil_switch; d.ssnow_potev = cfg->ssnow_potev;
@@ -575,6 +650,8 @@ int cable_b200_destroy(cable_handle *h) {
   if (h->d_redo) cudaFree(h->d_redo);
   if (h->d_order) cudaFree(h->d_order);
   cudaFree(h->leaf_scr_d); cudaFree(h->leaf_scr_f);
+  if (h->d_tbl) cudaFree(h->d_tbl);
+  if (h->d_tbl_d) cudaFree(h->d_tbl_d);
   if (h->arena) cudaFree(h->arena);
   delete h;
   return CABLE_OK;
@@ -649,7 +726,13 @@ int cable_b200_upload(cable_handle *h, unsigned role_mask) {
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_compute));
   if (role_mask & PARAM) { int rc = build_tile_order(h); if (rc) return rc; }
+  if (role_mask & PARAM) { int rc = build_param_tables(h); if (rc) return rc; }
   return CABLE_OK;
+}
+
+int cable_b200_param_table_classes(cable_handle *h) {
+  if (!h) return fail(CABLE_E_ARG, "null handle");
+  return h->tbl_classes;
 }
 
 int cable_b200_download(cable_handle *h, unsigned role_mask, unsigned flag_mask) {

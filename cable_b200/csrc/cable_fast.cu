@@ -15,9 +15,6 @@ using namespace cblf;
 #ifndef CBL_MINB_A
 #define CBL_MINB_A 1
 #endif
-#ifndef CBL_BLOCK_A
-#define CBL_BLOCK_A 768
-#endif
 #ifndef CBL_SMALL_BLOCK
 #define CBL_SMALL_BLOCK 128
 #endif
@@ -31,7 +28,7 @@ static int launch(const DevPtrs &d, const DevCfg &c, int mp, int i0, int i1, flo
   static bool once[64] = {};             // function attributes are per device
   int dev = 0; cudaGetDevice(&dev); dev &= 63;
   if (!once[dev]) {
-    if (max_l1) cudaFuncSetAttribute(cbm_kernel<1, BL, MB, LV, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    if (max_l1 != -2) cudaFuncSetAttribute(cbm_kernel<1, BL, MB, LV, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, max_l1);   // per cent shared; 0 = max L1
     cudaGetLastError();
     once[dev] = true;
   }

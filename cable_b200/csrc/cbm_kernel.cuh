@@ -100,14 +100,44 @@ cbm_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ DevCfg c, 
   const int i = (PHASE == 1 && d.tile_order) ? d.tile_order[i_lin] : i_lin;
   Tile t;
 
+  // ---- per-PFT / per-soil-type parameter tables staged in shared memory (cbm_types.cuh, CBL_CLASS_*): one coalesced read
+  // of the ~3 KB table block per thread block replaces a global load per tile and veg%* / soil%* member
+#ifndef CBL_TABLES
+#define CBL_TABLES 1          // 0: compile the tables out (tuning aid)
+#endif
+#if CBL_TABLES >= 1
+  __shared__ float s_tbl[TBL_COUNT * CBL_TBL_KEYS];
+  __shared__ double s_tbl_d[2 * CBL_TBL_KEYS];
+  const int tcls = (CBL_TABLES == 2) ? 0 : d.tbl_classes;
+#else
+  float *s_tbl = nullptr; double *s_tbl_d = nullptr;
+  constexpr int tcls = 0;
+#endif
+  if (tcls) {
+    for (int k = threadIdx.x; k < TBL_COUNT * CBL_TBL_KEYS; k += BLOCK) s_tbl[k] = d.tbl[k];
+    if (threadIdx.x < 2 * CBL_TBL_KEYS) s_tbl_d[threadIdx.x] = d.tbl_d[threadIdx.x];
+    __syncthreads();
+  }
   // ---- load forcing, per-tile parameters, prognostic state (+ exchange fields in kernel B): coalesced SoA reads ----
+  // (veg%iveg / soil%isoilm are the first rows of their types in the registry, so the keys are loaded before their members)
+#define CBL_TBL_KEY(T) min(max(CBL_CLASS_##T == 1 ? t.veg_iveg : t.soil_isoilm, 0), CBL_TBL_KEYS - 1)
 #define CABLE_F1(T, m, ct, role, flags)                                                          \
-  if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) t.T##_##m = CBL_LD(&d.T##_##m[i]);
+  if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) {                                 \
+    if (CBL_TBL_ON(T, m, ct, role, flags) && (tcls & CBL_CLASS_##T)) t.T##_##m = (ct)s_tbl[TBL_##T##_##m * CBL_TBL_KEYS + CBL_TBL_KEY(T)]; \
+    else if (CBL_TBLD_ON(T, m, ct, role, flags) && (tcls & CBL_CLASS_##T)) t.T##_##m = (ct)s_tbl_d[CBL_TBLD_ROW(m) * CBL_TBL_KEYS + CBL_TBL_KEY(T)]; \
+    else t.T##_##m = CBL_LD(&d.T##_##m[i]);                                                      \
+  }
 #define CABLE_FA(T, m, ct, n1, n2, role, flags)                                                  \
   if (load_in_phase(PHASE, CBL_ROLE_##role, CBL_FLAGS(flags))) {                                 \
-    _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = CBL_LD(&d.T##_##m[i + smp * k]); \
+    if (CBL_TBL_ON(T, m, ct, role, flags) && (tcls & CBL_CLASS_##T)) {                           \
+      const int key_ = CBL_TBL_KEY(T);                                                           \
+      _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = (ct)s_tbl[(TBL_##T##_##m + k) * CBL_TBL_KEYS + key_]; \
+    } else {                                                                                     \
+      _Pragma("unroll") for (int k = 0; k < (n1) * (n2); k++) t.T##_##m[k] = CBL_LD(&d.T##_##m[i + smp * k]); \
+    }                                                                                            \
   }
 #include "../../include/cable_b200_fields.def"
+#undef CBL_TBL_KEY
 
   bool veg_branch = false, veg_mask = false;
   if (PHASE & 1) {

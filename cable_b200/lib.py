@@ -55,6 +55,7 @@ EXPORTS = [
     "cable_b200_step", "cable_b200_cbm", "cable_b200_sync", "cable_b200_device_ptr",
     "cable_b200_compute_stream", "cable_b200_profile", "cable_b200_get_counters",
     "cable_b200_reset_counters", "cable_b200_grid_reduce", "cable_b200_mark_dirty", "cable_b200_set_output_mask",
+    "cable_b200_param_table_classes",
     # driver stages either side of cbm()
     "cable_b200_driver_init", "cable_b200_set_met_async", "cable_b200_upload_lai", "cable_b200_post_step",
     "cable_b200_output_plan", "cable_b200_driver_field_id", "cable_b200_output_accumulate",
@@ -110,6 +111,7 @@ def load() -> C.CDLL:
     lib.cable_b200_get_counters.argtypes = [H, C.POINTER(Counters)]
     lib.cable_b200_reset_counters.argtypes = [H]
     lib.cable_b200_grid_reduce.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.cable_b200_param_table_classes.argtypes = [H]
     lib.cable_b200_mark_dirty.argtypes = [H, C.c_int]
     lib.cable_b200_set_output_mask.argtypes = [H, C.c_void_p, C.c_int]
     lib.cable_b200_driver_init.argtypes = [H, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -177,6 +177,12 @@ int          cable_b200_upload(cable_handle *h, unsigned role_mask);
 int          cable_b200_download(cable_handle *h, unsigned role_mask,
                                  unsigned flag_mask);
 
+/* Which parameter classes the kernels serve from per-type tables staged in shared memory instead of the per-tile
+ * arrays: bit 0 = veg%* (every member a pure function of veg%iveg over this handle's tiles, as init_veg_from_vegin
+ * fills them, cable_parameters.F90:3277), bit 1 = soil%* by soil%isoilm.  Decided at cable_b200_upload(PARAM) and again
+ * after cable_b200_mark_dirty of a parameter; a class that fails the check is read per tile as the interface says.  */
+int          cable_b200_param_table_classes(cable_handle *h);
+
 /* A host-side write to a resident field (PARAM or STATE) between two steps -- a restart read, a parameter the
  * driver changes mid-run, casa feedback into veg%vcmax ... -- is announced per field; the next cable_b200_cbm() /
  * cable_b200_step() uploads the bound array before it runs.  (The reference cbm reads the host arrays every call;

@@ -198,3 +198,48 @@ def test_post_step_is_the_last_reader_of_its_forcing_slot():
             got[mode] = {n: h.driver_download(n) for n in ("bal_wbal_tot", "bal_precip_tot", "bal_Radbalsum", "bal_ebal_tot")}
     for n in got["sync"]:
         assert np.array_equal(got["sync"][n], got["ahead"][n]), n
+
+
+def test_parameter_tables_in_shared_memory_are_bit_identical_and_fall_back(monkeypatch):
+    """veg%* by veg%iveg and soil%* by soil%isoilm are served from per-type tables staged in shared memory when every member
+    is a pure function of its key (as init_veg_from_vegin / the soil-type table fill them); results are bit-identical to the
+    per-tile reads, and a class whose member stops being a function of the key (here: a per-tile veg%vcmax, as casa_feedback
+    writes it) falls back to the per-tile arrays -- also after cable_b200_mark_dirty in mid-run."""
+    cfg, grid, T, F = make_case(400, start_doy=200)
+    cfg.output_level = 2
+    runs = {}
+    for mode in ("tables", "per_tile", "perturbed"):
+        monkeypatch.setenv("CABLE_B200_TABLES", "0" if mode == "per_tile" else "1")
+        X = {k: v.copy() for k, v in T.items()}
+        if mode == "perturbed":
+            X["veg_vcmax"][0, ::7] *= np.float32(1.03)
+        with CableB200(grid.mp, cfg) as h:
+            h.bind(X); h.upload_params(); h.upload_state()
+            classes = [h.param_table_classes()]
+            for k in range(5):
+                F.fill(X, k)
+                if mode == "tables" and k == 3:
+                    X["veg_vcmax"][0, ::7] *= np.float32(1.03)
+                    h.mark_dirty("veg_vcmax")
+                h.cbm(k + 1, DELS)
+                classes.append(h.param_table_classes())
+        runs[mode] = (X, classes)
+    assert runs["tables"][1][:4] == [3, 3, 3, 3] and runs["tables"][1][4:] == [2, 2], runs["tables"][1]
+    assert set(runs["per_tile"][1]) == {0} and set(runs["perturbed"][1]) == {2}
+    # same inputs for the first three steps: identical bits whichever way the parameters were read -- check on a fresh pair
+    A = {k: v.copy() for k, v in T.items()}; Bt = {k: v.copy() for k, v in T.items()}
+    for X, tables in ((A, "1"), (Bt, "0")):
+        monkeypatch.setenv("CABLE_B200_TABLES", tables)
+        with CableB200(grid.mp, cfg) as h:
+            h.bind(X); h.upload_params(); h.upload_state()
+            for k in range(4):
+                F.fill(X, k); h.cbm(k + 1, DELS)
+    for f in output_fields():
+        assert np.array_equal(A[f.name], Bt[f.name], equal_nan=True), f.name
+    # the perturbed-from-the-start run equals the oracle with the same per-tile parameter
+    Y = {k: v.copy() for k, v in T.items()}
+    Y["veg_vcmax"][0, ::7] *= np.float32(1.03)
+    o = Oracle(Y, cfg, cr_math=True)
+    for k in range(5):
+        F.fill(Y, k); o.cbm(k + 1, DELS)
+    _assert_parity(Y, runs["perturbed"][0])
