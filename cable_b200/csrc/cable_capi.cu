@@ -121,8 +121,12 @@ bool carbon_tables(int mvtype, float *rw, float *tfcl, float *tvclst) {   // cab
 
 }  // namespace
 
+struct cable_casa_state;            // CASA-CNP daily step (casa_capi.inc)
+namespace { void casa_free(cable_handle *h); }
+
 struct cable_handle {
   int mp = 0, device = 0;
+  cable_casa_state *casa = nullptr;
   cable_cfg cfg{};
   DevCfg dcfg{};
   char *arena = nullptr; size_t arena_bytes = 0;
@@ -632,6 +636,7 @@ int cable_b200_destroy(cable_handle *h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   cable_b200_comm_destroy(h);          // while the streams still exist
+  casa_free(h);
   for (int id = 0; id < NFIELDS; id++) if (h->host_pinned[id]) cudaHostUnregister(h->host[id]);
   for (auto ev : h->ev_forcing_ready) cudaEventDestroy(ev);
   for (auto ev : h->ev_slot_free) cudaEventDestroy(ev);
@@ -1415,3 +1420,5 @@ int cable_b200_driver_download(cable_handle *h, const char *name, void *host) {
 }
 
 }  // extern "C"
+
+#include "casa_capi.inc"

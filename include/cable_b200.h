@@ -345,6 +345,39 @@ int          cable_b200_output_gather_async(cable_handle *h, int root, float *ho
 /* copy a driver array (float, or double for "bal_owb") to the host; synchronous */
 int          cable_b200_driver_download(cable_handle *h, const char *name, void *host);
 
+/* ---------------------------------------------------------------------------
+ * CASA-CNP daily biogeochemistry (BASELINE config 5) on the same resident tile layout.
+ * Replaces, for a caller that runs with icycle > 0,
+ *     CALL bgcdriver(ktau, kstart, kend, dels, met, ssnow, canopy, veg, soil, climate, casabiome, casapool, casaflux,
+ *                    casamet, casabal, phen, pop, spinConv, spinup, ktauday, idoy, loy, dump_read, dump_write, LALLOC)
+ * (src/science/casa-cnp/bgcdriver.F90:7; call site src/offline/cable_serial.F90:621-629): every step it accumulates the day's
+ * casamet%tairk / tsoil / moist and casaflux%meangpp / meanrleaf from the device-resident met%tk, ssnow%tgg, ssnow%wb,
+ * canopy%fpn, canopy%frday; at the end of a day it runs biogeochem (biogeochem_casa.F90:7) for every tile.
+ * Members of casa_biome / casa_pool / casa_flux / casa_met / casa_balance / phen_variable are bound by name
+ * "<type>_<member>" (registry: include/cable_b200_casa_fields.def, generated from the reference's own type definitions);
+ * casabiome / phen%TKshed rows are per vegetation type (mvtype), casabiome%xkplab/xkpsorb/xkpocc per soil order (12).
+ * "soil_silt" / "soil_clay" (REAL (mp)) are bound through the same call.  Unsupported switches are rejected at init:
+ * CALL_POP, LALLOC = 2, cable_user%SRF, PHENOLOGY_SWITCH = 'climate', l_landuse.                                      */
+typedef struct cable_casa_cfg {
+  int struct_bytes;
+  int icycle;                  /* 1: C, 2: C+N, 3: C+N+P (casadimension)                        */
+  int lalloc;                  /* LALLOC of bgcdriver: 0 fixed, 1 dynamic, 3 LA:SA               */
+  int call_climate;            /* cable_user%call_climate (casa_rplant acclimation branch)      */
+  int l_limit_labile;          /* cable_user%l_limit_labile                                      */
+  int mvtype;                  /* rows of the casabiome tables                                   */
+  int call_pop, srf, phenology_climate, l_landuse;   /* must be 0                                */
+} cable_casa_cfg;
+void         cable_b200_casa_default_cfg(cable_casa_cfg *cfg);
+int          cable_b200_casa_nfields(void);
+int          cable_b200_casa_field_id(const char *name);
+int          cable_b200_casa_field_info(int id, cable_field_info *out, int *key);   /* key: 0 tile, 1 veg type, 2 soil order */
+int          cable_b200_casa_init(cable_handle *h, const cable_casa_cfg *cfg);
+int          cable_b200_casa_bind(cable_handle *h, const char *name, void *host);
+int          cable_b200_casa_upload(cable_handle *h);      /* every bound array H2D                  */
+int          cable_b200_casa_download(cable_handle *h);    /* every bound per-tile array D2H          */
+int          cable_b200_bgcdriver(cable_handle *h, int ktau, int kstart, int kend, float dels, int ktauday, int idoy, int loy);
+int          cable_b200_casa_biogeochem(cable_handle *h, int idoy);   /* biogeochem alone (bgcdriver's dump_read branch) */
+
 #ifdef __cplusplus
 }
 #endif

@@ -314,7 +314,8 @@ class Interp:
             elif bare in mapping.values():
                 return None                    # renamed away
         if uname in self.stub_modules:
-            return ("stub", uname, remote)
+            # only names a USE statement imports explicitly resolve to a stub; a blanket USE of a stubbed module exports nothing
+            return ("stub", uname, remote) if (only is not None and only[0] == "only") else None
         um = self.module(uname)
         return self.lookup_in_module(um, remote, seen)
 

@@ -1,0 +1,111 @@
+"""GPU: the CASA-CNP daily step (cable_b200_casa_biogeochem / cable_b200_bgcdriver) against golden vectors produced by the
+reference's own Fortran source (tests/golden/make_casa_golden.py: /root/reference's biogeochem and bgcdriver executed by the
+interpreter in oracle/frun).  All CASA state is REAL(r_2): the bar is 1e-9 relative with identical inputs (the device's
+exp / pow differ from glibc's by <= 1 ulp), 2e-5 where the inputs come from the device's own cbm steps."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_casa_golden as G           # noqa: E402
+from cable_b200 import casa, lib, synth  # noqa: E402
+from cable_b200.cbm import CableB200     # noqa: E402
+from util import DELS, make_case         # noqa: E402
+
+pytestmark = pytest.mark.gpu
+BALANCES = ("casabal_cbalance", "casabal_nbalance", "casabal_pbalance", "casabal_sumcbal", "casabal_sumnbal", "casabal_sumpbal")
+GOLD = os.path.join(HERE, "golden", "fortran_casa_v1.npz")
+
+
+def _rel(got, want):
+    a, b = want.astype(np.float64), got.astype(np.float64)
+    floor = 1e-6 * max(float(np.abs(a).max()), 1e-300)
+    return float((np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)).max())
+
+
+@pytest.mark.parametrize("case", list(G.BIO))
+def test_biogeochem_matches_the_fortran_run(case):
+    z = np.load(GOLD)
+    cfg, grid, T, A, silt, clay, ccfg = G.bio_inputs(case)
+    cfg.call_climate = ccfg.call_climate
+    worst = 0.0
+    with CableB200(grid.mp, cfg) as h:
+        h.bind(T); h.upload_params(); h.upload_state()
+        cs = casa.Casa(h, ccfg)
+        cs.bind(A, silt, clay); cs.upload()
+        for day in range(G.NDAYS):
+            idoy = 1 if day == 0 else 364 + day
+            A["casaflux_crmplant"][0] = 0.12 * A["casaflux_cgpp"][0]
+            cs.upload()
+            cs.biogeochem(idoy)
+            cs.download()
+            for f in casa.FIELDS:
+                key = f"bio/{case}/day{day}/{f.name}"
+                if key not in z.files:
+                    continue
+                want = z[key]
+                if f.dtype == np.int32:
+                    assert np.array_equal(A[f.name], want), (case, day, f.name)
+                    continue
+                assert np.all(np.isfinite(A[f.name])), (case, day, f.name)
+                if f.name in BALANCES:          # residuals of pools of order 1e3-1e4 gC/m2: rounding noise, judged absolutely
+                    assert float(np.abs(A[f.name] - want).max()) <= 1e-8, (case, day, f.name)
+                    continue
+                r = _rel(A[f.name], want)
+                assert r <= 1e-9, (case, day, f.name, r)
+                worst = max(worst, r)
+    print(f"{case}: worst relative difference vs the Fortran run {worst:.2e}")
+    # the cases must exercise both signs of NPP (except the acclimation cases, which have no NPP < 0 branch)
+    cn = z[f"bio/{case}/day{G.NDAYS - 1}/casaflux_cnpp"][0]
+    assert (cn > 0).any()
+
+
+@pytest.mark.parametrize("case", list(G.DRV))
+def test_bgcdriver_after_device_cbm_steps(case):
+    """Two model days of [cbm step -> bgcdriver] on the device (daily accumulation of casamet / casaflux from the resident cbm
+    state, biogeochem at the end of each day) against [pinned oracle cbm -> the reference's Fortran bgcdriver]."""
+    z = np.load(GOLD)
+    cfg, grid, T, F = make_case(G.NLAND, start_doy=G.DOY)
+    ccfg = G.casa_cfg(G.DRV[case])
+    A = casa.synth_casa(grid, T, ccfg, seed=31)
+    silt, clay = casa.soil_texture(T)
+    cfg.output_level = 1
+    with CableB200(grid.mp, cfg) as h:
+        h.bind(T); h.upload_params(); h.upload_state()
+        cs = casa.Casa(h, ccfg)
+        cs.bind(A, silt, clay); cs.upload()
+        for k in range(16):
+            F.fill(T, k)
+            h.set_forcing_async(0); h.step(k + 1, DELS, 0)
+            cs.bgcdriver(k + 1, 1, 10000, DELS, 8, G.DOY + k // 8)
+            h.sync()
+        cs.download()
+    for f in casa.FIELDS:
+        key = f"drv/{case}/{f.name}"
+        if key not in z.files or f.dtype == np.int32:
+            continue
+        r = _rel(A[f.name], z[key])
+        # balances are differences of large pools: judge them against the pool scale
+        tol = 2e-5
+        if f.name in BALANCES:
+            assert float(np.abs(A[f.name]).max()) < 1e-6, (f.name, float(np.abs(A[f.name]).max()))
+            continue
+        assert r <= tol, (case, f.name, r)
+
+
+def test_casa_init_rejects_what_is_not_on_the_device():
+    cfg, grid, T, F = make_case(4)
+    with CableB200(grid.mp, cfg) as h:
+        for bad in (dict(icycle=0), dict(icycle=4), dict(lalloc=2), dict(call_pop=1), dict(srf=1), dict(phenology_climate=1), dict(l_landuse=1)):
+            c = casa.default_cfg()
+            for k, v in bad.items():
+                setattr(c, k, v)
+            with pytest.raises(lib.CableError):
+                casa.Casa(h, c)
+        c = casa.default_cfg()
+        cs = casa.Casa(h, c)
+        with pytest.raises(lib.CableError):
+            cs.bgcdriver(1, 1, 10, DELS, 8, 1)          # no step has run
