@@ -519,6 +519,50 @@ def run_b200(args) -> None:
     mirror_all = dropin_leg(None)
     mirror_all["api"] = "cable_b200_cbm, output_level=1, no mask: every prognostic + driver-visible array mirrored to the host each step"
 
+    # ---- (2c) BASELINE config 5: the same grid with CASA-CNP biogeochemistry (icycle = 3, dynamic allocation): per step
+    # cbm -> bgcdriver (daily accumulation; biogeochem for every tile at the end of each model day = every 8th step) ->
+    # sumcflux / balances, all device-resident (cable_serial.F90:594-715)
+    casa_leg = None
+    if not args.no_casa:
+        from cable_b200 import casa as casa_mod
+        cfg5 = lib.default_cfg(); cfg5.n_forcing_slots = RING; cfg5.output_level = 1; cfg5.icycle = 3
+        ccfg = casa_mod.default_cfg(); ccfg.icycle = 3; ccfg.lalloc = 1
+        h.close()
+        for n, a in state0.items():
+            tiles[n][...] = a
+        h = CableB200(mp, cfg5, device=local)
+        h.bind(tiles); h.upload_params(); h.upload_state()
+        for k in range(RING):
+            h.bind(fsets[k]); h.set_forcing_async(k)
+        h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+        cs = casa_mod.Casa(h, ccfg)
+        A = casa_mod.synth_casa(grid, tiles, ccfg, seed=31)
+        silt, clay = casa_mod.soil_texture(tiles)
+        cs.bind(A, silt, clay); cs.upload()
+        ktauday = int(86400 / DELS)
+        def casa_step(k):
+            h.step(k + 1, DELS, k % RING)
+            cs.bgcdriver(k + 1, 1, 1 << 30, DELS, ktauday, 172 + k // ktauday)
+            h.post_step(k + 1, 1, DELS)
+        for k in range(ktauday):
+            casa_step(k)
+        h.sync(); h.reset_counters(); barrier()
+        Kc = 2 * ktauday
+        t0 = time.perf_counter()
+        for k in range(ktauday, ktauday + Kc):
+            casa_step(k)
+        h.sync(); barrier()
+        t_c = max_over_ranks(time.perf_counter() - t0)
+        cc = h.counters()
+        cs.download()
+        npp = A["casaflux_cnpp"][0]
+        casa_leg = {"value": mp_total * Kc / t_c, "unit": "tile-timesteps/s", "ms_per_step": t_c / Kc * 1e3, "steps": Kc,
+                    "gpu_launches": int(cc.kernel_launches), "biogeochem_calls": Kc // ktauday,
+                    "outputs_finite": bool(np.isfinite(npp).all() and np.isfinite(A["casapool_cplant"]).all()),
+                    "workload": "BASELINE config 5 on the same grid: cbm + bgcdriver (icycle=3 C+N+P, LALLOC=1; biogeochem for every "
+                                "tile once per model day = every 8th step) + sumcflux/balances, device-resident; groundwater "
+                                "(gw_model) is rejected by the reference snapshot itself (cable_canopy.F90:463-464)"}
+
     # ---- (3) CPU baseline on this box's host cores (rank 0, N=1 only) -----------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -581,6 +625,7 @@ def run_b200(args) -> None:
                            "tile expansion) -> cable_b200_step -> cable_b200_post_step -> cable_b200_output_fetch_async "
                            "(grid-cell output rows D2H every step, output%averaging='all')"},
             "e2e_dropin_mirror": mirror,
+            "config5_casa_cnp": casa_leg,
             "e2e_dropin_mirror_all": mirror_all,
             "gpu_launches": launches,
             "clocks": clocks,
@@ -608,6 +653,7 @@ def main() -> None:
     ap.add_argument("--no-flush", action="store_true", help="small shards: do not flush L2 between timed steps")
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-casa", action="store_true", help="skip the config-5 (CASA-CNP) leg")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 on their own (NCCL prints its
     # version banner there at NCCL_DEBUG=VERSION and above) are sent to stderr for the whole run, and print() gets the

@@ -122,7 +122,11 @@ bool carbon_tables(int mvtype, float *rw, float *tfcl, float *tvclst) {   // cab
 }  // namespace
 
 struct cable_casa_state;            // CASA-CNP daily step (casa_capi.inc)
-namespace { void casa_free(cable_handle *h); }
+namespace {
+void casa_free(cable_handle *h);
+int casa_icycle(const cable_handle *h);                   // icycle of sumcflux: 0 without CASA; -1 when cfg.icycle > 0 but no CASA state
+void casa_sumcflux_ptrs(cable_handle *h, PostIn &p);
+}
 
 struct cable_handle {
   int mp = 0, device = 0;
@@ -1166,7 +1170,8 @@ int cable_b200_upload_lai(cable_handle *h) {
 
 int cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels, int do_mass_bal, int do_energy_bal) {
   if (!h || !h->drv.on) return fail(CABLE_E_ARG, "post_step: call cable_b200_driver_init first");
-  if (h->cfg.icycle > 1) return fail(CABLE_E_UNSUPPORTED, "post_step: sumcflux with icycle > 1 needs CASA-CNP (out of scope)");
+  const int icycle = casa_icycle(h);
+  if (icycle < 0) return fail(CABLE_E_ARG, "post_step: icycle > 0 needs the CASA-CNP state (cable_b200_casa_init) for sumcflux");
   if (h->ctr.steps <= 0) return fail(CABLE_E_ARG, "post_step: no step has run");
   CUDA_TRY(cudaSetDevice(h->device));
   // met%* live in the forcing slot of the step just enqueued; dev_ptr ignores the slot for resident fields
@@ -1174,6 +1179,9 @@ int cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels, int 
   PostIn p{};
   p.smelt = F(FID_ssnow_smelt); p.rnof1 = F(FID_ssnow_rnof1); p.rnof2 = F(FID_ssnow_rnof2); p.runoff = F(FID_ssnow_runoff);
   p.tscrn = F(FID_canopy_tscrn); p.fpn = F(FID_canopy_fpn); p.frday = F(FID_canopy_frday); p.frp = F(FID_canopy_frp);
+  p.fnpp = F(FID_canopy_fnpp); p.fgpp = F(FID_canopy_fgpp); p.fra = F(FID_canopy_fra);
+  p.icycle = icycle;
+  if (icycle > 0) casa_sumcflux_ptrs(h, p);
   p.frpw = F(FID_canopy_frpw); p.frpr = F(FID_canopy_frpr); p.frs = F(FID_canopy_frs); p.fnee = F(FID_canopy_fnee);
   p.precip = F(FID_met_precip); p.delwc = F(FID_canopy_delwc); p.snowd = F(FID_ssnow_snowd); p.osnowd = F(FID_ssnow_osnowd);
   p.fevw = F(FID_canopy_fevw); p.fev = F(FID_canopy_fev); p.cls = F(FID_ssnow_cls); p.rlam = F(FID_air_rlam);

@@ -76,8 +76,11 @@ __global__ void met_expand_kernel(const float *__restrict__ land, const int nlan
 // ---- post-step driver statements ------------------------------------------------------------------------------
 struct PostIn {               // outputs of cbm on the device (registry fields)
   float *smelt, *rnof1, *rnof2, *runoff;                       // scaled in place, as the reference does
-  const float *tscrn, *fpn, *frday, *frp, *frpw, *frpr, *frs;
-  float *fnee;
+  const float *tscrn, *fpn, *frday;
+  float *frp, *frpw, *frpr, *frs, *fnee, *fnpp, *fgpp, *fra;   // rewritten from casaflux when icycle > 0
+  // CASA-CNP (icycle > 0, casa_sumcflux.F90:60-75, 99-108): casaflux%crmplant (mp,3), crgplant, crsoil, cnpp, cgpp, clabloss
+  const double *crmplant, *crgplant, *crsoil, *cnpp, *cgpp, *clabloss;
+  int icycle;
   const float *precip, *delwc, *snowd, *osnowd, *fevw, *fev, *cls, *rlam, *fsd, *fld, *albedo, *transd, *otss, *tv,
               *fnv, *fns, *fhs, *ga, *fhv, *fh, *qcan, *qssabs, *flws;
   const double *wbtot, *fevc, *fes;
@@ -103,7 +106,18 @@ __global__ void post_step_kernel(const PostIn p, const DriverArrays a, const int
   const float tscrn = p.tscrn[i];
   a.tscrn_max_daily[i] = fmaxf(a.tscrn_max_daily[i], tscrn);
   a.tscrn_min_daily[i] = fminf(a.tscrn_min_daily[i], tscrn);
-  // sumcflux, icycle <= 1 (casa_sumcflux.F90:76-102)
+  // sumcflux (casa_sumcflux.F90:60-108)
+  if (p.icycle > 0) {          // :60-75: respiration and productivity from the day's CASA fluxes (r_2 / REAL 86400.0 -> REAL)
+    const double rw = p.crmplant[i + m * 1], rr = p.crmplant[i + m * 2];
+    const float frp_c = (float)(((rw + rr) + p.crgplant[i]) / (double)86400.0f);
+    p.frp[i] = frp_c;
+    p.frs[i] = (float)(p.crsoil[i] / (double)86400.0f);
+    p.frpw[i] = (float)(rw / (double)86400.0f);
+    p.frpr[i] = (float)(rr / (double)86400.0f);
+    p.fnpp[i] = (float)(p.cnpp[i] / (double)86400.0f);
+    p.fgpp[i] = (float)(p.cgpp[i] / (double)86400.0f);
+    p.fra[i] = frp_c + p.frday[i];
+  }
   const float fpn = p.fpn[i], frday = p.frday[i], frp = p.frp[i], frpw = p.frpw[i], frpr = p.frpr[i], frs = p.frs[i];
   if (ktau == kstart) {
     a.sumpn[i] = fpn * dels; a.sumrd[i] = frday * dels; a.dsumpn[i] = fpn * dels; a.dsumrd[i] = frday * dels;
@@ -116,7 +130,8 @@ __global__ void post_step_kernel(const PostIn p, const DriverArrays a, const int
     a.sumrp[i] = a.sumrp[i] + frp * dels; a.dsumrp[i] = a.dsumrp[i] + frp * dels;
     a.sumrs[i] = a.sumrs[i] + frs * dels;
   }
-  p.fnee[i] = fpn + frs + frp;                                                    // :96
+  if (p.icycle <= 1) p.fnee[i] = fpn + frs + frp;                                 // :99-100
+  else p.fnee[i] = (float)(((p.crsoil[i] - p.cnpp[i]) + p.clabloss[i]) / (double)86400.0f);   // :106 (l_vcmaxFeedbk = .FALSE.)
   const double fes_cls = p.fes[i] / (double)p.cls[i];
   const double dels_rlam_num = (double)dels, rlam = (double)p.rlam[i];
   if (do_mass_bal) {                                                              // cable_checks.F90:472-551

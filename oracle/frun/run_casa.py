@@ -32,7 +32,8 @@ class FortranCasa:
         I.call("phenvariable", "alloc_phenvariable", S["phen"], np.int32(mp))
         for short, tn, al in (("veg", "veg_parameter_type", "alloc_veg_parameter_type"), ("soil", "soil_parameter_type", "alloc_soil_parameter_type"),
                               ("met", "met_type", "alloc_met_type"), ("ssnow", "soil_snow_type", "alloc_soil_snow_type"),
-                              ("canopy", "canopy_type", "alloc_canopy_type")):
+                              ("canopy", "canopy_type", "alloc_canopy_type"), ("bgc", "bgc_pool_type", "alloc_bgc_pool_type"),
+                              ("sum_flux", "sum_flux_type", "alloc_sum_flux_type")):
             s = I.new_struct(I.lookup_in_module(dt, "$type:" + tn))
             I.call("cable_def_types_mod", al, s, np.int32(mp))
             S[short] = s
@@ -80,3 +81,18 @@ class FortranCasa:
                     S["phen"], S["pop"], np.bool_(False), np.bool_(False), np.int32(ktauday), np.int32(idoy), np.int32(loy),
                     np.bool_(False), np.bool_(False), np.int32(self.cfg.lalloc))
         self.pull()
+
+    SUMCFLUX_CANOPY = ("frp", "frs", "frpw", "frpr", "fnpp", "fgpp", "fra", "fnee")
+    SUMCFLUX_SUMS = ("sumpn", "sumrp", "sumrpw", "sumrpr", "sumrs", "sumrd", "dsumpn", "dsumrp", "dsumrd")
+
+    def sumcflux(self, ktau, kstart, kend, dels):
+        """CALL sumcflux (casa_sumcflux.F90:37; call site cable_serial.F90:713) after bgcdriver: canopy%fpn / frday are the ones
+        bgcdriver was given; canopy%frp / frs / frpw / frpr come from self.tiles when icycle == 0 (cbm's simple carbon)"""
+        S, T = self.S, self.tiles
+        for n in ("frp", "frs", "frpw", "frpr"):
+            S["canopy"].f[n].a[...] = T["canopy_" + n][0]
+        self.I.call("sumcflux_mod", "sumcflux", np.int32(ktau), np.int32(kstart), np.int32(kend), np.float32(dels), S["bgc"], S["canopy"],
+                    S["soil"], S["ssnow"], S["sum_flux"], S["veg"], S["met"], S["casaflux"], np.bool_(False))
+        out = {"canopy_" + n: S["canopy"].f[n].a.copy() for n in self.SUMCFLUX_CANOPY}
+        out.update({"sum_flux_" + n: S["sum_flux"].f[n].a.copy() for n in self.SUMCFLUX_SUMS})
+        return out

@@ -92,6 +92,7 @@ def run_drv(name):
     from util import make_case, DELS
     cfg, grid, T, F = make_case(NLAND, start_doy=DOY)
     ccfg = casa_cfg(DRV[name])
+    cfg.icycle = ccfg.icycle                                   # cbm skips its simple carbon model, as in a CASA run (cbm:214)
     A = casa.synth_casa(grid, T, ccfg, seed=31)
     silt, clay = casa.soil_texture(T)
     o = Oracle(T, cfg, cr_math=True)
@@ -99,7 +100,9 @@ def run_drv(name):
     for k in range(16):
         F.fill(T, k); o.cbm(k + 1, DELS)
         fc.bgcdriver(k + 1, 1, 10000, DELS, 8, DOY + k // 8)
+        post = fc.sumcflux(k + 1, 1, 10000, DELS)              # cable_serial.F90:713, right after bgcdriver
     out = {f"drv/{name}/{f.name}": A[f.name].copy() for f in casa.FIELDS if f.key == 0}
+    out.update({f"drv/{name}/post/{n}": v for n, v in post.items()})
     print(name, "done; NPP>0:", int((A["casaflux_cnpp"][0] > 0).sum()), flush=True)
     return out
 

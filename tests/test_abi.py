@@ -248,3 +248,25 @@ def test_generated_host_mirror_types_are_up_to_date():
     finally:
         open(path, "w").write(before)
         os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns))            # keep make from rebuilding the library
+
+
+def test_casa_registry_matches_def_file_and_reference_types():
+    """include/cable_b200_casa_fields.def (generated from the reference's casa_variable.F90 / casa_phenology.F90 by
+    tests/golden/gen_casa_registry.py) is what the library was compiled with; where /root/reference is present the member
+    names are checked against the type definitions in the source text."""
+    from cable_b200 import casa
+    L = casa._bind_lib()
+    assert L.cable_b200_casa_nfields() == len(casa.FIELDS) > 200
+    codes = {np.float32: 0, np.float64: 1, np.int32: 2}
+    for f in casa.FIELDS:
+        info = lib.FieldInfo(); key = C.c_int(-1)
+        assert L.cable_b200_casa_field_info(f.id, C.byref(info), C.byref(key)) == 0
+        assert info.name.decode() == f.name and (info.dtype, info.n1, info.n2, key.value) == (codes[f.dtype], f.n1, f.n2, f.key)
+        assert L.cable_b200_casa_field_id(f.name.encode()) == f.id
+    cfg = casa.default_cfg()
+    assert cfg.struct_bytes == C.sizeof(casa.CasaCfg) and (cfg.icycle, cfg.lalloc, cfg.mvtype) == (1, 0, 17)
+    src = "/root/reference/src/science/casa-cnp/casa_variable.F90"
+    if os.path.exists(src):
+        txt = open(src).read().lower() + open("/root/reference/src/science/casa-cnp/casa_phenology.F90").read().lower()
+        for f in casa.FIELDS:
+            assert re.search(r"\b" + re.escape(f.member) + r"\b", txt), f.name

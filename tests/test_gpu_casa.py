@@ -77,16 +77,28 @@ def test_bgcdriver_after_device_cbm_steps(case):
     A = casa.synth_casa(grid, T, ccfg, seed=31)
     silt, clay = casa.soil_texture(T)
     cfg.output_level = 1
+    cfg.icycle = ccfg.icycle                          # cbm leaves its simple carbon model out, as in a CASA run (cbm:214)
     with CableB200(grid.mp, cfg) as h:
         h.bind(T); h.upload_params(); h.upload_state()
+        h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
         cs = casa.Casa(h, ccfg)
         cs.bind(A, silt, clay); cs.upload()
-        for k in range(16):
+        for k in range(16):                           # the order of cable_serial.F90:594-715: cbm, bgcdriver, sumcflux
             F.fill(T, k)
             h.set_forcing_async(0); h.step(k + 1, DELS, 0)
             cs.bgcdriver(k + 1, 1, 10000, DELS, 8, G.DOY + k // 8)
+            h.post_step(k + 1, 1, DELS)
             h.sync()
         cs.download()
+        h.download_state(); h.download_diag()
+        post = {"sum_flux_" + n: h.driver_download("sum_flux_" + n) for n in
+                ("sumpn", "sumrp", "sumrpw", "sumrpr", "sumrs", "sumrd", "dsumpn", "dsumrp", "dsumrd")}
+        post.update({"canopy_" + n: T["canopy_" + n][0] for n in ("frp", "frs", "frpw", "frpr", "fnpp", "fgpp", "fra", "fnee")})
+    # sumcflux with icycle > 0 (casa_sumcflux.F90:60-108) against the Fortran run's canopy%* / sum_flux%*
+    for n, got in post.items():
+        want = z[f"drv/{case}/post/{n}"]
+        r = _rel(got, want)
+        assert r <= 2e-5, (case, "sumcflux", n, r)
     for f in casa.FIELDS:
         key = f"drv/{case}/{f.name}"
         if key not in z.files or f.dtype == np.int32:
