@@ -152,6 +152,16 @@ struct cable_handle {
   void *host[NFIELDS]{};
   bool host_pinned[NFIELDS]{};
   cudaStream_t s_compute = nullptr, s_compute2 = nullptr, s_copy = nullptr, s_d2h = nullptr;
+  // The resident step as a pipeline (cable_b200_step, pipe_chunk > 0): the shard is cut into chunks of pipe_chunk tiles, chunk j
+  // runs its kernels A -> B on chain stream j % S, and NOTHING joins the chains at the end of a step: a chunk of step k+1
+  // depends only on the same chunk of step k (same stream), so kernel B of one chunk and the uneven tail of every launch
+  // overlap kernel A of the next chunk / the next step.  Every other entry point reaches the compute stream through
+  // main_stream(), which joins the chains first.
+  int pipe_chunk = 0;
+  std::vector<cudaStream_t> s_chain;
+  std::vector<cudaEvent_t> ev_chain_done, ev_chain_slot;     // [S], [nslots * S]: chain c has finished its share of the latest step / of the latest step that read forcing slot s
+  bool chains_pending = false;
+  bool prof_open = false; std::vector<int> prof_steps;       // profile intervals: event pair k covers prof_steps[k] steps
   cudaEvent_t ev_join_c2 = nullptr;
   int chunk_tiles = 0;
   std::vector<cudaEvent_t> ev_chunk_in, ev_chunk_done;   // pipelined cable_b200_cbm()
@@ -199,6 +209,40 @@ struct cable_handle {
   bool profile = false;
   std::vector<cudaEvent_t> prof_ev; size_t prof_n = 0;
 };
+
+namespace {
+// The compute stream for everything except the pipelined resident step: joins the step's chain streams first, so whatever
+// is enqueued next sees every chunk of every enqueued step (and, in profile mode, closes the open timing interval).
+cudaStream_t main_stream(cable_handle *h) {
+  if (h->chains_pending) {
+    for (size_t c = 0; c < h->s_chain.size(); c++) {
+      cudaEventRecord(h->ev_chain_done[c], h->s_chain[c]);
+      cudaStreamWaitEvent(h->s_compute, h->ev_chain_done[c], 0);
+    }
+    h->chains_pending = false;
+    if (h->prof_open) { cudaEventRecord(h->prof_ev[h->prof_n - 1], h->s_compute); h->prof_open = false; }
+  }
+  return h->s_compute;
+}
+// `st` must not overwrite forcing slot `slot` before its readers are done: the last step that read it (every chain of the
+// pipelined step) and the post-step kernels
+void wait_slot_free(cable_handle *h, cudaStream_t st, int slot) {
+  cudaStreamWaitEvent(st, h->ev_slot_free[slot], 0);
+  const size_t S = h->s_chain.size();
+  for (size_t c = 0; c < S; c++) cudaStreamWaitEvent(st, h->ev_chain_slot[(size_t)slot * S + c], 0);
+}
+// a timing interval (event pair) on the compute stream covering `steps` steps
+int prof_begin(cable_handle *h) {
+  if (h->prof_n + 2 > h->prof_ev.size()) {
+    size_t old = h->prof_ev.size(); h->prof_ev.resize(old + 512);
+    for (size_t k = old; k < h->prof_ev.size(); k++) cudaEventCreate(&h->prof_ev[k]);
+  }
+  h->prof_steps.resize(h->prof_ev.size() / 2, 1);
+  h->prof_steps[h->prof_n / 2] = 0;
+  h->prof_n += 2;
+  return (int)h->prof_n - 2;
+}
+}  // namespace
 
 namespace {
 
@@ -427,9 +471,9 @@ int build_param_tables(cable_handle *h) {
     CUDA_TRY(cudaMalloc(&h->d_tbl, tbl.size() * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->d_tbl_d, tbld.size() * sizeof(double)));
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_tbl, tbl.data(), tbl.size() * sizeof(float), cudaMemcpyHostToDevice, h->s_compute));
-  CUDA_TRY(cudaMemcpyAsync(h->d_tbl_d, tbld.data(), tbld.size() * sizeof(double), cudaMemcpyHostToDevice, h->s_compute));
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaMemcpyAsync(h->d_tbl, tbl.data(), tbl.size() * sizeof(float), cudaMemcpyHostToDevice, main_stream(h)));
+  CUDA_TRY(cudaMemcpyAsync(h->d_tbl_d, tbld.data(), tbld.size() * sizeof(double), cudaMemcpyHostToDevice, main_stream(h)));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   return CABLE_OK;
 }
 
@@ -439,7 +483,7 @@ int flush_dirty(cable_handle *h) {
   bool param = false;
   for (int id = 0; id < NFIELDS; id++) {
     if (!h->dirty[id]) continue;
-    int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc;
+    int rc = copy_field(h, id, -1, true, main_stream(h)); if (rc) return rc;
     h->dirty[id] = false;
     param = param || g_fields[id].role == PARAM;
   }
@@ -626,6 +670,22 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
     cudaEventCreateWithFlags(&h->ev_chunk_done[c], cudaEventDisableTiming);
   }
   h->ev_forcing_ready.resize(h->nslots); h->ev_slot_free.resize(h->nslots); h->slot_has_data.assign(h->nslots, 0);
+  {
+    // pipelined resident step: chunks of whole kernel-A rounds (one 640-thread block per SM) on S chain streams
+    int S = 4; h->pipe_chunk = h->sms * CBL_BLOCK_A;       // 4 chains: 0.945 ms/step against 1.005 unpipelined at 310 000 tiles (profiles/r02_pipe_probe.txt)
+    if (const char *e = getenv("CABLE_B200_PIPE_STREAMS")) S = atoi(e);
+    if (const char *e = getenv("CABLE_B200_PIPE_CHUNK")) h->pipe_chunk = atoi(e);
+    { int l = CBL_BLOCK_A; while (l % 256) l += CBL_BLOCK_A;     // chunk edges: multiples of lcm(kernel A's block, the 256-tile redo-flag slice)
+      h->pipe_chunk = h->pipe_chunk / l * l; }
+    if (S < 1 || h->pipe_chunk <= 0 || !h->split || h->xsw) { S = 0; h->pipe_chunk = 0; }
+    h->s_chain.resize(S); h->ev_chain_done.resize(S); h->ev_chain_slot.resize((size_t)S * h->nslots);
+    int lo_ = 0, hi_ = 0; cudaDeviceGetStreamPriorityRange(&lo_, &hi_);
+    for (int c = 0; c < S; c++) {
+      cudaStreamCreateWithPriority(&h->s_chain[c], cudaStreamNonBlocking, hi_);
+      cudaEventCreateWithFlags(&h->ev_chain_done[c], cudaEventDisableTiming);
+    }
+    for (auto &ev : h->ev_chain_slot) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  }
   for (int s = 0; s < h->nslots; s++) {
     cudaEventCreateWithFlags(&h->ev_forcing_ready[s], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_slot_free[s], cudaEventDisableTiming);
@@ -644,6 +704,9 @@ int cable_b200_destroy(cable_handle *h) {
   for (int id = 0; id < NFIELDS; id++) if (h->host_pinned[id]) cudaHostUnregister(h->host[id]);
   for (auto ev : h->ev_forcing_ready) cudaEventDestroy(ev);
   for (auto ev : h->ev_slot_free) cudaEventDestroy(ev);
+  for (auto st : h->s_chain) cudaStreamDestroy(st);
+  for (auto ev : h->ev_chain_done) cudaEventDestroy(ev);
+  for (auto ev : h->ev_chain_slot) cudaEventDestroy(ev);
   for (auto ev : h->prof_ev) cudaEventDestroy(ev);
   if (h->s_compute) cudaStreamDestroy(h->s_compute);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
@@ -708,8 +771,8 @@ static int build_tile_order(cable_handle *h) {
     std::stable_sort(order.begin() + w0, order.begin() + w1, [iveg](int a, int b) { return iveg[a] < iveg[b]; });
   }
   if (!h->d_order) CUDA_TRY(cudaMalloc(&h->d_order, (size_t)h->mp * sizeof(int)));
-  CUDA_TRY(cudaMemcpyAsync(h->d_order, order.data(), (size_t)h->mp * sizeof(int), cudaMemcpyHostToDevice, h->s_compute));
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaMemcpyAsync(h->d_order, order.data(), (size_t)h->mp * sizeof(int), cudaMemcpyHostToDevice, main_stream(h)));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   return CABLE_OK;
 }
 
@@ -722,18 +785,18 @@ int cable_b200_upload(cable_handle *h, unsigned role_mask) {
     if (!(f.role & role_mask) || (f.flags & CABLE_FLAG_HOSTONLY)) continue;
     if (f.role == FORCING) continue;                       // forcing goes through set_forcing_async
     if (f.role == PARAM && (f.flags & CABLE_FLAG_OPTIN) && !optin_param_needed(h, id)) {
-      if (h->host[id]) { int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc; }
+      if (h->host[id]) { int rc = copy_field(h, id, -1, true, main_stream(h)); if (rc) return rc; }
       continue;
     }
     if ((f.role & (PARAM | STATE)) && !h->host[id])
       return fail(CABLE_E_UNBOUND, std::string("field not bound: ") + f.name);
-    int rc = copy_field(h, id, -1, true, h->s_compute); if (rc) return rc;
+    int rc = copy_field(h, id, -1, true, main_stream(h)); if (rc) return rc;
   }
   if ((role_mask & STATE) && h->cfg.l_new_roughness_soil) {     // canopy%us feeds the next ruff_resist (cable_roughness.F90:197)
     if (!h->host[FID_canopy_us]) return fail(CABLE_E_UNBOUND, "field not bound: canopy_us (l_new_roughness_soil)");
-    int rc = copy_field(h, FID_canopy_us, -1, true, h->s_compute); if (rc) return rc;
+    int rc = copy_field(h, FID_canopy_us, -1, true, main_stream(h)); if (rc) return rc;
   }
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   if (role_mask & PARAM) { int rc = build_tile_order(h); if (rc) return rc; }
   if (role_mask & PARAM) { int rc = build_param_tables(h); if (rc) return rc; }
   return CABLE_OK;
@@ -751,9 +814,9 @@ int cable_b200_download(cable_handle *h, unsigned role_mask, unsigned flag_mask)
     const cable_field_info &f = g_fields[id];
     if (!(f.role & role_mask) || (f.flags & CABLE_FLAG_HOSTONLY) || f.role == FORCING) continue;
     if (f.role == DIAG && flag_mask && !(f.flags & flag_mask)) continue;
-    int rc = copy_field(h, id, 0, false, h->s_compute); if (rc) return rc;
+    int rc = copy_field(h, id, 0, false, main_stream(h)); if (rc) return rc;
   }
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   return CABLE_OK;
 }
 
@@ -787,7 +850,7 @@ int cable_b200_set_output_mask(cable_handle *h, const int *field_ids, int n) {
   h->out_mask_on = n > 0;
   memcpy(h->out_mask, m, sizeof(m));
   // the captured drop-in pipelines copy the previous selection
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
   h->graphs.clear();
   return CABLE_OK;
@@ -797,7 +860,7 @@ int cable_b200_set_forcing_async(cable_handle *h, int slot) {
   if (!h || slot < 0 || slot >= h->nslots) return fail(CABLE_E_ARG, "set_forcing_async: bad slot");
   CUDA_TRY(cudaSetDevice(h->device));
   // do not overwrite a slot a running step still reads
-  CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_slot_free[slot], 0));
+  wait_slot_free(h, h->s_copy, slot);
   for (int id = 0; id < NFIELDS; id++) {
     if (!is_forcing_input(h, id)) continue;
     if (!h->host[id]) return fail(CABLE_E_UNBOUND, std::string("forcing field not bound: ") + g_fields[id].name);
@@ -813,37 +876,57 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
   if (!h || slot < 0 || slot >= h->nslots) return fail(CABLE_E_ARG, "step: bad slot");
   if (!(dels > 0.f)) return fail(CABLE_E_ARG, "step: dels must be > 0");
   CUDA_TRY(cudaSetDevice(h->device));
-  if (h->slot_has_data[slot]) CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_forcing_ready[slot], 0));
   { int rc = flush_dirty(h); if (rc) return rc; }
   const DevPtrs d = make_ptrs(h, slot);
   const int first = (h->soil_snow_calls == 0) ? 1 : 0;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->profile) {
-    if (h->prof_n + 2 > h->prof_ev.size()) {
-      size_t old = h->prof_ev.size(); h->prof_ev.resize(old + 512);
-      for (size_t k = old; k < h->prof_ev.size(); k++) cudaEventCreate(&h->prof_ev[k]);
+  const int S = (int)h->s_chain.size();
+  if (S > 0 && h->pipe_chunk > 0 && h->mp > h->pipe_chunk) {
+    // ---- pipelined: chunk j on chain stream j % S, no join at the end of the step (see cable_handle::pipe_chunk).
+    // The chains first see whatever the compute stream has been given since they last forked from it (uploads, the
+    // post-step kernels of the previous step, ...): with nothing in between, that event has already fired.
+    cudaStream_t sm = h->s_compute;                       // not main_stream(): the step must not join its own pipeline
+    if (h->profile && !h->prof_open) {
+      const int k = prof_begin(h);
+      CUDA_TRY(cudaEventRecord(h->prof_ev[k], h->chains_pending ? h->s_chain[0] : sm));
+      h->prof_open = true;
     }
-    e0 = h->prof_ev[h->prof_n++]; e1 = h->prof_ev[h->prof_n++];
-    CUDA_TRY(cudaEventRecord(e0, h->s_compute));
-  }
-  // Kernel A runs one block per SM, so a shard is walked in whole "rounds" of sms*BLOCK_A tiles and the last round
-  // leaves SMs idle (310 000 tiles = 2.73 rounds).  The tiles of the full rounds and the remainder therefore go out
-  // as two chains A->B on two streams (the first at higher priority): kernel B of the full rounds starts while the
-  // remainder's kernel A still occupies only part of the chip, and fills the idle SMs.
-  const int round_tiles = h->sms * CBL_BLOCK_A;
-  const int head = h->step_chains > 1 ? (h->mp / round_tiles) * round_tiles : 0;
-  if (h->split && head > 0 && head < h->mp) {
-    CUDA_TRY(cudaEventRecord(h->ev_fork, h->s_compute));
-    CUDA_TRY(cudaStreamWaitEvent(h->s_compute2, h->ev_fork, 0));
-    { int rc = launch_range(h, d, dels, first, 0, head, h->s_compute); if (rc) return rc; }
-    { int rc = launch_range(h, d, dels, first, head, h->mp, h->s_compute2); if (rc) return rc; }
-    CUDA_TRY(cudaEventRecord(h->ev_join_c2, h->s_compute2));
-    CUDA_TRY(cudaStreamWaitEvent(h->s_compute, h->ev_join_c2, 0));
+    if (h->prof_open) h->prof_steps[h->prof_n / 2 - 1]++;
+    CUDA_TRY(cudaEventRecord(h->ev_fork, sm));
+    for (int c = 0; c < S; c++) {
+      CUDA_TRY(cudaStreamWaitEvent(h->s_chain[c], h->ev_fork, 0));
+      if (h->slot_has_data[slot]) CUDA_TRY(cudaStreamWaitEvent(h->s_chain[c], h->ev_forcing_ready[slot], 0));
+    }
+    int j = 0;
+    for (int i0 = 0; i0 < h->mp; i0 += h->pipe_chunk, j++) {
+      const int i1 = (i0 + h->pipe_chunk < h->mp) ? i0 + h->pipe_chunk : h->mp;
+      int rc = launch_range(h, d, dels, first, i0, i1, h->s_chain[j % S]); if (rc) return rc;
+    }
+    for (int c = 0; c < S; c++) CUDA_TRY(cudaEventRecord(h->ev_chain_slot[(size_t)slot * S + c], h->s_chain[c]));
+    h->chains_pending = true;
   } else {
-    int rc = launch_range(h, d, dels, first, 0, h->mp, h->s_compute); if (rc) return rc;
+    cudaStream_t sm = main_stream(h);
+    if (h->slot_has_data[slot]) CUDA_TRY(cudaStreamWaitEvent(sm, h->ev_forcing_ready[slot], 0));
+    int k = -1;
+    if (h->profile) { k = prof_begin(h); h->prof_steps[k / 2] = 1; CUDA_TRY(cudaEventRecord(h->prof_ev[k], sm)); }
+    // Kernel A runs one block per SM, so a shard is walked in whole "rounds" of sms*BLOCK_A tiles and the last round
+    // leaves SMs idle.  The tiles of the full rounds and the remainder therefore go out as two chains A->B on two
+    // streams (the first at higher priority): kernel B of the full rounds starts while the remainder's kernel A still
+    // occupies only part of the chip, and fills the idle SMs.
+    const int round_tiles = h->sms * CBL_BLOCK_A;
+    const int head = h->step_chains > 1 ? (h->mp / round_tiles) * round_tiles : 0;
+    if (h->split && head > 0 && head < h->mp) {
+      CUDA_TRY(cudaEventRecord(h->ev_fork, sm));
+      CUDA_TRY(cudaStreamWaitEvent(h->s_compute2, h->ev_fork, 0));
+      { int rc = launch_range(h, d, dels, first, 0, head, sm); if (rc) return rc; }
+      { int rc = launch_range(h, d, dels, first, head, h->mp, h->s_compute2); if (rc) return rc; }
+      CUDA_TRY(cudaEventRecord(h->ev_join_c2, h->s_compute2));
+      CUDA_TRY(cudaStreamWaitEvent(sm, h->ev_join_c2, 0));
+    } else {
+      int rc = launch_range(h, d, dels, first, 0, h->mp, sm); if (rc) return rc;
+    }
+    if (k >= 0) CUDA_TRY(cudaEventRecord(h->prof_ev[k + 1], sm));
+    CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], sm));
   }
-  if (h->profile) CUDA_TRY(cudaEventRecord(e1, h->s_compute));
-  CUDA_TRY(cudaEventRecord(h->ev_slot_free[slot], h->s_compute));
   h->soil_snow_calls++;
   h->ctr.steps++;
   h->last_slot = slot;
@@ -871,7 +954,7 @@ int enqueue_pipelined_step(cable_handle *h, const DevPtrs &d, float dels, int fi
   for (int c = 0; c < nch; c++) {
     const int i0 = c * per, i1 = (i0 + per < h->mp) ? i0 + per : h->mp;
     if (i0 >= i1) break;
-    cudaStream_t st = (c & 1) ? h->s_compute2 : h->s_compute;
+    cudaStream_t st = (c & 1) ? h->s_compute2 : main_stream(h);
     CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chunk_in[c], 0));
     { int rc = launch_range(h, d, dels, first, i0, i1, st); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(h->ev_chunk_done[c], st));
@@ -923,7 +1006,7 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
   // a previous asynchronous user of this slot (set_forcing_async/step) must have drained
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
   { int rc = flush_dirty(h); if (rc) return rc; }
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   const long long launches0 = h->ctr.kernel_launches, h2d0 = h->ctr.h2d_bytes, d2h0 = h->ctr.d2h_bytes;
   if (h->use_graph && !first) {
     // The whole pipeline (hundreds of strided copies + kernels) is replayed as ONE graph launch: the per-call
@@ -932,9 +1015,9 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
     auto it = h->graphs.find(key);
     if (it == h->graphs.end()) {
       cudaGraph_t g = nullptr;
-      CUDA_TRY(cudaStreamBeginCapture(h->s_compute, cudaStreamCaptureModeThreadLocal));
+      CUDA_TRY(cudaStreamBeginCapture(main_stream(h), cudaStreamCaptureModeThreadLocal));
       int rc = CABLE_OK;
-      cudaError_t e = cudaEventRecord(h->ev_fork, h->s_compute);
+      cudaError_t e = cudaEventRecord(h->ev_fork, main_stream(h));
       if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_copy, h->ev_fork, 0);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_d2h, h->ev_fork, 0);
       if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_compute2, h->ev_fork, 0);
@@ -942,10 +1025,10 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
       if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_join_copy, h->s_copy);
       if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_join_d2h, h->s_d2h);
       if (e == cudaSuccess && !rc) e = cudaEventRecord(h->ev_join_c2, h->s_compute2);
-      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->s_compute, h->ev_join_c2, 0);
-      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->s_compute, h->ev_join_copy, 0);
-      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(h->s_compute, h->ev_join_d2h, 0);
-      cudaError_t e2 = cudaStreamEndCapture(h->s_compute, &g);
+      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(main_stream(h), h->ev_join_c2, 0);
+      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(main_stream(h), h->ev_join_copy, 0);
+      if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(main_stream(h), h->ev_join_d2h, 0);
+      cudaError_t e2 = cudaStreamEndCapture(main_stream(h), &g);
       if (rc) { if (g) cudaGraphDestroy(g); return rc; }
       if (e != cudaSuccess || e2 != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(CABLE_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2)); }
       cudaGraphExec_t ge = nullptr;
@@ -960,7 +1043,7 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
     }
     h->ctr.kernel_launches = launches0 + h->graph_launches;
     h->ctr.h2d_bytes = h2d0 + h->graph_h2d; h->ctr.d2h_bytes = d2h0 + h->graph_d2h;
-    CUDA_TRY(cudaGraphLaunch(it->second, h->s_compute));
+    CUDA_TRY(cudaGraphLaunch(it->second, main_stream(h)));
   } else {
     int rc = enqueue_pipelined_step(h, d, dels, first, slot); if (rc) return rc;
   }
@@ -968,7 +1051,7 @@ int cable_b200_cbm(cable_handle *h, int ktau, float dels) {
   h->soil_snow_calls++;
   h->ctr.steps++;
   h->last_slot = slot;
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   CUDA_TRY(cudaStreamSynchronize(h->s_compute2));
   CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
@@ -979,7 +1062,7 @@ int cable_b200_sync(cable_handle *h) {
   if (!h) return fail(CABLE_E_ARG, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
   return CABLE_OK;
 }
@@ -989,7 +1072,7 @@ void *cable_b200_device_ptr(cable_handle *h, int id, int slot) {
   return dev_ptr(h, id, slot);
 }
 
-void *cable_b200_compute_stream(cable_handle *h) { return h ? (void *)h->s_compute : nullptr; }
+void *cable_b200_compute_stream(cable_handle *h) { return h ? (void *)main_stream(h) : nullptr; }   // joins the step pipeline first
 
 int cable_b200_profile(cable_handle *h, int enable) {
   if (!h) return fail(CABLE_E_ARG, "null handle");
@@ -1000,10 +1083,10 @@ int cable_b200_profile(cable_handle *h, int enable) {
 int cable_b200_get_counters(cable_handle *h, cable_counters *out) {
   if (!h || !out) return fail(CABLE_E_ARG, "null");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   for (size_t k = 0; k + 1 < h->prof_n; k += 2) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->prof_ev[k], h->prof_ev[k + 1]) == cudaSuccess) { h->ctr.kernel_ms += ms; h->ctr.kernel_ms_count++; }
+    if (cudaEventElapsedTime(&ms, h->prof_ev[k], h->prof_ev[k + 1]) == cudaSuccess) { h->ctr.kernel_ms += ms; h->ctr.kernel_ms_count += h->prof_steps[k / 2]; }
   }
   h->prof_n = 0;
   unsigned long long w = 0;
@@ -1018,7 +1101,7 @@ int cable_b200_get_counters(cable_handle *h, cable_counters *out) {
 int cable_b200_reset_counters(cable_handle *h) {
   if (!h) return fail(CABLE_E_ARG, "null");
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->s_compute);
+  cudaStreamSynchronize(main_stream(h));
   const long long steps = h->ctr.steps;       // steps also drives the forcing-slot rotation: keep it
   h->ctr = cable_counters{}; h->ctr.steps = steps;
   h->prof_n = 0;
@@ -1034,7 +1117,7 @@ int cable_b200_grid_reduce(cable_handle *h, int id, int comp, const float *d_pat
     return fail(CABLE_E_ARG, "grid_reduce: field must be a resident f32 field");
   CUDA_TRY(cudaSetDevice(h->device));
   const float *x = (const float *)dev_ptr(h, id, 0) + (size_t)comp * h->mp;
-  grid_reduce_kernel<<<(nland + 127) / 128, 128, 0, h->s_compute>>>(x, d_patchfrac, d_cstart, d_cend, nland, d_out);
+  grid_reduce_kernel<<<(nland + 127) / 128, 128, 0, main_stream(h)>>>(x, d_patchfrac, d_cstart, d_cend, nland, d_out);
   CUDA_TRY(cudaGetLastError());
   h->ctr.kernel_launches++;
   return CABLE_OK;
@@ -1138,7 +1221,7 @@ int cable_b200_set_met_async(cable_handle *h, int slot, const float *met_land, c
   if (slot < 0 || slot >= h->nslots || !met_land || !cv) return fail(CABLE_E_ARG, "set_met_async: bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
   auto &v = h->drv;
-  CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_slot_free[slot], 0));     // a running step may still read the slot
+  wait_slot_free(h, h->s_copy, slot);     // a running step may still read the slot
   const size_t bytes = (size_t)CABLE_MET_NROWS * v.nland * sizeof(float);
   CUDA_TRY(cudaMemcpyAsync(v.d_met_land[slot], met_land, bytes, cudaMemcpyHostToDevice, h->s_copy));
   h->ctr.h2d_bytes += (long long)bytes;
@@ -1161,7 +1244,7 @@ int cable_b200_upload_lai(cable_handle *h) {
   if (!h->host[FID_veg_vlai]) return fail(CABLE_E_UNBOUND, "forcing field not bound: veg_vlai");
   CUDA_TRY(cudaSetDevice(h->device));
   for (int s = 0; s < h->nslots; s++) {
-    CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_slot_free[s], 0));
+    wait_slot_free(h, h->s_copy, s);
     int rc = copy_field(h, FID_veg_vlai, s, true, h->s_copy); if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(h->s_copy));
@@ -1191,11 +1274,11 @@ int cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels, int 
   p.qcan = F(FID_rad_qcan); p.qssabs = F(FID_rad_qssabs); p.flws = F(FID_rad_flws);
   p.wbtot = (const double *)dev_ptr(h, FID_ssnow_wbtot, 0); p.fevc = (const double *)dev_ptr(h, FID_canopy_fevc, 0);
   p.fes = (const double *)dev_ptr(h, FID_canopy_fes, 0);
-  post_step_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(p, h->drv.arr, h->mp, ktau, kstart, dels, do_mass_bal, do_energy_bal);
+  post_step_kernel<<<(h->mp + 255) / 256, 256, 0, main_stream(h)>>>(p, h->drv.arr, h->mp, ktau, kstart, dels, do_mass_bal, do_energy_bal);
   CUDA_TRY(cudaGetLastError());
   h->ctr.kernel_launches++;
   // this kernel is the slot's last reader (met%precip/fsd/fld): a prefetch into the slot must wait for it, not only for the step
-  CUDA_TRY(cudaEventRecord(h->ev_slot_free[h->last_slot], h->s_compute));
+  CUDA_TRY(cudaEventRecord(h->ev_slot_free[h->last_slot], main_stream(h)));
   return CABLE_OK;
 }
 
@@ -1226,7 +1309,7 @@ int cable_b200_output_plan(cable_handle *h, int nrows, const int *field_id, cons
       o.src = drv_ptr(h, k);
     }
   }
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute)); CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h))); CUDA_TRY(cudaStreamSynchronize(h->s_d2h));
   cudaFree(v.d_rows); cudaFree(v.d_agg); cudaFree(v.d_out[0]); cudaFree(v.d_out[1]);
   v.d_rows = nullptr; v.d_agg = nullptr; v.d_out[0] = v.d_out[1] = nullptr;
   CUDA_TRY(cudaMalloc(&v.d_rows, nrows * sizeof(OutRow)));
@@ -1236,10 +1319,10 @@ int cable_b200_output_plan(cable_handle *h, int nrows, const int *field_id, cons
   v.rows = rows; v.agg_counter = 0; v.out_buf = 0;
   // 'point' rows have no reset value (aggregator.F90 never resets them) and the accumulate pass reads every row before
   // it overwrites: give them a defined first value (compute-sanitizer initcheck, tools/gpu_sanitize.sh)
-  CUDA_TRY(cudaMemsetAsync(v.d_agg, 0, (size_t)nrows * h->mp * sizeof(double), h->s_compute));
-  aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, h->mp);
+  CUDA_TRY(cudaMemsetAsync(v.d_agg, 0, (size_t)nrows * h->mp * sizeof(double), main_stream(h)));
+  aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, main_stream(h)>>>(v.d_rows, nrows, v.d_agg, h->mp);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   return CABLE_OK;
 }
 
@@ -1247,7 +1330,7 @@ int cable_b200_output_accumulate(cable_handle *h) {
   if (!h || !h->drv.on || h->drv.rows.empty()) return fail(CABLE_E_ARG, "output_accumulate: no output plan");
   CUDA_TRY(cudaSetDevice(h->device));
   auto &v = h->drv;
-  aggregate_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, (int)v.rows.size(), v.d_agg, h->mp, v.agg_counter);
+  aggregate_kernel<<<(h->mp + 255) / 256, 256, 0, main_stream(h)>>>(v.d_rows, (int)v.rows.size(), v.d_agg, h->mp, v.agg_counter);
   CUDA_TRY(cudaGetLastError());
   v.agg_counter++;
   h->ctr.kernel_launches++;
@@ -1264,19 +1347,19 @@ int reduce_rows(cable_handle *h, int &b_out) {
   auto &v = h->drv;
   const int nrows = (int)v.rows.size(), b = v.out_buf;
   // the D2H that last used this staging buffer must have drained
-  CUDA_TRY(cudaStreamWaitEvent(h->s_compute, v.ev_out_free[b], 0));
+  CUDA_TRY(cudaStreamWaitEvent(main_stream(h), v.ev_out_free[b], 0));
   const dim3 grid((v.nland + 127) / 128, nrows);
-  output_reduce_kernel<<<grid, 128, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, v.agg_counter > 0 ? 1 : 0, v.d_patchfrac,
+  output_reduce_kernel<<<grid, 128, 0, main_stream(h)>>>(v.d_rows, nrows, v.d_agg, v.agg_counter > 0 ? 1 : 0, v.d_patchfrac,
                                                        v.d_cstart, v.d_cend, v.nland, h->mp, v.d_out[b]);
   CUDA_TRY(cudaGetLastError());
   h->ctr.kernel_launches++;
   if (v.agg_counter > 0) {
-    aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, h->s_compute>>>(v.d_rows, nrows, v.d_agg, h->mp);
+    aggregate_reset_kernel<<<(h->mp + 255) / 256, 256, 0, main_stream(h)>>>(v.d_rows, nrows, v.d_agg, h->mp);
     CUDA_TRY(cudaGetLastError());
     h->ctr.kernel_launches++;
     v.agg_counter = 0;
   }
-  CUDA_TRY(cudaEventRecord(v.ev_reduced, h->s_compute));
+  CUDA_TRY(cudaEventRecord(v.ev_reduced, main_stream(h)));
   CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, v.ev_reduced, 0));
   b_out = b;
   v.out_buf ^= 1;
@@ -1422,7 +1505,7 @@ int cable_b200_driver_download(cable_handle *h, const char *name, void *host) {
   const int k = cable_b200_driver_field_id(name);
   if (k < 0) return fail(CABLE_E_ARG, std::string("driver_download: unknown driver array ") + (name ? name : "(null)"));
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaStreamSynchronize(h->s_compute));
+  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
   CUDA_TRY(cudaMemcpy(host, drv_ptr(h, k), (size_t)h->mp * (g_drv_names[k].f64 ? 8 : 4), cudaMemcpyDeviceToHost));
   return CABLE_OK;
 }

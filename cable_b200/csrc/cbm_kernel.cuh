@@ -64,8 +64,13 @@ __host__ __device__ constexpr int store_in_phase(int phase, unsigned role, unsig
 // XSW = 1: the instantiation that also carries the rarely used cable_user switches (litter, l_rev_corr,
 // l_new_roughness_soil, soil_thermal_fix); chosen at launch when any of them is set.  XSW = 0 is the default program,
 // unchanged by their existence.
+// CBL_REGPAD_A (tuning): kernel A's big-block build is compiled for BLOCK + CBL_REGPAD_A threads, i.e. with a lower register
+// cap than its block needs, so that blocks of kernel B (other chunk chains of the pipelined step) fit on the SM next to it
+#ifndef CBL_REGPAD_A
+#define CBL_REGPAD_A 0
+#endif
 template <int PHASE, int BLOCK, int MINB, int LVL, int XSW>
-__global__ void __launch_bounds__(BLOCK, MINB)
+__global__ void __launch_bounds__(BLOCK + ((PHASE == 1 && BLOCK == CBL_BLOCK_A) ? CBL_REGPAD_A : 0), MINB)
 cbm_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ DevCfg c, const int mp, const int i0, const int i1,
            const float dels, const int first_call, unsigned long long *warn_counter, int *redo) {
   // `c` (every module-scope input of the reference cbm, cbm_types.cuh) travels as a kernel parameter: it sits in the

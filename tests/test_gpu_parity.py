@@ -338,3 +338,38 @@ def test_device_grid_reduction_matches_reference_rule():
         got = out.cpu().numpy()
     want = grid_cell_average(T["canopy_fe"][0], grid.patchfrac, grid.cstart, grid.cend)
     np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)     # fmad=false on device; same order of accumulation
+
+
+def test_pipelined_resident_step_is_bit_identical(monkeypatch):
+    """The resident step as chunk chains on several streams with no join between steps (cable_b200_step, pipe_chunk) against
+    the unpipelined launch on the same inputs: identical bits in every state / driver-visible field and in the driver's
+    accumulators, with post_step (which must join the chains, then fork them again) after some of the steps only."""
+    def run(streams):
+        monkeypatch.setenv("CABLE_B200_PIPE_STREAMS", str(streams))
+        monkeypatch.setenv("CABLE_B200_PIPE_CHUNK", "20480")          # 5 chunks of the 96 000-tile shard (small-range kernels)
+        cfg = lib.default_cfg(); cfg.n_forcing_slots = 4; cfg.output_level = 1
+        grid = synth.make_grid(19200, 5); T = synth.make_tiles(grid, cfg)
+        F = synth.Forcing(grid, T, DELS, start_doy=100)
+        fs = []
+        for k in range(10):
+            F.fill(T, k); fs.append({n: T[n].copy() for n in synth.FORCING_FIELDS})
+        with CableB200(grid.mp, cfg) as h:
+            h.bind(T); h.upload_params(); h.upload_state()
+            h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+            for k in range(10):
+                h.bind(fs[k])
+                h.set_forcing_async(k % 4)                   # the ring: a slot is rewritten while earlier steps are still in flight
+                h.step(k + 1, DELS, k % 4)
+                if k in (2, 3, 7):
+                    h.post_step(k + 1, 1, DELS)
+            h.download_state(); h.download_diag()
+            acc = {n: h.driver_download(n) for n in ("sum_flux_sumpn", "bal_wbal", "bal_ebal")}
+            launches = h.counters().kernel_launches
+        return T, acc, launches
+    Ta, acca, la = run(0)
+    Tb, accb, lb = run(4)
+    assert lb > la                                            # 5 chunks x (A fast, A, B) per step against 2 chains
+    for f in output_fields():
+        assert np.array_equal(Ta[f.name], Tb[f.name], equal_nan=True), f.name
+    for n in acca:
+        assert np.array_equal(acca[n], accb[n], equal_nan=True), n
