@@ -158,6 +158,7 @@ struct cable_handle {
   // overlap kernel A of the next chunk / the next step.  Every other entry point reaches the compute stream through
   // main_stream(), which joins the chains first.
   int pipe_chunk = 0;
+  int big_min = 0, big_min_pipe = 0; // ranges of at least this many tiles run kernel A as CBL_BLOCK_A-thread blocks, one per SM (launch_range)
   std::vector<cudaStream_t> s_chain;
   std::vector<cudaEvent_t> ev_chain_done, ev_chain_slot;     // [S], [nslots * S]: chain c has finished its share of the latest step / of the latest step that read forcing slot s
   bool chains_pending = false;
@@ -311,7 +312,7 @@ int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s
 }
 
 // launch the step kernels for tiles [i0, i1) on the compute stream
-int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, int i0, int i1, cudaStream_t st) {
+int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, int i0, int i1, cudaStream_t st, bool in_pipeline = false) {
   if (i1 <= i0) return CABLE_OK;
   DevPtrs d = d_in;
   // the thread -> tile table permutes inside aligned windows: usable when the range is made of whole windows
@@ -351,7 +352,7 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
     // 8-GPU run, a pipeline chunk) take 256-thread blocks, three per SM, so that every SM still gets work
     // kernel A runs first as its CBL_FASTDIV build (cable_fast.cu: IEEE divisions / square roots without the slow-path
     // scaffolding); the ordinary build that follows only computes the blocks that build flagged (normally none)
-    const bool big = i1 - i0 >= h->sms * CBL_BLOCK_A;
+    const bool big = i1 - i0 >= (in_pipeline ? h->big_min_pipe : h->big_min);
     if (h->fastdiv) {
       const int bl = big ? CBL_BLOCK_A : CBL_SMALL_BLOCK, nblk = (i1 - i0 + bl - 1) / bl;
       if (i0 % 256) return fail(CABLE_E_ARG, "launch_range: range start must be a multiple of 256 (redo-flag slices)");
@@ -672,6 +673,14 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   h->ev_forcing_ready.resize(h->nslots); h->ev_slot_free.resize(h->nslots); h->slot_has_data.assign(h->nslots, 0);
   {
     // pipelined resident step: chunks of whole kernel-A rounds (one 640-thread block per SM) on S chain streams
+    // kernel A's geometry: up to one wave of the small blocks (sms x CBL_SMALL_MINB x CBL_SMALL_BLOCK tiles) the small, high-register
+    // geometry has the shorter dependent chain; well beyond it one round of big blocks (even partly filled) is faster
+    // (profiles/r02_mid_probe.txt: a launch on its own ties at ~1.4 waves -- 77 500 tiles 0.43 ms either way, 57 000 tiles 0.365
+    // small / 0.395 big; as the remainder chunk of the pipelined step, next to big blocks of other chunks, 60 280 tiles cost
+    // 0.575 ms/step small and 0.510 big)
+    h->big_min_pipe = h->sms * CBL_SMALL_MINB * CBL_SMALL_BLOCK + 1;
+    h->big_min = 80000;
+    if (const char *e = getenv("CABLE_B200_BIG_MIN")) h->big_min = h->big_min_pipe = atoi(e);
     int S = 4; h->pipe_chunk = h->sms * CBL_BLOCK_A;       // 4 chains: 0.945 ms/step against 1.005 unpipelined at 310 000 tiles (profiles/r02_pipe_probe.txt)
     if (const char *e = getenv("CABLE_B200_PIPE_STREAMS")) S = atoi(e);
     if (const char *e = getenv("CABLE_B200_PIPE_CHUNK")) h->pipe_chunk = atoi(e);
@@ -899,7 +908,7 @@ int cable_b200_step(cable_handle *h, int ktau, float dels, int slot) {
     int j = 0;
     for (int i0 = 0; i0 < h->mp; i0 += h->pipe_chunk, j++) {
       const int i1 = (i0 + h->pipe_chunk < h->mp) ? i0 + h->pipe_chunk : h->mp;
-      int rc = launch_range(h, d, dels, first, i0, i1, h->s_chain[j % S]); if (rc) return rc;
+      int rc = launch_range(h, d, dels, first, i0, i1, h->s_chain[j % S], true); if (rc) return rc;
     }
     for (int c = 0; c < S; c++) CUDA_TRY(cudaEventRecord(h->ev_chain_slot[(size_t)slot * S + c], h->s_chain[c]));
     h->chains_pending = true;
