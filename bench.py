@@ -606,19 +606,20 @@ def run_b200(args) -> None:
                          "traffic": traffic, "peak_source": which, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_tile_step": ALGO_BYTES_PER_TILE_STEP,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_TILE_STEP * mp,
-                         "launch": "one step over all tiles = two A->B chains (full rounds of 148 x 768 tiles, remainder): kernel A "
-                                   "(surface+canopy, CBL_FASTDIV build, then the ordinary build over the blocks it handed "
-                                   "back -- normally none) + kernel B (soil/snow/carbon); kernel_ms is the whole step, "
-                                   "timed with CUDA events on the library's streams",
+                         "launch": "one step over all tiles = chunk chains on four streams, no join between steps (a chunk = one round of "
+                                   "148 x 640 tiles; 310 000 tiles = 3 rounds + a 25 840-tile remainder): per chunk kernel A (surface+canopy, "
+                                   "CBL_FASTDIV build, then the ordinary build over the blocks it handed back -- normally none) -> kernel B "
+                                   "(soil/snow/carbon); kernel_ms = the timed region's first launch to the last chain's end, CUDA events on "
+                                   "the library's streams, / steps",
                          "ncu": prof,
                          "pipe": pipe_roof(prof, value / world, clocks),
                          "issue": issue_roof(prof, mp, kern_ms, clocks),
                          "note": "instruction-issue / latency-bound step (fp64 islands, ~300 correctly rounded transcendentals "
-                                 "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 48 %, FP64 pipe 21-25 %, "
-                                 "DRAM 5-23 % in the ncu capture; the HBM fraction is reported because it is the official "
-                                 "denominator.  traffic > algorithmic bytes: per-tile parameter arrays of the reference "
-                                 "interface (230 B/tile), driver-visible diagnostics (336 B/tile at output_level=1), the A->B "
-                                 "exchange (132 B/tile) and register-spill write-backs"},
+                                 "and 4 x (<=20) data-dependent iterations per tile-step): issue-active 48 %, FP64 pipe 24 %, 22.8 of 32 "
+                                 "lanes active, DRAM 5-20 % in the ncu capture (profiles/r02_cbm_kernels_ncu_summary.txt); the HBM fraction "
+                                 "is reported because it is the official denominator, `issue` is the roof that binds.  traffic > "
+                                 "algorithmic bytes: driver-visible diagnostics (336 B/tile at output_level=1), the A->B exchange "
+                                 "(132 B/tile) and write-backs of kernel A's ~1 KB/thread of spill slots"},
             "e2e": {"value": e2e, "unit": "tile-timesteps/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "steps": Ke, "gpu_launches": e2e_launches, "outputs_finite": e2e_finite, "output_rows": len(rows),
                     "api": "offline driver loop through the C ABI, host buffers: cable_b200_set_met_async (met slice H2D + "

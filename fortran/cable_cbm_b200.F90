@@ -21,6 +21,7 @@ MODULE cable_cbm_module
   IMPLICIT NONE
   PRIVATE
   PUBLIC cbm
+  PUBLIC b200_device_handle          ! the device handle, for the CASA-CNP shim (fortran/cable_bgcdriver_b200.F90)
 
   !> struct cable_cfg of include/cable_b200.h (field order and types must match)
   TYPE, BIND(C) :: cable_cfg
@@ -87,6 +88,11 @@ MODULE cable_cbm_module
   TYPE(C_PTR), SAVE :: handle = C_NULL_PTR
 
 CONTAINS
+
+  FUNCTION b200_device_handle() RESULT(h)
+    TYPE(C_PTR) :: h
+    h = handle
+  END FUNCTION b200_device_handle
 
   SUBROUTINE cbm( ktau, dels, air, bgc, canopy, met, bal, rad, rough, soil,                     &
                   ssnow, sum_flux, veg, climate, xk, c1, rhoch )

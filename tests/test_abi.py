@@ -270,3 +270,39 @@ def test_casa_registry_matches_def_file_and_reference_types():
         txt = open(src).read().lower() + open("/root/reference/src/science/casa-cnp/casa_phenology.F90").read().lower()
         for f in casa.FIELDS:
             assert re.search(r"\b" + re.escape(f.member) + r"\b", txt), f.name
+
+
+def test_bgcdriver_shim_matches_the_reference_signature_and_the_c_abi():
+    """fortran/cable_bgcdriver_b200.F90 (CASA-CNP drop-in): module and procedure carry the reference's names, `bgcdriver` its 25
+    dummy arguments in the reference's order (bgcdriver.F90:7-10, parsed from the reference source where it is present), every
+    BIND(C) interface names an exported symbol with its prototype's parameter count, TYPE cable_casa_cfg mirrors the C struct,
+    and the bind list is what tools/gen_casa_fortran_binds.py renders from the CASA registry (one bind per row)."""
+    import ctypes as C
+    import subprocess
+    import sys
+    from cable_b200 import casa
+    path = os.path.join(ROOT, "fortran", "cable_bgcdriver_b200.F90")
+    shim = _shim_blocks(path)
+    assert ("module", "bgcdriver_mod", []) in shim
+    drv = [b for b in shim if b[0] == "subroutine" and b[1] == "bgcdriver"]
+    want = ["ktau", "kstart", "kend", "dels", "met", "ssnow", "canopy", "veg", "soil", "climate", "casabiome", "casapool", "casaflux",
+            "casamet", "casabal", "phen", "pop", "spinconv", "spinup", "ktauday", "idoy", "loy", "dump_read", "dump_write", "lalloc"]
+    assert len(drv) == 1 and drv[0][2] == want
+    ref = "/root/reference/src/science/casa-cnp/bgcdriver.F90"
+    if os.path.exists(ref):
+        rb = [b for b in _shim_blocks(ref) if b[0] == "subroutine" and b[1] == "bgcdriver"]
+        assert rb and rb[0][2] == want
+    protos = _c_prototypes()
+    bound = [b for b in shim if b[1].startswith("cable_b200_") and b[0] in ("function", "subroutine")]
+    assert {b[1] for b in bound} == {"cable_b200_casa_default_cfg", "cable_b200_casa_init", "cable_b200_casa_bind",
+                                     "cable_b200_casa_upload", "cable_b200_casa_download", "cable_b200_bgcdriver"}
+    for kind, name, args in bound:
+        assert name in casa.EXPORTS and len(args) == protos[name], (name, args, protos[name])
+    t = _shim_types(path)
+    assert t["cable_casa_cfg"] == [(n.lower(), "integer", "c_int", 1) for n, _ in casa.CasaCfg._fields_]
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_casa_fortran_binds.py"), "--check"]) == 0
+    inc = open(os.path.join(ROOT, "fortran", "cable_b200_casa_binds.inc")).read()
+    binds = re.findall(r"CALL cbind\('(\w+)', C_LOC\(([\w%]+)\)\)", inc)
+    assert [b[0] for b in binds] == [f.name for f in casa.FIELDS] and all(b[1] == f"{f.type}%{f.member}" for b, f in zip(binds, casa.FIELDS))
+    assert '#include "cable_b200_casa_binds.inc"' in open(path).read()
+    assert "b200_device_handle" in open(os.path.join(ROOT, "fortran", "cable_cbm_b200.F90")).read()

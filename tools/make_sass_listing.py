@@ -4,8 +4,9 @@ import collections, os, re, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(root, "cable_b200", "libcable_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-want = {"kernelA_cbm_kernel_1_768_1_1": "cbm_kernelILi1ELi768ELi1ELi1ELi0E", "kernelB_cbm_kernel_2_128_6_1": "cbm_kernelILi2ELi128ELi6ELi1ELi0E",
-        "driver_kernels": None}
+tag_round = sys.argv[2] if len(sys.argv) > 2 else "r02"
+want = {"kernelA_fast_cbm_kernel_1_640_1_1": "4cblf10cbm_kernelILi1ELi640ELi1ELi1ELi0E", "kernelA_small_fast_cbm_kernel_1_128_3_1": "4cblf10cbm_kernelILi1ELi128ELi3ELi1ELi0E",
+        "kernelB_cbm_kernel_2_128_6_1": "3cbl10cbm_kernelILi2ELi128ELi6ELi1ELi0E", "casa_kernels": None, "driver_kernels": None}
 cur, out = None, collections.defaultdict(list)
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
@@ -14,12 +15,13 @@ for line in sass.splitlines():
         for tag, key in want.items():
             if key and key in fn: cur = tag
         if cur is None and any(k in fn for k in ("met_expand", "post_step", "aggregate_kernel", "output_reduce", "grid_reduce")): cur = "driver_kernels"
+        if cur is None and "casa" in fn: cur = "casa_kernels"
         if cur: out[cur].append(f"// Function : {fn}")
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);\s*/\*", line)
     if m and cur: out[cur].append(f"/*{m.group(1)}*/ {m.group(2).strip()} ;")
 for tag, lines in out.items():
-    path = os.path.join(root, "profiles", f"r01_sass_{tag}.txt")
+    path = os.path.join(root, "profiles", f"{tag_round}_sass_{tag}.txt")
     ops = collections.Counter()
     for l in lines:
         m = re.match(r"/\*[0-9a-f]+\*/ (?:@!?U?P\d+ )?([A-Z0-9_]+)", l)

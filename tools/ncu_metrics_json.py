@@ -46,10 +46,10 @@ TILES = 310000
 for k in kernels:
     k["flops_fp64_per_tile_step"] = k["flops_fp64"] / TILES
     k["flops_fp32_per_tile_step"] = k["flops_fp32"] / TILES
-json.dump({"source": rep.split("/")[-1], "command": "ncu --set full --clock-control none --import-source on -k regex:cbm_kernel -s 36 -c 6 python tools/quick_perf.py 62000 12 (tools/gpu_profile.sh): the six launches of one resident step = two A->B chains (full rounds of 148 x 768 tiles, then the remainder), each chain: kernel A CBL_FASTDIV build, ordinary kernel A over the blocks it handed back (none here), kernel B",
+json.dump({"source": rep.split("/")[-1], "command": "ncu --set full --clock-control none --import-source on -k regex:cbm_kernel -s 96 -c 12 python tools/quick_perf.py 62000 12 (tools/gpu_profile.sh): the twelve launches of one resident step = four chunk chains (three rounds of 148 x 640 tiles, then the 25 840-tile remainder as 128-thread blocks), each chain: kernel A CBL_FASTDIV build, ordinary kernel A over the blocks it handed back (none here), kernel B.  Under ncu the launches are serialised; in the timed step the chains overlap on four streams",
            "tiles": TILES,
            "flops_per_tile_step": {"fp64": sum(k["flops_fp64_per_tile_step"] for k in kernels), "fp32": sum(k["flops_fp32_per_tile_step"] for k in kernels),
                                    "how": "executed, counted by ncu (smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul,ffma,fadd,fmul}_pred_on; FMA = 2), "
-                                          "all six launches of the step; includes the fp64 evaluation of the correctly rounded fp32 intrinsics and the IEEE divide / square-root sequences"},
+                                          "all twelve launches of the step; includes the fp64 evaluation of the correctly rounded fp32 intrinsics and the IEEE divide / square-root sequences"},
            "kernels": kernels}, open(out, "w"), indent=1)
 print(open(out).read()[:1500])
