@@ -198,6 +198,11 @@ struct cable_handle {
     double *d_agg = nullptr; int agg_counter = 0;
     float *d_out[2] = {nullptr, nullptr}; cudaEvent_t ev_out_free[2] = {nullptr, nullptr}; int out_buf = 0;
     cudaEvent_t ev_reduced = nullptr;
+    // pipelined step: the output reduction runs per chunk on the chain streams (reduce_rows)
+    std::vector<int> h_cstart;                   // host copy of landpt%cstart: land points that start in a chunk
+    std::vector<int> h_cend;
+    std::vector<cudaEvent_t> ev_red;             // [chunks] chunk j's share of the reduction is done
+    float *d_partial = nullptr;                  // [2 staging buffers][chunks][rows]: running sums of land points that cross a chunk edge
   } drv;
   // multi-GPU gather of the output block (cable_b200_comm_init / cable_b200_output_gather_async)
   struct Comm {
@@ -231,6 +236,31 @@ void wait_slot_free(cable_handle *h, cudaStream_t st, int slot) {
   cudaStreamWaitEvent(st, h->ev_slot_free[slot], 0);
   const size_t S = h->s_chain.size();
   for (size_t c = 0; c < S; c++) cudaStreamWaitEvent(st, h->ev_chain_slot[(size_t)slot * S + c], 0);
+}
+// Per-tile work that follows a step (post-step statements, CASA accumulation / biogeochem) rides the step pipeline: chunk j's
+// share goes to chunk j's chain stream, behind that chunk's kernels, so it needs no join.  Without a pipeline: one launch
+// over [0, mp) on the compute stream.  fn(i0, i1, stream) enqueues the work for tiles [i0, i1).
+bool piped(const cable_handle *h) { return !h->s_chain.empty() && h->pipe_chunk > 0 && h->mp > h->pipe_chunk; }
+template <class F>
+int per_chunk(cable_handle *h, F fn) {
+  if (!piped(h)) return fn(0, h->mp, main_stream(h));
+  const int S = (int)h->s_chain.size();
+  // the chains see what the compute stream has been given since they last forked from it (free when nothing was)
+  CUDA_TRY(cudaEventRecord(h->ev_fork, h->s_compute));
+  for (int c = 0; c < S; c++) CUDA_TRY(cudaStreamWaitEvent(h->s_chain[c], h->ev_fork, 0));
+  int j = 0;
+  for (int i0 = 0; i0 < h->mp; i0 += h->pipe_chunk, j++) {
+    const int i1 = (i0 + h->pipe_chunk < h->mp) ? i0 + h->pipe_chunk : h->mp;
+    int rc = fn(i0, i1, h->s_chain[j % S]); if (rc) return rc;
+  }
+  h->chains_pending = true;
+  return CABLE_OK;
+}
+// forcing slot `slot` has a new last reader on every chain
+int mark_slot_read_by_chains(cable_handle *h, int slot) {
+  const size_t S = h->s_chain.size();
+  for (size_t c = 0; c < S; c++) CUDA_TRY(cudaEventRecord(h->ev_chain_slot[(size_t)slot * S + c], h->s_chain[c]));
+  return CABLE_OK;
 }
 // a timing interval (event pair) on the compute stream covering `steps` steps
 int prof_begin(cable_handle *h) {
@@ -1169,6 +1199,8 @@ void driver_free(cable_handle *h) {
   cudaFree(v.arr_block); cudaFree(v.d_rows); cudaFree(v.d_agg); cudaFree(v.d_out[0]); cudaFree(v.d_out[1]);
   for (int b = 0; b < 2; b++) if (v.ev_out_free[b]) cudaEventDestroy(v.ev_out_free[b]);
   if (v.ev_reduced) cudaEventDestroy(v.ev_reduced);
+  for (auto ev : v.ev_red) cudaEventDestroy(ev);
+  cudaFree(v.d_partial);
   v = cable_handle::Driver{};
 }
 
@@ -1221,6 +1253,11 @@ int cable_b200_driver_init(cable_handle *h, int nland, const int *cstart, const 
   }
   for (int b = 0; b < 2; b++) CUDA_TRY(cudaEventCreateWithFlags(&v.ev_out_free[b], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&v.ev_reduced, cudaEventDisableTiming));
+  v.h_cstart.assign(cstart, cstart + nland); v.h_cend.assign(cend, cend + nland);
+  if (piped(h)) {
+    v.ev_red.resize((h->mp + h->pipe_chunk - 1) / h->pipe_chunk);
+    for (auto &ev : v.ev_red) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
   v.on = true;
   return CABLE_OK;
 }
@@ -1283,10 +1320,16 @@ int cable_b200_post_step(cable_handle *h, int ktau, int kstart, float dels, int 
   p.qcan = F(FID_rad_qcan); p.qssabs = F(FID_rad_qssabs); p.flws = F(FID_rad_flws);
   p.wbtot = (const double *)dev_ptr(h, FID_ssnow_wbtot, 0); p.fevc = (const double *)dev_ptr(h, FID_canopy_fevc, 0);
   p.fes = (const double *)dev_ptr(h, FID_canopy_fes, 0);
-  post_step_kernel<<<(h->mp + 255) / 256, 256, 0, main_stream(h)>>>(p, h->drv.arr, h->mp, ktau, kstart, dels, do_mass_bal, do_energy_bal);
-  CUDA_TRY(cudaGetLastError());
-  h->ctr.kernel_launches++;
+  const DriverArrays arr = h->drv.arr;
+  const int mp = h->mp;
+  { int rc = per_chunk(h, [&](int i0, int i1, cudaStream_t st) {
+      post_step_kernel<<<(i1 - i0 + 255) / 256, 256, 0, st>>>(p, arr, mp, i0, i1, ktau, kstart, dels, do_mass_bal, do_energy_bal);
+      CUDA_TRY(cudaGetLastError());
+      h->ctr.kernel_launches++;
+      return (int)CABLE_OK; });
+    if (rc) return rc; }
   // this kernel is the slot's last reader (met%precip/fsd/fld): a prefetch into the slot must wait for it, not only for the step
+  if (piped(h)) return mark_slot_read_by_chains(h, h->last_slot);
   CUDA_TRY(cudaEventRecord(h->ev_slot_free[h->last_slot], main_stream(h)));
   return CABLE_OK;
 }
@@ -1325,6 +1368,8 @@ int cable_b200_output_plan(cable_handle *h, int nrows, const int *field_id, cons
   CUDA_TRY(cudaMemcpy(v.d_rows, rows.data(), nrows * sizeof(OutRow), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&v.d_agg, (size_t)nrows * h->mp * sizeof(double)));
   for (int b = 0; b < 2; b++) CUDA_TRY(cudaMalloc(&v.d_out[b], (size_t)nrows * v.nland * sizeof(float)));
+  cudaFree(v.d_partial); v.d_partial = nullptr;
+  if (!v.ev_red.empty()) CUDA_TRY(cudaMalloc(&v.d_partial, (size_t)2 * v.ev_red.size() * nrows * sizeof(float)));
   v.rows = rows; v.agg_counter = 0; v.out_buf = 0;
   // 'point' rows have no reset value (aggregator.F90 never resets them) and the accumulate pass reads every row before
   // it overwrites: give them a defined first value (compute-sanitizer initcheck, tools/gpu_sanitize.sh)
@@ -1355,11 +1400,43 @@ namespace {
 int reduce_rows(cable_handle *h, int &b_out) {
   auto &v = h->drv;
   const int nrows = (int)v.rows.size(), b = v.out_buf;
+  if (piped(h) && v.agg_counter == 0 && !v.ev_red.empty()) {
+    // One sample per interval on a pipelined step: chunk j's share of the reduction runs on chunk j's chain, behind that
+    // chunk's kernels -- no join.  Land points are reduced where they START; one whose tiles cross into chunk j+1 hands its
+    // running sum forward (output_reduce_kernel), so the only coupling is chunk j+1 waiting for chunk j's (tiny) launch.
+    const int S = (int)h->s_chain.size(), nch = (int)v.ev_red.size();
+    CUDA_TRY(cudaEventRecord(h->ev_fork, h->s_compute));
+    for (int c = 0; c < S; c++) CUDA_TRY(cudaStreamWaitEvent(h->s_chain[c], h->ev_fork, 0));
+    float *partial = v.d_partial + (size_t)b * nch * nrows;
+    for (int j = 0; j < nch; j++) {
+      cudaStream_t st = h->s_chain[j % S];
+      const int i0 = j * h->pipe_chunk, i1 = (i0 + h->pipe_chunk < h->mp) ? i0 + h->pipe_chunk : h->mp;
+      int l0 = (int)(std::lower_bound(v.h_cstart.begin(), v.h_cstart.end(), i0) - v.h_cstart.begin());
+      const int l1 = (int)(std::lower_bound(v.h_cstart.begin(), v.h_cstart.end(), i1) - v.h_cstart.begin());
+      const bool carried_in = l0 > 0 && v.h_cend[l0 - 1] >= i0;        // the land point before l0 started in chunk j-1 and ends here
+      if (carried_in) { l0--; CUDA_TRY(cudaStreamWaitEvent(st, v.ev_red[j - 1], 0)); }
+      CUDA_TRY(cudaStreamWaitEvent(st, v.ev_out_free[b], 0));          // the D2H that last used this staging buffer (and its partial sums) must have drained
+      if (l1 > l0) {
+        const dim3 grid((l1 - l0 + 127) / 128, nrows);
+        output_reduce_kernel<<<grid, 128, 0, st>>>(v.d_rows, nrows, v.d_agg, 0, v.d_patchfrac, v.d_cstart, v.d_cend, v.nland, h->mp,
+                                                   v.d_out[b], l0, l1, i0, i1, j > 0 ? partial + (size_t)(j - 1) * nrows : nullptr,
+                                                   partial + (size_t)j * nrows);
+        CUDA_TRY(cudaGetLastError());
+        h->ctr.kernel_launches++;
+      }
+      CUDA_TRY(cudaEventRecord(v.ev_red[j], st));
+      CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, v.ev_red[j], 0));
+    }
+    h->chains_pending = true;
+    b_out = b;
+    v.out_buf ^= 1;
+    return CABLE_OK;
+  }
   // the D2H that last used this staging buffer must have drained
   CUDA_TRY(cudaStreamWaitEvent(main_stream(h), v.ev_out_free[b], 0));
   const dim3 grid((v.nland + 127) / 128, nrows);
   output_reduce_kernel<<<grid, 128, 0, main_stream(h)>>>(v.d_rows, nrows, v.d_agg, v.agg_counter > 0 ? 1 : 0, v.d_patchfrac,
-                                                       v.d_cstart, v.d_cend, v.nland, h->mp, v.d_out[b]);
+                                                       v.d_cstart, v.d_cend, v.nland, h->mp, v.d_out[b], 0, v.nland, 0, h->mp, nullptr, nullptr);
   CUDA_TRY(cudaGetLastError());
   h->ctr.kernel_launches++;
   if (v.agg_counter > 0) {

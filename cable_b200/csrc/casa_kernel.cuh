@@ -59,10 +59,10 @@ CD double dmin(double a, double b) { return a < b ? a : b; }
 #define B2(f, k) d.casabiome_##f[iv + mv * (k)]
 
 // ---- bgcdriver's daily accumulation of casamet / casaflux from the cbm state (bgcdriver.F90:74-105) ----------------------
-__global__ void casa_accumulate_kernel(const CasaPtrs d, const int mp, const int first_of_run, const int first_of_day,
-                                       const int end_of_day, const int ktauday, const float dels) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= mp) return;
+__global__ void casa_accumulate_kernel(const CasaPtrs d, const int mp, const int i0, const int i1, const int first_of_run,
+                                       const int first_of_day, const int end_of_day, const int ktauday, const float dels) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;       // tiles [i0, i1): the shard, or one chunk of the step pipeline
+  if (i >= i1) return;
   const size_t smp = (size_t)mp;
   if (first_of_run) {                                                   // IF(ktau == kstart)
     T1(casamet_tairk) = 0.0;
@@ -93,9 +93,9 @@ __global__ void casa_accumulate_kernel(const CasaPtrs d, const int mp, const int
 }
 
 // ---- biogeochem (biogeochem_casa.F90:7-182) --------------------------------------------------------------------------------
-__global__ void casa_biogeochem_kernel(const CasaPtrs d, const CasaCfg c, const int mp, const int idoy) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= mp) return;
+__global__ void casa_biogeochem_kernel(const CasaPtrs d, const CasaCfg c, const int mp, const int i0, const int i1, const int idoy) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
   const size_t smp = (size_t)mp;
   const int mv = c.mvtype, icycle = c.icycle, LALLOC = c.lalloc;
   const int iv = d.veg_iveg[i] - 1;                                     // 0-based row of the casabiome tables

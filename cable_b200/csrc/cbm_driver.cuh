@@ -93,10 +93,10 @@ struct DriverArrays {         // driver-owned per-tile arrays (not part of cbm's
   float *radbal, *ebalsoil, *ebalveg, *ebal, *ebal_tot, *radbalsum;
 };
 
-__global__ void post_step_kernel(const PostIn p, const DriverArrays a, const int mp, const int ktau, const int kstart,
-                                 const float dels, const int do_mass_bal, const int do_energy_bal) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= mp) return;
+__global__ void post_step_kernel(const PostIn p, const DriverArrays a, const int mp, const int i0, const int i1, const int ktau,
+                                 const int kstart, const float dels, const int do_mass_bal, const int do_energy_bal) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;       // tiles [i0, i1): the whole shard, or one chunk of the step pipeline
+  if (i >= i1) return;
   const size_t m = (size_t)mp;
   // cable_serial.F90:602-605
   p.smelt[i] = p.smelt[i] * dels;
@@ -245,17 +245,25 @@ __global__ void aggregate_reset_kernel(const OutRow *__restrict__ rows, const in
 __global__ void output_reduce_kernel(const OutRow *__restrict__ rows, const int nrows, const double *__restrict__ agg,
                                      const int from_agg, const float *__restrict__ patchfrac,
                                      const int *__restrict__ cstart, const int *__restrict__ cend, const int nland,
-                                     const int mp, float *__restrict__ out) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+                                     const int mp, float *__restrict__ out, const int l0, const int l1,
+                                     const int i0, const int i1, const float *__restrict__ partial_in, float *__restrict__ partial_out) {
+  // Land points [l0, l1) restricted to tiles [i0, i1): everything (l0 = 0, l1 = nland, i0 = 0, i1 = mp), or one chunk of the
+  // step pipeline.  A land point whose tiles cross a chunk edge is summed in tile order across the two launches: the first
+  // leaves its running sum in partial_out[r] instead of `out`, the second (l0 = that land point) starts from partial_in[r] --
+  // the same left-to-right fp32 sum as one pass.
+  const int l = l0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int r = blockIdx.y;
-  if (l >= nland) return;
+  if (l >= l1) return;
   const OutRow row = rows[r];
-  float s = 0.0f;
-  for (int i = cstart[l]; i <= cend[l]; i++) {
+  const int c0 = cstart[l], c1 = cend[l];
+  float s = (c0 < i0) ? partial_in[r] : 0.0f;
+  const int a = c0 < i0 ? i0 : c0, b = c1 < i1 ? c1 : i1 - 1;
+  for (int i = a; i <= b; i++) {
     const float v = from_agg ? (float)agg[(size_t)r * mp + i] : agg_sample(row, i);    // written as real32
     s = s + v * patchfrac[i];
   }
-  out[(size_t)r * nland + l] = s;
+  if (c1 >= i1) partial_out[r] = s;
+  else out[(size_t)r * nland + l] = s;
 }
 
 }  // namespace cbl

@@ -342,34 +342,51 @@ def test_device_grid_reduction_matches_reference_rule():
 
 def test_pipelined_resident_step_is_bit_identical(monkeypatch):
     """The resident step as chunk chains on several streams with no join between steps (cable_b200_step, pipe_chunk) against
-    the unpipelined launch on the same inputs: identical bits in every state / driver-visible field and in the driver's
-    accumulators, with post_step (which must join the chains, then fork them again) after some of the steps only."""
+    the unpipelined launch on the same inputs: identical bits in every state / driver-visible field, in the driver's
+    accumulators and in every step's grid-cell output block.  The offline-driver loop rides the pipeline (post-step statements
+    and the output reduction run per chunk on the chain streams; a land point that straddles two chunks couples neighbours);
+    some steps go without post_step / output so that both the joined and the unjoined orders are exercised, and a ragged grid
+    (1..5 patches per land point) puts land points across the chunk edges."""
+    from util import ragged_case
+    rows = [("canopy_fe", 0, "mean"), ("ssnow_tgg", 2, "mean"), ("ssnow_wb", 0, "mean"), ("ssnow_runoff", 0, "mean"),
+            ("bal_wbal", 0, "mean"), ("canopy_fnee", 0, "mean")]
+
     def run(streams):
         monkeypatch.setenv("CABLE_B200_PIPE_STREAMS", str(streams))
-        monkeypatch.setenv("CABLE_B200_PIPE_CHUNK", "20480")          # 5 chunks of the 96 000-tile shard (small-range kernels)
+        monkeypatch.setenv("CABLE_B200_PIPE_CHUNK", "20480")          # ~5 chunks (small-range kernels), edges inside land points
         cfg = lib.default_cfg(); cfg.n_forcing_slots = 4; cfg.output_level = 1
-        grid = synth.make_grid(19200, 5); T = synth.make_tiles(grid, cfg)
-        F = synth.Forcing(grid, T, DELS, start_doy=100)
-        fs = []
-        for k in range(10):
-            F.fill(T, k); fs.append({n: T[n].copy() for n in synth.FORCING_FIELDS})
+        cfg, grid, T, F, idx = ragged_case(32000, cfg=cfg, start_doy=100)
+        assert grid.mp > 4 * 20480 and np.any((grid.cstart < 20480) & (grid.cend >= 20480))
+        conv = lib.MetConvert(tair_offset=0.0, psurf_scale=0.01, rainf_scale=DELS, co2_scale=1.0e-6, snowf_from_tair=1)
+        slices = [np.ascontiguousarray(F.land_slice(k), np.float32) for k in range(10)]
+        outs = []
         with CableB200(grid.mp, cfg) as h:
             h.bind(T); h.upload_params(); h.upload_state()
             h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+            h.output_plan(rows)
+            T["veg_vlai"][0] = F.lai(0)[idx]; h.upload_lai()
             for k in range(10):
-                h.bind(fs[k])
-                h.set_forcing_async(k % 4)                   # the ring: a slot is rewritten while earlier steps are still in flight
+                h.set_met_async(k % 4, slices[k], conv)      # the ring: a slot is rewritten while earlier steps are still in flight
                 h.step(k + 1, DELS, k % 4)
-                if k in (2, 3, 7):
+                if k not in (0, 5):
                     h.post_step(k + 1, 1, DELS)
+                if k not in (1, 5, 6):
+                    out = np.zeros((len(rows), grid.nland), np.float32)
+                    h.output_fetch_async(out); outs.append(out)
+                    if k % 2:
+                        h.output_wait()
+            h.output_wait()
             h.download_state(); h.download_diag()
             acc = {n: h.driver_download(n) for n in ("sum_flux_sumpn", "bal_wbal", "bal_ebal")}
             launches = h.counters().kernel_launches
-        return T, acc, launches
-    Ta, acca, la = run(0)
-    Tb, accb, lb = run(4)
-    assert lb > la                                            # 5 chunks x (A fast, A, B) per step against 2 chains
+        return T, acc, launches, outs
+    Ta, acca, la, oa = run(0)
+    Tb, accb, lb, ob = run(4)
+    assert lb > la                                            # chunks x (A fast, A, B) per step against 2 chains
     for f in output_fields():
         assert np.array_equal(Ta[f.name], Tb[f.name], equal_nan=True), f.name
     for n in acca:
         assert np.array_equal(acca[n], accb[n], equal_nan=True), n
+    assert len(oa) == len(ob) == 7
+    for k, (x, y) in enumerate(zip(oa, ob)):
+        assert np.array_equal(x, y, equal_nan=True) and np.isfinite(x).all() and np.abs(x).max() > 0, k
