@@ -683,13 +683,14 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
     h->chunk_tiles = wave * waves_per_chunk;
     h->nchunks = (mp + h->chunk_tiles - 1) / h->chunk_tiles;
   }
+  int edge = CBL_ORDER_WINDOW; while (edge % 256) edge += CBL_ORDER_WINDOW;
   if (const char *e = getenv("CABLE_B200_CHUNKS")) {        // explicit override: equal chunks
     h->nchunks = atoi(e) > 0 ? atoi(e) : 1;
-    h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + CBL_ORDER_WINDOW - 1) / CBL_ORDER_WINDOW * CBL_ORDER_WINDOW;
+    h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + edge - 1) / edge * edge;
   }
-  if (h->nchunks > 64) { h->nchunks = 64; h->chunk_tiles = ((mp + 63) / 64 + CBL_ORDER_WINDOW - 1) / CBL_ORDER_WINDOW * CBL_ORDER_WINDOW; }
-  // chunk edges are multiples of 768 = 3 x 256: two concurrently launched ranges never share a 256-tile redo-flag entry
-  // (launch_range checks it)
+  if (h->nchunks > 64) { h->nchunks = 64; h->chunk_tiles = ((mp + 63) / 64 + edge - 1) / edge * edge; }
+  // chunk edges are multiples of lcm(kernel A's block, 256): two concurrently launched ranges never share a 256-tile
+  // redo-flag entry (launch_range checks it)
   if (const char *e = getenv("CABLE_B200_GRAPH")) h->use_graph = atoi(e);
   if (const char *e = getenv("CABLE_B200_TRACE")) { h->trace = atoi(e); if (h->trace) h->use_graph = 0; }
   cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
