@@ -59,7 +59,7 @@ class CasaCfg(C.Structure):
 
 EXPORTS = ["cable_b200_casa_default_cfg", "cable_b200_casa_nfields", "cable_b200_casa_field_id", "cable_b200_casa_field_info",
            "cable_b200_casa_init", "cable_b200_casa_bind", "cable_b200_casa_upload", "cable_b200_casa_download",
-           "cable_b200_bgcdriver", "cable_b200_casa_biogeochem"]
+           "cable_b200_bgcdriver", "cable_b200_casa_biogeochem", "cable_b200_casa_feedback"]
 
 
 def _bind_lib():
@@ -75,6 +75,7 @@ def _bind_lib():
     L.cable_b200_casa_upload.argtypes = [H]; L.cable_b200_casa_download.argtypes = [H]
     L.cable_b200_bgcdriver.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
     L.cable_b200_casa_biogeochem.argtypes = [H, C.c_int]
+    L.cable_b200_casa_feedback.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int]
     L._casa_bound = True
     return L
 
@@ -123,6 +124,10 @@ class Casa:
 
     def bgcdriver(self, ktau, kstart, kend, dels, ktauday, idoy, loy=365):
         _lib.check(self.L.cable_b200_bgcdriver(self.h._h, int(ktau), int(kstart), int(kend), float(dels), int(ktauday), int(idoy), int(loy)))
+
+    def feedback(self, slot=0, vcmax=True, lai=False, walker2014=False):
+        """casa_feedback / l_laiFeedbk before the step that reads forcing slot `slot` (cable_serial.F90:587-590)"""
+        _lib.check(self.L.cable_b200_casa_feedback(self.h._h, int(slot), int(vcmax), int(lai), int(walker2014)))
 
     def biogeochem(self, idoy):
         _lib.check(self.L.cable_b200_casa_biogeochem(self.h._h, int(idoy)))

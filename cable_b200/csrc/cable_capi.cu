@@ -142,6 +142,7 @@ struct cable_handle {
   bool any_dirty = false;
   float *d_tbl = nullptr; double *d_tbl_d = nullptr;   // per-PFT / per-soil-type parameter tables (cbm_types.cuh)
   int tbl_classes = 0, tbl_enable = 1;
+  bool veg_tables_off = false;       // cable_b200_casa_feedback made veg%vcmax / ejmax per-tile on the device
   // preferred shared-memory share of the unified L1 array, per cent.  -1 = the driver's default.  The kernels hold ~3.5 KB of
   // static shared memory (parameter tables): a preference BELOW what they need (0 = all to L1, as in round 1 when they had
   // none) costs 45 % of the step on B200 (1.47 vs 1.00 ms, profiles/r02_carveout_sweep.txt); 8-15 % and the default tie.
@@ -496,7 +497,7 @@ int build_param_tables(cable_handle *h) {
         }
       }
     }
-    if (ok) h->tbl_classes |= cls;
+    if (ok && !(cls == 1 && h->veg_tables_off)) h->tbl_classes |= cls;
   }
   if (!h->d_tbl) {
     CUDA_TRY(cudaMalloc(&h->d_tbl, tbl.size() * sizeof(float)));

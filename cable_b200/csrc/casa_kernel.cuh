@@ -92,6 +92,43 @@ __global__ void casa_accumulate_kernel(const CasaPtrs d, const int mp, const int
   }
 }
 
+// ---- casa_feedback (src/science/casa-cnp/casa_feedback.F90:37-115; call site cable_serial.F90:587-590): prognostic Vcmax from
+// the leaf N and P pools, and (l_laiFeedbk) veg%vlai = casamet%glai, before the step that reads them.  REAL locals:
+// the r_2 pool ratios are converted where the reference assigns them to its REAL arrays.
+__global__ void casa_feedback_kernel(const CasaPtrs d, const CasaCfg c, const int mp, const int i0, const int i1,
+                                     const int do_vcmax, const int walker2014, const int do_lai,
+                                     float *__restrict__ veg_vcmax, float *__restrict__ veg_ejmax, float *__restrict__ veg_vlai) {
+  const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  const size_t smp = (size_t)mp;
+  const int mv = c.mvtype;
+  if (do_vcmax) {
+    const int ivt = d.veg_iveg[i], iv = ivt - 1;
+    float ncleafx = (float)B2(rationcplantmax, LEAF), npleafx = 14.2f, npleafx_coef = 1.0f;
+    const double glai = T1(casamet_glai), cl = T2(casapool_cplant, LEAF), nl = T2(casapool_nplant, LEAF), pl = T2(casapool_pplant, LEAF);
+    if (T1(casamet_iveg2) != icewater && glai > B1(glaimin) && cl > 0.0) {
+      ncleafx = (float)dmin(B2(rationcplantmax, LEAF), dmax(B2(rationcplantmin, LEAF), nl / cl));
+      if (c.icycle > 2 && pl > 0.0) npleafx = fminf(30.0f, fmaxf(8.0f, (float)(nl / pl)));
+    }
+    if (!walker2014) {                                                   // cable_user%vcmax = 'standard'
+      if (glai > B1(glaimin)) {
+        if ((ivt == 2 || ivt == 12 || ivt == 13) && nl > 0.0 && pl > 0.0) npleafx_coef = 0.4f + 9.0f / npleafx;
+        // r_2 + r_2 * REAL * REAL / r_2, then * REAL literal, stored to REAL
+        veg_vcmax[i] = (float)((B1(nintercept) + B1(nslope) * (double)npleafx_coef * (double)ncleafx / B1(sla)) * (double)1.0e-6f);
+      }
+    } else {                                                             // 'Walker2014'
+      const float nleafx = (float)((double)ncleafx / B1(sla)), pleafx = nleafx / npleafx;
+      if (ivt == 7) veg_vcmax[i] = 1.0e-5f;
+      else {   // vcmax_np (casa_cnp.F90:2362): binary32 EXP / LOG, correctly rounded
+        const float ln = (float)log((double)nleafx), lp = (float)log((double)pleafx);
+        veg_vcmax[i] = (float)exp((double)(3.946f + 0.921f * ln + 0.121f * lp + 0.282f * lp * ln)) * 1.0e-6f;
+      }
+    }
+    veg_ejmax[i] = 2.0f * veg_vcmax[i];                                  // :113, every tile
+  }
+  if (do_lai) veg_vlai[i] = (float)T1(casamet_glai);                     // cable_serial.F90:590
+}
+
 // ---- biogeochem (biogeochem_casa.F90:7-182) --------------------------------------------------------------------------------
 __global__ void casa_biogeochem_kernel(const CasaPtrs d, const CasaCfg c, const int mp, const int i0, const int i1, const int idoy) {
   const int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;

@@ -377,6 +377,11 @@ int          cable_b200_casa_upload(cable_handle *h);      /* every bound array 
 int          cable_b200_casa_download(cable_handle *h);    /* every bound per-tile array D2H          */
 int          cable_b200_bgcdriver(cable_handle *h, int ktau, int kstart, int kend, float dels, int ktauday, int idoy, int loy);
 int          cable_b200_casa_biogeochem(cable_handle *h, int idoy);   /* biogeochem alone (bgcdriver's dump_read branch) */
+/* IF (l_vcmaxFeedbk) CALL casa_feedback(ktau, veg, casabiome, casapool, casamet)  (src/science/casa-cnp/casa_feedback.F90:37);
+ * IF (l_laiFeedbk .AND. icycle > 0) veg%vlai = casamet%glai   (src/offline/cable_serial.F90:587-590) -- on the device, for the
+ * step that will read forcing slot `slot` (after that slot's upload, before cable_b200_step).  vcmax_walker2014: cable_user%vcmax
+ * = 'Walker2014' instead of 'standard'. */
+int          cable_b200_casa_feedback(cable_handle *h, int slot, int l_vcmaxfeedbk, int l_laifeedbk, int vcmax_walker2014);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,8 @@ TRACE = ("casaflux_cnpp", "casapool_cplant", "casapool_nsoilmin", "casapool_psoi
 BIO = {"c_fixed": (1, 0, 0, 0), "cn_dynamic": (2, 1, 0, 0), "cnp_fixed": (3, 0, 0, 0), "cnp_dynamic": (3, 1, 0, 1),
        "cnp_lasa": (3, 3, 0, 0), "cn_climate": (2, 0, 1, 0), "cnp_climate_dyn": (3, 1, 1, 0)}
 DRV = {"drv_cnp": (3, 1, 0, 0), "drv_c": (1, 0, 0, 0)}
+# casa_feedback: name -> (icycle, cable_user%vcmax)
+FB = {"fb_cn_standard": (2, "standard"), "fb_cnp_standard": (3, "standard"), "fb_cnp_walker": (3, "Walker2014")}
 NLAND, DOY = 24, 200
 
 
@@ -107,12 +109,38 @@ def run_drv(name):
     return out
 
 
+def fb_inputs(name):
+    """synthetic pools with every branch of casa_feedback present: bare leaf pools, LAI below glaimin, zero leaf P"""
+    cfg, grid, T, A, silt, clay, ccfg = bio_inputs("cnp_fixed")
+    ccfg.icycle = FB[name][0]
+    A["casapool_cplant"][0][::11] = 0.0
+    A["casamet_glai"][0][::7] = 0.05
+    A["casapool_pplant"][0][::13] = 0.0
+    A["casapool_nplant"][0][5::23] *= 4.0                      # N:C above ratioNCplantmax, N:P above 30
+    A["casapool_pplant"][0][3::19] *= 6.0                      # N:P below 8
+    return cfg, grid, T, A, silt, clay, ccfg
+
+
+def run_fb(name):
+    from cable_b200 import casa
+    from oracle.frun.run_casa import FortranCasa
+    cfg, grid, T, A, silt, clay, ccfg = fb_inputs(name)
+    fc = FortranCasa(T, A, casa.FIELDS, ccfg, silt, clay)
+    S = fc.S
+    fc.I.lookup_in_module(fc.I.module("cable_common_module"), "cable_user").f["vcmax"].s = FB[name][1]
+    S["veg"].f["vcmax"].a[...] = T["veg_vcmax"][0]; S["veg"].f["ejmax"].a[...] = T["veg_ejmax"][0]
+    fc.I.call("feedback_mod", "casa_feedback", np.int32(1), S["veg"], S["casabiome"], S["casapool"], S["casamet"])
+    out = {f"fb/{name}/veg_vcmax": S["veg"].f["vcmax"].a.copy(), f"fb/{name}/veg_ejmax": S["veg"].f["ejmax"].a.copy()}
+    print(name, "vcmax changed on", int((out[f"fb/{name}/veg_vcmax"] != T["veg_vcmax"][0]).sum()), "of", grid.mp, "tiles", flush=True)
+    return out
+
+
 def _job(j):
-    return run_bio(j[1]) if j[0] == "bio" else run_drv(j[1])
+    return {"bio": run_bio, "drv": run_drv, "fb": run_fb}[j[0]](j[1])
 
 
 def main():
-    jobs = [("bio", n) for n in BIO] + [("drv", n) for n in DRV]
+    jobs = [("bio", n) for n in BIO] + [("drv", n) for n in DRV] + [("fb", n) for n in FB]
     with mp_.get_context("fork").Pool(8) as pool:
         parts = pool.map(_job, jobs)
     merged = {}

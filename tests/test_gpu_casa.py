@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(HERE, "golden"))
 import make_casa_golden as G           # noqa: E402
 from cable_b200 import casa, lib, synth  # noqa: E402
 from cable_b200.cbm import CableB200     # noqa: E402
+from cable_b200.registry import BY_NAME, ROLE  # noqa: E402
 from util import DELS, make_case         # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -127,3 +128,35 @@ def test_casa_init_rejects_what_is_not_on_the_device():
         cs = casa.Casa(h, c)
         with pytest.raises(lib.CableError):
             cs.bgcdriver(1, 1, 10, DELS, 8, 1)          # no step has run
+
+
+@pytest.mark.parametrize("case", list(G.FB))
+def test_casa_feedback_matches_the_fortran_run(case):
+    """Prognostic Vcmax (casa_feedback.F90:37-115, 'standard' and 'Walker2014') and l_laiFeedbk (cable_serial.F90:590) on the
+    device against the reference's Fortran source: veg%vcmax / veg%ejmax bit for bit (binary32 results of binary64 pool
+    ratios), and the step that follows reads them per tile although the handle started on the per-PFT tables."""
+    z = np.load(GOLD)
+    cfg, grid, T, A, silt, clay, ccfg = G.fb_inputs(case)
+    cfg.n_forcing_slots = 2
+    F = synth.Forcing(grid, T, DELS, start_doy=G.DOY)
+    with CableB200(grid.mp, cfg) as h:
+        h.bind(T); h.upload_params(); h.upload_state()
+        assert h._lib.cable_b200_param_table_classes(h._h) & 1          # vegetation parameters start in the shared-memory tables
+        cs = casa.Casa(h, ccfg)
+        cs.bind(A, silt, clay); cs.upload()
+        F.fill(T, 0); h.set_forcing_async(1)
+        cs.feedback(1, vcmax=True, lai=True, walker2014=G.FB[case][1] == "Walker2014")
+        assert not (h._lib.cable_b200_param_table_classes(h._h) & 1)
+        h.step(1, DELS, 1); h.sync()
+        vc0 = T["veg_vcmax"].copy()
+        lib.check(h._lib.cable_b200_download(h._h, ROLE["PARAM"], 0))
+        from cuda.bindings import runtime as cudart                                          # the slot's veg%vlai lives only on the device
+        lai = np.empty(grid.mp, np.float32)
+        err, = cudart.cudaMemcpy(lai.ctypes.data, h._lib.cable_b200_device_ptr(h._h, BY_NAME["veg_vlai"].id, 1), lai.nbytes,
+                                 cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        assert int(err) == 0
+        h.download_state(); h.download_diag()
+    assert np.array_equal(T["veg_vcmax"][0], z[f"fb/{case}/veg_vcmax"]) and np.array_equal(T["veg_ejmax"][0], z[f"fb/{case}/veg_ejmax"])
+    assert (T["veg_vcmax"][0] != vc0[0]).sum() > grid.mp // 2
+    assert np.array_equal(lai, A["casamet_glai"][0].astype(np.float32))
+    assert np.all(np.isfinite(T["canopy_fpn"])) and np.abs(T["canopy_fpn"]).max() > 0
