@@ -78,6 +78,43 @@ def driver(nland, steps):
     return launches
 
 
+def casa_pipelined(nland, steps):
+    """the offline-driver loop with CASA-CNP on a PIPELINED step (chunk chains; post-step, CASA kernels and the output
+    reduction per chunk on the chain streams, a ragged grid so that land points cross the chunk edges)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import ragged_case
+    from cable_b200 import casa
+    os.environ["CABLE_B200_PIPE_CHUNK"] = "1280"; os.environ["CABLE_B200_PIPE_STREAMS"] = "3"
+    cfg = lib.default_cfg(); cfg.output_level = 1; cfg.n_forcing_slots = 2; cfg.icycle = 3
+    cfg, grid, T, F, idx = ragged_case(nland, cfg=cfg, start_doy=190)
+    assert grid.mp > 2 * 1280
+    ccfg = casa.default_cfg(); ccfg.icycle = 3; ccfg.lalloc = 1
+    rows = [("canopy_fe", 0, "mean"), ("ssnow_tgg", 5, "mean"), ("canopy_fnee", 0, "mean"), ("bal_wbal", 0, "mean")]
+    out = np.zeros((len(rows), grid.nland), np.float32)
+    with CableB200(grid.mp, cfg, device=0) as h:
+        h.bind(T); h.upload_params(); h.upload_state()
+        h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+        h.output_plan(rows)
+        cs = casa.Casa(h, ccfg)
+        A = casa.synth_casa(grid, T, ccfg, seed=5)
+        silt, clay = casa.soil_texture(T)
+        cs.bind(A, silt, clay); cs.upload()
+        T["veg_vlai"][0] = F.lai(0)[idx]; h.upload_lai()
+        for k in range(steps):
+            h.set_met_async(k % 2, np.ascontiguousarray(F.land_slice(k), np.float32), lib.MetConvert(**CONVERT))
+            cs.feedback(k % 2, vcmax=True, lai=k > 1)
+            h.step(k + 1, DELS, k % 2)
+            cs.bgcdriver(k + 1, 1, 1000, DELS, 2, 190 + k // 2)            # a two-step "day": biogeochem every other step
+            h.post_step(k + 1, 1, DELS)
+            h.output_fetch_async(out); h.output_wait()
+        cs.download(); h.sync()
+        launches = h.counters().kernel_launches
+    assert np.isfinite(out).all() and np.abs(out[0]).max() > 0 and np.isfinite(A["casapool_cplant"]).all()
+    for k in ("CABLE_B200_PIPE_CHUNK", "CABLE_B200_PIPE_STREAMS"):
+        del os.environ[k]
+    return launches, grid.mp
+
+
 if __name__ == "__main__":
     nland = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -86,3 +123,5 @@ if __name__ == "__main__":
         print(f"drop-in cbm: {mp} tiles x {steps} steps from doy {doy}, gs_switch {gs}: {launches} launches, "
               f"worst relative difference vs oracle {worst:.2e}", flush=True)
     print(f"driver stages: {driver(nland, 4)} launches, outputs finite", flush=True)
+    l, mp = casa_pipelined(max(nland, 900), 4)
+    print(f"driver stages + CASA-CNP on the pipelined step: {mp} tiles x 4 steps, {l} launches, outputs finite", flush=True)

@@ -12,5 +12,5 @@ for tool in ${SAN_TOOLS:-memcheck racecheck synccheck initcheck}; do
   timeout -s KILL ${SAN_TIMEOUT:-55} compute-sanitizer --tool $tool $extra --print-limit 20 python tests/checks/sanitize_case.py $NL ${SAN_STEPS:-2} \
     > gpurun_out/sanitize_${tool}${SAN_TAG}.log 2>&1
   echo "== $tool rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|LEAK SUMMARY' gpurun_out/sanitize_${tool}${SAN_TAG}.log | tr '\n' ' ')"
-  grep -E "^drop-in|^driver" gpurun_out/sanitize_${tool}${SAN_TAG}.log
+  grep -E "^drop-in|^driver|Error|error" gpurun_out/sanitize_${tool}${SAN_TAG}.log
 done
