@@ -25,15 +25,6 @@ int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, const void *cfg, si
                   int first, unsigned long long *warn, int *redo, int big, int lvl, int max_l1, cudaStream_t st);
 void cblf_debug_dump();
 
-// scratch rows / shared memory of kernel A's dryLeaf pass pool (0 when the pool is compiled out)
-#if CBL_COMPACT
-constexpr int SD_ROWS = SD_ND, SF_ROWS = SF_NF;
-constexpr size_t pool_smem_bytes(int block) { return leaf_pool_smem_bytes(block); }
-#else
-constexpr int SD_ROWS = 1, SF_ROWS = 1;
-constexpr size_t pool_smem_bytes(int) { return 0; }
-#endif
-
 // occupancy targets of the three kernel variants (tuned on B200); build-time so that only the
 // variants that ship are compiled
 #ifndef CBL_MINB_A
@@ -179,7 +170,6 @@ struct cable_handle {
   unsigned long long *d_warn = nullptr;
   int *d_order = nullptr;          // kernel A's thread -> tile table (build_tile_order), null = identity
   int tile_order = 0;              // CABLE_B200_TILE_ORDER=1 switches it on (measured slower, see build_tile_order)
-  double *leaf_scr_d = nullptr; float *leaf_scr_f = nullptr;   // dryLeaf pass-pool scratch (kernel A)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
   int fastdiv = 1;                     // kernel A's CBL_FASTDIV build first (CABLE_B200_FASTDIV=0: ordinary build only)
@@ -314,7 +304,6 @@ DevPtrs make_ptrs(const cable_handle *h, int slot) {
   d.tbl = h->d_tbl; d.tbl_d = h->d_tbl_d; d.tbl_classes = h->tbl_classes;
   d.met_tvair_in = (const float *)dev_in_ptr(h, FID_met_tvair, slot);
   d.canopy_oldcansto_in = (const float *)dev_in_ptr(h, FID_canopy_oldcansto, slot);
-  d.leaf_scr_d = h->leaf_scr_d; d.leaf_scr_f = h->leaf_scr_f;
   d.tile_order = nullptr;                          // set per launch (launch_range)
   return d;
 }
@@ -352,19 +341,17 @@ int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, in
   // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
   // CBL_MINB_x = resident blocks per SM the compiler must allow (register cap 65536 / (BLOCK*MINB)).
 #define CBL_LAUNCH_X(PH, BL, MB, LV, XS) {                                                                                     \
-    const size_t sm_ = ((PH) & 1) ? pool_smem_bytes(BL) : 0;                                                                 \
     {                                                                                                                          \
       static bool once_[64] = {};   /* per instantiation and device */                                                        \
       const int dv_ = h->device & 63;                                                                                          \
       if (!once_[dv_]) {                                                                                                       \
-        if (sm_ > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
-        /* no shared memory in the default build: give the whole unified array to L1, which holds the spill slots */          \
-        if (sm_ == 0 && h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout); \
+        /* shared-memory share of the unified array (handle::carveout; the kernels hold 3.5 KB of static tables) */            \
+        if (h->max_l1) cudaFuncSetAttribute(cbm_kernel<PH, BL, MB, LV, XS>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout); \
         cudaGetLastError();                                                                                                    \
         once_[dv_] = true;                                                                                                     \
       }                                                                                                                        \
     }                                                                                                                          \
-    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, sm_, st>>>(d, h->dcfg, h->mp, i0, i1, dels, first, h->d_warn, redo_); }
+    cbm_kernel<PH, BL, MB, LV, XS><<<(i1 - i0 + (BL) - 1) / (BL), BL, 0, st>>>(d, h->dcfg, h->mp, i0, i1, dels, first, h->d_warn, redo_); }
 #define CBL_LAUNCH(PH, BL, MB, LV) CBL_LAUNCH_X(PH, BL, MB, LV, 0)
 #define CBL_DISPATCH(PH, BL, MB)                                                     \
   switch (h->cfg.output_level) { case 0: CBL_LAUNCH(PH, BL, MB, 0); break; case 1: CBL_LAUNCH(PH, BL, MB, 1); break; default: CBL_LAUNCH(PH, BL, MB, 2); break; }
@@ -655,10 +642,6 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
   if (e != cudaSuccess) { delete h; return fail(CABLE_E_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   cudaMemset(h->arena, 0, h->arena_bytes);
-  cudaMalloc(&h->leaf_scr_d, (size_t)mp * SD_ROWS * sizeof(double));
-  cudaMalloc(&h->leaf_scr_f, (size_t)mp * SF_ROWS * sizeof(float));
-  cudaMemset(h->leaf_scr_d, 0, (size_t)mp * SD_ROWS * sizeof(double));
-  cudaMemset(h->leaf_scr_f, 0, (size_t)mp * SF_ROWS * sizeof(float));
   cudaMalloc(&h->d_redo, ((size_t)mp / 64 + 2) * sizeof(int));
   cudaMemset(h->d_redo, 0, ((size_t)mp / 64 + 2) * sizeof(int));
   cudaMalloc(&h->d_warn, 2 * sizeof(unsigned long long));       // [0] dryLeaf soft warnings, [1] blocks recomputed after a fast-path miss
@@ -762,7 +745,6 @@ int cable_b200_destroy(cable_handle *h) {
   if (h->d_warn) cudaFree(h->d_warn);
   if (h->d_redo) cudaFree(h->d_redo);
   if (h->d_order) cudaFree(h->d_order);
-  cudaFree(h->leaf_scr_d); cudaFree(h->leaf_scr_f);
   if (h->d_tbl) cudaFree(h->d_tbl);
   if (h->d_tbl_d) cudaFree(h->d_tbl_d);
   if (h->arena) cudaFree(h->arena);

@@ -249,8 +249,9 @@ struct CanopyWork {
 
 // ---- dryLeaf: cbl_dryLeaf.F90:10-666 -----------------------------------------------------------------------------
 // Everything one pass of the coupled leaf-temperature / photosynthesis / stomata iteration reads and writes for ONE
-// tile.  Keeping it in one struct lets the same pass code run on the owning thread's registers (CBL_COMPACT=0) or on
-// a record fetched from shared/global memory by whichever thread the block's pass pool hands the tile to (=1).
+// tile, in the owning thread's registers.  (Round 1 also carried a variant that re-packed a block's still-active tiles
+// between passes through shared-memory records of this struct -- bit-identical, lanes 21.5 -> 27.7 of 32, but 1.30 -> 1.73
+// ms/step; DESIGN.md 7.  It was removed in round 2: git history, commit e1c7806 and earlier.)
 // sunlit/shaded leaf loop unrolled (1) or rolled (0).  Rolled halves the footprint of the hottest loop, which paid
 // while kernel A was instruction-fetch bound; with the phase barriers in place the unrolled form is 2 % faster
 // (two independent dependency chains per thread).
@@ -463,28 +464,10 @@ CBL_DEV bool leaf_pass(LeafPass &p, const DevCfg &c, const float dels, const int
   return false;
 }
 
-#ifndef CBL_COMPACT
-#define CBL_COMPACT 0
-#endif
-#if CBL_COMPACT
-// Shared-memory record of a tile in the block's pass pool: what a pass needs that is neither in global memory nor
-// recomputable (values of THIS stability iteration) + the pass-to-pass state.  SoA over the block's slots.
-enum { LR_TVAIR = 0, LR_DVA, LR_CMOLAR, LR_PSYC, LR_DSATDK, LR_FWSOIL, LR_FWET, LR_DLEAF3, LR_FVLAI0, LR_FVLAI1, LR_SCALEX0,
-       LR_SCALEX1, LR_QCAN0, LR_QCAN1, LR_GRADIS0, LR_GRADIS1, LR_RNISO0, LR_RNISO1,
-       LR_TLFX, LR_DSX, LR_ABSD, LR_DELTLFY, LR_GW0, LR_GW1, LR_PSYCST0, LR_PSYCST1, LR_GSWX0, LR_GSWX1, LR_NF };
-enum { LD_GBHU0 = 0, LD_GBHU1, LD_CSX0, LD_CSX1, LD_ND };
-// global scratch rows (per tile): best iterate and latest-pass results that the owner reads back after the loop
-enum { SD_RNY = 0, SD_HCY, SD_ECY, SD_ECX, SD_GBHF0, SD_GBHF1, SD_ND };
-enum { SF_TLFY = 0, SF_RDY0, SF_RDY1, SF_ANY0, SF_ANY1, SF_OLDEV0, SF_NF = SF_OLDEV0 + K::ms };
-__host__ __device__ constexpr size_t leaf_pool_smem_bytes(int block) {
-  return (size_t)block * (LD_ND * sizeof(double) + LR_NF * sizeof(float) + sizeof(int)) + 32 * sizeof(int);
-}
-#endif
 
-// dryLeaf for the calling thread's tile.  `d`, `tile`, `smp`: global arrays / this thread's tile / mp (pool mode only).
+// dryLeaf for the calling thread's tile
 template <bool XSW>
-CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int iter, const DevPtrs &d, const int tile,
-                     const size_t smp) {
+CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int iter) {
   if (iter == 1) { w.fwsoil = fwsoil_calc(t, c); t.canopy_fwsoil = (double)w.fwsoil; }
   const bool veg = t.canopy_vlaiw > K::lai_thresh;
   LeafPass p;
@@ -531,123 +514,12 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
   p.deltlfy = p.abs_deltlf;
   leaf_pass_prepare(p, c);
 
-#if !CBL_COMPACT
-  (void)d; (void)tile; (void)smp;
   if (veg) {
     for (int k = 1; k <= K::maxiter; k++) {
       bool captured;
       if (!leaf_pass<XSW>(p, c, dels, k, captured)) break;
     }
   }
-#else
-  // ---- the block's pass pool: every pass, the tiles that still iterate are re-packed onto the lowest-numbered
-  // threads, so a pass costs ceil(active/32) warps instead of every warp that still owns one active tile, and no
-  // warp waits at the barrier behind another warp's stragglers.  A tile's arithmetic is unchanged; only the thread
-  // that executes it varies, so results are bit-identical to the per-owner loop.
-  extern __shared__ __align__(16) unsigned char leaf_smem[];
-  const int nslot = (int)blockDim.x, me = (int)threadIdx.x, lane = me & 31, wid = me >> 5;
-  double *rd = reinterpret_cast<double *>(leaf_smem);
-  float *rf = reinterpret_cast<float *>(rd + (size_t)LD_ND * nslot);
-  int *s_list = reinterpret_cast<int *>(rf + (size_t)LR_NF * nslot);
-  int *s_wtot = s_list + nslot;
-  const int tile0 = tile - me;                      // first tile of this block (shadow threads never enter the pool)
-  bool act = veg && w.valid;
-  if (act) {
-    rf[LR_TVAIR * nslot + me] = p.tvair; rf[LR_DVA * nslot + me] = p.dva; rf[LR_CMOLAR * nslot + me] = p.cmolar;
-    rf[LR_PSYC * nslot + me] = p.psyc; rf[LR_DSATDK * nslot + me] = p.dsatdk; rf[LR_FWSOIL * nslot + me] = p.fwsoil;
-    rf[LR_FWET * nslot + me] = p.fwet; rf[LR_DLEAF3 * nslot + me] = p.dleaf3;
-    rf[LR_FVLAI0 * nslot + me] = p.fvlai[0]; rf[LR_FVLAI1 * nslot + me] = p.fvlai[1];
-    rf[LR_SCALEX0 * nslot + me] = p.scalex[0]; rf[LR_SCALEX1 * nslot + me] = p.scalex[1];
-    rf[LR_QCAN0 * nslot + me] = p.qcan[0]; rf[LR_QCAN1 * nslot + me] = p.qcan[1];
-    rf[LR_GRADIS0 * nslot + me] = p.gradis[0]; rf[LR_GRADIS1 * nslot + me] = p.gradis[1];
-    rf[LR_RNISO0 * nslot + me] = p.rniso[0]; rf[LR_RNISO1 * nslot + me] = p.rniso[1];
-    rf[LR_TLFX * nslot + me] = p.tlfx; rf[LR_DSX * nslot + me] = p.dsx; rf[LR_ABSD * nslot + me] = p.abs_deltlf;
-    rf[LR_DELTLFY * nslot + me] = p.deltlfy;
-    rf[LR_GW0 * nslot + me] = p.gw[0]; rf[LR_GW1 * nslot + me] = p.gw[1];
-    rf[LR_PSYCST0 * nslot + me] = p.psycst[0]; rf[LR_PSYCST1 * nslot + me] = p.psycst[1];
-    rf[LR_GSWX0 * nslot + me] = p.gswx[0]; rf[LR_GSWX1 * nslot + me] = p.gswx[1];
-    rd[LD_GBHU0 * nslot + me] = p.gbhu[0]; rd[LD_GBHU1 * nslot + me] = p.gbhu[1];
-    rd[LD_CSX0 * nslot + me] = p.csx[0]; rd[LD_CSX1 * nslot + me] = p.csx[1];
-#pragma unroll
-    for (int kk = 0; kk < K::ms; kk++) d.ssnow_evapfbl[tile + smp * kk] = 0.0;     // pass-to-pass state lives in its own array
-  }
-  for (int k = 1; k <= K::maxiter; k++) {
-    const unsigned bal = __ballot_sync(0xffffffffu, act);
-    if (lane == 0) s_wtot[wid] = __popc(bal);
-    __syncthreads();
-    int base = 0, total = 0;
-    for (int w2 = 0; w2 < (nslot >> 5); w2++) { const int n = s_wtot[w2]; base += (w2 < wid) ? n : 0; total += n; }
-    if (total == 0) break;                            // block-uniform
-    if (act) s_list[base + __popc(bal & ((1u << lane) - 1u))] = me;
-    __syncthreads();
-    if (me < total) {
-      const int s = s_list[me], ti = tile0 + s;
-      LeafPass q;
-      q.tvair = rf[LR_TVAIR * nslot + s]; q.dva = rf[LR_DVA * nslot + s]; q.cmolar = rf[LR_CMOLAR * nslot + s];
-      q.psyc = rf[LR_PSYC * nslot + s]; q.dsatdk = rf[LR_DSATDK * nslot + s]; q.fwsoil = rf[LR_FWSOIL * nslot + s];
-      q.fwet = rf[LR_FWET * nslot + s]; q.dleaf3 = rf[LR_DLEAF3 * nslot + s];
-      q.fvlai[0] = rf[LR_FVLAI0 * nslot + s]; q.fvlai[1] = rf[LR_FVLAI1 * nslot + s];
-      q.scalex[0] = rf[LR_SCALEX0 * nslot + s]; q.scalex[1] = rf[LR_SCALEX1 * nslot + s];
-      q.qcan[0] = rf[LR_QCAN0 * nslot + s]; q.qcan[1] = rf[LR_QCAN1 * nslot + s];
-      q.gradis[0] = rf[LR_GRADIS0 * nslot + s]; q.gradis[1] = rf[LR_GRADIS1 * nslot + s];
-      q.rniso[0] = rf[LR_RNISO0 * nslot + s]; q.rniso[1] = rf[LR_RNISO1 * nslot + s];
-      q.tlfx = rf[LR_TLFX * nslot + s]; q.dsx = rf[LR_DSX * nslot + s]; q.abs_deltlf = rf[LR_ABSD * nslot + s];
-      q.deltlfy = rf[LR_DELTLFY * nslot + s];
-      q.gw[0] = rf[LR_GW0 * nslot + s]; q.gw[1] = rf[LR_GW1 * nslot + s];
-      q.psycst[0] = rf[LR_PSYCST0 * nslot + s]; q.psycst[1] = rf[LR_PSYCST1 * nslot + s];
-      q.gswx[0] = rf[LR_GSWX0 * nslot + s]; q.gswx[1] = rf[LR_GSWX1 * nslot + s];
-      q.gbhu[0] = rd[LD_GBHU0 * nslot + s]; q.gbhu[1] = rd[LD_GBHU1 * nslot + s];
-      q.csx[0] = rd[LD_CSX0 * nslot + s]; q.csx[1] = rd[LD_CSX1 * nslot + s];
-      // per-tile constants straight from the arrays this kernel loaded them from (L1/L2 resident)
-      q.tk = __ldg(&d.met_tk[ti]); q.ca = __ldg(&d.met_ca[ti]); q.rlam = K::hl; q.dleaf = __ldg(&d.veg_dleaf[ti]);
-      q.vcmax = __ldg(&d.veg_vcmax[ti]); q.frac4 = __ldg(&d.veg_frac4[ti]); q.ejmax = __ldg(&d.veg_ejmax[ti]);
-      q.conkc0 = __ldg(&d.veg_conkc0[ti]); q.conko0 = __ldg(&d.veg_conko0[ti]); q.ekc = __ldg(&d.veg_ekc[ti]);
-      q.eko = __ldg(&d.veg_eko[ti]); q.a1gs = __ldg(&d.veg_a1gs[ti]); q.d0gs = __ldg(&d.veg_d0gs[ti]); q.g1 = __ldg(&d.veg_g1[ti]);
-      q.alpha = __ldg(&d.veg_alpha[ti]); q.convex = __ldg(&d.veg_convex[ti]); q.cfrd = __ldg(&d.veg_cfrd[ti]);
-      q.swilt = __ldg(&d.soil_swilt[ti]);
-      if (c.gs_switch == CABLE_GS_MEDLYN) { q.gswmin[0] = q.gswmin[1] = __ldg(&d.veg_g0[ti]); }
-      else { const float gm = __ldg(&d.veg_gswmin[ti]); q.gswmin[0] = mx(1.e-6f, q.scalex[0] * gm); q.gswmin[1] = mx(1.e-6f, q.scalex[1] * gm); }
-#pragma unroll
-      for (int kk = 0; kk < K::ms; kk++) {
-        q.froot[kk] = __ldg(&d.veg_froot[ti + smp * kk]); q.wbliq[kk] = __ldg(&d.ssnow_wbliq[ti + smp * kk]);
-        q.evapfbl[kk] = d.ssnow_evapfbl[ti + smp * kk];
-      }
-      bool captured;
-      leaf_pass_prepare(q, c);
-      leaf_pass<XSW>(q, c, dels, k, captured);
-      rf[LR_TLFX * nslot + s] = q.tlfx; rf[LR_DSX * nslot + s] = q.dsx; rf[LR_ABSD * nslot + s] = q.abs_deltlf;
-      rf[LR_DELTLFY * nslot + s] = q.deltlfy;
-      rf[LR_GW0 * nslot + s] = q.gw[0]; rf[LR_GW1 * nslot + s] = q.gw[1];
-      rf[LR_PSYCST0 * nslot + s] = q.psycst[0]; rf[LR_PSYCST1 * nslot + s] = q.psycst[1];
-      rf[LR_GSWX0 * nslot + s] = q.gswx[0]; rf[LR_GSWX1 * nslot + s] = q.gswx[1];
-      rd[LD_CSX0 * nslot + s] = q.csx[0]; rd[LD_CSX1 * nslot + s] = q.csx[1];
-#pragma unroll
-      for (int kk = 0; kk < K::ms; kk++) d.ssnow_evapfbl[ti + smp * kk] = q.evapfbl[kk];
-      d.leaf_scr_d[ti + smp * SD_ECX] = q.ecx; d.leaf_scr_d[ti + smp * SD_GBHF0] = q.gbhf[0]; d.leaf_scr_d[ti + smp * SD_GBHF1] = q.gbhf[1];
-      if (captured) {
-        d.leaf_scr_d[ti + smp * SD_RNY] = q.rny; d.leaf_scr_d[ti + smp * SD_HCY] = q.hcy; d.leaf_scr_d[ti + smp * SD_ECY] = q.ecy;
-        d.leaf_scr_f[ti + smp * SF_TLFY] = q.tlfy; d.leaf_scr_f[ti + smp * SF_RDY0] = q.rdy[0]; d.leaf_scr_f[ti + smp * SF_RDY1] = q.rdy[1];
-        d.leaf_scr_f[ti + smp * SF_ANY0] = q.an_y[0]; d.leaf_scr_f[ti + smp * SF_ANY1] = q.an_y[1];
-#pragma unroll
-        for (int kk = 0; kk < K::ms; kk++) d.leaf_scr_f[ti + smp * (SF_OLDEV0 + kk)] = q.oldevapfbl[kk];
-      }
-    }
-    __syncthreads();
-    if (act) act = rf[LR_ABSD * nslot + me] > 0.1f;
-  }
-  if (veg && w.valid) {      // the owner takes its tile back
-    p.tlfx = rf[LR_TLFX * nslot + me]; p.dsx = rf[LR_DSX * nslot + me];
-    p.gswx[0] = rf[LR_GSWX0 * nslot + me]; p.gswx[1] = rf[LR_GSWX1 * nslot + me];
-    p.csx[0] = rd[LD_CSX0 * nslot + me]; p.csx[1] = rd[LD_CSX1 * nslot + me];
-    p.ecx = d.leaf_scr_d[tile + smp * SD_ECX]; p.gbhf[0] = d.leaf_scr_d[tile + smp * SD_GBHF0]; p.gbhf[1] = d.leaf_scr_d[tile + smp * SD_GBHF1];
-    p.rny = d.leaf_scr_d[tile + smp * SD_RNY]; p.hcy = d.leaf_scr_d[tile + smp * SD_HCY]; p.ecy = d.leaf_scr_d[tile + smp * SD_ECY];
-    p.tlfy = d.leaf_scr_f[tile + smp * SF_TLFY]; p.rdy[0] = d.leaf_scr_f[tile + smp * SF_RDY0]; p.rdy[1] = d.leaf_scr_f[tile + smp * SF_RDY1];
-    p.an_y[0] = d.leaf_scr_f[tile + smp * SF_ANY0]; p.an_y[1] = d.leaf_scr_f[tile + smp * SF_ANY1];
-#pragma unroll
-    for (int kk = 0; kk < K::ms; kk++) { p.oldevapfbl[kk] = d.leaf_scr_f[tile + smp * (SF_OLDEV0 + kk)]; p.evapfbl[kk] = d.ssnow_evapfbl[tile + smp * kk]; }
-  }
-  __syncthreads();           // the records are free for the next stability iteration
-#endif
 
   // hand the results back to the tile (:608-666)
   w.tlfx = p.tlfx; w.dsx = p.dsx; w.tlfy = p.tlfy; w.rny = p.rny; w.hcy = p.hcy; w.ecy = p.ecy;
@@ -724,8 +596,7 @@ CBL_DEV void within_canopy(Tile &t, const CanopyWork &w, float rt0, const float 
 
 // define_canopy: cable_canopy.F90:10-1048.  Returns number of dryLeaf soft warnings.
 template <bool XSW>
-CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg, const DevPtrs &d, const int tile,
-                          const size_t smp, const bool valid, bool &veg_branch) {
+CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg, const bool valid, bool &veg_branch) {
   CanopyWork w;
   w.warn = 0; w.valid = valid;
   const float cr = K::capp * K::rmair;
@@ -806,7 +677,7 @@ CBL_DEV int define_canopy(Tile &t, const DevCfg &c, float dels, bool sunlit_veg,
       w.gbhu[1] = (double)dv(2.0f, t.rough_coexp) * gbvtop * (double)(1.0f - m_exp(-mn(hc * lai, 20.0f))) - w.gbhu[0];
     }
     w.rny = (double)w.sum_rniso; w.hcy = 0.0; w.ecy = w.rny - w.hcy;
-    dryLeaf<XSW>(t, c, w, dels, iter, d, tile, smp);
+    dryLeaf<XSW>(t, c, w, dels, iter);
     CBL_PHASE_BARRIER(CBL_SYNC_A, 2 * (iter - 1) + 1);  // re-align after the data-dependent number of dryLeaf passes
     wetLeaf(t, w, dels);
     // vegetation fluxes and temperature (:418-456)

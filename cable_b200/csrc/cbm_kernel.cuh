@@ -167,7 +167,7 @@ cbm_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ DevCfg c, 
     t.rad_albedo_T = (t.rad_albedo[0] + t.rad_albedo[1]) * 0.5f;
     t.ssnow_otss_0 = t.ssnow_otss;
     t.ssnow_otss = t.ssnow_tss;
-    const int warn = define_canopy<XSW != 0>(t, c, dels, sunlit_veg, d, i, smp, valid, veg_branch);
+    const int warn = define_canopy<XSW != 0>(t, c, dels, sunlit_veg, valid, veg_branch);
     t.ssnow_owetfac = t.ssnow_wetfac;
 #if CBL_FASTDIV
     __syncthreads();

@@ -71,9 +71,6 @@ enum TblSlot {
 struct DevPtrs {
 #define CABLE_FA(T, m, ct, n1, n2, role, flags) ct *__restrict__ T##_##m;
 #include "../../include/cable_b200_fields.def"
-  // per-tile scratch of kernel A's dryLeaf pass pool (cbm_canopy.cuh): best iterate / latest-pass results in flight
-  double *leaf_scr_d;
-  float *leaf_scr_f;
   // kernel A only: thread -> tile map, a permutation inside every aligned window of CBL_ORDER_WINDOW tiles that puts
   // tiles of one vegetation type side by side (null: identity).  See cable_capi.cu build_tile_order().
   const int *__restrict__ tile_order;
