@@ -160,3 +160,47 @@ def test_casa_feedback_matches_the_fortran_run(case):
     assert (T["veg_vcmax"][0] != vc0[0]).sum() > grid.mp // 2
     assert np.array_equal(lai, A["casamet_glai"][0].astype(np.float32))
     assert np.all(np.isfinite(T["canopy_fpn"])) and np.abs(T["canopy_fpn"]).max() > 0
+
+
+def test_config5_full_size_pools_close_their_balances():
+    """BASELINE config 5 at its full size (62 000 land points x 5 tiles): two model days of cbm + bgcdriver + sumcflux on the
+    device (the first day absorbs the synthetic pools' inconsistent sorbed / labile P: casa_delsoil re-equilibrates them), then
+    the reference's own closure diagnostics (casa_cnpbal, casa_cnp.F90:2117-2236): the carbon / nitrogen /
+    phosphorus pool changes of every vegetated tile balance the day's fluxes.  A size-independent property: the tiles are
+    independent, so what holds for the 120-tile golden cases must hold for each of the 310 000."""
+    cfg, grid, T, F = make_case(62000, start_doy=G.DOY)
+    cfg.output_level = 1; cfg.icycle = 3; cfg.n_forcing_slots = 8
+    ccfg = casa.default_cfg(); ccfg.icycle = 3; ccfg.lalloc = 0
+    A = casa.synth_casa(grid, T, ccfg, seed=31)
+    silt, clay = casa.soil_texture(T)
+    fs = []
+    for k in range(8):
+        F.fill(T, k); fs.append({n: T[n].copy() for n in synth.FORCING_FIELDS})
+    with CableB200(grid.mp, cfg) as h:
+        h.bind(T); h.upload_params(); h.upload_state()
+        h.driver_init(grid.cstart, grid.cend, grid.patchfrac, grid.lat[grid.tile2land])
+        cs = casa.Casa(h, ccfg)
+        cs.bind(A, silt, clay); cs.upload()
+        for k in range(8):
+            h.bind(fs[k]); h.set_forcing_async(k)
+        for k in range(16):
+            h.step(k + 1, DELS, k % 8)
+            cs.bgcdriver(k + 1, 1, 10000, DELS, 8, G.DOY + k // 8)
+            h.post_step(k + 1, 1, DELS)
+        cs.download()
+        h.download_diag()
+    veg = A["casamet_iveg2"][0] != 0
+    assert veg.sum() > 250000
+    for f in casa.FIELDS:
+        if f.key == 0 and f.dtype != np.int32:
+            assert np.isfinite(A[f.name][..., veg]).all(), f.name
+    pools = A["casapool_cplant"].sum(0) + A["casapool_clitter"].sum(0) + A["casapool_csoil"].sum(0)
+    assert float(np.abs(A["casabal_cbalance"][0][veg]).max()) < 1e-9 * float(pools.max())
+    # the Fortran run's own residuals on its 120 tiles: N ~1e-10, P ~1e-8 with single tiles up to 1e-4 (fortran_casa_v1.npz)
+    assert np.quantile(np.abs(A["casabal_nbalance"][0][veg]), 0.999) < 1e-6
+    pb = np.abs(A["casabal_pbalance"][0][veg])
+    assert np.median(pb) < 1e-6 and np.quantile(pb, 0.999) < 1e-4
+    npp = A["casaflux_cnpp"][0][veg]
+    assert (npp > 0).mean() > 0.3 and (npp < 0).any()                      # a July day: both hemispheres, both signs
+    # sumcflux's icycle > 0 branch: canopy%fnpp is the day's NPP per second (casa_sumcflux.F90:72)
+    assert np.array_equal(T["canopy_fnpp"][0], (A["casaflux_cnpp"][0] / np.float64(np.float32(86400.0))).astype(np.float32))
