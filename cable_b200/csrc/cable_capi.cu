@@ -656,18 +656,18 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&h->ev_join_c2, cudaEventDisableTiming);
   // drop-in call pipelining: tiles are cut into chunks so that forcing H2D, the kernels and the D2H of results of
-  // different chunks overlap (PCIe is full duplex); tiny shards are not worth cutting
-  // A chunk is a whole number of full waves (148 SMs x resident blocks x 128 tiles), so cutting the shard does not
-  // add partial waves; chunks alternate between two compute streams so one chunk's tail overlaps the next one's head.
+  // different chunks overlap (PCIe is full duplex).  The call is bound by the D2H of the mirrored fields, one strided copy
+  // per field component and chunk: TWO equal chunks keep the copies large (280 copies of ~350 KB reach 31 GB/s, 140 of
+  // ~700 KB 34 GB/s, profiles/r02_dropin_probe.txt) and still hide the second chunk's kernels; shards of less than one
+  // round of kernel A are not cut.  Chunks alternate between two compute streams.
+  int edge = CBL_ORDER_WINDOW; while (edge % 256) edge += CBL_ORDER_WINDOW;
   {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->sms = sms;
     const int wave = sms * CBL_MINB_A * CBL_BLOCK_A;
-    int waves_per_chunk = 1;
-    if (const char *e = getenv("CABLE_B200_CHUNK_WAVES")) waves_per_chunk = atoi(e) > 0 ? atoi(e) : 1;
-    h->chunk_tiles = wave * waves_per_chunk;
-    h->nchunks = (mp + h->chunk_tiles - 1) / h->chunk_tiles;
+    h->nchunks = mp > wave ? 2 : 1;
+    if (const char *e = getenv("CABLE_B200_CHUNK_WAVES")) { const int w = atoi(e) > 0 ? atoi(e) : 1; h->nchunks = (mp + wave * w - 1) / (wave * w); }
+    h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + edge - 1) / edge * edge;
   }
-  int edge = CBL_ORDER_WINDOW; while (edge % 256) edge += CBL_ORDER_WINDOW;
   if (const char *e = getenv("CABLE_B200_CHUNKS")) {        // explicit override: equal chunks
     h->nchunks = atoi(e) > 0 ? atoi(e) : 1;
     h->chunk_tiles = ((mp + h->nchunks - 1) / h->nchunks + edge - 1) / edge * edge;
