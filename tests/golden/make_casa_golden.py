@@ -26,7 +26,15 @@ TRACE = ("casaflux_cnpp", "casapool_cplant", "casapool_nsoilmin", "casapool_psoi
          "casaflux_crsoil", "casaflux_fraccalloc", "casaflux_kplant")      # stored after every day; every field after the last
 # name -> (icycle, lalloc, call_climate, l_limit_labile)
 BIO = {"c_fixed": (1, 0, 0, 0), "cn_dynamic": (2, 1, 0, 0), "cnp_fixed": (3, 0, 0, 0), "cnp_dynamic": (3, 1, 0, 1),
-       "cnp_lasa": (3, 3, 0, 0), "cn_climate": (2, 0, 1, 0), "cnp_climate_dyn": (3, 1, 1, 0)}
+       "cnp_lasa": (3, 3, 0, 0), "cn_climate": (2, 0, 1, 0), "cnp_climate_dyn": (3, 1, 1, 0),
+       "cnp_year_sweep": (3, 1, 0, 0)}
+# day of year of every biogeochem call: the default wraps a year end; the sweep visits every month, so that every tile walks
+# through all four phenology phases (casa_cnp.F90:2305-2360) with its leaf onset / fall rates
+IDOY = {"cnp_year_sweep": [1] + [15 + 30 * m for m in range(12)]}
+
+
+def idoys(name):
+    return IDOY.get(name, [1 if day == 0 else 364 + day for day in range(NDAYS)])
 DRV = {"drv_cnp": (3, 1, 0, 0), "drv_c": (1, 0, 0, 0)}
 # casa_feedback: name -> (icycle, cable_user%vcmax)
 FB = {"fb_cn_standard": (2, "standard"), "fb_cnp_standard": (3, "standard"), "fb_cnp_walker": (3, "Walker2014")}
@@ -70,8 +78,8 @@ def run_bio(name):
     fc = FortranCasa(T, A, casa.FIELDS, ccfg, silt, clay)
     S = fc.S
     out = {}
-    for day in range(NDAYS):
-        idoy = 1 if day == 0 else 364 + day                    # day 0: idoy == 1 resets the annual sums
+    days = idoys(name)
+    for day, idoy in enumerate(days):                          # day 0: idoy == 1 resets the annual sums
         xs = [np.zeros(grid.mp, np.float64) for _ in range(7)]; ys = [np.zeros(grid.mp, np.float32) for _ in range(15)]
         # the leaf maintenance respiration is an input of every day (bgcdriver sets it from the day's mean)
         S["casaflux"].f["crmplant"].a[:, 0] = 0.12 * S["casaflux"].f["cgpp"].a
@@ -80,9 +88,11 @@ def run_bio(name):
                   S["climate"], *xs, *ys)
         fc.pull()
         for f in casa.FIELDS:
-            if f.key == 0 and (day == NDAYS - 1 or f.name in TRACE):
+            if f.key == 0 and (day == len(days) - 1 or f.name in TRACE):
                 out[f"bio/{name}/day{day}/{f.name}"] = A[f.name].copy()
     neg = int((A["casaflux_cnpp"][0] < 0).sum()); pos = int((A["casaflux_cnpp"][0] > 0).sum())
+    if name in IDOY:
+        print(name, "phenology phases seen at the end:", np.bincount(A["phen_phase"][0], minlength=4).tolist(), flush=True)
     print(name, "tiles", grid.mp, "NPP>0", pos, "NPP<0", neg, "statements", fc.I.nstmt, flush=True)
     return out
 
