@@ -514,12 +514,27 @@ CBL_DEV void dryLeaf(Tile &t, const DevCfg &c, CanopyWork &w, float dels, int it
   p.deltlfy = p.abs_deltlf;
   leaf_pass_prepare(p, c);
 
+  // DO WHILE (ANY(abs_deltlf > 0.1) .AND. k < MAXITER) (cbl_dryLeaf.F90:236): the reference's ANY runs over all mp tiles and
+  // masks the body per tile; here the vote is taken per warp (every lane of the warp is here: shadow threads included, and the
+  // blocks of the redo launch return as a whole), so the loop control is warp-uniform and only the body is predicated.
+#ifndef CBL_WARP_VOTE
+#define CBL_WARP_VOTE 1
+#endif
+#if CBL_WARP_VOTE
+  bool active = veg;
+  for (int k = 1; k <= K::maxiter; k++) {
+    if (!__any_sync(0xffffffffu, active)) break;
+    bool captured;
+    if (active) active = leaf_pass<XSW>(p, c, dels, k, captured);
+  }
+#else
   if (veg) {
     for (int k = 1; k <= K::maxiter; k++) {
       bool captured;
       if (!leaf_pass<XSW>(p, c, dels, k, captured)) break;
     }
   }
+#endif
 
   // hand the results back to the tile (:608-666)
   w.tlfx = p.tlfx; w.dsx = p.dsx; w.tlfy = p.tlfy; w.rny = p.rny; w.hcy = p.hcy; w.ecy = p.ecy;
