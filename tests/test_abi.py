@@ -236,18 +236,20 @@ def test_fortran_bind_list_is_generated_from_the_registry_and_names_real_members
 
 
 def test_generated_host_mirror_types_are_up_to_date():
-    """cable_b200/csrc/host_mirror_types.inc (the C++ mirror of the reference's derived types) is what
-    tools/gen_host_mirror.py renders from the registry today."""
+    """cable_b200/csrc/host_mirror_types.inc and casa_host_mirror_types.inc (the C++ mirrors of the reference's derived types)
+    are what tools/gen_host_mirror.py renders from the two registries today."""
     import subprocess
     import sys
-    path = os.path.join(ROOT, "cable_b200", "csrc", "host_mirror_types.inc")
-    before, st = open(path).read(), os.stat(path)
+    paths = [os.path.join(ROOT, "cable_b200", "csrc", n) for n in ("host_mirror_types.inc", "casa_host_mirror_types.inc")]
+    before = [(open(p).read(), os.stat(p)) for p in paths]
     try:
         subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_host_mirror.py")], stdout=subprocess.DEVNULL)
-        assert open(path).read() == before
+        for p, (txt, _) in zip(paths, before):
+            assert open(p).read() == txt, p
     finally:
-        open(path, "w").write(before)
-        os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns))            # keep make from rebuilding the library
+        for p, (txt, st) in zip(paths, before):
+            open(p, "w").write(txt)
+            os.utime(p, ns=(st.st_atime_ns, st.st_mtime_ns))            # keep make from rebuilding the library
 
 
 def test_casa_registry_matches_def_file_and_reference_types():
