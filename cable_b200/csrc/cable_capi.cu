@@ -168,8 +168,6 @@ struct cable_handle {
   std::vector<cudaEvent_t> ev_forcing_ready, ev_slot_free;
   std::vector<char> slot_has_data;
   unsigned long long *d_warn = nullptr;
-  int *d_order = nullptr;          // kernel A's thread -> tile table (build_tile_order), null = identity
-  int tile_order = 0;              // CABLE_B200_TILE_ORDER=1 switches it on (measured slower, see build_tile_order)
   long long soil_snow_calls = 0;       // the reference's  INTEGER, SAVE :: ktau  (cbl_soilsnow_main.F90:60)
   int last_slot = 0;                   // forcing slot of the most recent step
   int fastdiv = 1;                     // kernel A's CBL_FASTDIV build first (CABLE_B200_FASTDIV=0: ordinary build only)
@@ -304,7 +302,6 @@ DevPtrs make_ptrs(const cable_handle *h, int slot) {
   d.tbl = h->d_tbl; d.tbl_d = h->d_tbl_d; d.tbl_classes = h->tbl_classes;
   d.met_tvair_in = (const float *)dev_in_ptr(h, FID_met_tvair, slot);
   d.canopy_oldcansto_in = (const float *)dev_in_ptr(h, FID_canopy_oldcansto, slot);
-  d.tile_order = nullptr;                          // set per launch (launch_range)
   return d;
 }
 
@@ -335,9 +332,6 @@ int copy_field(cable_handle *h, int id, int slot, bool to_device, cudaStream_t s
 int launch_range(cable_handle *h, const DevPtrs &d_in, float dels, int first, int i0, int i1, cudaStream_t st, bool in_pipeline = false) {
   if (i1 <= i0) return CABLE_OK;
   DevPtrs d = d_in;
-  // the thread -> tile table permutes inside aligned windows: usable when the range is made of whole windows
-  const bool whole_windows = (i0 % CBL_ORDER_WINDOW) == 0 && ((i1 % CBL_ORDER_WINDOW) == 0 || i1 == h->mp);
-  d.tile_order = (h->d_order && whole_windows) ? h->d_order : nullptr;
   // kernel A (surface + canopy) then kernel B (soil/snow/carbon) on the same stream, or the fused variant.
   // CBL_MINB_x = resident blocks per SM the compiler must allow (register cap 65536 / (BLOCK*MINB)).
 #define CBL_LAUNCH_X(PH, BL, MB, LV, XS) {                                                                                     \
@@ -584,7 +578,6 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   if (const char *e = getenv("CABLE_B200_SPLIT")) h->split = atoi(e);
   if (const char *e = getenv("CABLE_B200_MAXL1")) h->max_l1 = atoi(e);
   if (const char *e = getenv("CABLE_B200_STEP_CHAINS")) h->step_chains = atoi(e);
-  if (const char *e = getenv("CABLE_B200_TILE_ORDER")) h->tile_order = atoi(e);
   if (const char *e = getenv("CABLE_B200_FASTDIV")) h->fastdiv = atoi(e);
   if (const char *e = getenv("CABLE_B200_TABLES")) h->tbl_enable = atoi(e);
   if (const char *e = getenv("CABLE_B200_CARVEOUT")) h->carveout = atoi(e);
@@ -660,7 +653,7 @@ int cable_b200_create(int mp, const cable_cfg *cfg, int device, cable_handle **o
   // per field component and chunk: TWO equal chunks keep the copies large (280 copies of ~350 KB reach 31 GB/s, 140 of
   // ~700 KB 34 GB/s, profiles/r02_dropin_probe.txt) and still hide the second chunk's kernels; shards of less than one
   // round of kernel A are not cut.  Chunks alternate between two compute streams.
-  int edge = CBL_ORDER_WINDOW; while (edge % 256) edge += CBL_ORDER_WINDOW;
+  int edge = CBL_BLOCK_A; while (edge % 256) edge += CBL_BLOCK_A;
   {
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->sms = sms;
     const int wave = sms * CBL_MINB_A * CBL_BLOCK_A;
@@ -744,7 +737,6 @@ int cable_b200_destroy(cable_handle *h) {
   if (h->drv.on) driver_free(h);
   if (h->d_warn) cudaFree(h->d_warn);
   if (h->d_redo) cudaFree(h->d_redo);
-  if (h->d_order) cudaFree(h->d_order);
   if (h->d_tbl) cudaFree(h->d_tbl);
   if (h->d_tbl_d) cudaFree(h->d_tbl_d);
   if (h->arena) cudaFree(h->arena);
@@ -772,33 +764,6 @@ int cable_b200_bind_field(cable_handle *h, int id, void *host) {
   return CABLE_OK;
 }
 
-// Kernel A's thread -> tile table.  Within each aligned window of CBL_ORDER_WINDOW tiles (one 768-thread block) the tiles
-// are listed by vegetation type (veg%iveg), original order kept inside a type.  Why: neighbouring tiles are the patches of
-// one land point, i.e. five different PFTs side by side, and a warp pays for the slowest of its lanes in every
-// tile-dependent branch (lake / ice / bare tiles skip the canopy altogether) and in the dryLeaf loop (1-20 passes); with
-// the oracle's pass counter on the 310 000-tile benchmark grid, lane efficiency of that loop rises from 0.64 to 0.72.
-// Measured on B200 (bit-identical digests, tools/state_hash.py): 1.272 -> 1.290 ms/step, i.e. it LOSES -- the block's ~200
-// field loads/stores become 32-sector gathers inside the window (8x the L1 wavefronts), and fewer warp-instructions do
-// not help a step that is bound by per-warp dependent-chain latency and the block's slowest tile.  Off by default
-// (CABLE_B200_TILE_ORDER=1 to enable); a physically permuted device layout would remove the gathers, not the latency bound.
-static int build_tile_order(cable_handle *h) {
-  if (!h->tile_order) return CABLE_OK;
-  int iveg_id = -1;
-  for (int id = 0; id < NFIELDS; id++) if (!strcmp(g_fields[id].name, "veg_iveg")) iveg_id = id;
-  if (iveg_id < 0 || !h->host[iveg_id]) return CABLE_OK;
-  const int *iveg = (const int *)h->host[iveg_id];
-  std::vector<int> order((size_t)h->mp);
-  for (int w0 = 0; w0 < h->mp; w0 += CBL_ORDER_WINDOW) {
-    const int w1 = std::min(h->mp, w0 + CBL_ORDER_WINDOW);
-    for (int i = w0; i < w1; i++) order[i] = i;
-    std::stable_sort(order.begin() + w0, order.begin() + w1, [iveg](int a, int b) { return iveg[a] < iveg[b]; });
-  }
-  if (!h->d_order) CUDA_TRY(cudaMalloc(&h->d_order, (size_t)h->mp * sizeof(int)));
-  CUDA_TRY(cudaMemcpyAsync(h->d_order, order.data(), (size_t)h->mp * sizeof(int), cudaMemcpyHostToDevice, main_stream(h)));
-  CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
-  return CABLE_OK;
-}
-
 int cable_b200_upload(cable_handle *h, unsigned role_mask) {
   if (!h) return fail(CABLE_E_ARG, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -820,7 +785,6 @@ int cable_b200_upload(cable_handle *h, unsigned role_mask) {
     int rc = copy_field(h, FID_canopy_us, -1, true, main_stream(h)); if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(main_stream(h)));
-  if (role_mask & PARAM) { int rc = build_tile_order(h); if (rc) return rc; }
   if (role_mask & PARAM) { int rc = build_param_tables(h); if (rc) return rc; }
   return CABLE_OK;
 }

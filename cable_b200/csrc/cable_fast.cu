@@ -43,7 +43,6 @@ int cblf_launch_A(const void *devptrs, size_t devptrs_bytes, const void *cfg, si
   memcpy(&d, devptrs, sizeof(d));
   DevCfg c;
   memcpy(&c, cfg, sizeof(c));
-  d.tile_order = nullptr;
 #define CBLF_LVL(BL, MB)                                                                           \
   switch (lvl) { case 0: return launch<BL, MB, 0>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); \
                  case 1: return launch<BL, MB, 1>(d, c, mp, i0, i1, dels, first, warn, redo, max_l1, st); \

@@ -97,12 +97,7 @@ cbm_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ DevCfg c, 
   const size_t smp = (size_t)mp;
   const int i_raw = i0 + blockIdx.x * BLOCK + threadIdx.x;
   const bool valid = i_raw < i1;
-  const int i_lin = valid ? i_raw : i1 - 1;
-  // Kernel A walks the tiles of its 768-tile window grouped by vegetation type (a table built at upload): warps are then
-  // more uniform in what the tile-dependent branches and the dryLeaf loop ask of them.  The block still reads and writes
-  // the same contiguous window of every field, so DRAM traffic is unchanged; which thread computes a tile has no effect
-  // on the tile's results.
-  const int i = (PHASE == 1 && d.tile_order) ? d.tile_order[i_lin] : i_lin;
+  const int i = valid ? i_raw : i1 - 1;
   Tile t;
 
   // ---- per-PFT / per-soil-type parameter tables staged in shared memory (cbm_types.cuh, CBL_CLASS_*): one coalesced read

@@ -71,9 +71,6 @@ enum TblSlot {
 struct DevPtrs {
 #define CABLE_FA(T, m, ct, n1, n2, role, flags) ct *__restrict__ T##_##m;
 #include "../../include/cable_b200_fields.def"
-  // kernel A only: thread -> tile map, a permutation inside every aligned window of CBL_ORDER_WINDOW tiles that puts
-  // tiles of one vegetation type side by side (null: identity).  See cable_capi.cu build_tile_order().
-  const int *__restrict__ tile_order;
   // per-slot copies of the two inputs that are not FORCING rows: met%tvair as set by the caller (met_tv_is_tk = 0) and
   // canopy%oldcansto as set by the caller (caller_duties = 0, cable_serial.F90:573).  They ride in the forcing slot so a
   // prefetched step never overwrites what a running step still reads.
@@ -91,7 +88,6 @@ struct DevPtrs {
 #ifndef CBL_BLOCK_A
 #define CBL_BLOCK_A 640
 #endif
-#define CBL_ORDER_WINDOW CBL_BLOCK_A
 
 // per-thread copy of one tile
 struct Tile {

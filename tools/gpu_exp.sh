@@ -10,9 +10,7 @@ run() { # label, env...
   for r in 1 2; do env "$@" timeout 120 python tools/quick_perf.py 62000 60 2>&1 | tail -1 | sed -e "s/^/$label: /" | tee -a gpurun_out/exp_perf.txt; done
 }
 run default X=1
-run order0 CABLE_B200_TILE_ORDER=0
 for v in cable_b200/variants/*.so; do
   [ -f "$v" ] || continue
   run "$(basename $v)" CABLE_B200_LIB=$v
-  run "$(basename $v)+order0" CABLE_B200_LIB=$v CABLE_B200_TILE_ORDER=0
 done

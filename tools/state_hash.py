@@ -1,7 +1,7 @@
 """Bit-identity check between builds / launch settings: run the resident step loop and print one SHA-256 over every
 prognostic and driver-visible diagnostic array.  Pure scheduling changes (tile order, block shape, barriers) and
 same-value math rewrites must leave the digest unchanged.
-usage: [CABLE_B200_LIB=...] [CABLE_B200_TILE_ORDER=0] python tools/state_hash.py [nland] [steps]"""
+usage: [CABLE_B200_LIB=...] [CABLE_B200_PIPE_STREAMS=0] python tools/state_hash.py [nland] [steps]"""
 import hashlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -23,4 +23,4 @@ for f in FIELDS:
     if f.flags & FLAG["HOSTONLY"]: continue
     if f.role == ROLE["STATE"] or (f.role == ROLE["DIAG"] and f.flags & FLAG["STAR"]):
         dig.update(np.ascontiguousarray(T[f.name]).tobytes())
-print(f"state_hash mp={g.mp} steps={steps} lib={os.path.basename(lib.LIB_PATH)} order={os.environ.get('CABLE_B200_TILE_ORDER', '1')}: {dig.hexdigest()[:32]}")
+print(f"state_hash mp={g.mp} steps={steps} lib={os.path.basename(lib.LIB_PATH)} pipe_streams={os.environ.get('CABLE_B200_PIPE_STREAMS', 'default')}: {dig.hexdigest()[:32]}")
