@@ -31,14 +31,14 @@ void cblf_debug_dump();
 #define CBL_MINB_A 1
 #endif
 #ifndef CBL_MINB_B
-#define CBL_MINB_B 6
+#define CBL_MINB_B 2            // with CBL_BLOCK_B = 384: 24 warps per SM at 85 registers
 #endif
 #ifndef CBL_MINB_FUSED
 #define CBL_MINB_FUSED 8
 #endif
 // threads per block of kernel A / B (A's phase barriers make its block the unit that shares instruction fetches)
 #ifndef CBL_BLOCK_B
-#define CBL_BLOCK_B 128
+#define CBL_BLOCK_B 384         // r02 sweep (profiles/r02_kernelB_geometry_probe.txt): 384 x 2 beats 128 x 4/5/6/8, 256 x 2/3, 512 x 1 by 1-2 % of the step
 #endif
 // kernel A's geometry for ranges that do not fill the chip with 768-thread blocks (a shard of a strong-scaling run, a
 // pipeline chunk, the remainder chain): such a launch is bound by the latency of one warp's dependent chain, not by

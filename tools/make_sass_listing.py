@@ -6,7 +6,7 @@ so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(root, "cable_b200", "lib
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 tag_round = sys.argv[2] if len(sys.argv) > 2 else "r02"
 want = {"kernelA_fast_cbm_kernel_1_640_1_1": "4cblf10cbm_kernelILi1ELi640ELi1ELi1ELi0E", "kernelA_small_fast_cbm_kernel_1_128_3_1": "4cblf10cbm_kernelILi1ELi128ELi3ELi1ELi0E",
-        "kernelB_cbm_kernel_2_128_6_1": "3cbl10cbm_kernelILi2ELi128ELi6ELi1ELi0E", "casa_kernels": None, "driver_kernels": None}
+        "kernelB_cbm_kernel_2_384_2_1": "3cbl10cbm_kernelILi2ELi384ELi2ELi1ELi0E", "casa_kernels": None, "driver_kernels": None}
 cur, out = None, collections.defaultdict(list)
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
