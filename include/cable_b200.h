@@ -199,8 +199,14 @@ int          cable_b200_set_output_mask(cable_handle *h, const int *field_ids, i
  * asynchronous H2D copy into ring slot `slot` on the side stream.            */
 int          cable_b200_set_forcing_async(cable_handle *h, int slot);
 
-/* one timestep for all mp tiles from forcing slot `slot`; asynchronous on
- * the compute stream (waits for that slot's upload event).                   */
+/* one timestep for all mp tiles from forcing slot `slot`; asynchronous (waits for that slot's upload event).
+ * Shards larger than one round of kernel A run as a PIPELINE: the tiles are cut into chunks, each chunk's kernels go to one of
+ * four internal chain streams, and consecutive steps are not joined -- a chunk of step k+1 only waits for the same chunk of
+ * step k.  The per-tile calls that follow a step (cable_b200_post_step, cable_b200_bgcdriver, cable_b200_casa_feedback, the
+ * output reduction of cable_b200_output_fetch_async / _gather_async) ride the same chains.  Every other entry point
+ * (download, sync, cbm, upload, mark_dirty, device-side access through cable_b200_compute_stream ...) first joins the chains,
+ * so the host never observes a partially stepped shard.  CABLE_B200_PIPE_STREAMS=0 in the environment switches the
+ * pipeline off (one launch chain per step, joined).                                                                       */
 int          cable_b200_step(cable_handle *h, int ktau, float dels, int slot);
 
 /* The drop-in call: exactly what CALL cbm(ktau, dels, ...) does as seen from
@@ -214,7 +220,7 @@ int          cable_b200_sync(cable_handle *h);
 /* device-side access (for device-resident drivers and for torch/NCCL plumbing
  * via the pointer; no torch types cross this boundary)                       */
 void        *cable_b200_device_ptr(cable_handle *h, int field_id, int slot);
-void        *cable_b200_compute_stream(cable_handle *h);      /* cudaStream_t */
+void        *cable_b200_compute_stream(cable_handle *h);      /* cudaStream_t; joins the step pipeline first: work enqueued on it sees every step issued so far */
 
 /* measurement */
 int          cable_b200_profile(cable_handle *h, int enable); /* event-time each launch */
