@@ -76,6 +76,21 @@ MODULE cable_driver_b200
        IMPORT :: C_INT, C_PTR
        TYPE(C_PTR), VALUE :: handle
      END FUNCTION
+     ! CASA-CNP on the device-resident loop (icycle > 0): bgcdriver and casa_feedback / l_laiFeedbk (fortran/cable_bgcdriver_b200.F90
+     ! holds the initialisation: cable_b200_casa_init / _bind / _upload)
+     INTEGER(C_INT) FUNCTION cable_b200_bgcdriver(handle, ktau, kstart, kend, dels, ktauday, idoy, loy) &
+          BIND(C, NAME="cable_b200_bgcdriver")
+       IMPORT :: C_INT, C_PTR, C_FLOAT
+       TYPE(C_PTR), VALUE :: handle
+       INTEGER(C_INT), VALUE :: ktau, kstart, kend, ktauday, idoy, loy
+       REAL(C_FLOAT), VALUE :: dels
+     END FUNCTION
+     INTEGER(C_INT) FUNCTION cable_b200_casa_feedback(handle, slot, l_vcmaxfeedbk, l_laifeedbk, vcmax_walker2014) &
+          BIND(C, NAME="cable_b200_casa_feedback")
+       IMPORT :: C_INT, C_PTR
+       TYPE(C_PTR), VALUE :: handle
+       INTEGER(C_INT), VALUE :: slot, l_vcmaxfeedbk, l_laifeedbk, vcmax_walker2014
+     END FUNCTION
   END INTERFACE
 
 CONTAINS
@@ -102,5 +117,33 @@ CONTAINS
     IF (rc == 0) rc = cable_b200_output_fetch_async(handle, out(:, :, 1 + MOD(ktau, 2)))
     IF (rc /= 0) ERROR STOP 999                                                ! cable_abort convention
   END SUBROUTINE serial_time_step
+
+  !> The same step with CASA-CNP (icycle > 0; cable_serial.F90:584-715): casa_feedback / l_laiFeedbk before cbm, bgcdriver after
+  !! it, then sumcflux (its icycle > 0 branch reads casaflux on the device) inside cable_b200_post_step.  Nothing here joins the
+  !! step pipeline: every call is per tile (or per land point) and rides the chunk chains.
+  SUBROUTINE serial_time_step_casa(handle, ktau, kstart, kend, dels, ktauday, idoy, loy, l_vcmaxFeedbk, l_laiFeedbk, &
+                                   met_slice, cv, out, do_bal)
+    TYPE(C_PTR), INTENT(IN) :: handle
+    INTEGER, INTENT(IN) :: ktau, kstart, kend, ktauday, idoy, loy
+    LOGICAL, INTENT(IN) :: l_vcmaxFeedbk, l_laiFeedbk
+    REAL, INTENT(IN) :: dels
+    REAL(C_FLOAT), INTENT(IN) :: met_slice(:, :)
+    TYPE(cable_met_convert), INTENT(IN) :: cv
+    REAL(C_FLOAT), INTENT(INOUT) :: out(:, :, :)
+    LOGICAL, INTENT(IN) :: do_bal
+    INTEGER(C_INT) :: rc, slot
+    slot = MOD(ktau, 2)
+    rc = cable_b200_set_met_async(handle, slot, met_slice, cv)
+    IF (rc == 0) rc = cable_b200_casa_feedback(handle, slot, MERGE(1_C_INT, 0_C_INT, l_vcmaxFeedbk), &
+                                               MERGE(1_C_INT, 0_C_INT, l_laiFeedbk), 0_C_INT)       ! cable_serial.F90:587-590
+    IF (rc == 0) rc = cable_b200_step(handle, INT(ktau, C_INT), dels, slot)                          ! CALL cbm           :594
+    IF (rc == 0) rc = cable_b200_bgcdriver(handle, INT(ktau, C_INT), INT(kstart, C_INT), INT(kend, C_INT), dels, &
+                                           INT(ktauday, C_INT), INT(idoy, C_INT), INT(loy, C_INT))   ! CALL bgcdriver     :621
+    IF (rc == 0) rc = cable_b200_post_step(handle, INT(ktau, C_INT), INT(kstart, C_INT), dels, &     ! CALL sumcflux      :713
+                                           MERGE(1_C_INT, 0_C_INT, do_bal), MERGE(1_C_INT, 0_C_INT, do_bal))
+    IF (rc == 0) rc = cable_b200_output_wait(handle)
+    IF (rc == 0) rc = cable_b200_output_fetch_async(handle, out(:, :, 1 + MOD(ktau, 2)))
+    IF (rc /= 0) ERROR STOP 999
+  END SUBROUTINE serial_time_step_casa
 
 END MODULE cable_driver_b200

@@ -148,8 +148,9 @@ def test_fortran_shims_parse_and_match_the_c_abi_and_the_reference_signature():
     bound = [b for b in cbm_shim + drv_shim if b[1].startswith("cable_b200_") and b[0] in ("function", "subroutine")]
     assert len(bound) >= 15
     for kind, name, args in bound:
-        assert name in lib.EXPORTS, name
+        assert name in lib.EXPORTS + casa.EXPORTS, name
         assert len(args) == protos[name], (name, args, protos[name])
+    assert any(b[0] == "subroutine" and b[1] == "serial_time_step_casa" for b in drv_shim)
 
 
 def _shim_types(path):
