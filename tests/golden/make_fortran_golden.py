@@ -38,6 +38,9 @@ CASES = {
     "xsw_thermal_rough":   (24, 6, 30, 10800.0, None, dict(soil_thermal_fix=1, l_new_roughness_soil=1)),
     "xsw_redistrb_climate": (24, 6, 200, 10800.0, None, dict(redistrb=1, call_climate=1, gs_switch=1)),
     "caller_inputs":       (24, 8, 200, 10800.0, None, dict(caller_duties=0, met_tv_is_tk=0)),
+    # ten model days through the spring melt: state carried over 80 steps (snow packs building up and melting, soil thawing,
+    # canopy storage filling and draining, snow age), so a difference that only shows after many steps has room to show
+    "leuning_ten_days":    (20, 80, 85, 10800.0, None, dict()),
 }
 
 

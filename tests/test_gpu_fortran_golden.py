@@ -18,6 +18,22 @@ from util import field_errors               # noqa: E402
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(HERE, "golden", "fortran_cbm_v1.npz")
 
+# Runoff rates are differences of REAL(r_2) water stores of order 1e3 mm divided by dels: where nothing drains they are the
+# rounding dust of those stores (1e-13 mm/s in the ten-day case, i.e. 1 ulp of a 2 000 mm column per step), and that dust
+# follows the last bit of the binary64 `**` in smoisturev -- glibc's in the Fortran run, CUDA's (or this library's lean one)
+# on the device; all three differ from each other in that bit.  Such fields are judged against an absolute floor of
+# 1e-10 mm/s (1e-6 mm per 3-hourly step) as well as against the field's own scale; everything else as the docstring says.
+ABS_FLOOR = {"ssnow_runoff": 1e-10, "ssnow_rnof1": 1e-10, "ssnow_rnof2": 1e-10}
+
+
+def errors(name, want, got, dtype):
+    mx, tol, rel = field_errors(want, got, dtype)
+    if mx > tol and name in ABS_FLOOR:
+        a, b = want.astype(np.float64), got.astype(np.float64)
+        rel = np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), ABS_FLOOR[name])
+        mx = float(rel.max())
+    return mx, tol
+
 
 @pytest.mark.parametrize("case", list(G.CASES))
 def test_device_matches_the_fortran_run(case):
@@ -32,7 +48,7 @@ def test_device_matches_the_fortran_run(case):
             h.cbm(k + 1, dels)
             for n in G.TRACE:
                 want = z[f"{case}/trace/{n}"][k]
-                mx, tol, _ = field_errors(want, T[n], want.dtype.type)
+                mx, tol = errors(n, want, T[n], want.dtype.type)
                 assert mx <= tol, (case, k + 1, n, mx)
     for f in FIELDS:
         key = f"{case}/final/{f.name}"
@@ -40,7 +56,7 @@ def test_device_matches_the_fortran_run(case):
             continue
         want = z[key]
         assert np.all(np.isfinite(T[f.name])), f.name
-        mx, tol, _ = field_errors(want, T[f.name], f.dtype)
+        mx, tol = errors(f.name, want, T[f.name], f.dtype)
         assert mx <= tol, (case, "final", f.name, mx)
         worst = max(worst, mx)
         ntot += 1; nbit += int(np.array_equal(want, T[f.name]))
