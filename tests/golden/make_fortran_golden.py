@@ -41,6 +41,8 @@ CASES = {
     # ten model days through the spring melt: state carried over 80 steps (snow packs building up and melting, soil thawing,
     # canopy storage filling and draining, snow age), so a difference that only shows after many steps has room to show
     "leuning_ten_days":    (20, 80, 85, 10800.0, None, dict()),
+    # ... and ten days of deep winter with the other stomatal model: multi-layer snow packs ageing, densifying and re-layering
+    "medlyn_winter_ten_days": (20, 80, 5, 10800.0, None, dict(gs_switch=1)),
 }
 
 
