@@ -87,3 +87,27 @@ def test_interpreter_still_reproduces_the_fixture_live():
         for n in G.TRACE:
             assert np.array_equal(T[n], z[f"{case}/trace/{n}"][k], equal_nan=True), (n, k)
     assert fc.I.nstmt > 10000
+
+
+def test_oracle_post_step_reproduces_the_fortran_driver_statements():
+    """The statements serialdrv runs right after CALL cbm -- dels scaling of the runoff terms (cable_serial.F90:602-605), sumcflux
+    (casa_sumcflux.F90:37, icycle = 0), mass_balance and energy_balance (cable_checks.F90:472, 565) -- executed from the
+    reference's Fortran source by oracle/frun (tests/golden/make_poststep_golden.py) against the C++ oracle's post-step
+    (oracle/o_driver.cpp) on the oracle's own cbm: every bal%* / sum_flux%* array, canopy%fnee and the scaled rates bit for bit,
+    on each of 14 steps (ktau == 1 initialisations, the ktau > 10 accumulation branch)."""
+    import make_poststep_golden as P
+    from oracle.pyoracle import OracleDriver
+    z = np.load(os.path.join(HERE, "golden", "fortran_poststep_v1.npz"))
+    cfg, grid, T, F = P.case_inputs()
+    o = Oracle(T, cfg, cr_math=True)
+    od = OracleDriver(o)
+    for k in range(P.NSTEPS):
+        F.fill(T, k); o.cbm(k + 1, P.DELS)
+        od.post_step(k + 1, 1, P.DELS)
+        for n in P.BAL + P.SUMS:
+            key = f"step{k}/bal_{n}" if n in P.BAL else f"step{k}/sum_flux_{n}"
+            assert np.array_equal(od.arrays[n], z[key]), (k + 1, n, float(np.abs(od.arrays[n] - z[key]).max()))
+        assert np.array_equal(T["canopy_fnee"][0], z[f"step{k}/canopy_fnee"]), k + 1
+        for n in P.SCALED:
+            assert np.array_equal(T["ssnow_" + n][0], z[f"step{k}/ssnow_{n}"]), (k + 1, n)
+    assert float(np.abs(z[f"step{P.NSTEPS - 1}/bal_wbal_tot"]).max()) > 0      # the ktau > 10 branch accumulated something
