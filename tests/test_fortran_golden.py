@@ -111,3 +111,25 @@ def test_oracle_post_step_reproduces_the_fortran_driver_statements():
         for n in P.SCALED:
             assert np.array_equal(T["ssnow_" + n][0], z[f"step{k}/ssnow_{n}"]), (k + 1, n)
     assert float(np.abs(z[f"step{P.NSTEPS - 1}/bal_wbal_tot"]).max()) > 0      # the ktau > 10 branch accumulated something
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+def test_oracle_coszen_is_the_fortran_sinbet():
+    """met%coszen of the oracle's met expansion (oracle/o_driver.cpp) against the reference's ELEMENTAL FUNCTION sinbet
+    (src/science/radiation/cbl_sinbet.F90:7-28) executed from source by oracle/frun on 2 000 random (doy, latitude, hour):
+    bit for bit -- three binary32 SIN / COS, each evaluated in binary64 and rounded once on both sides."""
+    from oracle import pyoracle
+    from oracle.frun.finterp import Interp
+    from oracle.frun.run_cbm import STUBS
+    I = Interp("/root/reference/src", stub_modules=STUBS)
+    rng = np.random.default_rng(3)
+    n = 2000
+    doy = rng.integers(1, 367, n).astype(np.float32); lat = rng.uniform(-89, 89, n).astype(np.float32); hod = rng.uniform(0, 24, n).astype(np.float32)
+    want = np.array([np.float32(I.call("cbl_sinbet_mod", "sinbet", doy[i], lat[i], hod[i])) for i in range(n)], np.float32)
+    tiles = {k: np.zeros((2 if k == "met_fsd" else 1, n), np.float32) for k in
+             ("met_fsd", "met_tk", "met_pmb", "met_qv", "met_ua", "met_precip", "met_precip_sn", "met_fld", "met_ca", "met_coszen", "met_doy")}
+    land = np.zeros((11, n), np.float32); land[9] = hod; land[10] = doy; land[1] = 280.0
+    cs = np.arange(n, dtype=np.int32)
+    pyoracle.met_expand(tiles, land, cs, cs, lat, 0.0, 0.01, 10800.0, 1e-6, True, cr_math=True)
+    assert np.array_equal(tiles["met_coszen"][0], want)
+    assert (want > 1e-8).mean() > 0.3 and (want == np.float32(1e-8)).any()          # day and night both present
