@@ -254,6 +254,9 @@ class Interp:
             return m
         if name in self.stub_modules or name in ("iso_c_binding", "iso_fortran_env", "mpi", "netcdf", "ieee_arithmetic"):
             m = Module(name); m.names = {}
+            if name == "iso_fortran_env":       # the kind constants (byte sizes, as gfortran / ifort / nvfortran define them)
+                m.names = {k: Arr(np.array(v, np.int32)) for k, v in (("int8", 1), ("int16", 2), ("int32", 4), ("int64", 8),
+                                                                      ("real32", 4), ("real64", 8))}
             self.modules[name] = m
             return m
         f = self.index.get(name)

@@ -133,3 +133,32 @@ def test_oracle_coszen_is_the_fortran_sinbet():
     pyoracle.met_expand(tiles, land, cs, cs, lat, 0.0, 0.01, 10800.0, 1e-6, True, cr_math=True)
     assert np.array_equal(tiles["met_coszen"][0], want)
     assert (want > 1e-8).mean() > 0.3 and (want == np.float32(1e-8)).any()          # day and night both present
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+def test_oracle_grid_reduction_is_the_fortran_grid_cell_average():
+    """The patch -> grid-cell reduction of the oracle (oracle/o_driver.cpp; the device's output_reduce_kernel is tested against
+    it bit for bit) against the reference's grid_cell_average_real32_1d (src/util/cable_grid_reductions.F90:49-75) executed
+    from source by oracle/frun, with the reference's own patch_type / land_type arrays, on a ragged grid (1..5 active patches
+    per land point): bit for bit -- the same left-to-right binary32 sum."""
+    from oracle import pyoracle
+    from oracle.frun.finterp import Interp, StructArr
+    from oracle.frun.run_cbm import STUBS
+    from util import ragged_case
+    I = Interp("/root/reference/src", stub_modules=tuple(s for s in STUBS if s not in ("cable_iovars", "cable_io_vars_module")))
+    cfg, grid, T, F, idx = ragged_case(300)
+    io = I.module("cable_io_vars_module")
+    pt, lt = I.lookup_in_module(io, "$type:patch_type"), I.lookup_in_module(io, "$type:land_type")
+    patch = StructArr([I.new_struct(pt) for _ in range(grid.mp)], (1,))
+    landpt = StructArr([I.new_struct(lt) for _ in range(grid.nland)], (1,))
+    for i, s in enumerate(patch.items):
+        s.f["frac"].a[...] = grid.patchfrac[i]
+    for l, s in enumerate(landpt.items):
+        s.f["cstart"].a[...] = grid.cstart[l] + 1; s.f["cend"].a[...] = grid.cend[l] + 1
+    rng = np.random.default_rng(5)
+    for scale in (300.0, 1e-6):
+        x = rng.normal(scale, 0.13 * scale, grid.mp).astype(np.float32)
+        want = np.zeros(grid.nland, np.float32)
+        I.call("cable_grid_reductions_mod", "grid_cell_average_real32_1d", x, want, patch, landpt)
+        assert np.array_equal(pyoracle.grid_reduce(x, grid.patchfrac, grid.cstart, grid.cend), want)
+    assert len(set((grid.cend - grid.cstart + 1).tolist())) == 5
